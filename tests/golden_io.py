@@ -1,0 +1,91 @@
+"""Load a golden case (tests/golden/*.npz) back into a host Problem + expected outputs."""
+from __future__ import annotations
+
+import os
+
+import numpy as np
+
+from compas_tno_b200.problems import FixedProblem
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+CASES = [
+    "cross6_q_zb_min",
+    "cross14_q_zb_min",
+    "cross14_q_zb_t",
+    "fan_q_zb_max",
+    "dome_q_zb_reac_min",
+    "dome_q_zb_t",
+    "dome_q_zb_lambdh_reac",
+    "dome_q_zb_lambdv",
+    "freeform_q_zb_min",
+]
+
+
+def var_offset(variables, k, nb, name):
+    pos = k
+    for v in ("zb", "t", "lambdh", "lambdv"):
+        if v == name:
+            return pos
+        if v in variables:
+            pos += nb if v == "zb" else 1
+    raise KeyError(name)
+
+
+def load_case(name, envelope_factory=None):
+    """Return (problem, objective, xs, expected dict with full dense J)."""
+    z = np.load(os.path.join(GOLDEN, name + ".npz"), allow_pickle=False)
+    P = FixedProblem.from_arrays(z["xyz"], z["edges"], z["fixed"], z["loads"], z["lb"], z["ub"], z["target"],
+                                 z["q_form"], ind=z["ind"])
+    # B, d as the golden generator had them (pinv can differ in the last bits across LAPACK builds)
+    P.B = z["B"].copy()
+    P.d = z["d"].reshape(-1, 1).copy()
+    P.d0 = P.d.copy()
+    P.variables = [str(v) for v in z["variables"]]
+    P.constraints = [str(c) for c in z["constraints"]]
+    P.features = ["fixed"]
+    P.thk = float(z["thk"])
+    for key in z.files:
+        if key.startswith("extra_"):
+            val = z[key]
+            attr = key[len("extra_"):]
+            setattr(P, attr, val.copy())
+    if "envelope" in z.files:
+        kind = str(z["envelope"])
+        if envelope_factory is None:
+            from oracle.envelopes_np import CrossVaultEnvelopeNP, DomeEnvelopeNP
+            envelope_factory = {"CrossVaultEnvelope": lambda t: CrossVaultEnvelopeNP((0.0, 10.0), (0.0, 10.0), t),
+                                "DomeEnvelope": lambda t: DomeEnvelopeNP((5.0, 5.0), 5.0, t)}
+        P.envelope = envelope_factory[kind](P.thk)
+    objective = str(z["objective"])
+    xs = z["x"]
+
+    m, n, nb, k = P.m, P.n, P.nb, P.k
+    N, nvar = xs.shape
+    J = []
+    for j in range(N):
+        fun = np.zeros((2 * m, nvar))
+        fun[:m, :k] = P.B
+        fun[m:, :k] = -P.B
+        if "lambdh" in P.variables:
+            c = var_offset(P.variables, k, nb, "lambdh")
+            fun[:m, c] = z["extra_d0"].ravel()
+            fun[m:, c] = -z["extra_d0"].ravel()
+        env = z["J_env"][j]
+        neg = -env
+        if "t" in P.variables:
+            c = var_offset(P.variables, k, nb, "t")
+            neg[:, c] = z["J_dub"][j]
+        J.append(np.vstack([fun, env, neg, z["J_reac"][j]]))
+    expected = dict(g=z["g"], J=np.array(J), f=z["f"], grad=z["grad"], X=z["X"], q=z["q"], mineig=z["mineig"])
+    return P, objective, xs, expected
+
+
+def rel_err(a, b):
+    """max |a - b| / max |b|  -- the relative measure used for all parity statements."""
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    scale = np.max(np.abs(b)) if b.size else 1.0
+    if scale == 0.0:
+        scale = 1.0
+    return float(np.max(np.abs(a - b)) / scale) if b.size else 0.0
