@@ -1,0 +1,109 @@
+"""ctypes binding of include/tno_b200.h.  Fails loudly when the CUDA library is missing."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libtno_b200.so")
+
+ABI_VERSION = 1
+
+# masks / enums (mirror include/tno_b200.h)
+VAR_Q, VAR_ZB, VAR_T, VAR_LAMBDH, VAR_LAMBDV = 1, 2, 4, 8, 16
+CON_FUNICULAR, CON_ENVELOPE, CON_REAC_BOUNDS = 1, 2, 4
+OBJ_NONE, OBJ_MIN, OBJ_MAX, OBJ_T, OBJ_NEG_LAST = 0, 1, 2, 3, 4
+ENV_FIXED, ENV_DOME, ENV_CROSSVAULT = 0, 1, 2
+KERNEL_AUTO, KERNEL_INTERLEAVED, KERNEL_ONCHIP = 0, 1, 2
+STATUS_OK, STATUS_NOT_PD, STATUS_NONFINITE = 0, 1, 2
+
+EXPORTS = [
+    "tno_abi_version", "tno_last_error", "tno_plan_create", "tno_plan_destroy", "tno_plan_query",
+    "tno_plan_symbolic", "tno_eval_batch", "tno_eval_batch_host", "tno_plan_launch_count",
+]
+
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int32)
+
+
+class ProblemDesc(C.Structure):
+    _fields_ = [
+        ("abi_version", C.c_int32), ("n", C.c_int32), ("m", C.c_int32), ("nb", C.c_int32), ("k", C.c_int32),
+        ("edges", _ip), ("fixed", _ip),
+        ("B", _dp), ("d", _dp), ("P", _dp), ("X", _dp), ("lb", _dp), ("ub", _dp), ("s", _dp),
+        ("qmin", _dp), ("qmax", _dp), ("b", _dp), ("px0", _dp), ("py0", _dp), ("pzv", _dp), ("pz0", _dp),
+        ("variables", C.c_uint32), ("constraints", C.c_uint32), ("objective", C.c_int32),
+        ("envelope_kind", C.c_int32), ("env_params", C.c_double * 8), ("thk", C.c_double),
+        ("device", C.c_int32), ("kernel", C.c_int32), ("ordering", C.c_int32), ("reserved", C.c_int32),
+    ]
+
+
+class PlanInfo(C.Structure):
+    _fields_ = [
+        ("n", C.c_int32), ("m", C.c_int32), ("ni", C.c_int32), ("nb", C.c_int32), ("k", C.c_int32),
+        ("nvar", C.c_int32), ("ng", C.c_int32), ("nrhs", C.c_int32), ("nnz_a", C.c_int32), ("nnz_l", C.c_int32),
+        ("etree_height", C.c_int32), ("max_colcount", C.c_int32), ("kernel", C.c_int32), ("chunk", C.c_int32),
+        ("scratch_bytes", C.c_int64), ("factor_flops", C.c_int64), ("solve_flops", C.c_int64), ("smem_bytes", C.c_int64),
+    ]
+
+    def as_dict(self):
+        return {name: int(getattr(self, name)) for name, _ in self._fields_}
+
+
+class BatchInputs(C.Structure):
+    _fields_ = [("pz_scale", C.c_void_p), ("reserved0", C.c_void_p), ("reserved1", C.c_void_p)]
+
+
+class Outputs(C.Structure):
+    _fields_ = [("f", C.c_void_p), ("grad", C.c_void_p), ("g", C.c_void_p), ("J", C.c_void_p),
+                ("z", C.c_void_p), ("q", C.c_void_p), ("gmin", C.c_void_p), ("status", C.c_void_p)]
+
+
+_lib = None
+
+
+def load():
+    """Load libtno_b200.so (building it first if the sources are newer).  No fallback."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH) or os.environ.get("TNO_REBUILD") == "1":
+        from ._build import build
+        build(force=True)
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError("compas_tno_b200: CUDA library %s is missing and could not be built; "
+                           "there is no CPU fallback" % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    lib.tno_abi_version.restype = C.c_int
+    lib.tno_last_error.restype = C.c_char_p
+    lib.tno_plan_create.argtypes = [C.POINTER(ProblemDesc), C.POINTER(C.c_void_p)]
+    lib.tno_plan_create.restype = C.c_int
+    lib.tno_plan_destroy.argtypes = [C.c_void_p]
+    lib.tno_plan_destroy.restype = None
+    lib.tno_plan_query.argtypes = [C.c_void_p, C.POINTER(PlanInfo)]
+    lib.tno_plan_query.restype = C.c_int
+    lib.tno_plan_symbolic.argtypes = [C.c_void_p, _ip, _ip, _ip, _ip, _ip]
+    lib.tno_plan_symbolic.restype = C.c_int
+    lib.tno_eval_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.POINTER(BatchInputs),
+                                   C.POINTER(Outputs), C.c_void_p]
+    lib.tno_eval_batch.restype = C.c_int
+    lib.tno_eval_batch_host.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.POINTER(Outputs)]
+    lib.tno_eval_batch_host.restype = C.c_int
+    lib.tno_plan_launch_count.argtypes = [C.c_void_p]
+    lib.tno_plan_launch_count.restype = C.c_int64
+    if lib.tno_abi_version() != ABI_VERSION:
+        raise RuntimeError("libtno_b200.so ABI %d != binding ABI %d" % (lib.tno_abi_version(), ABI_VERSION))
+    _lib = lib
+    return lib
+
+
+class TnoError(RuntimeError):
+    pass
+
+
+def check(rc):
+    if rc != 0:
+        msg = load().tno_last_error().decode("utf-8", "replace")
+        if rc == -1:
+            raise NotImplementedError("tno_b200: " + msg)  # mirrors the reference's NotImplementedError
+        raise TnoError("tno_b200 error %d: %s" % (rc, msg))

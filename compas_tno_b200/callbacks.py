@@ -1,0 +1,126 @@
+"""Drop-in replacements for the four callables the reference stores on ``Problem``.
+
+Same names, argument order and return shapes as the reference's
+``constr_wrapper`` (src/compas_tno/problems/constraints.py:20),
+``sensitivities_wrapper`` (problems/jacobian.py:53), ``f_min_thrust`` / ``f_max_thrust`` /
+``f_reduce_thk`` / ``f_tight_crosssection`` (problems/objectives.py:91,151,415,438) and their
+gradients (problems/derivatives.py:223,336,183,203).  Each call evaluates a batch of one on the
+GPU; the four callbacks of one solver iterate share a single launch sequence through a one-entry
+cache keyed on the bytes of x (the reference factorises the same matrix three times instead,
+SURVEY.md Appendix D.8).
+
+``accelerate(problem, objective)`` performs what ``set_up_general_optimisation`` does at
+src/compas_tno/problems/setup.py:466-469, with these shims instead of the numpy callbacks.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from .plan import TnoPlan
+
+__all__ = [
+    "accelerate", "constr_wrapper", "sensitivities_wrapper", "f_min_thrust", "f_max_thrust", "gradient_fmin",
+    "gradient_fmax", "f_reduce_thk", "gradient_reduce_thk", "f_tight_crosssection", "gradient_tight_crosssection",
+    "objective_selector", "evaluate_batch",
+]
+
+_ATTR = "_tno_b200_state"
+
+
+class _State:
+    def __init__(self, problem, objective, device, kernel):
+        self.plan = TnoPlan(problem, objective=objective, device=device, kernel=kernel)
+        self.objective = objective
+        self.key = None
+        self.res = None
+
+    def eval1(self, x, problem):
+        x = np.ascontiguousarray(np.asarray(x, dtype=np.float64).reshape(-1))
+        key = x.tobytes()
+        if key != self.key:
+            self.res = self.plan.evaluate_host(x.reshape(1, -1), ("f", "grad", "g", "J", "z", "q", "status"))
+            self.key = key
+            # the reference's callbacks leave q and the updated geometry on the problem (constraints.py:90-95)
+            try:
+                problem.q = self.res["q"][0].reshape(-1, 1).copy()
+                problem.X[:, 2] = self.res["z"][0]
+            except Exception:
+                pass
+        return self.res
+
+
+def _state(problem, objective=None):
+    if isinstance(problem, list):  # the solvers pass args=[problem]
+        problem = problem[0]
+    st = getattr(problem, _ATTR, None)
+    if st is None or (objective is not None and st.objective != objective):
+        device = getattr(problem, "_tno_b200_device", 0)
+        kernel = getattr(problem, "_tno_b200_kernel", "auto")
+        st = _State(problem, objective if objective is not None else "min", device, kernel)
+        setattr(problem, _ATTR, st)
+    return st, problem
+
+
+def constr_wrapper(variables, M):
+    st, M = _state(M)
+    return st.eval1(variables, M)["g"][0].copy()
+
+
+def sensitivities_wrapper(variables, M):
+    st, M = _state(M)
+    return st.eval1(variables, M)["J"][0].copy()
+
+
+def _objective(name):
+    def fobj(variables, problem):
+        st, problem = _state(problem, name)
+        return float(st.eval1(variables, problem)["f"][0])
+
+    def fgrad(variables, problem):
+        st, problem = _state(problem, name)
+        return st.eval1(variables, problem)["grad"][0].copy()
+
+    return fobj, fgrad
+
+
+f_min_thrust, gradient_fmin = _objective("min")
+f_max_thrust, gradient_fmax = _objective("max")
+f_reduce_thk, gradient_reduce_thk = _objective("t")
+f_tight_crosssection, gradient_tight_crosssection = _objective("n")
+
+_SELECT = {
+    "min": (f_min_thrust, gradient_fmin),
+    "max": (f_max_thrust, gradient_fmax),
+    "t": (f_reduce_thk, gradient_reduce_thk),
+    "s": (f_tight_crosssection, gradient_tight_crosssection),
+    "n": (f_tight_crosssection, gradient_tight_crosssection),
+    "max_load": (f_tight_crosssection, gradient_tight_crosssection),
+}
+
+
+def objective_selector(objective):
+    """Same contract as problems/objectives.py:27-88, restricted to the accelerated objectives."""
+    if objective not in _SELECT:
+        print("Please, provide a valid objective for the optimisation")
+        raise NotImplementedError
+    return _SELECT[objective]
+
+
+def accelerate(problem, objective="min", device=0, kernel="auto"):
+    """Install the GPU callbacks on ``problem`` (reference setup.py:466-469) and return it."""
+    problem._tno_b200_device = device
+    problem._tno_b200_kernel = kernel
+    if hasattr(problem, _ATTR):
+        delattr(problem, _ATTR)
+    objective = {"s": "n", "max_load": "n"}.get(objective, objective)
+    fobj, fgrad = objective_selector(objective)
+    _state(problem, objective)
+    problem.fobj, problem.fgrad = fobj, fgrad
+    problem.fconstr, problem.fjac = constr_wrapper, sensitivities_wrapper
+    return problem
+
+
+def evaluate_batch(problem, xs, objective="min", outputs=("f", "grad", "g", "J", "z", "status"), device=0):
+    """The batched entry point the reference does not have: all callbacks for every row of xs."""
+    st, problem = _state(problem, {"s": "n", "max_load": "n"}.get(objective, objective))
+    return st.plan.evaluate_host(xs, outputs)

@@ -1,0 +1,572 @@
+// Kernel family 1: "interleaved" -- one thread per candidate, values batch-interleaved in HBM.
+//
+// Every per-candidate number lives in a scratch "slot"; slot s of candidate c is stored at
+// scratch[s * NC + c], so the 32 lanes of a warp (32 consecutive candidates, all executing the same
+// symbolic program) always touch 256 contiguous bytes.  Pattern indices are warp-uniform loads.
+// This family has no size limit (the factor does not have to fit on chip) and is the general path;
+// the on-chip family (tno_onchip.cu) is selected when factor + right-hand sides fit in shared memory.
+//
+// Math restated from the reference (paths relative to /root/reference/src/compas_tno/):
+//   q = B q_ind + d                     algorithms/equilibrium.py:190
+//   X_free = (Ci^T Q Ci)^-1 (P_i - Ci^T Q Cb X_b)     algorithms/equilibrium.py:230-234
+//   dz/dq_ind, dz/dzb, dz/dlambda       problems/jacobian.py:157-160,190-192,297-308,348-353
+//   reactions, f, grad f, reac_bounds   problems/objectives.py:144-146, derivatives.py:303-331,
+//                                       constraints.py:146-149, jacobian.py:204-255
+// The matrix is negative definite on this branch (compression = negative q), so we factor
+// -(Ci^T Q Ci) = L D L^T with a fixed pattern and no pivoting; D > 0 is checked per candidate.
+#include <cstdio>
+
+#include "tno_plan.hpp"
+
+namespace tno {
+
+#define WS(slot) ws[(int64_t)(slot) * NC + c]
+
+__global__ void k_pack(DevPlan P, double* __restrict__ ws, int64_t NC, int64_t ncand, const double* __restrict__ x,
+                       int64_t ldx, const double* __restrict__ pz_scale) {
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= ncand) return;
+  const int nvar = P.var.nvar;
+  for (int j = 0; j < nvar; ++j) WS(P.slot.s_x + j) = x[c * ldx + j];
+  WS(P.slot.s_pzs) = pz_scale ? pz_scale[c] : 1.0;
+}
+
+// q_e = lambdh * d_e + sum_j B[e, j] q_ind[j]
+__global__ void k_q(DevPlan P, double* __restrict__ ws, int64_t NC, int64_t ncand, int etile) {
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= ncand) return;
+  const int e0 = blockIdx.y * etile;
+  const int e1 = min(P.m, e0 + etile);
+  const int k = P.k;
+  const double lam = P.var.o_lambdh >= 0 ? WS(P.slot.s_x + P.var.o_lambdh) : 1.0;
+  for (int e = e0; e < e1; ++e) {
+    double acc = lam * P.d[e];
+    const double* Brow = P.B + (int64_t)e * k;
+    for (int j = 0; j < k; ++j) acc = fma(Brow[j], WS(P.slot.s_x + j), acc);
+    WS(P.slot.s_q + e) = acc;
+  }
+}
+
+// values of -(Ci^T Q Ci) scattered into the pattern of L (fill positions get 0)
+__global__ void k_assemble(DevPlan P, double* __restrict__ ws, int64_t NC, int64_t ncand, int ptile) {
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= ncand) return;
+  const int p0 = blockIdx.y * ptile;
+  const int p1 = min(P.nnz_l, p0 + ptile);
+  for (int p = p0; p < p1; ++p) {
+    double acc = 0.0;
+    for (int t = P.asm_ptr[p]; t < P.asm_ptr[p + 1]; ++t) acc += (double)P.asm_coef[t] * WS(P.slot.s_q + P.asm_edge[t]);
+    WS(P.slot.s_l + p) = acc;
+  }
+}
+
+// right-looking L D L^T; the diagonal slot ends up holding 1 / d_j
+__global__ void k_factor(DevPlan P, double* __restrict__ ws, int64_t NC, int64_t ncand, int32_t* __restrict__ status) {
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= ncand) return;
+  int st = 0;
+  const int sl = P.slot.s_l;
+  for (int j = 0; j < P.ni; ++j) {
+    const int p0 = P.colptr[j], p1 = P.colptr[j + 1];
+    const double dj = WS(sl + p0);
+    if (!(dj > 0.0)) st |= TNO_STATUS_NOT_PD;
+    const double inv = 1.0 / dj;
+    WS(sl + p0) = inv;
+    int64_t t = P.upd_ptr[j];
+    for (int pa = p0 + 1; pa < p1; ++pa) {
+      const double va = WS(sl + pa);
+      const double la = va * inv;
+      {
+        const int tg = P.upd_pos[t++];
+        WS(sl + tg) = fma(-va, la, WS(sl + tg));
+      }
+      for (int pb = pa + 1; pb < p1; ++pb) {
+        const int tg = P.upd_pos[t++];
+        WS(sl + tg) = fma(-WS(sl + pb), la, WS(sl + tg));
+      }
+      WS(sl + pa) = la;
+    }
+  }
+  status[c] = st;
+}
+
+__device__ __forceinline__ double zfixed(const DevPlan& P, const double* ws, int64_t NC, int64_t c, int b) {
+  return P.var.o_zb >= 0 ? WS(P.slot.s_x + P.var.o_zb + b) : P.X[3 * P.fixed[b] + 2];
+}
+
+// phase-1 right-hand sides of  -(Ci^T Q Ci) X = -(P_i - Ci^T Q Cb X_b)  and the zb / lambdv blocks
+__global__ void k_rhs1(DevPlan P, double* __restrict__ ws, int64_t NC, int64_t ncand, int rtile) {
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= ncand) return;
+  const int r0 = blockIdx.y * rtile;
+  const int r1 = min(P.ni, r0 + rtile);
+  const int nrhs = P.rhs.nrhs;
+  const double lamh = P.var.o_lambdh >= 0 ? WS(P.slot.s_x + P.var.o_lambdh) : 1.0;
+  const double lamv = P.var.o_lambdv >= 0 ? WS(P.slot.s_x + P.var.o_lambdv) : 1.0;
+  const double pzs = WS(P.slot.s_pzs);
+  for (int r = r0; r < r1; ++r) {
+    const int v = P.row_vertex[r];
+    double px, py, pz;
+    if (P.var.o_lambdh >= 0) {
+      px = lamh * P.px0[v];
+      py = lamh * P.py0[v];
+    } else {
+      px = P.P[3 * v + 0];
+      py = P.P[3 * v + 1];
+    }
+    pz = (P.var.o_lambdv >= 0) ? (lamv * P.pzv[v] + P.pz0[v]) : P.P[3 * v + 2];
+    pz *= pzs;
+    double bx = -px, by = -py, bz = -pz;
+    const int base = P.slot.s_r + r * nrhs;
+    if (P.rhs.c_zb >= 0)
+      for (int b = 0; b < P.nb; ++b) WS(base + P.rhs.c_zb + b) = 0.0;
+    for (int t = P.vadj_ptr[v]; t < P.vadj_ptr[v + 1]; ++t) {
+      const int o = P.vadj_other[t];
+      const int ro = P.vrow[o];
+      if (ro >= 0) continue;
+      const int b = -1 - ro;
+      const double qe = WS(P.slot.s_q + P.vadj_edge[t]);
+      bx = fma(-qe, P.X[3 * o + 0], bx);
+      by = fma(-qe, P.X[3 * o + 1], by);
+      bz = fma(-qe, zfixed(P, ws, NC, c, b), bz);
+      if (P.rhs.c_zb >= 0) WS(base + P.rhs.c_zb + b) -= qe;
+    }
+    WS(base + P.rhs.cx) = bx;
+    WS(base + P.rhs.cy) = by;
+    WS(base + P.rhs.cz) = bz;
+    if (P.rhs.c_lambdv >= 0) WS(base + P.rhs.c_lambdv) = -P.pzv[v];
+  }
+}
+
+// L D L^T solve of RB right-hand-side columns [col0, col0+RB) (guarded by ncols) for one candidate
+template <int RB>
+__global__ void k_solve(DevPlan P, double* __restrict__ ws, int64_t NC, int64_t ncand, int col0, int ncols) {
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= ncand) return;
+  const int cb = col0 + blockIdx.y * RB;
+  const int nr = min(RB, col0 + ncols - cb);
+  const int nrhs = P.rhs.nrhs;
+  const int sl = P.slot.s_l, sr = P.slot.s_r + cb;
+  double y[RB];
+  // forward (unit lower) fused with the diagonal scaling
+  for (int j = 0; j < P.ni; ++j) {
+    const int p0 = P.colptr[j], p1 = P.colptr[j + 1];
+#pragma unroll
+    for (int r = 0; r < RB; ++r) y[r] = (r < nr) ? WS(sr + j * nrhs + r) : 0.0;
+    for (int p = p0 + 1; p < p1; ++p) {
+      const double l = WS(sl + p);
+      const int i = P.rowidx[p];
+#pragma unroll
+      for (int r = 0; r < RB; ++r)
+        if (r < nr) WS(sr + i * nrhs + r) = fma(-l, y[r], WS(sr + i * nrhs + r));
+    }
+    const double inv = WS(sl + p0);
+#pragma unroll
+    for (int r = 0; r < RB; ++r)
+      if (r < nr) WS(sr + j * nrhs + r) = y[r] * inv;
+  }
+  // backward (unit upper = L^T)
+  for (int j = P.ni - 1; j >= 0; --j) {
+    const int p0 = P.colptr[j], p1 = P.colptr[j + 1];
+    if (p1 - p0 == 1) continue;
+#pragma unroll
+    for (int r = 0; r < RB; ++r) y[r] = (r < nr) ? WS(sr + j * nrhs + r) : 0.0;
+    for (int p = p0 + 1; p < p1; ++p) {
+      const double l = WS(sl + p);
+      const int i = P.rowidx[p];
+#pragma unroll
+      for (int r = 0; r < RB; ++r)
+        if (r < nr) y[r] = fma(-l, WS(sr + i * nrhs + r), y[r]);
+    }
+#pragma unroll
+    for (int r = 0; r < RB; ++r)
+      if (r < nr) WS(sr + j * nrhs + r) = y[r];
+  }
+}
+
+__device__ __forceinline__ double zval(const DevPlan& P, const double* ws, int64_t NC, int64_t c, int v) {
+  const int r = P.vrow[v];
+  return r >= 0 ? WS(P.slot.s_r + r * P.rhs.nrhs + P.rhs.cz) : zfixed(P, ws, NC, c, -1 - r);
+}
+__device__ __forceinline__ double xval(const DevPlan& P, const double* ws, int64_t NC, int64_t c, int v, int axis) {
+  const int r = P.vrow[v];
+  return r >= 0 ? WS(P.slot.s_r + r * P.rhs.nrhs + axis) : P.X[3 * v + axis];
+}
+
+// phase-2 right-hand sides:  Ci^T W B  (k columns) and  Ci^T W d0  (lambdh column), W = diag(C z)
+__global__ void k_rhs2(DevPlan P, double* __restrict__ ws, int64_t NC, int64_t ncand, int rtile) {
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= ncand) return;
+  const int r0 = blockIdx.y * rtile;
+  const int r1 = min(P.ni, r0 + rtile);
+  const int nrhs = P.rhs.nrhs, k = P.k;
+  for (int r = r0; r < r1; ++r) {
+    const int v = P.row_vertex[r];
+    const int base = P.slot.s_r + r * nrhs;
+    const double zv = WS(base + P.rhs.cz);
+    const int a0 = P.vadj_ptr[v], a1 = P.vadj_ptr[v + 1];
+    for (int j = 0; j < k; ++j) {
+      double acc = 0.0;
+      for (int t = a0; t < a1; ++t) {
+        const double zo = zval(P, ws, NC, c, P.vadj_other[t]);
+        const double sg = (double)P.vadj_sign[t];
+        const double w = sg > 0 ? (zv - zo) : (zo - zv);  // (C z)_e
+        acc = fma(sg * w, P.B[(int64_t)P.vadj_edge[t] * k + j], acc);
+      }
+      WS(base + P.rhs.c_q + j) = acc;
+    }
+    if (P.rhs.c_lambdh >= 0) {
+      double acc = 0.0;
+      for (int t = a0; t < a1; ++t) {
+        const double zo = zval(P, ws, NC, c, P.vadj_other[t]);
+        const double sg = (double)P.vadj_sign[t];
+        const double w = sg > 0 ? (zv - zo) : (zo - zv);
+        acc = fma(sg * w, P.d[P.vadj_edge[t]], acc);
+      }
+      WS(base + P.rhs.c_lambdh) = acc;
+    }
+  }
+}
+
+__device__ __forceinline__ void envelope_eval(const DevPlan& P, double x, double y, double t, double* ub, double* lb,
+                                               double* dub, double* dlb) {
+  // closed forms of the parametric envelopes (compas_tna is not vendored)
+  const double dx = x - P.env[0], dy = y - P.env[1];
+  double d2;
+  if (P.envelope_kind == TNO_ENV_DOME) {
+    d2 = dx * dx + dy * dy;
+  } else {
+    const double dd = (fabs(dy) >= fabs(dx)) ? dx : dy;
+    d2 = dd * dd;
+  }
+  const double re = P.env[2] + 0.5 * t, ri = P.env[2] - 0.5 * t;
+  const double u = sqrt(re * re - d2);
+  *ub = u;
+  *dub = re / (2.0 * u);
+  const double in = ri * ri - d2;
+  if (in > 0.0) {
+    const double l = sqrt(in);
+    *lb = l;
+    *dlb = -ri / (2.0 * l);
+  } else {
+    *lb = P.env[3];
+    *dlb = 0.0;
+  }
+}
+
+// reactions, objective, gradient, reac_bounds rows, envelope update, feasibility margin, status
+__global__ void k_epilogue(DevPlan P, double* __restrict__ ws, int64_t NC, int64_t ncand, double* __restrict__ f_out,
+                           double* __restrict__ gmin_out, int32_t* __restrict__ status) {
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= ncand) return;
+  const int n = P.n, m = P.m, nb = P.nb, k = P.k, nvar = P.var.nvar, nrhs = P.rhs.nrhs;
+  const bool has_t = P.var.o_t >= 0;
+  const double lamh = P.var.o_lambdh >= 0 ? WS(P.slot.s_x + P.var.o_lambdh) : 1.0;
+  const double lamv = P.var.o_lambdv >= 0 ? WS(P.slot.s_x + P.var.o_lambdv) : 1.0;
+  const double pzs = WS(P.slot.s_pzs);
+  double gmin = 1e300;
+  bool bad = false;
+
+  if (P.constraints & TNO_CON_FUNICULAR) {
+    for (int e = 0; e < m; ++e) {
+      const double q = WS(P.slot.s_q + e);
+      gmin = fmin(gmin, fmin(q - P.qmin[e], P.qmax[e] - q));
+      bad |= !isfinite(q);
+    }
+  }
+  if (has_t) {
+    const double t = WS(P.slot.s_x + P.var.o_t);
+    for (int v = 0; v < n; ++v) {
+      double ub, lb, dub, dlb;
+      envelope_eval(P, xval(P, ws, NC, c, v, 0), xval(P, ws, NC, c, v, 1), t, &ub, &lb, &dub, &dlb);
+      WS(P.slot.s_env + v) = ub;
+      WS(P.slot.s_env + n + v) = lb;
+      WS(P.slot.s_env + 2 * n + v) = dub;
+      WS(P.slot.s_env + 3 * n + v) = dlb;
+    }
+  }
+  if (P.constraints & TNO_CON_ENVELOPE) {
+    for (int v = 0; v < n; ++v) {
+      const double z = zval(P, ws, NC, c, v);
+      const double ub = has_t ? WS(P.slot.s_env + v) : P.ub[v];
+      const double lb = has_t ? WS(P.slot.s_env + n + v) : P.lb[v];
+      gmin = fmin(gmin, fmin(z - lb, ub - z));
+      bad |= !isfinite(z);
+    }
+  }
+
+  const bool want_thrust = (P.objective == TNO_OBJ_MIN || P.objective == TNO_OBJ_MAX);
+  const bool want_reac = (P.constraints & TNO_CON_REAC_BOUNDS) != 0;
+  double f = 0.0;
+  if (want_thrust)
+    for (int j = 0; j < nvar; ++j) WS(P.slot.s_grad + j) = 0.0;
+
+  if (want_thrust || want_reac) {
+    const double osign = (P.objective == TNO_OBJ_MAX) ? -1.0 : 1.0;
+    for (int b = 0; b < nb; ++b) {
+      const int vb = P.fixed[b];
+      const int a0 = P.vadj_ptr[vb], a1 = P.vadj_ptr[vb + 1];
+      const double xb = P.X[3 * vb + 0], yb = P.X[3 * vb + 1], zb = zfixed(P, ws, NC, c, b);
+      double px, py, pz;
+      if (P.var.o_lambdh >= 0) {
+        px = lamh * P.px0[vb];
+        py = lamh * P.py0[vb];
+      } else {
+        px = P.P[3 * vb + 0];
+        py = P.P[3 * vb + 1];
+      }
+      pz = (P.var.o_lambdv >= 0) ? (lamv * P.pzv[vb] + P.pz0[vb]) : P.P[3 * vb + 2];
+      pz *= pzs;
+      // R_b = Cb^T Q C X - P_b
+      double Rx = 0.0, Ry = 0.0, Rz = 0.0;
+      for (int t = a0; t < a1; ++t) {
+        const int o = P.vadj_other[t];
+        const double sg = (double)P.vadj_sign[t];
+        const double qe = WS(P.slot.s_q + P.vadj_edge[t]);
+        const double xo = xval(P, ws, NC, c, o, 0), yo = xval(P, ws, NC, c, o, 1), zo = zval(P, ws, NC, c, o);
+        const double u = sg > 0 ? (xb - xo) : (xo - xb);
+        const double vv = sg > 0 ? (yb - yo) : (yo - yb);
+        const double w = sg > 0 ? (zb - zo) : (zo - zb);
+        Rx = fma(sg * qe, u, Rx);
+        Ry = fma(sg * qe, vv, Ry);
+        Rz = fma(sg * qe, w, Rz);
+      }
+      Rx -= px;
+      Ry -= py;
+      Rz -= pz;
+      if (want_thrust) {
+        const double Rn = sqrt(Rx * Rx + Ry * Ry);
+        f += Rn;
+        const double cx = osign * Rx / Rn, cy = osign * Ry / Rn;
+        // grad_j += cx * (Cb^T U B)[b, j] + cy * (Cb^T V B)[b, j]
+        for (int j = 0; j < k; ++j) {
+          double gx = 0.0, gy = 0.0;
+          for (int t = a0; t < a1; ++t) {
+            const int o = P.vadj_other[t];
+            const double sg = (double)P.vadj_sign[t];
+            const double xo = xval(P, ws, NC, c, o, 0), yo = xval(P, ws, NC, c, o, 1);
+            const double u = sg > 0 ? (xb - xo) : (xo - xb);
+            const double vv = sg > 0 ? (yb - yo) : (yo - yb);
+            const double Bej = P.B[(int64_t)P.vadj_edge[t] * k + j];
+            gx = fma(sg * u, Bej, gx);
+            gy = fma(sg * vv, Bej, gy);
+          }
+          WS(P.slot.s_grad + j) += cx * gx + cy * gy;
+        }
+      }
+      if (want_reac) {
+        // constraints.py:146-149 and jacobian.py:204-255, 310-346, 355-373 (restated literally)
+        const int vbv = vb;
+        const double sx = Rx < 0 ? -1.0 : 1.0, sy = Ry < 0 ? -1.0 : 1.0, sz = Rz < 0 ? -1.0 : 1.0;
+        const double rz2 = Rz * Rz;
+        const double rise = zb - (P.s ? P.s[vbv] : 0.0);
+        const double gx_ = fabs(P.b[2 * b + 0]) - rise * fabs(Rx / Rz);
+        const double gy_ = fabs(P.b[2 * b + 1]) - rise * fabs(Ry / Rz);
+        WS(P.slot.s_rg + b) = gx_;
+        WS(P.slot.s_rg + nb + b) = gy_;
+        gmin = fmin(gmin, fmin(gx_, gy_));
+        bad |= !isfinite(gx_) || !isfinite(gy_);
+        const int rowx = P.slot.s_rj + b * nvar, rowy = P.slot.s_rj + (nb + b) * nvar;
+        for (int j = 0; j < nvar; ++j) {
+          WS(rowx + j) = 0.0;
+          WS(rowy + j) = 0.0;
+        }
+        const bool has_env = (P.constraints & TNO_CON_ENVELOPE) != 0;  // dz/dq is only formed with 'envelope'
+        // q_ind columns
+        for (int j = 0; j < k; ++j) {
+          double dRx = 0.0, dRy = 0.0, dRz = 0.0;
+          for (int t = a0; t < a1; ++t) {
+            const int o = P.vadj_other[t];
+            const int e = P.vadj_edge[t];
+            const double sg = (double)P.vadj_sign[t];
+            const double qe = WS(P.slot.s_q + e);
+            const double xo = xval(P, ws, NC, c, o, 0), yo = xval(P, ws, NC, c, o, 1), zo = zval(P, ws, NC, c, o);
+            const double u = sg > 0 ? (xb - xo) : (xo - xb);
+            const double vv = sg > 0 ? (yb - yo) : (yo - yb);
+            const double w = sg > 0 ? (zb - zo) : (zo - zb);
+            const double Bej = P.B[(int64_t)e * k + j];
+            dRx = fma(sg * u, Bej, dRx);
+            dRy = fma(sg * vv, Bej, dRy);
+            dRz = fma(sg * w, Bej, dRz);
+            const int ro = P.vrow[o];
+            if (has_env && ro >= 0) {
+              const double dzo = WS(P.slot.s_r + ro * nrhs + P.rhs.c_q + j);
+              // (C dz)_e with dz_b = 0:  head - tail
+              dRz = fma(sg * qe, sg > 0 ? -dzo : dzo, dRz);
+            }
+          }
+          WS(rowx + j) = zb * sx * (-Rz * dRx + Rx * dRz) / rz2 / sz;
+          WS(rowy + j) = zb * sy * (-Rz * dRy + Ry * dRz) / rz2 / sz;
+        }
+        // zb columns:  dRz/dzb = Cb^T Q C A ;  the reference adds COLUMN b of it to row b
+        if (P.var.o_zb >= 0) {
+          for (int cb = 0; cb < nb; ++cb) {
+            // entry (cb, b) of Cb^T Q C A : row cb = support cb
+            const int vc = P.fixed[cb];
+            double acc = 0.0;
+            for (int t = P.vadj_ptr[vc]; t < P.vadj_ptr[vc + 1]; ++t) {
+              const int o = P.vadj_other[t];
+              const double sg = (double)P.vadj_sign[t];
+              const double qe = WS(P.slot.s_q + P.vadj_edge[t]);
+              const int ro = P.vrow[o];
+              const double Ao = ro >= 0 ? WS(P.slot.s_r + ro * nrhs + P.rhs.c_zb + b) : ((-1 - ro) == b ? 1.0 : 0.0);
+              const double Ac = (cb == b) ? 1.0 : 0.0;
+              const double diff = sg > 0 ? (Ac - Ao) : (Ao - Ac);
+              acc = fma(sg * qe, diff, acc);
+            }
+            double vx = sz * zb * fabs(Rx) / rz2 * acc;
+            double vy = sz * zb * fabs(Ry) / rz2 * acc;
+            if (cb == b) {
+              vx += -fabs(Rx / Rz);
+              vy += -fabs(Ry / Rz);
+            }
+            WS(rowx + P.var.o_zb + cb) = vx;
+            WS(rowy + P.var.o_zb + cb) = vy;
+          }
+        }
+        if (P.var.o_lambdh >= 0) {
+          double dRx = 0.0, dRy = 0.0, dRz = 0.0;
+          for (int t = a0; t < a1; ++t) {
+            const int o = P.vadj_other[t];
+            const int e = P.vadj_edge[t];
+            const double sg = (double)P.vadj_sign[t];
+            const double qe = WS(P.slot.s_q + e);
+            const double xo = xval(P, ws, NC, c, o, 0), yo = xval(P, ws, NC, c, o, 1), zo = zval(P, ws, NC, c, o);
+            const double u = sg > 0 ? (xb - xo) : (xo - xb);
+            const double vv = sg > 0 ? (yb - yo) : (yo - yb);
+            const double w = sg > 0 ? (zb - zo) : (zo - zb);
+            const double d0 = P.d[e];
+            dRx = fma(sg * u, d0, dRx);
+            dRy = fma(sg * vv, d0, dRy);
+            dRz = fma(sg * w, d0, dRz);
+            const int ro = P.vrow[o];
+            if (ro >= 0) {
+              const double dzo = WS(P.slot.s_r + ro * nrhs + P.rhs.c_lambdh);
+              dRz = fma(sg * qe, sg > 0 ? -dzo : dzo, dRz);
+            }
+          }
+          dRx -= P.px0[vb];
+          dRy -= P.py0[vb];
+          WS(rowx + P.var.o_lambdh) = zb * sx * (-Rz * dRx + Rx * dRz) / rz2 / sz;
+          WS(rowy + P.var.o_lambdh) = zb * sy * (-Rz * dRy + Ry * dRz) / rz2 / sz;
+        }
+        if (P.var.o_lambdv >= 0) {
+          double dRz = 0.0;
+          for (int t = a0; t < a1; ++t) {
+            const int o = P.vadj_other[t];
+            const double sg = (double)P.vadj_sign[t];
+            const double qe = WS(P.slot.s_q + P.vadj_edge[t]);
+            const int ro = P.vrow[o];
+            if (ro >= 0) {
+              const double dzo = WS(P.slot.s_r + ro * nrhs + P.rhs.c_lambdv);
+              dRz = fma(sg * qe, sg > 0 ? -dzo : dzo, dRz);
+            }
+          }
+          dRz -= P.pzv[vb];
+          WS(rowx + P.var.o_lambdv) = sz * zb * fabs(Rx) / rz2 * dRz;
+          WS(rowy + P.var.o_lambdv) = sz * zb * fabs(Ry) / rz2 * dRz;
+        }
+      }
+    }
+  }
+
+  if (P.objective == TNO_OBJ_MAX) f = -f;
+  if (P.objective == TNO_OBJ_T) f = WS(P.slot.s_x + nvar - 1);
+  if (P.objective == TNO_OBJ_NEG_LAST) f = -WS(P.slot.s_x + nvar - 1);
+  bad |= !isfinite(f);
+  if (f_out) f_out[c] = f;
+  if (gmin_out) gmin_out[c] = gmin;
+  if (bad) status[c] |= TNO_STATUS_NONFINITE;
+}
+
+// Table-driven transposing emitter: out[c][e] = sa * ws[a][c] + sb * ws[b][c] + const.
+// A CTA stages TW elements x 32 candidates in shared memory: reads are coalesced along the candidate
+// axis of the scratch, writes are coalesced along the element axis of the user-facing row-major output.
+constexpr int EMIT_TW = 128;
+__global__ void __launch_bounds__(256) k_emit(const EmitDesc2* __restrict__ table, int64_t count, double* __restrict__ out,
+                                              int64_t out_stride, const double* __restrict__ ws, int64_t NC, int64_t ncand) {
+  __shared__ double tile[EMIT_TW][33];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t e0 = (int64_t)blockIdx.x * EMIT_TW;
+  const int64_t cand0 = (int64_t)blockIdx.y * 32;
+  const int ne = (int)min((int64_t)EMIT_TW, count - e0);
+  const int64_t c = cand0 + lane;
+  for (int e = warp; e < ne; e += 8) {
+    const EmitDesc2 d = table[e0 + e];
+    double v = d.c;
+    if (c < ncand) {
+      if (d.slot_a >= 0) v = fma((double)d.sign_a, ws[(int64_t)d.slot_a * NC + c], v);
+      if (d.slot_b >= 0) v = fma((double)d.sign_b, ws[(int64_t)d.slot_b * NC + c], v);
+    }
+    tile[e][lane] = v;
+  }
+  __syncthreads();
+  for (int cc = warp; cc < 32; cc += 8) {
+    const int64_t cg = cand0 + cc;
+    if (cg >= ncand) continue;
+    double* o = out + cg * out_stride + e0;
+    for (int e = lane; e < ne; e += 32) o[e] = tile[e][cc];
+  }
+}
+
+__global__ void k_copy_status(const int32_t* __restrict__ src, int32_t* __restrict__ dst, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = src[i];
+}
+
+static inline dim3 grid1(int64_t ncand, int block, int gy = 1) {
+  return dim3((unsigned)((ncand + block - 1) / block), (unsigned)gy, 1);
+}
+
+int run_interleaved(Plan* PL, const double* x_dev, int64_t N, int64_t ldx, const tno_batch_inputs* opt,
+                    const tno_outputs* out, cudaStream_t stream) {
+  const DevPlan& P = PL->dp;
+  const int64_t NC = PL->chunk;
+  double* ws = PL->scratch;
+  int32_t* st = PL->status_scratch;
+  const int TB = 128;
+  for (int64_t c0 = 0; c0 < N; c0 += NC) {
+    const int64_t nc = std::min(NC, N - c0);
+    const double* xs = x_dev + c0 * ldx;
+    const double* pzs = (opt && opt->pz_scale) ? opt->pz_scale + c0 : nullptr;
+    k_pack<<<grid1(nc, TB), TB, 0, stream>>>(P, ws, NC, nc, xs, ldx, pzs);
+    const int etile = 32;
+    k_q<<<grid1(nc, TB, (P.m + etile - 1) / etile), TB, 0, stream>>>(P, ws, NC, nc, etile);
+    const int ptile = 128;
+    k_assemble<<<grid1(nc, TB, (P.nnz_l + ptile - 1) / ptile), TB, 0, stream>>>(P, ws, NC, nc, ptile);
+    k_factor<<<grid1(nc, TB), TB, 0, stream>>>(P, ws, NC, nc, st);
+    const int rtile = 32;
+    const int gyr = (P.ni + rtile - 1) / rtile;
+    k_rhs1<<<grid1(nc, TB, gyr), TB, 0, stream>>>(P, ws, NC, nc, rtile);
+    constexpr int RB = 4;
+    k_solve<RB><<<grid1(nc, TB, (P.rhs.nrhs1 + RB - 1) / RB), TB, 0, stream>>>(P, ws, NC, nc, 0, P.rhs.nrhs1);
+    PL->launches += 6;
+    if (P.rhs.nrhs2 > 0) {
+      k_rhs2<<<grid1(nc, TB, gyr), TB, 0, stream>>>(P, ws, NC, nc, rtile);
+      k_solve<RB><<<grid1(nc, TB, (P.rhs.nrhs2 + RB - 1) / RB), TB, 0, stream>>>(P, ws, NC, nc, P.rhs.nrhs1, P.rhs.nrhs2);
+      PL->launches += 2;
+    }
+    k_epilogue<<<grid1(nc, TB), TB, 0, stream>>>(P, ws, NC, nc, out->f ? out->f + c0 : nullptr,
+                                                 out->gmin ? out->gmin + c0 : nullptr, st);
+    PL->launches += 1;
+    auto emit = [&](const EmitTable& T, double* dst) {
+      if (!dst || T.count == 0) return;
+      dim3 g((unsigned)((T.count + EMIT_TW - 1) / EMIT_TW), (unsigned)((nc + 31) / 32), 1);
+      k_emit<<<g, 256, 0, stream>>>(T.dev, T.count, dst + c0 * T.count, T.count, ws, NC, nc);
+      PL->launches += 1;
+    };
+    emit(PL->t_g, out->g);
+    emit(PL->t_grad, out->grad);
+    emit(PL->t_z, out->z);
+    emit(PL->t_q, out->q);
+    emit(PL->t_J, out->J);
+    if (out->status) {
+      k_copy_status<<<grid1(nc, 256), 256, 0, stream>>>(st, out->status + c0, nc);
+      PL->launches += 1;
+    }
+  }
+  TNO_CUDA_OK(cudaGetLastError());
+  return TNO_OK;
+}
+
+}  // namespace tno

@@ -1,0 +1,152 @@
+// Internal plan layout shared by the C ABI and the kernel families.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "../../include/tno_b200.h"
+#include "tno_symbolic.hpp"
+
+namespace tno {
+
+// Column layout of the right-hand-side panel R (ni rows x nrhs columns, permuted row order).
+//   phase 1 (independent of z):  [ x | y | z | Az_0..Az_{nb-1} (zb variable) | z_lambdv (lambdv variable) ]
+//   phase 2 (needs W = diag(C z)): [ Dq_0..Dq_{k-1} | z_lambdh (lambdh variable) ]
+struct RhsLayout {
+  int cx = 0, cy = 1, cz = 2;
+  int c_zb = -1;      // first Az column
+  int c_lambdv = -1;
+  int c_q = -1;       // first Dq column
+  int c_lambdh = -1;
+  int nrhs1 = 0, nrhs2 = 0, nrhs = 0;
+};
+
+// Offsets of x = [q_ind | zb | t | lambdh | lambdv]  (-1 = absent)
+struct VarLayout {
+  int o_q = 0, o_zb = -1, o_t = -1, o_lambdh = -1, o_lambdv = -1;
+  int nvar = 0;
+};
+
+// Offsets of g / rows of J
+struct ConLayout {
+  int r_fun = -1, r_env = -1, r_reac = -1;
+  int ng = 0;
+};
+
+// Per-candidate scratch "slots" (one double each) of the interleaved kernel family.
+struct SlotLayout {
+  int s_x = 0;      // nvar
+  int s_pzs = 0;    // 1
+  int s_q = 0;      // m
+  int s_l = 0;      // nnz_l
+  int s_r = 0;      // ni * nrhs, row-major by permuted row
+  int s_env = 0;    // 4 * n : ub, lb, dub/dt, dlb/dt  (thickness variable only)
+  int s_grad = 0;   // nvar
+  int s_rg = 0;     // 2 nb   reac_bounds constraint values
+  int s_rj = 0;     // 2 nb * nvar   reac_bounds Jacobian rows
+  int nslots = 0;
+};
+
+// Element descriptor of the table-driven emitter:
+//   out[e] = sign_a * scratch[slot_a] + sign_b * scratch[slot_b] + c      (slot < 0: term absent)
+struct EmitDesc2 {
+  int32_t slot_a;
+  int32_t slot_b;
+  float sign_a;
+  float sign_b;
+  double c;
+};
+
+// Device-resident constant data of a plan (all pointers are device pointers).
+struct DevPlan {
+  int n, m, ni, nb, k;
+  uint32_t variables, constraints;
+  int objective, envelope_kind;
+  double env[8];
+  VarLayout var;
+  ConLayout con;
+  RhsLayout rhs;
+  SlotLayout slot;
+  int nnz_l;
+  // symbolic
+  const int* colptr;
+  const int* rowidx;
+  const int64_t* upd_ptr;
+  const int* upd_pos;
+  const int* asm_ptr;       // nnz_l + 1
+  const int* asm_edge;
+  const float* asm_coef;
+  // topology
+  const int* edge_u;
+  const int* edge_v;
+  const int* vrow;          // n: permuted row of a free vertex, or -1 - b for support b
+  const int* row_vertex;    // ni
+  const int* fixed;         // nb vertex ids
+  const int* vadj_ptr;      // n + 1
+  const int* vadj_edge;
+  const int* vadj_other;
+  const float* vadj_sign;   // C[e, v]
+  // values
+  const double* B;          // m x k
+  const double* d;          // m
+  const double* P;          // n x 3
+  const double* X;          // n x 3
+  const double* lb;
+  const double* ub;
+  const double* s;
+  const double* qmin;
+  const double* qmax;
+  const double* b;          // nb x 2
+  const double* px0;
+  const double* py0;
+  const double* pzv;
+  const double* pz0;
+};
+
+struct EmitTable {
+  EmitDesc2* dev = nullptr;
+  int64_t count = 0;
+};
+
+struct Plan {
+  tno_plan_info info{};
+  DevPlan dp{};
+  Symbolic sym;
+  int device = 0;
+  int kernel = TNO_KERNEL_INTERLEAVED;
+  std::vector<void*> dev_allocs;       // everything to cudaFree at destroy
+  // emit tables
+  EmitTable t_g, t_grad, t_z, t_q, t_J;
+  // scratch (interleaved family): nslots x chunk doubles
+  double* scratch = nullptr;
+  int32_t* status_scratch = nullptr;
+  int64_t chunk = 0;
+  int64_t scratch_bytes = 0;
+  // host-call staging
+  cudaStream_t stream = nullptr;
+  double* h_pinned = nullptr;
+  size_t h_pinned_bytes = 0;
+  double* d_stage = nullptr;
+  size_t d_stage_bytes = 0;
+  int64_t launches = 0;
+  int sm_count = 148;
+};
+
+// kernel family entry points (defined in the .cu files); all asynchronous on `stream`
+int run_interleaved(Plan* P, const double* x_dev, int64_t N, int64_t ldx, const tno_batch_inputs* opt,
+                    const tno_outputs* out, cudaStream_t stream);
+
+void set_error(const std::string& msg);
+
+#define TNO_CUDA_OK(call)                                                                     \
+  do {                                                                                        \
+    cudaError_t e__ = (call);                                                                 \
+    if (e__ != cudaSuccess) {                                                                 \
+      ::tno::set_error(std::string(#call) + ": " + cudaGetErrorString(e__));                  \
+      return TNO_ECUDA;                                                                       \
+    }                                                                                         \
+  } while (0)
+
+}  // namespace tno

@@ -1,0 +1,265 @@
+"""TnoPlan: one symbolic analysis per form diagram, batched evaluation on the GPU.
+
+Host-side mirror of what the reference's solver loop does with a ``Problem``
+(src/compas_tno/solvers/solver.py:126-129 fetches fobj / fgrad / fconstr / fjac and
+calls them once per iterate); here one call evaluates N iterates.
+torch is used only for device tensor handles, streams and pinned host buffers.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Iterable, Optional, Sequence
+
+import numpy as np
+
+from . import _lib
+from .envelopes import abi_envelope
+
+_VAR_BITS = {"q": _lib.VAR_Q, "zb": _lib.VAR_ZB, "t": _lib.VAR_T, "n": _lib.VAR_T,
+             "lambdh": _lib.VAR_LAMBDH, "lambdv": _lib.VAR_LAMBDV}
+_CON_BITS = {"funicular": _lib.CON_FUNICULAR, "envelope": _lib.CON_ENVELOPE, "reac_bounds": _lib.CON_REAC_BOUNDS}
+_OBJ = {None: _lib.OBJ_NONE, "none": _lib.OBJ_NONE, "min": _lib.OBJ_MIN, "max": _lib.OBJ_MAX, "t": _lib.OBJ_T,
+        "n": _lib.OBJ_NEG_LAST, "s": _lib.OBJ_NEG_LAST, "max_load": _lib.OBJ_NEG_LAST}
+_KERNELS = {"auto": _lib.KERNEL_AUTO, "interleaved": _lib.KERNEL_INTERLEAVED, "onchip": _lib.KERNEL_ONCHIP}
+_ORDERINGS = {"auto": 0, "natural": 1, "mindeg": 2, "nested": 3}
+
+ALL_OUTPUTS = ("f", "grad", "g", "J", "z", "q", "gmin", "status")
+
+
+def _f64(a, shape=None):
+    if a is None:
+        return None
+    out = np.ascontiguousarray(np.asarray(a, dtype=np.float64))
+    if shape is not None:
+        out = out.reshape(shape)
+    return out
+
+
+def _edges_from_C(Cmat):
+    """(m, 2) int32 (u, v) with C[e, u] = -1 and C[e, v] = +1, from a scipy sparse or dense C."""
+    Cd = Cmat.tocoo() if hasattr(Cmat, "tocoo") else None
+    if Cd is None:
+        from scipy.sparse import coo_matrix
+        Cd = coo_matrix(np.asarray(Cmat))
+    m = Cd.shape[0]
+    edges = np.full((m, 2), -1, dtype=np.int32)
+    for r, c, v in zip(Cd.row, Cd.col, Cd.data):
+        if v < 0:
+            edges[r, 0] = c
+        elif v > 0:
+            edges[r, 1] = c
+    if (edges < 0).any():
+        raise ValueError("connectivity matrix rows must hold exactly one -1 and one +1")
+    return edges
+
+
+class TnoPlan:
+    """Everything shared by all candidates of one form diagram, resident on one GPU.
+
+    ``problem`` is any object with the reference's ``Problem`` attribute names
+    (reference src/compas_tno/problems/problems.py:39-224): C, fixed, B, d (d0), P, X, lb, ub, s,
+    qmin, qmax, variables, constraints, features and, as applicable, b, px0, py0, pzv, pz0, envelope, thk.
+    """
+
+    def __init__(self, problem, objective: Optional[str] = "min", device: int = 0, kernel: str = "auto",
+                 ordering: str = "auto"):
+        self._lib = _lib.load()
+        self._handle = C.c_void_p()
+        M = problem
+        variables = list(M.variables or [])
+        constraints = list(M.constraints or [])
+        features = list(M.features or [])
+        if "fixed" not in features:
+            raise NotImplementedError("only the fixed-plan problem (features=['fixed']) is accelerated")
+        bad = [v for v in variables if v not in _VAR_BITS] + [c for c in constraints if c not in _CON_BITS]
+        if bad:
+            raise NotImplementedError("not accelerated: %s" % bad)
+        if "q" not in variables:
+            variables = ["q"] + variables
+        if objective not in _OBJ:
+            raise NotImplementedError("objective %r is not accelerated" % (objective,))
+        self.variables, self.constraints, self.objective = variables, constraints, objective
+
+        n, m, nb, k = int(M.n), int(M.m), int(M.nb), int(M.k)
+        keep = []  # keep numpy buffers alive until tno_plan_create returns
+
+        def dptr(a, shape):
+            if a is None:
+                return None
+            arr = _f64(a, shape)
+            keep.append(arr)
+            return arr.ctypes.data_as(C.POINTER(C.c_double))
+
+        edges = np.ascontiguousarray(_edges_from_C(M.C), dtype=np.int32)
+        fixed = np.ascontiguousarray(np.asarray(M.fixed, dtype=np.int32))
+        keep += [edges, fixed]
+        d_src = M.d0 if ("lambdh" in variables and getattr(M, "d0", None) is not None) else M.d
+        env_kind, env_params = abi_envelope(getattr(M, "envelope", None)) if ("t" in variables or "n" in variables) \
+            else (_lib.ENV_FIXED, [0.0] * 8)
+
+        D = _lib.ProblemDesc()
+        D.abi_version = _lib.ABI_VERSION
+        D.n, D.m, D.nb, D.k = n, m, nb, k
+        D.edges = edges.ctypes.data_as(C.POINTER(C.c_int32))
+        D.fixed = fixed.ctypes.data_as(C.POINTER(C.c_int32))
+        D.B = dptr(M.B, (m, k))
+        D.d = dptr(d_src, (m,))
+        D.P = dptr(M.P, (n, 3))
+        D.X = dptr(M.X, (n, 3))
+        D.lb = dptr(getattr(M, "lb", None), (n,))
+        D.ub = dptr(getattr(M, "ub", None), (n,))
+        D.s = dptr(getattr(M, "s", None), (n,))
+        D.qmin = dptr(np.broadcast_to(np.asarray(M.qmin, dtype=np.float64).reshape(-1), (m,)), (m,))
+        D.qmax = dptr(np.broadcast_to(np.asarray(M.qmax, dtype=np.float64).reshape(-1), (m,)), (m,))
+        D.b = dptr(getattr(M, "b", None), (nb, 2)) if "reac_bounds" in constraints else None
+        D.px0 = dptr(getattr(M, "px0", None), (n,)) if "lambdh" in variables else None
+        D.py0 = dptr(getattr(M, "py0", None), (n,)) if "lambdh" in variables else None
+        D.pzv = dptr(getattr(M, "pzv", None), (n,)) if "lambdv" in variables else None
+        D.pz0 = dptr(getattr(M, "pz0", None), (n,)) if "lambdv" in variables else None
+        D.variables = sum({_VAR_BITS[v] for v in variables})
+        D.constraints = sum({_CON_BITS[c] for c in constraints})
+        D.objective = _OBJ[objective]
+        D.envelope_kind = env_kind
+        for i, v in enumerate(env_params):
+            D.env_params[i] = v
+        D.thk = float(np.asarray(M.thk).reshape(-1)[0]) if getattr(M, "thk", None) is not None else 0.0
+        D.device = int(device)
+        D.kernel = _KERNELS[kernel]
+        D.ordering = _ORDERINGS[ordering]
+        _lib.check(self._lib.tno_plan_create(C.byref(D), C.byref(self._handle)))
+        del keep
+        self.device = int(device)
+        info = _lib.PlanInfo()
+        _lib.check(self._lib.tno_plan_query(self._handle, C.byref(info)))
+        self._info = info
+        self.n, self.m, self.ni, self.nb, self.k = n, m, int(info.ni), nb, k
+        self.nvar, self.ng = int(info.nvar), int(info.ng)
+
+    # ------------------------------------------------------------------------------------------
+    @property
+    def info(self) -> Dict[str, int]:
+        info = _lib.PlanInfo()
+        _lib.check(self._lib.tno_plan_query(self._handle, C.byref(info)))
+        return info.as_dict()
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._lib.tno_plan_launch_count(self._handle))
+
+    @property
+    def bytes_per_eval(self) -> int:
+        """Algorithmic bytes of one evaluation: x in; z, f, grad, g, dense J out."""
+        return 8 * (self.nvar + self.n + 1 + self.nvar + self.ng + self.ng * self.nvar)
+
+    def symbolic(self):
+        i = self._info
+        perm = np.zeros(i.ni, np.int32)
+        colptr = np.zeros(i.ni + 1, np.int32)
+        rowidx = np.zeros(i.nnz_l, np.int32)
+        parent = np.zeros(i.ni, np.int32)
+        level = np.zeros(i.ni, np.int32)
+        p = lambda a: a.ctypes.data_as(C.POINTER(C.c_int32))  # noqa: E731
+        _lib.check(self._lib.tno_plan_symbolic(self._handle, p(perm), p(colptr), p(rowidx), p(parent), p(level)))
+        return dict(perm=perm, colptr=colptr, rowidx=rowidx, parent=parent, level=level)
+
+    def close(self):
+        if getattr(self, "_handle", None) and self._handle.value:
+            self._lib.tno_plan_destroy(self._handle)
+            self._handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _shape(self, name, N):
+        return {"f": (N,), "grad": (N, self.nvar), "g": (N, self.ng), "J": (N, self.ng, self.nvar),
+                "z": (N, self.n), "q": (N, self.m), "gmin": (N,), "status": (N,)}[name]
+
+    # ------------------------------------------------------------------------------------------
+    def evaluate_host(self, x, outputs: Iterable[str] = ALL_OUTPUTS, pz_scale=None) -> Dict[str, np.ndarray]:
+        """Host buffers in, host buffers out (tno_eval_batch_host); no torch involved."""
+        x = _f64(x)
+        if x.ndim == 1:
+            x = x.reshape(1, -1)
+        N, ld = x.shape
+        if ld != self.nvar:
+            raise ValueError("x has %d columns, the problem has %d variables" % (ld, self.nvar))
+        res, O = {}, _lib.Outputs()
+        for name in outputs:
+            arr = np.empty(self._shape(name, N), dtype=np.int32 if name == "status" else np.float64)
+            res[name] = arr
+            setattr(O, name, arr.ctypes.data)
+        pz = _f64(pz_scale, (N,)) if pz_scale is not None else None
+        _lib.check(self._lib.tno_eval_batch_host(self._handle, x.ctypes.data, N, ld,
+                                                 pz.ctypes.data if pz is not None else None, C.byref(O)))
+        return res
+
+    def evaluate_device(self, x, outputs: Iterable[str] = ALL_OUTPUTS, pz_scale=None, out=None, stream=None):
+        """Device tensors in, device tensors out (tno_eval_batch); asynchronous on the current torch stream."""
+        import torch
+        if not x.is_cuda or x.dtype != torch.float64 or x.dim() != 2 or x.stride(1) != 1:
+            raise ValueError("x must be a 2-D float64 CUDA tensor with unit inner stride")
+        if x.device.index != self.device:
+            raise ValueError("x lives on cuda:%s, the plan on cuda:%d" % (x.device.index, self.device))
+        N = x.shape[0]
+        if x.shape[1] != self.nvar:
+            raise ValueError("x has %d columns, the problem has %d variables" % (x.shape[1], self.nvar))
+        res, O = {}, _lib.Outputs()
+        for name in outputs:
+            t = None if out is None else out.get(name)
+            if t is None:
+                t = torch.empty(self._shape(name, N), device=x.device,
+                                dtype=torch.int32 if name == "status" else torch.float64)
+            elif tuple(t.shape) != self._shape(name, N) or not t.is_contiguous():
+                raise ValueError("bad preallocated output %r" % name)
+            res[name] = t
+            setattr(O, name, t.data_ptr())
+        opt = _lib.BatchInputs()
+        if pz_scale is not None:
+            opt.pz_scale = pz_scale.data_ptr()
+        st = torch.cuda.current_stream(x.device).cuda_stream if stream is None else stream
+        _lib.check(self._lib.tno_eval_batch(self._handle, x.data_ptr(), N, x.stride(0), C.byref(opt), C.byref(O),
+                                            C.c_void_p(st)))
+        return res
+
+    def evaluate_batch(self, x_host, to_host: Sequence[str] = ("f", "gmin", "status"),
+                       on_device: Sequence[str] = ("grad", "g", "J", "z"), pz_scale=None, buffers=None):
+        """End-to-end call: pinned host x -> device, evaluate, ``to_host`` outputs -> pinned host.
+
+        Outputs named in ``on_device`` are materialised in HBM (for an on-device consumer) and returned as
+        CUDA tensors; ``to_host`` ones come back as pinned CPU tensors.  Synchronises before returning.
+        """
+        import torch
+        dev = torch.device("cuda", self.device)
+        xh = x_host if isinstance(x_host, torch.Tensor) else torch.from_numpy(_f64(x_host))
+        if xh.dim() == 1:
+            xh = xh.reshape(1, -1)
+        N = xh.shape[0]
+        buffers = buffers if buffers is not None else {}
+        xd = buffers.get("x_dev")
+        if xd is None or xd.shape != xh.shape:
+            xd = torch.empty(xh.shape, dtype=torch.float64, device=dev)
+            buffers["x_dev"] = xd
+        xd.copy_(xh, non_blocking=True)
+        pzd = None
+        if pz_scale is not None:
+            pzh = pz_scale if isinstance(pz_scale, torch.Tensor) else torch.from_numpy(_f64(pz_scale))
+            pzd = pzh.to(dev, non_blocking=True)
+        names = tuple(dict.fromkeys(tuple(to_host) + tuple(on_device)))
+        res = self.evaluate_device(xd, names, pz_scale=pzd, out=buffers.get("out"))
+        buffers["out"] = res
+        ret = {}
+        for name in names:
+            if name in to_host:
+                h = buffers.get("h_" + name)
+                if h is None or h.shape != res[name].shape:
+                    h = torch.empty(res[name].shape, dtype=res[name].dtype, pin_memory=True)
+                    buffers["h_" + name] = h
+                h.copy_(res[name], non_blocking=True)
+                ret[name] = h
+            else:
+                ret[name] = res[name]
+        torch.cuda.current_stream(dev).synchronize()
+        return ret

@@ -1,0 +1,190 @@
+/*
+ * tno_b200.h -- C ABI of the B200-native batched thrust-network evaluator.
+ *
+ * The reference (compas_tno 0.3.0, pure Python) has no FFI; its seam for this path is the
+ * Python callable protocol stored on `Problem` (src/compas_tno/problems/problems.py:214-218,
+ * written by src/compas_tno/problems/setup.py:466-469, consumed by
+ * src/compas_tno/solvers/solver.py:126-129):
+ *
+ *     fconstr(x, problem) -> g   (ng,)        constr_wrapper         problems/constraints.py:20
+ *     fjac   (x, problem) -> J   (ng, nvar)   sensitivities_wrapper  problems/jacobian.py:53
+ *     fobj   (x, problem) -> f   scalar       f_min_thrust / ...     problems/objectives.py:91,151,415,438
+ *     fgrad  (x, problem) -> df  (nvar,)      gradient_fmin / ...    problems/derivatives.py:223,336,183,203
+ *
+ * all built on  q_from_variables / xyz_from_q  (algorithms/equilibrium.py:163-192, :195-236).
+ * The entry points below are what a binding for that protocol needs: one plan per form diagram
+ * (= everything `Problem` carries that is shared by all candidates) and one batched evaluation
+ * returning f, grad f, g, J, z and a status word for N variable vectors at once.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no C++ / torch types cross this boundary.
+ *   - all floating point data is IEEE fp64; index data is int32; row-major ("C") layouts.
+ *   - every function returns 0 on success and a negative TNO_E* code otherwise; the message is
+ *     available from tno_last_error() (thread local).  Per-candidate numerical failures are
+ *     reported in `status[]`, never through the return code.
+ *   - a plan is immutable after creation.  tno_eval_batch is asynchronous on the given CUDA
+ *     stream and uses plan-owned scratch memory: concurrent calls on ONE plan must be ordered
+ *     by the caller (use one plan per stream for concurrency).
+ *   - there is no CPU fallback: without a CUDA device tno_plan_create fails with TNO_ENODEVICE.
+ */
+#ifndef TNO_B200_H
+#define TNO_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TNO_ABI_VERSION 1
+
+/* error codes */
+#define TNO_OK 0
+#define TNO_EINVAL (-1)    /* bad argument / unsupported combination (reference raises NotImplementedError) */
+#define TNO_ENODEVICE (-2) /* no usable CUDA device */
+#define TNO_ECUDA (-3)     /* CUDA runtime error */
+#define TNO_ENOMEM (-4)
+
+/* variables present in x, in the reference's unpacking order (problems/constraints.py:47-88):
+ *   x = [ q_ind (k) | zb (nb) | t (1) | lambdh (1) | lambdv (1) ]                                  */
+#define TNO_VAR_Q 1u
+#define TNO_VAR_ZB 2u
+#define TNO_VAR_T 4u      /* 't' or 'n': thickness handed to the parametric envelope */
+#define TNO_VAR_LAMBDH 8u
+#define TNO_VAR_LAMBDV 16u
+
+/* constraint blocks, stacked in this order (problems/constraints.py:104-155) */
+#define TNO_CON_FUNICULAR 1u   /* q - qmin ; qmax - q                      2m rows */
+#define TNO_CON_ENVELOPE 2u    /* z - lb ; ub - z                          2n rows */
+#define TNO_CON_REAC_BOUNDS 4u /* |b| - (zb - s) |R_xy / R_z|              2nb rows */
+
+/* objectives (problems/objectives.py:27-88) */
+#define TNO_OBJ_NONE 0
+#define TNO_OBJ_MIN 1        /* f_min_thrust  / gradient_fmin */
+#define TNO_OBJ_MAX 2        /* f_max_thrust  / gradient_fmax */
+#define TNO_OBJ_T 3          /* f_reduce_thk  / gradient_reduce_thk          f = +x[-1] */
+#define TNO_OBJ_NEG_LAST 4   /* f_tight_crosssection ('n','s','max_load')    f = -x[-1] */
+
+/* parametric envelopes (arithmetic lives in the un-vendored compas_tna; closed forms recovered from
+ * the reference fixtures) */
+#define TNO_ENV_FIXED 0      /* ub / lb constant (thickness is not a variable) */
+#define TNO_ENV_DOME 1       /* env_params = { xc, yc, R, lb_outside } */
+#define TNO_ENV_CROSSVAULT 2 /* env_params = { xc, yc, rho, lb_outside } */
+
+/* kernel families (tno_problem_desc.kernel) */
+#define TNO_KERNEL_AUTO 0
+#define TNO_KERNEL_INTERLEAVED 1 /* thread per candidate, batch-interleaved scratch in HBM; any size */
+#define TNO_KERNEL_ONCHIP 2      /* factor + right-hand sides resident in shared memory; size limited */
+
+/* per-candidate status bits */
+#define TNO_STATUS_OK 0
+#define TNO_STATUS_NOT_PD 1    /* a pivot of -(Ci^T Q Ci) was <= 0: the reference's LU would still run */
+#define TNO_STATUS_NONFINITE 2 /* NaN / Inf in an output (the reference propagates these silently) */
+
+typedef struct tno_plan tno_plan;
+
+/* Everything of `Problem` (reference problems/problems.py:39-224) the path reads.  Host pointers,
+ * copied during tno_plan_create.  Optional arrays may be NULL as noted. */
+typedef struct tno_problem_desc {
+  int32_t abi_version; /* = TNO_ABI_VERSION */
+  int32_t n;           /* vertices                                      Problem.n  */
+  int32_t m;           /* edges                                         Problem.m  */
+  int32_t nb;          /* supports                                      Problem.nb */
+  int32_t k;           /* independent edges                             Problem.k  */
+  const int32_t* edges; /* m x 2 (u, v): C[e,u] = -1, C[e,v] = +1       Problem.C  */
+  const int32_t* fixed; /* nb, in the order of form.supports()          Problem.fixed */
+  const double* B;      /* m x k                                        Problem.B  */
+  const double* d;      /* m   particular solution (d0 when lambdh is a variable)  Problem.d / d0 */
+  const double* P;      /* n x 3 loads                                  Problem.P  */
+  const double* X;      /* n x 3 coordinates; z of supports is used when zb is not a variable  Problem.X */
+  const double* lb;     /* n                                            Problem.lb */
+  const double* ub;     /* n                                            Problem.ub */
+  const double* s;      /* n   middle surface (reac_bounds only; NULL = 0)          Problem.s  */
+  const double* qmin;   /* m                                            Problem.qmin */
+  const double* qmax;   /* m                                            Problem.qmax */
+  const double* b;      /* nb x 2 reaction bounds (reac_bounds only)    Problem.b  */
+  const double* px0;    /* n  (lambdh only)                             Problem.px0 */
+  const double* py0;    /* n  (lambdh only)                             Problem.py0 */
+  const double* pzv;    /* n  (lambdv only)                             Problem.pzv */
+  const double* pz0;    /* n  (lambdv only)                             Problem.pz0 */
+  uint32_t variables;   /* TNO_VAR_* mask; TNO_VAR_Q is mandatory */
+  uint32_t constraints; /* TNO_CON_* mask */
+  int32_t objective;    /* TNO_OBJ_* */
+  int32_t envelope_kind; /* TNO_ENV_*; must be parametric when TNO_VAR_T is set */
+  double env_params[8];
+  double thk;           /* Problem.thk (informational unless the envelope needs it) */
+  int32_t device;       /* CUDA device ordinal */
+  int32_t kernel;       /* TNO_KERNEL_* */
+  int32_t ordering;     /* 0 = auto (minimum degree), 1 = natural, 2 = minimum degree, 3 = nested dissection */
+  int32_t reserved;
+} tno_problem_desc;
+
+/* What the symbolic analysis found; all sizes a caller needs to allocate outputs. */
+typedef struct tno_plan_info {
+  int32_t n, m, ni, nb, k;
+  int32_t nvar;        /* length of x */
+  int32_t ng;          /* length of g */
+  int32_t nrhs;        /* right-hand sides solved per candidate (x, y, z, zb block, q_ind block, lambda) */
+  int32_t nnz_a;       /* lower-triangle non-zeros of Ci^T Q Ci */
+  int32_t nnz_l;       /* non-zeros of its Cholesky factor */
+  int32_t etree_height;
+  int32_t max_colcount;
+  int32_t kernel;      /* TNO_KERNEL_* actually selected */
+  int32_t chunk;       /* candidates processed per launch sequence */
+  int64_t scratch_bytes;   /* plan-owned device scratch */
+  int64_t factor_flops;    /* flops of one numeric factorisation */
+  int64_t solve_flops;     /* flops of all triangular solves of one evaluation */
+  int64_t smem_bytes;      /* dynamic shared memory per CTA of the main kernel */
+} tno_plan_info;
+
+/* Optional per-candidate inputs that are not part of x (device pointers, NULL = not used). */
+typedef struct tno_batch_inputs {
+  const double* pz_scale; /* N   vertical load multiplier: P[:,2] *= pz_scale[j] (Monte-Carlo self-weight) */
+  const double* reserved0;
+  const double* reserved1;
+} tno_batch_inputs;
+
+/* Output buffers (device pointers for tno_eval_batch, host pointers for tno_eval_batch_host).
+ * Any pointer may be NULL: that output is then not produced. */
+typedef struct tno_outputs {
+  double* f;       /* N                       objective */
+  double* grad;    /* N x nvar                gradient of the objective */
+  double* g;       /* N x ng                  constraints, g >= 0 feasible */
+  double* J;       /* N x ng x nvar           dense Jacobian of g, row-major per candidate */
+  double* z;       /* N x n                   node heights (all vertices, supports included) */
+  double* q;       /* N x m                   force densities */
+  double* gmin;    /* N                       min_r g[r]  (feasibility margin) */
+  int32_t* status; /* N                       TNO_STATUS_* bits */
+} tno_outputs;
+
+int tno_abi_version(void);
+const char* tno_last_error(void);
+
+int tno_plan_create(const tno_problem_desc* desc, tno_plan** out_plan);
+void tno_plan_destroy(tno_plan* plan);
+int tno_plan_query(const tno_plan* plan, tno_plan_info* info);
+
+/* Copy the symbolic analysis out (host arrays sized from tno_plan_info): perm[ni] maps factor row ->
+ * free-vertex position, colptr[ni+1] / rowidx[nnz_l] the pattern of L, parent[ni] the elimination
+ * tree, level[ni] the level-set index of each column.  Any pointer may be NULL. */
+int tno_plan_symbolic(const tno_plan* plan, int32_t* perm, int32_t* colptr, int32_t* rowidx,
+                      int32_t* parent, int32_t* level);
+
+/* Evaluate N candidates.  x_dev: device pointer, candidate j at x_dev + j * ldx (ldx >= nvar).
+ * `cuda_stream` is a cudaStream_t (NULL = default stream).  Asynchronous. */
+int tno_eval_batch(tno_plan* plan, const double* x_dev, int64_t n_candidates, int64_t ldx,
+                   const tno_batch_inputs* opt, const tno_outputs* out_dev, void* cuda_stream);
+
+/* Same with HOST buffers: stages x through pinned memory, runs tno_eval_batch on the plan's own
+ * stream, copies the requested outputs back and synchronises.  This is the call behind the
+ * batch-1 drop-in callbacks and the end-to-end figure of bench.py. */
+int tno_eval_batch_host(tno_plan* plan, const double* x_host, int64_t n_candidates, int64_t ldx,
+                        const double* pz_scale_host, const tno_outputs* out_host);
+
+/* Number of kernel launches issued by this plan so far (bench.py reports it as gpu_launches). */
+int64_t tno_plan_launch_count(const tno_plan* plan);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TNO_B200_H */

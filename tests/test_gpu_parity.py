@@ -1,0 +1,129 @@
+"""GPU: the CUDA path, through the C ABI, against (a) the reference's golden outputs and (b) the oracle.
+
+Tolerances are north_star's: node heights, objectives, constraints 1e-10 relative; Jacobians and
+gradients 1e-8 relative (relative = max |a - b| / max |b|, see golden_io.rel_err).
+"""
+import numpy as np
+import pytest
+
+from golden_io import CASES, load_case, rel_err
+
+pytestmark = pytest.mark.gpu
+
+TOL_VAL = 1e-10
+TOL_JAC = 1e-8
+
+
+@pytest.fixture(scope="module")
+def tno():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    import compas_tno_b200 as pkg
+    return pkg
+
+
+@pytest.mark.parametrize("kernel", ["interleaved"])
+@pytest.mark.parametrize("name", CASES)
+def test_golden_parity_host_abi(tno, name, kernel):
+    from compas_tno_b200.plan import TnoPlan
+    P, objective, xs, exp = load_case(name)
+    plan = TnoPlan(P, objective=objective, kernel=kernel)
+    assert (plan.nvar, plan.ng) == (xs.shape[1], exp["g"].shape[1])
+    got = plan.evaluate_host(xs)
+    free, fixed = P.free, P.fixed
+    assert np.all(got["status"] == 0), got["status"]
+    assert rel_err(got["q"], exp["q"]) < TOL_VAL
+    assert rel_err(got["z"], exp["X"][:, :, 2]) < TOL_VAL
+    assert rel_err(got["g"], exp["g"]) < TOL_VAL
+    assert rel_err(got["f"], exp["f"]) < TOL_VAL
+    assert rel_err(got["grad"], exp["grad"] if exp["grad"].shape[1] == plan.nvar else
+                   np.pad(exp["grad"], ((0, 0), (0, plan.nvar - exp["grad"].shape[1])))) < TOL_JAC
+    assert got["J"].shape == exp["J"].shape
+    assert rel_err(got["J"], exp["J"]) < TOL_JAC
+    # block-wise too, so that a small block cannot hide behind a large one
+    m, n = P.m, P.n
+    for lo, hi in ((0, 2 * m), (2 * m, 2 * m + 2 * n), (2 * m + 2 * n, plan.ng)):
+        if hi > lo:
+            assert rel_err(got["J"][:, lo:hi], exp["J"][:, lo:hi]) < TOL_JAC
+    assert np.allclose(got["gmin"], exp["g"].min(axis=1), rtol=1e-9, atol=1e-9)
+    plan.close()
+
+
+@pytest.mark.parametrize("name", ["cross14_q_zb_min", "dome_q_zb_reac_min"])
+def test_device_api_matches_host_api(tno, name):
+    import torch
+    from compas_tno_b200.plan import TnoPlan
+    P, objective, xs, exp = load_case(name)
+    plan = TnoPlan(P, objective=objective)
+    xd = torch.from_numpy(xs).cuda()
+    res = plan.evaluate_device(xd)
+    torch.cuda.synchronize()
+    host = plan.evaluate_host(xs)
+    for key in ("f", "grad", "g", "J", "z", "q", "gmin"):
+        assert np.array_equal(res[key].cpu().numpy(), host[key]), key
+    assert plan.launch_count > 0
+
+
+def test_random_batch_against_oracle(tno):
+    """Seeded random candidates around the fixture solution; batch large enough to cross chunk logic."""
+    from compas_tno_b200.plan import TnoPlan
+    from oracle import callbacks_np as onp
+    P, objective, xs, _ = load_case("cross14_q_zb_min")
+    rng = np.random.default_rng(20261019)
+    N = 300
+    X = xs[0] * (1.0 + 0.05 * rng.uniform(-1, 1, size=(N, xs.shape[1])))
+    plan = TnoPlan(P, objective=objective)
+    got = plan.evaluate_host(X)
+    ref = onp.evaluate_batch(X[:40], P, objective)
+    assert rel_err(got["z"][:40], ref["z"]) < TOL_VAL
+    assert rel_err(got["g"][:40], ref["g"]) < TOL_VAL
+    assert rel_err(got["f"][:40], ref["f"]) < TOL_VAL
+    assert rel_err(got["grad"][:40], ref["grad"]) < TOL_JAC
+    assert rel_err(got["J"][:40], ref["J"]) < TOL_JAC
+    # size-independent properties on the whole batch
+    m, n, k = P.m, P.n, P.k
+    J, g = got["J"], got["g"]
+    assert np.array_equal(J[:, :m, :k], np.broadcast_to(P.B, (N, m, k)))
+    assert np.array_equal(J[:, m:2 * m], -J[:, :m])
+    assert np.array_equal(J[:, 2 * m + n:2 * m + 2 * n], -J[:, 2 * m:2 * m + n])
+    assert np.allclose(g[:, :m] + g[:, m:2 * m], (P.qmax - P.qmin).ravel()[None, :], rtol=0, atol=1e-9)
+    assert np.allclose(g[:, 2 * m:2 * m + n] + g[:, 2 * m + n:], (P.ub - P.lb).ravel()[None, :], rtol=0, atol=1e-9)
+    # linearity of z in the loads for fixed q:  z(q, s * pz) - z_b part ... checked via pz_scale
+    s = rng.uniform(0.8, 1.2, size=N)
+    got2 = plan.evaluate_host(X, outputs=("z",), pz_scale=s)
+    got0 = plan.evaluate_host(X, outputs=("z",), pz_scale=np.zeros(N))
+    lin = got0["z"] + s[:, None] * (got["z"] - got0["z"])
+    assert rel_err(got2["z"], lin) < 1e-11
+
+
+def test_indefinite_candidate_is_flagged_not_fatal(tno):
+    from compas_tno_b200.plan import TnoPlan
+    P, objective, xs, _ = load_case("cross6_q_zb_min")
+    X = np.repeat(xs[:1], 3, axis=0)
+    X[1, : P.k] *= -1.0          # tension everywhere: -(Ci^T Q Ci) becomes negative definite
+    plan = TnoPlan(P, objective=objective)
+    got = plan.evaluate_host(X, outputs=("f", "z", "status"))
+    assert got["status"][0] == 0 and got["status"][2] == 0
+    assert got["status"][1] & 1
+    assert np.array_equal(got["z"][0], got["z"][2])
+
+
+def test_dropin_callbacks_slsqp(tno):
+    """The four shims drive scipy's SLSQP exactly like the reference's callbacks (solvers/scipy.py:172)."""
+    from scipy.optimize import fmin_slsqp
+    from compas_tno_b200 import callbacks as cb
+    from oracle import callbacks_np as onp
+    P, objective, xs, _ = load_case("cross6_q_zb_min")
+    cb.accelerate(P, "min")
+    x0 = xs[0].copy()
+    g_gpu = P.fconstr(x0, P)
+    M = onp.clone_problem(P)
+    assert rel_err(g_gpu, onp.constr_wrapper(x0, M)) < TOL_VAL
+    assert rel_err(P.fjac(x0, P), onp.sensitivities_wrapper(x0, M)) < TOL_JAC
+    assert abs(P.fobj(x0, P) - onp.f_min_thrust(x0, M)) < 1e-10 * abs(onp.f_min_thrust(x0, M))
+    assert rel_err(P.fgrad(x0, P), onp.gradient_fmin(x0, M)) < TOL_JAC
+    bounds = [(-1e4, 1e-8)] * P.k + [(float(P.lb[i, 0]), float(P.ub[i, 0])) for i in P.fixed]
+    out = fmin_slsqp(P.fobj, x0, args=[P], f_ieqcons=P.fconstr, fprime=P.fgrad, fprime_ieqcons=P.fjac,
+                     bounds=bounds, iter=30, iprint=0, full_output=True)
+    assert np.all(np.isfinite(out[0]))
+    assert out[1] <= P.fobj(x0, P) + 1e-6 or out[3] != 0
