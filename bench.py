@@ -1,0 +1,361 @@
+#!/usr/bin/env python
+"""bench.py -- q-evals/sec of the batched thrust-network evaluation on B200 (BASELINE.json metric).
+
+One "step" = one pass of the hot path (z, f, grad f, g, dense J, feasibility margin, status) over one batch of
+synthetic candidates of the discretisation-20 cross vault (the configuration north_star quotes its target on).
+
+    python bench.py --gpus 1 --steps 10 --warmup 3            # this repo's CUDA path
+    python bench.py --impl reference --steps 2 --warmup 1     # CPU arm: the oracle port of the reference callbacks
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus 8 --steps 10 --warmup 3               # candidates sharded across ranks, weak scaling
+
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "q-evals/sec (z+constraints+Jacobian, fp64)"
+UNIT = "evals/s"
+
+
+# ------------------------------------------------------------------------------------------------------
+def build_workload(name, n_states=12):
+    from compas_tno_b200 import workloads as W
+    if name.startswith("crossvault_disc"):
+        n = int(name[len("crossvault_disc"):])
+        P, xs = W.crossvault_problem(n, n_states=n_states)
+        objective = "min"
+    elif name == "dome_16x20":
+        P, xs = W.dome_problem(20, 16, constraints=("funicular", "envelope", "reac_bounds"), n_states=n_states)
+        objective = "max"
+    else:
+        raise SystemExit("unknown workload %r" % name)
+    return P, xs, objective
+
+
+def candidates(P, xs, N, seed):
+    from compas_tno_b200 import workloads as W
+    return W.sample_candidates(P, xs, N, seed=seed, basis=getattr(P, "candidate_basis", None))
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device = device
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, power, reasons = [], [], [], set()
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax.append(float(f[2]))
+                power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(smax)), "power_w_max": float(max(power)),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def measured_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ------------------------------------------------------------------------------------------------------
+def _cpu_worker(args):
+    """Evaluate a slice of candidates with the oracle port (one private Problem copy per worker)."""
+    os.environ.setdefault("OMP_NUM_THREADS", "1")
+    os.environ.setdefault("OPENBLAS_NUM_THREADS", "1")
+    os.environ.setdefault("MKL_NUM_THREADS", "1")
+    import warnings
+    warnings.simplefilter("ignore")
+    from threadpoolctl import threadpool_limits
+    P, X, objective = args
+    from oracle import callbacks_np as onp
+    M = onp.clone_problem(P)
+    t = time.perf_counter()
+    with threadpool_limits(limits=1):      # one BLAS thread per worker process: no oversubscription
+        for x in X:
+            onp.evaluate(x, M, objective)
+    return time.perf_counter() - t
+
+
+def cpu_evals_per_s(P, X, objective, cores):
+    """Oracle port (same scipy calls and call order as the reference callbacks) on ``cores`` processes."""
+    import multiprocessing as mp
+    from threadpoolctl import threadpool_limits
+    chunks = [c for c in np.array_split(X, cores) if len(c)]
+    with threadpool_limits(limits=1):
+        if cores == 1:
+            t = time.perf_counter()
+            _cpu_worker((P, chunks[0], objective))
+            return len(X) / (time.perf_counter() - t)
+        with mp.get_context("fork").Pool(len(chunks)) as pool:
+            pool.map(_cpu_worker, [(P, c[:1], objective) for c in chunks])   # spin the workers up (untimed)
+            t = time.perf_counter()
+            pool.map(_cpu_worker, [(P, c, objective) for c in chunks])
+            return len(X) / (time.perf_counter() - t)
+
+
+def strip_problem(P):
+    """Picklable, light copy for the worker processes."""
+    from oracle import callbacks_np as onp
+    return onp.clone_problem(P)
+
+
+# ------------------------------------------------------------------------------------------------------
+def run_reference(args):
+    """CPU arm: the reference's algorithm (oracle port; the pure-Python reference cannot travel to the box)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    P, xs, objective = build_workload(args.workload, n_states=4)
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    per_step = max(cores * args.cpu_evals_per_core, cores)
+    X = candidates(P, xs, per_step * (args.steps + args.warmup), seed=20261019)
+    SP = strip_problem(P)
+    for w in range(args.warmup):
+        cpu_evals_per_s(SP, X[w * per_step:(w + 1) * per_step], objective, cores)
+    t0 = time.perf_counter()
+    for s in range(args.steps):
+        lo = (args.warmup + s) * per_step
+        cpu_evals_per_s(SP, X[lo:lo + per_step], objective, cores)
+    dt = time.perf_counter() - t0
+    value = per_step * args.steps / dt
+    sample = "%d candidates per step (%d per core) of %s, oracle/callbacks_np.py: constr_wrapper + sensitivities_wrapper + objective + gradient" % (
+        per_step, args.cpu_evals_per_core, args.workload)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": args.workload, "candidates_per_step": per_step, "objective": objective},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from compas_tno_b200.plan import TnoPlan
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    P, xs, objective = build_workload(args.workload)
+    plan = TnoPlan(P, objective=objective, device=local, kernel=args.kernel)
+    info = plan.info
+    B_alg = plan.bytes_per_eval
+    N = args.batch                                       # candidates per GPU per step (weak scaling)
+    X = candidates(P, xs, N, seed=20261019 + rank)       # each rank owns a different slice of the sweep
+    x_dev = torch.from_numpy(X).to(dev)
+    names = ("f", "grad", "g", "J", "z", "gmin", "status")
+    out = {k: torch.empty(plan._shape(k, N), device=dev, dtype=torch.int32 if k == "status" else torch.float64) for k in names}
+    gather_f = torch.empty(world * N, device=dev, dtype=torch.float64) if world > 1 else None
+    gather_s = torch.empty(world * N, device=dev, dtype=torch.int32) if world > 1 else None
+
+    def step():
+        plan.evaluate_device(x_dev, names, out=out)
+        if world > 1:   # the path's only exchange: objectives + feasibility flags
+            dist.all_gather_into_tensor(gather_f, out["f"])
+            dist.all_gather_into_tensor(gather_s, out["status"])
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    launches0 = plan.launch_count
+    plan.profile(True)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    prof = plan.profile_read()
+    plan.profile(False)
+    launches = plan.launch_count - launches0
+    if world > 1:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    value = world * N * args.steps / (ms * 1e-3)
+    status_bad = int((out["status"] != 0).sum().item())
+
+    # ---- roofline of the dominant kernel (CUDA-event timed inside the library, same timed region) ----
+    peak, peak_src = measured_peak()
+    roofline = None
+    if prof:
+        dom = max(prof.items(), key=lambda kv: kv[1][0])
+        total_kernel_ms = sum(v[0] for v in prof.values())
+        name, (kms, kcount) = dom
+        # algorithmic bytes attributed to a launch: B_alg x candidates the launch processes
+        per_launch_bytes = B_alg * N * args.steps / kcount
+        achieved = per_launch_bytes / (kms / kcount * 1e-3) / 1e9
+        roofline = {"bound": "hbm", "kernel": name, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                    "traffic": None, "peak_source": peak_src, "kernel_share_of_step": kms / total_kernel_ms,
+                    "bytes_per_eval": B_alg, "evals_per_launch": N * args.steps / kcount,
+                    "whole_step": {"achieved": value / world * B_alg / 1e9, "frac": value / world * B_alg / 1e9 / peak},
+                    "kernels_ms_per_step": {k: v[0] / args.steps for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])}}
+
+    # ---- end to end through the host-buffer API: pinned x -> device, evaluate, every output -> pinned host ----
+    e2e = None
+    Ne = min(args.e2e_batch, N)
+    xh = torch.from_numpy(X[:Ne].copy()).pin_memory()
+    bufs = {}
+    host_names = ("f", "grad", "g", "J", "z", "gmin", "status")
+    for _ in range(2):
+        plan.evaluate_batch(xh, to_host=host_names, on_device=(), buffers=bufs)
+    barrier()
+    t0 = time.perf_counter()
+    esteps = max(2, args.steps // 2)
+    for _ in range(esteps):
+        res = plan.evaluate_batch(xh, to_host=host_names, on_device=(), buffers=bufs)
+    barrier()
+    dt = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([dt], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+    d2h = sum(res[k].numel() * res[k].element_size() for k in host_names)
+    e2e = {"value": world * Ne * esteps / dt, "unit": UNIT, "h2d_bytes_per_step": int(xh.numel() * 8), "d2h_bytes_per_step": int(d2h),
+           "candidates_per_step": Ne, "note": "every output incl. the dense J copied to pinned host memory (PCIe-bound)"}
+    # the sweep use-case: only objectives + feasibility cross PCIe, g / J / z stay in HBM for an on-device consumer
+    bufs2 = {}
+    xh2 = torch.from_numpy(X).pin_memory()
+    for _ in range(2):
+        plan.evaluate_batch(xh2, buffers=bufs2)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(esteps):
+        plan.evaluate_batch(xh2, buffers=bufs2)
+    barrier()
+    dt2 = time.perf_counter() - t0
+    e2e["objectives_only"] = {"value": world * N * esteps / dt2, "unit": UNIT, "h2d_bytes_per_step": int(xh2.numel() * 8),
+                              "d2h_bytes_per_step": int(N * (8 + 8 + 4)), "note": "f, gmin, status to host; grad, g, J, z materialised in HBM"}
+
+    # ---- CPU baseline (rank 0, N = 1 only): bounded sample of the same workload ----
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+        ns = max(cores * args.cpu_evals_per_core, cores)
+        SP = strip_problem(P)
+        cpu_evals_per_s(SP, X[:cores], objective, cores)  # warm the pool / caches
+        v = cpu_evals_per_s(SP, X[:ns], objective, cores)
+        v1 = cpu_evals_per_s(SP, X[:max(4, args.cpu_evals_per_core // 2)], objective, 1)
+        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "single_core_value": v1,
+               "sample": "%d candidates of %s through oracle/callbacks_np.py (reference call order: constr_wrapper, "
+                         "sensitivities_wrapper, objective, gradient), one process per core" % (ns, args.workload)}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": args.workload, "candidates_per_gpu_per_step": N, "objective": objective,
+                       "variables": plan.variables, "constraints": plan.constraints, "n": plan.n, "m": plan.m, "k": plan.k,
+                       "nvar": plan.nvar, "ng": plan.ng, "nnz_l": info["nnz_l"], "etree_height": info["etree_height"],
+                       "kernel_family": {1: "interleaved", 2: "onchip"}.get(info["kernel"], str(info["kernel"])),
+                       "l2_policy": "outputs per step (%.2f GB) exceed the 126 MB L2; inputs re-read each step" % (N * B_alg / 1e9),
+                       "parallelism": "candidates sharded, plan replicated, all_gather(f, status)" if world > 1 else "single GPU"},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+            "status_nonzero": status_bad,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="crossvault_disc20")
+    ap.add_argument("--batch", type=int, default=16384, help="candidates per GPU per step")
+    ap.add_argument("--e2e-batch", type=int, default=2048)
+    ap.add_argument("--kernel", default="auto", choices=["auto", "interleaved", "onchip"])
+    ap.add_argument("--cpu-evals-per-core", type=int, default=24)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

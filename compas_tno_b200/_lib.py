@@ -20,6 +20,7 @@ STATUS_OK, STATUS_NOT_PD, STATUS_NONFINITE = 0, 1, 2
 EXPORTS = [
     "tno_abi_version", "tno_last_error", "tno_plan_create", "tno_plan_destroy", "tno_plan_query",
     "tno_plan_symbolic", "tno_eval_batch", "tno_eval_batch_host", "tno_plan_launch_count",
+    "tno_plan_profile", "tno_plan_profile_read",
 ]
 
 _dp = C.POINTER(C.c_double)
@@ -91,6 +92,10 @@ def load():
     lib.tno_eval_batch_host.restype = C.c_int
     lib.tno_plan_launch_count.argtypes = [C.c_void_p]
     lib.tno_plan_launch_count.restype = C.c_int64
+    lib.tno_plan_profile.argtypes = [C.c_void_p, C.c_int]
+    lib.tno_plan_profile.restype = C.c_int
+    lib.tno_plan_profile_read.argtypes = [C.c_void_p, C.c_int32, C.c_char_p, _dp, C.POINTER(C.c_int64)]
+    lib.tno_plan_profile_read.restype = C.c_int
     if lib.tno_abi_version() != ABI_VERSION:
         raise RuntimeError("libtno_b200.so ABI %d != binding ABI %d" % (lib.tno_abi_version(), ABI_VERSION))
     _lib = lib

@@ -92,6 +92,11 @@ void tno_plan_destroy(tno_plan* plan) {
   if (P->scratch) cudaFree(P->scratch);
   if (P->status_scratch) cudaFree(P->status_scratch);
   if (P->d_stage) cudaFree(P->d_stage);
+  for (auto& r : P->prof_recs) {
+    cudaEventDestroy(r.a);
+    cudaEventDestroy(r.b);
+  }
+  for (auto& e : P->prof_pool) cudaEventDestroy(e);
   if (P->stream) cudaStreamDestroy(P->stream);
   delete P;
 }
@@ -445,6 +450,46 @@ int tno_plan_symbolic(const tno_plan* plan, int32_t* perm, int32_t* colptr, int3
 }
 
 int64_t tno_plan_launch_count(const tno_plan* plan) { return plan ? reinterpret_cast<const Plan*>(plan)->launches : 0; }
+
+int tno_plan_profile(tno_plan* plan, int enable) {
+  Plan* P = reinterpret_cast<Plan*>(plan);
+  if (!P) return fail(TNO_EINVAL, "null plan");
+  for (auto& r : P->prof_recs) {
+    P->prof_pool.push_back(r.a);
+    P->prof_pool.push_back(r.b);
+  }
+  P->prof_recs.clear();
+  for (int i = 0; i < KK_COUNT; ++i) {
+    P->prof_ms[i] = 0.0;
+    P->prof_launches[i] = 0;
+  }
+  P->profiling = enable != 0;
+  return TNO_OK;
+}
+
+int tno_plan_profile_read(tno_plan* plan, int32_t max_kinds, char* names, double* total_ms, int64_t* launches) {
+  Plan* P = reinterpret_cast<Plan*>(plan);
+  if (!P || !names || !total_ms || !launches) return fail(TNO_EINVAL, "null argument");
+  TNO_CUDA_OK(cudaSetDevice(P->device));
+  for (auto& r : P->prof_recs) {
+    TNO_CUDA_OK(cudaEventSynchronize(r.b));
+    float ms = 0.f;
+    TNO_CUDA_OK(cudaEventElapsedTime(&ms, r.a, r.b));
+    P->prof_ms[r.kind] += ms;
+    P->prof_launches[r.kind] += 1;
+    P->prof_pool.push_back(r.a);
+    P->prof_pool.push_back(r.b);
+  }
+  P->prof_recs.clear();
+  const int nk = std::min<int>(max_kinds, KK_COUNT);
+  for (int i = 0; i < nk; ++i) {
+    std::strncpy(names + 32 * i, kKernelNames[i], 31);
+    names[32 * i + 31] = 0;
+    total_ms[i] = P->prof_ms[i];
+    launches[i] = P->prof_launches[i];
+  }
+  return nk;
+}
 
 int tno_eval_batch(tno_plan* plan, const double* x_dev, int64_t N, int64_t ldx, const tno_batch_inputs* opt,
                    const tno_outputs* out_dev, void* cuda_stream) {

@@ -518,6 +518,10 @@ static inline dim3 grid1(int64_t ncand, int block, int gy = 1) {
   return dim3((unsigned)((ncand + block - 1) / block), (unsigned)gy, 1);
 }
 
+const char* const kKernelNames[KK_COUNT] = {"k_pack", "k_q", "k_assemble", "k_factor", "k_rhs1", "k_solve(phase1)", "k_rhs2",
+                                            "k_solve(phase2)", "k_epilogue", "k_emit(g,grad,z,q)", "k_emit(J)", "k_copy_status",
+                                            "k_onchip"};
+
 int run_interleaved(Plan* PL, const double* x_dev, int64_t N, int64_t ldx, const tno_batch_inputs* opt,
                     const tno_outputs* out, cudaStream_t stream) {
   const DevPlan& P = PL->dp;
@@ -525,46 +529,47 @@ int run_interleaved(Plan* PL, const double* x_dev, int64_t N, int64_t ldx, const
   double* ws = PL->scratch;
   int32_t* st = PL->status_scratch;
   const int TB = 128;
+#define LAUNCH(kind, kernel, grid, block, ...)              \
+  do {                                                      \
+    PL->prof_begin(kind, stream);                           \
+    kernel<<<grid, block, 0, stream>>>(__VA_ARGS__);        \
+    PL->prof_end(stream);                                   \
+    PL->launches += 1;                                      \
+  } while (0)
   for (int64_t c0 = 0; c0 < N; c0 += NC) {
     const int64_t nc = std::min(NC, N - c0);
     const double* xs = x_dev + c0 * ldx;
     const double* pzs = (opt && opt->pz_scale) ? opt->pz_scale + c0 : nullptr;
-    k_pack<<<grid1(nc, TB), TB, 0, stream>>>(P, ws, NC, nc, xs, ldx, pzs);
+    LAUNCH(KK_PACK, k_pack, grid1(nc, TB), TB, P, ws, NC, nc, xs, ldx, pzs);
     const int etile = 32;
-    k_q<<<grid1(nc, TB, (P.m + etile - 1) / etile), TB, 0, stream>>>(P, ws, NC, nc, etile);
+    LAUNCH(KK_Q, k_q, grid1(nc, TB, (P.m + etile - 1) / etile), TB, P, ws, NC, nc, etile);
     const int ptile = 128;
-    k_assemble<<<grid1(nc, TB, (P.nnz_l + ptile - 1) / ptile), TB, 0, stream>>>(P, ws, NC, nc, ptile);
-    k_factor<<<grid1(nc, TB), TB, 0, stream>>>(P, ws, NC, nc, st);
+    LAUNCH(KK_ASSEMBLE, k_assemble, grid1(nc, TB, (P.nnz_l + ptile - 1) / ptile), TB, P, ws, NC, nc, ptile);
+    LAUNCH(KK_FACTOR, k_factor, grid1(nc, TB), TB, P, ws, NC, nc, st);
     const int rtile = 32;
     const int gyr = (P.ni + rtile - 1) / rtile;
-    k_rhs1<<<grid1(nc, TB, gyr), TB, 0, stream>>>(P, ws, NC, nc, rtile);
+    LAUNCH(KK_RHS1, k_rhs1, grid1(nc, TB, gyr), TB, P, ws, NC, nc, rtile);
     constexpr int RB = 4;
-    k_solve<RB><<<grid1(nc, TB, (P.rhs.nrhs1 + RB - 1) / RB), TB, 0, stream>>>(P, ws, NC, nc, 0, P.rhs.nrhs1);
-    PL->launches += 6;
+    LAUNCH(KK_SOLVE1, k_solve<RB>, grid1(nc, TB, (P.rhs.nrhs1 + RB - 1) / RB), TB, P, ws, NC, nc, 0, P.rhs.nrhs1);
     if (P.rhs.nrhs2 > 0) {
-      k_rhs2<<<grid1(nc, TB, gyr), TB, 0, stream>>>(P, ws, NC, nc, rtile);
-      k_solve<RB><<<grid1(nc, TB, (P.rhs.nrhs2 + RB - 1) / RB), TB, 0, stream>>>(P, ws, NC, nc, P.rhs.nrhs1, P.rhs.nrhs2);
-      PL->launches += 2;
+      LAUNCH(KK_RHS2, k_rhs2, grid1(nc, TB, gyr), TB, P, ws, NC, nc, rtile);
+      LAUNCH(KK_SOLVE2, k_solve<RB>, grid1(nc, TB, (P.rhs.nrhs2 + RB - 1) / RB), TB, P, ws, NC, nc, P.rhs.nrhs1, P.rhs.nrhs2);
     }
-    k_epilogue<<<grid1(nc, TB), TB, 0, stream>>>(P, ws, NC, nc, out->f ? out->f + c0 : nullptr,
-                                                 out->gmin ? out->gmin + c0 : nullptr, st);
-    PL->launches += 1;
-    auto emit = [&](const EmitTable& T, double* dst) {
+    LAUNCH(KK_EPILOGUE, k_epilogue, grid1(nc, TB), TB, P, ws, NC, nc, out->f ? out->f + c0 : nullptr,
+           out->gmin ? out->gmin + c0 : nullptr, st);
+    auto emit = [&](int kind, const EmitTable& T, double* dst) {
       if (!dst || T.count == 0) return;
       dim3 g((unsigned)((T.count + EMIT_TW - 1) / EMIT_TW), (unsigned)((nc + 31) / 32), 1);
-      k_emit<<<g, 256, 0, stream>>>(T.dev, T.count, dst + c0 * T.count, T.count, ws, NC, nc);
-      PL->launches += 1;
+      LAUNCH(kind, k_emit, g, 256, T.dev, T.count, dst + c0 * T.count, T.count, ws, NC, nc);
     };
-    emit(PL->t_g, out->g);
-    emit(PL->t_grad, out->grad);
-    emit(PL->t_z, out->z);
-    emit(PL->t_q, out->q);
-    emit(PL->t_J, out->J);
-    if (out->status) {
-      k_copy_status<<<grid1(nc, 256), 256, 0, stream>>>(st, out->status + c0, nc);
-      PL->launches += 1;
-    }
+    emit(KK_EMIT_SMALL, PL->t_g, out->g);
+    emit(KK_EMIT_SMALL, PL->t_grad, out->grad);
+    emit(KK_EMIT_SMALL, PL->t_z, out->z);
+    emit(KK_EMIT_SMALL, PL->t_q, out->q);
+    emit(KK_EMIT_J, PL->t_J, out->J);
+    if (out->status) LAUNCH(KK_STATUS, k_copy_status, grid1(nc, 256), 256, st, out->status + c0, nc);
   }
+#undef LAUNCH
   TNO_CUDA_OK(cudaGetLastError());
   return TNO_OK;
 }

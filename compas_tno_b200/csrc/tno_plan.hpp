@@ -110,8 +110,41 @@ struct EmitTable {
   int64_t count = 0;
 };
 
+// optional per-kernel timing (CUDA events on the launching stream)
+enum KernelKind { KK_PACK = 0, KK_Q, KK_ASSEMBLE, KK_FACTOR, KK_RHS1, KK_SOLVE1, KK_RHS2, KK_SOLVE2, KK_EPILOGUE,
+                  KK_EMIT_SMALL, KK_EMIT_J, KK_STATUS, KK_ONCHIP, KK_COUNT };
+extern const char* const kKernelNames[KK_COUNT];
+struct ProfRec {
+  int kind;
+  cudaEvent_t a, b;
+};
+
 struct Plan {
   tno_plan_info info{};
+  bool profiling = false;
+  std::vector<ProfRec> prof_recs;
+  std::vector<cudaEvent_t> prof_pool;
+  double prof_ms[KK_COUNT] = {0};
+  int64_t prof_launches[KK_COUNT] = {0};
+  void prof_begin(int kind, cudaStream_t s) {
+    if (!profiling) return;
+    ProfRec r;
+    r.kind = kind;
+    for (cudaEvent_t* e : {&r.a, &r.b}) {
+      if (prof_pool.empty()) {
+        cudaEventCreate(e);
+      } else {
+        *e = prof_pool.back();
+        prof_pool.pop_back();
+      }
+    }
+    cudaEventRecord(r.a, s);
+    prof_recs.push_back(r);
+  }
+  void prof_end(cudaStream_t s) {
+    if (!profiling) return;
+    cudaEventRecord(prof_recs.back().b, s);
+  }
   DevPlan dp{};
   Symbolic sym;
   int device = 0;

@@ -151,6 +151,25 @@ class TnoPlan:
         """Algorithmic bytes of one evaluation: x in; z, f, grad, g, dense J out."""
         return 8 * (self.nvar + self.n + 1 + self.nvar + self.ng + self.ng * self.nvar)
 
+    def profile(self, enable: bool = True):
+        """Start (and reset) or stop per-kernel CUDA-event timing inside the library."""
+        _lib.check(self._lib.tno_plan_profile(self._handle, 1 if enable else 0))
+
+    def profile_read(self):
+        """{kernel name: (total_ms, launches)} of the kernels timed since ``profile(True)``."""
+        kmax = 32
+        names = C.create_string_buffer(32 * kmax)
+        ms = (C.c_double * kmax)()
+        cnt = (C.c_int64 * kmax)()
+        nk = self._lib.tno_plan_profile_read(self._handle, kmax, names, ms, cnt)
+        if nk < 0:
+            _lib.check(nk)
+        out = {}
+        for i in range(nk):
+            if cnt[i]:
+                out[names.raw[32 * i:32 * i + 32].split(b"\0")[0].decode()] = (float(ms[i]), int(cnt[i]))
+        return out
+
     def symbolic(self):
         i = self._info
         perm = np.zeros(i.ni, np.int32)

@@ -1,0 +1,193 @@
+"""Synthetic form diagrams and candidate batches for benchmarks and tests.
+
+``compas_tna`` (FormDiagram.create_cross / create_circular_radial_spaced, Envelope.apply_*) is not
+vendored with the reference, so the plan geometry follows the reference *fixtures*
+(``data/crossvault_form.json``: validated identical for n = 14; ``data/analysis.json``: 16 meridians x 20
+equally spaced hoops) and loads / bounds are documented synthetic stand-ins:
+  * pz_i = -rho * t * A_i with rho = 20 and A_i the plan tributary area (NOT claimed equal to
+    compas_tna's self-weight lumping),
+  * ub / lb from the closed-form envelopes of ``envelopes.py``.
+Everything here is one-time host set-up (numpy / scipy); the hot path is in the CUDA library.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from .envelopes import CrossVaultEnvelope, DomeEnvelope
+from .problems import FixedProblem, cross_form_arrays
+
+SEED = 20261019
+
+
+def radial_form_arrays(n_hoops: int = 20, n_parallels: int = 16, center=(5.0, 5.0), radius: float = 5.0):
+    """Radial / circular form diagram: 1 apex + n_hoops rings of n_parallels vertices, equally spaced radii.
+    Meridian segments and hoop edges; the outermost ring is the support ring and has no hoop edges
+    (in the reference fixture those are ``_is_edge: false``)."""
+    xc, yc = center
+    pts = [(xc, yc)]
+    for h in range(1, n_hoops + 1):
+        r = radius * h / n_hoops
+        for p in range(n_parallels):
+            a = 2.0 * np.pi * p / n_parallels
+            pts.append((xc + r * np.cos(a), yc + r * np.sin(a)))
+    vid = lambda h, p: 1 + (h - 1) * n_parallels + (p % n_parallels)  # noqa: E731
+    edges = []
+    for p in range(n_parallels):
+        edges.append((0, vid(1, p)))
+    for h in range(1, n_hoops + 1):
+        for p in range(n_parallels):
+            if h < n_hoops:
+                edges.append((vid(h, p), vid(h + 1, p)))
+                edges.append((vid(h, p), vid(h, p + 1)))
+    fixed = [vid(n_hoops, p) for p in range(n_parallels)]
+    return np.array(pts, dtype=np.float64), np.array(edges, dtype=np.int64), fixed
+
+
+def _tributary_areas(xy, edges):
+    """Plan tributary area per vertex: half the length-weighted star (good enough for a synthetic load)."""
+    n = len(xy)
+    a = np.zeros(n)
+    L = np.linalg.norm(xy[edges[:, 0]] - xy[edges[:, 1]], axis=1)
+    np.add.at(a, edges[:, 0], 0.25 * L * L)
+    np.add.at(a, edges[:, 1], 0.25 * L * L)
+    return a
+
+
+def compressive_basis(problem: FixedProblem, n_states: int = 12, seed: int = SEED):
+    """``n_states`` compression-only equilibrium states q = B y + d of the fixed plan.
+
+    On the cross form n^2 of the 2n(n+2) edges are structurally forced to q = 0 under vertical load
+    (SURVEY.md section 8d), so a random perturbation of q_ind produces tension and an indefinite
+    Ci^T Q Ci.  Compressive states form a convex cone; we pick points of it with small LPs in the k
+    independent parameters:   max sum_e c_e t_e   s.t.  (B y + d)_e <= -t_e,  0 <= t_e <= u_e
+    with random caps u_e in [0.5, 1.5] (t_e stays 0 exactly on the forced-zero edges).
+    Convex combinations of the returned states are again compressive equilibrium states.
+    Returns Y (n_states, k)."""
+    from scipy.optimize import linprog
+    from scipy.sparse import csr_matrix, hstack, identity, vstack
+    rng = np.random.default_rng(seed)
+    m, k = problem.m, problem.k
+    B = csr_matrix(problem.B)
+    d = problem.d.ravel()
+    # stage 1: which edges can be strictly compressed at all?   max sum t  s.t.  B y + d + t <= 0, 0 <= t <= 1
+    res = linprog(np.concatenate([np.zeros(k), -np.ones(m)]), A_ub=hstack([B, identity(m, format="csr")], format="csr"),
+                  b_ub=-d, bounds=[(-1e3, 1e3)] * k + [(0.0, 1.0)] * m, method="highs")
+    if res.status != 0:
+        raise RuntimeError("no compressive state found: %s" % res.message)
+    active = res.x[k:] > 1e-7
+    # stage 2: well-conditioned states:  min s  s.t.  -s <= (B y + d)_e <= -u_e (active), <= 0 (forced-zero edges)
+    ones = csr_matrix(np.ones((m, 1)))
+    A_ub = vstack([hstack([B, csr_matrix((m, 1))]), hstack([-B, -ones])], format="csr")
+    states = []
+    for _ in range(n_states):
+        u = np.where(active, rng.uniform(0.5, 1.5, size=m), 0.0)
+        b_ub = np.concatenate([-d - u, d])
+        c = np.concatenate([np.zeros(k), [1.0]])
+        res = linprog(c, A_ub=A_ub, b_ub=b_ub, bounds=[(None, None)] * k + [(0.0, None)], method="highs")
+        if res.status != 0:
+            raise RuntimeError("no compressive state found: %s" % res.message)
+        states.append(res.x[:k])
+    return np.array(states)
+
+
+def compressive_state(problem: FixedProblem, seed: int = SEED):
+    """Mean of a few basis states: (q_ind*, q*)."""
+    Y = compressive_basis(problem, 4, seed)
+    y = Y.mean(axis=0)
+    q = problem.B @ y.reshape(-1, 1) + problem.d
+    return y, q.ravel()
+
+
+def crossvault_problem(n_div: int = 20, thk: float = 0.5, span: float = 10.0, rho: float = 20.0,
+                       variables=("q", "zb"), constraints=("funicular", "envelope"), n_states: int = 12):
+    """Cross vault on the orthogonal cross form diagram of discretisation ``n_div``.
+    Returns (problem, x_star) with x_star = [q_ind*, zb*(, t)]."""
+    xy, edges, fixed = cross_form_arrays(n_div, span)
+    env = CrossVaultEnvelope((0.0, span), (0.0, span), thk)
+    ub, lb = env.compute_bounds(xy[:, 0], xy[:, 1], thk)
+    mid = env.compute_middle(xy[:, 0], xy[:, 1])
+    xyz = np.column_stack([xy, mid.ravel()])
+    h = span / n_div
+    on_x = (np.isclose(xy[:, 0], 0) | np.isclose(xy[:, 0], span)).astype(float)
+    on_y = (np.isclose(xy[:, 1], 0) | np.isclose(xy[:, 1], span)).astype(float)
+    area = h * h * (1 - 0.5 * on_x) * (1 - 0.5 * on_y)
+    loads = np.zeros((len(xy), 3))
+    loads[:, 2] = -rho * thk * area
+    P = FixedProblem.from_arrays(xyz, edges, fixed, loads, lb.ravel(), ub.ravel(), mid.ravel())
+    P.variables, P.constraints, P.features = list(variables), list(constraints), ["fixed"]
+    P.thk, P.envelope = thk, env
+    zb = mid.ravel()[P.fixed]
+    return _finish(P, zb, mid.ravel(), variables, thk, n_states)
+
+
+def dome_problem(n_hoops: int = 20, n_parallels: int = 16, thk: float = 0.5, radius: float = 5.0, rho: float = 20.0,
+                 variables=("q", "zb"), constraints=("funicular", "envelope"), n_states: int = 12):
+    """Hemispherical dome on the radial form diagram.  Returns (problem, x_star)."""
+    c = (radius, radius)
+    xy, edges, fixed = radial_form_arrays(n_hoops, n_parallels, c, radius)
+    env = DomeEnvelope(c, radius, thk)
+    ub, lb = env.compute_bounds(xy[:, 0], xy[:, 1], thk)
+    mid = env.compute_middle(xy[:, 0], xy[:, 1])
+    xyz = np.column_stack([xy, mid.ravel()])
+    loads = np.zeros((len(xy), 3))
+    loads[:, 2] = -rho * thk * _tributary_areas(xy, edges)
+    P = FixedProblem.from_arrays(xyz, edges, fixed, loads, lb.ravel(), ub.ravel(), mid.ravel())
+    P.variables, P.constraints, P.features = list(variables), list(constraints), ["fixed"]
+    P.thk, P.envelope = thk, env
+    if "reac_bounds" in constraints:
+        P.b = env_bound_react(env, xy, fixed, thk)
+    zb = np.full(len(fixed), 0.0)
+    return _finish(P, zb, mid.ravel(), variables, thk, n_states)
+
+
+def _finish(P, zb, mid, variables, thk, n_states):
+    """Basis of compressive states, each scaled so that its highest node touches the middle surface's crown
+    (heights above the supports scale like 1 / |q|); x* = their mean.  Stores the basis on the problem."""
+    from scipy.sparse import diags
+    from scipy.sparse.linalg import splu
+    Y = compressive_basis(P, n_states)
+    crown = float(mid.max() - zb.mean())
+    Xb = P.X[P.fixed].copy()
+    Xb[:, 2] = zb
+    for i in range(len(Y)):
+        q = (P.B @ Y[i].reshape(-1, 1) + P.d).ravel()
+        Q = diags(q)
+        zi = splu((P.Cit @ Q @ P.Ci).tocsc()).solve(P.P[P.free, 2] - (P.Cit @ Q @ P.Cb) @ Xb[:, 2])
+        rise = float(zi.max() - zb.mean())
+        if rise > 0 and not np.any(np.abs(P.d) > 0):
+            Y[i] *= rise / crown
+    P.candidate_basis = Y
+    y = Y.mean(axis=0)
+    P.q = P.B @ y.reshape(-1, 1) + P.d
+    x_star = np.concatenate([y, zb] + ([np.array([thk])] if ("t" in variables or "n" in variables) else []))
+    return P, x_star
+
+
+def env_bound_react(env, xy, fixed, thk):
+    d = xy[fixed] - np.array([env.xc, env.yc])
+    r = np.linalg.norm(d, axis=1, keepdims=True)
+    return 0.5 * thk * d / r
+
+
+def sample_candidates(problem, x_star, N: int, seed: int = SEED, sigma: float = 0.05, basis=None):
+    """Candidate batch (adapted): q_ind_j = s_j * sum_i w_ji Y_i with Dirichlet weights
+    over the compressive basis states ``basis`` (default: x* only) and s_j ~ U(1 - sigma, 1 + sigma), which keeps
+    every candidate a compression-only equilibrium state; zb ~ U(lb_b, ub_b) where the envelope is defined
+    there, else x*'s value; trailing scalar variables (t, lambda) perturbed by sigma."""
+    rng = np.random.default_rng(seed)
+    k, nb = problem.k, problem.nb
+    x_star = np.asarray(x_star, dtype=np.float64)
+    X = np.repeat(x_star[None, :], N, axis=0)
+    if basis is not None and len(basis) > 1:
+        Wt = rng.dirichlet(np.ones(len(basis)), size=N)
+        X[:, :k] = Wt @ np.asarray(basis)
+    X[:, :k] *= 1.0 + sigma * rng.uniform(-1, 1, size=(N, 1))
+    if "zb" in problem.variables:
+        lo = problem.lb.ravel()[problem.fixed]
+        hi = problem.ub.ravel()[problem.fixed]
+        ok = (hi > lo) & (lo > -0.5)
+        zb = rng.uniform(np.where(ok, lo, 0.0), np.where(ok, hi, 1.0), size=(N, nb))
+        X[:, k:k + nb] = np.where(ok[None, :], zb, X[:, k:k + nb])
+    if X.shape[1] > k + nb:
+        X[:, k + nb:] *= 1.0 + sigma * rng.uniform(-1, 1, size=(N, X.shape[1] - k - nb))
+    return np.ascontiguousarray(X)

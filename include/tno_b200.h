@@ -184,6 +184,13 @@ int tno_eval_batch_host(tno_plan* plan, const double* x_host, int64_t n_candidat
 /* Number of kernel launches issued by this plan so far (bench.py reports it as gpu_launches). */
 int64_t tno_plan_launch_count(const tno_plan* plan);
 
+/* Per-kernel device timing with CUDA events recorded on the launching stream (used by bench.py for the
+ * roofline of the dominant kernel; off by default).  enable != 0 clears the counters and starts recording.
+ * tno_plan_profile_read synchronises the recorded events and returns the number of kernel kinds; for kind i
+ * names + 32 * i is its NUL-terminated name, total_ms[i] the summed duration, launches[i] the launch count. */
+int tno_plan_profile(tno_plan* plan, int enable);
+int tno_plan_profile_read(tno_plan* plan, int32_t max_kinds, char* names, double* total_ms, int64_t* launches);
+
 #ifdef __cplusplus
 }
 #endif

@@ -123,7 +123,17 @@ def test_dropin_callbacks_slsqp(tno):
     assert abs(P.fobj(x0, P) - onp.f_min_thrust(x0, M)) < 1e-10 * abs(onp.f_min_thrust(x0, M))
     assert rel_err(P.fgrad(x0, P), onp.gradient_fmin(x0, M)) < TOL_JAC
     bounds = [(-1e4, 1e-8)] * P.k + [(float(P.lb[i, 0]), float(P.ub[i, 0])) for i in P.fixed]
-    out = fmin_slsqp(P.fobj, x0, args=[P], f_ieqcons=P.fconstr, fprime=P.fgrad, fprime_ieqcons=P.fjac,
-                     bounds=bounds, iter=30, iprint=0, full_output=True)
-    assert np.all(np.isfinite(out[0]))
-    assert out[1] <= P.fobj(x0, P) + 1e-6 or out[3] != 0
+    kw = dict(bounds=bounds, iter=12, iprint=0, full_output=True)
+    out_gpu = fmin_slsqp(P.fobj, x0, args=[P], f_ieqcons=P.fconstr, fprime=P.fgrad, fprime_ieqcons=P.fjac, **kw)
+
+    def cpu(fn):
+        return lambda x, M_: fn(x, M)
+    cw = lambda x, M_: onp.constr_wrapper(x, M)  # noqa: E731
+    # the oracle objective reads the state left by the constraint call, like the reference
+    fo = lambda x, M_: (onp.constr_wrapper(x, M), onp.f_min_thrust(x, M))[1]  # noqa: E731
+    fg = lambda x, M_: (onp.constr_wrapper(x, M), onp.gradient_fmin(x, M))[1]  # noqa: E731
+    out_cpu = fmin_slsqp(fo, x0, args=[None], f_ieqcons=cw, fprime=fg, fprime_ieqcons=cpu(onp.sensitivities_wrapper), **kw)
+    assert np.all(np.isfinite(out_gpu[0]))
+    assert out_gpu[2] == out_cpu[2]                       # same number of iterations
+    assert rel_err(out_gpu[0], out_cpu[0]) < 1e-6         # same iterate after 12 SLSQP steps
+    assert abs(out_gpu[1] - out_cpu[1]) < 1e-6 * max(1.0, abs(out_cpu[1]))
