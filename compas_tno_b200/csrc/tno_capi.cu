@@ -14,6 +14,17 @@ namespace tno {
 static thread_local std::string g_error;
 void set_error(const std::string& msg) { g_error = msg; }
 
+int upload_bytes(Plan* P, const void* host, size_t bytes, const void** dev) {
+  *dev = nullptr;
+  if (bytes == 0) return TNO_OK;
+  void* p = nullptr;
+  TNO_CUDA_OK(cudaMalloc(&p, bytes));
+  P->dev_allocs.push_back(p);
+  TNO_CUDA_OK(cudaMemcpy(p, host, bytes, cudaMemcpyHostToDevice));
+  *dev = p;
+  return TNO_OK;
+}
+
 namespace {
 
 template <class T>
@@ -229,6 +240,13 @@ int tno_plan_create(const tno_problem_desc* D, tno_plan** out_plan) {
     asm_ptr[p + 1] = (int)asm_edge.size();
   }
 
+  P->h_vrow = vrow;
+  P->h_vadj_ptr = vadj_ptr;
+  P->h_vadj_edge = vadj_edge;
+  P->h_vadj_other = vadj_other;
+  P->h_vadj_sign = vadj_sign;
+  P->h_fixed = fixed;
+
   // ---- layouts ----------------------------------------------------------------------------
   DevPlan& dp = P->dp;
   dp.n = n; dp.m = m; dp.ni = ni; dp.nb = nb; dp.k = k;
@@ -423,8 +441,17 @@ int tno_plan_create(const tno_problem_desc* D, tno_plan** out_plan) {
   I.factor_flops = S.factor_flops;
   I.solve_flops = (int64_t)4 * nnz_l * R.nrhs;
   P->kernel = TNO_KERNEL_INTERLEAVED;
-  I.kernel = P->kernel;
   I.smem_bytes = 0;
+  if (D->kernel != TNO_KERNEL_INTERLEAVED) {
+    if ((rc = build_onchip(P, D))) return rc;
+    if (P->onchip_ok) {
+      P->kernel = TNO_KERNEL_ONCHIP;
+      I.smem_bytes = (int64_t)P->oc.smem_doubles * 8;
+    } else if (D->kernel == TNO_KERNEL_ONCHIP) {
+      return fail(TNO_EINVAL, "problem does not fit the on-chip kernel family (shared memory / 16-bit index limits)");
+    }
+  }
+  I.kernel = P->kernel;
 
   guard.p = nullptr;
   *out_plan = reinterpret_cast<tno_plan*>(P);
@@ -498,6 +525,7 @@ int tno_eval_batch(tno_plan* plan, const double* x_dev, int64_t N, int64_t ldx, 
   if (N < 0 || ldx < P->dp.var.nvar) return fail(TNO_EINVAL, "bad N / ldx");
   if (N == 0) return TNO_OK;
   TNO_CUDA_OK(cudaSetDevice(P->device));
+  if (P->kernel == TNO_KERNEL_ONCHIP) return run_onchip(P, x_dev, N, ldx, opt, out_dev, (cudaStream_t)cuda_stream);
   int rc = ensure_scratch(P, N);
   if (rc) return rc;
   return run_interleaved(P, x_dev, N, ldx, opt, out_dev, (cudaStream_t)cuda_stream);

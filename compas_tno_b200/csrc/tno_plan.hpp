@@ -105,6 +105,43 @@ struct DevPlan {
   const double* pz0;
 };
 
+// Device data of the on-chip kernel family (tno_onchip.cu): level-ordered index streams, all 16-bit.
+struct DevOnchip {
+  int W;                 // columns of the shared-memory right-hand-side panel (= nrhs - 2: x, y are transient)
+  int n1;                // persistent phase-1 columns: z | Az | z_lambdv  -> panel columns [0, n1)
+  int c_z, c_zb, c_lambdv, c_q, c_lambdh;   // panel column of each block (-1 = absent); x -> W-2, y -> W-1 in phase 1
+  int nlevels;
+  int nsup;              // number of (support, incident edge) pairs
+  uint32_t nvar_magic;   // ceil(2^32 / nvar) for the flat index -> (row, col) split
+  // smem layout in doubles
+  int o_x, o_l, o_r, o_small, smem_doubles;
+  int o_qsup, o_react, o_gxy, o_red;   // inside the small region
+  const double* Bt;      // k x m (transposed B): coalesced over edges
+  // factorisation (pull form, L D L^T): items = entries of L ordered by level of their column
+  const int* f_lev_ptr;          // nlevels + 1
+  const int* f_lev_lpi;          // lanes per item in each level (power of two <= 32)
+  const unsigned short* f_item_pos;   // position of the entry in the CSC value array
+  const unsigned short* f_item_col;   // its column j
+  const unsigned long long* f_pairs;  // per pair: pos(i,c) | pos(j,c) << 16 | colptr[c] << 32, ordered by item
+  const int* f_item_pptr;        // items + 1 : pair range of each item
+  const int* rowptr;             // CSR of the strictly lower part of L (row j: columns c < j)
+  const uint32_t* row_bd;        // per CSR entry: pos(j, c) | colptr[c] << 16
+  const uint32_t* row_pc;        // per CSR entry: pos(j, c) | c << 16          (forward solve)
+  const unsigned short* ent_dp;  // per CSC position: position of the diagonal of its column
+  // solves: rows (= columns) ordered by level
+  const int* s_lev_ptr;          // nlevels + 1
+  const unsigned short* s_row;
+  const unsigned short* rowidx16;  // CSC row indices
+  // topology helpers
+  const int* edge_sup;           // m: index into the qsup array or -1
+  const int* sup_ptr;            // nb + 1 : ranges of (support, incident edge) pairs
+  const int* sup_edge;           // nsup
+  const int* sup_other;          // nsup: vertex at the other end
+  const float* sup_sign;         // nsup: C[e, support]
+  const int* colsrc;             // nvar: panel column feeding Jacobian column c (-1: thickness column)
+  int o_env;                     // smem offset of dub[n] | dlb[n] (thickness variable), else -1
+};
+
 struct EmitTable {
   EmitDesc2* dev = nullptr;
   int64_t count = 0;
@@ -146,7 +183,13 @@ struct Plan {
     cudaEventRecord(prof_recs.back().b, s);
   }
   DevPlan dp{};
+  DevOnchip oc{};
+  bool onchip_ok = false;
+  int onchip_threads = 256;
+  int onchip_ctas_per_sm = 1;
   Symbolic sym;
+  std::vector<int> h_vrow, h_vadj_ptr, h_vadj_edge, h_vadj_other, h_fixed;
+  std::vector<float> h_vadj_sign;
   int device = 0;
   int kernel = TNO_KERNEL_INTERLEAVED;
   std::vector<void*> dev_allocs;       // everything to cudaFree at destroy
@@ -171,7 +214,16 @@ struct Plan {
 int run_interleaved(Plan* P, const double* x_dev, int64_t N, int64_t ldx, const tno_batch_inputs* opt,
                     const tno_outputs* out, cudaStream_t stream);
 
+int build_onchip(Plan* P, const tno_problem_desc* D);   // host schedule + upload; sets onchip_ok
+int run_onchip(Plan* P, const double* x_dev, int64_t N, int64_t ldx, const tno_batch_inputs* opt,
+               const tno_outputs* out, cudaStream_t stream);
+
 void set_error(const std::string& msg);
+int upload_bytes(Plan* P, const void* host, size_t bytes, const void** dev);
+template <class T>
+inline int upload_vec(Plan* P, const std::vector<T>& h, const T** dev) {
+  return upload_bytes(P, h.data(), h.size() * sizeof(T), (const void**)dev);
+}
 
 #define TNO_CUDA_OK(call)                                                                     \
   do {                                                                                        \

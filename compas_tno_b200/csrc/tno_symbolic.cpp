@@ -305,6 +305,7 @@ void analyse(int ni, const std::vector<std::pair<int, int>>& edges, int ordering
     S->dot_ptr.assign(nnz + 1, 0);
     S->dot_a.clear();
     S->dot_b.clear();
+    S->dot_c.clear();
     // entry e = L(i, j), i >= j:  pairs over columns c < j present in both row i and row j
     for (int j = 0; j < ni; ++j) {
       for (int p = S->colptr[j]; p < S->colptr[j + 1]; ++p) {
@@ -317,6 +318,7 @@ void analyse(int ni, const std::vector<std::pair<int, int>>& edges, int ordering
           if (ca == cb) {
             S->dot_a.push_back(S->rowpos[a]);
             S->dot_b.push_back(S->rowpos[b]);
+            S->dot_c.push_back(ca);
             ++a;
             ++b;
           } else if (ca < cb) {

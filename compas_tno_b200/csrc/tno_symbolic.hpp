@@ -34,7 +34,7 @@ struct Symbolic {
   // pull ("dot product") form used by the on-chip kernel: for every entry e of L (position order),
   // pairs (pa, pb) with  L[e] = A[e] - sum L[pa] * L[pb]
   std::vector<int64_t> dot_ptr;  // nnz_l+1
-  std::vector<int> dot_a, dot_b;
+  std::vector<int> dot_a, dot_b, dot_c;   // dot_c: the common column of the pair
   // row-wise view of L (CSR, strictly lower part): for the backward / pull-form forward solve
   std::vector<int> rowptr;       // ni+1
   std::vector<int> rowcol;       // column of each strictly-lower entry, ascending

@@ -22,12 +22,17 @@ def tno():
     return pkg
 
 
-@pytest.mark.parametrize("kernel", ["interleaved"])
+@pytest.mark.parametrize("kernel", ["interleaved", "onchip"])
 @pytest.mark.parametrize("name", CASES)
 def test_golden_parity_host_abi(tno, name, kernel):
     from compas_tno_b200.plan import TnoPlan
     P, objective, xs, exp = load_case(name)
-    plan = TnoPlan(P, objective=objective, kernel=kernel)
+    try:
+        plan = TnoPlan(P, objective=objective, kernel=kernel)
+    except NotImplementedError:
+        assert kernel == "onchip" and name == "freeform_q_zb_min"   # k = 360: panel does not fit in shared memory
+        pytest.skip("on-chip family does not fit this problem; the interleaved family covers it")
+    assert plan.info["kernel"] == {"interleaved": 1, "onchip": 2}[kernel]
     assert (plan.nvar, plan.ng) == (xs.shape[1], exp["g"].shape[1])
     got = plan.evaluate_host(xs)
     free, fixed = P.free, P.fixed
@@ -64,7 +69,8 @@ def test_device_api_matches_host_api(tno, name):
     assert plan.launch_count > 0
 
 
-def test_random_batch_against_oracle(tno):
+@pytest.mark.parametrize("kernel", ["interleaved", "onchip"])
+def test_random_batch_against_oracle(tno, kernel):
     """Seeded random candidates around the fixture solution; batch large enough to cross chunk logic."""
     from compas_tno_b200.plan import TnoPlan
     from oracle import callbacks_np as onp
@@ -72,7 +78,7 @@ def test_random_batch_against_oracle(tno):
     rng = np.random.default_rng(20261019)
     N = 300
     X = xs[0] * (1.0 + 0.05 * rng.uniform(-1, 1, size=(N, xs.shape[1])))
-    plan = TnoPlan(P, objective=objective)
+    plan = TnoPlan(P, objective=objective, kernel=kernel)
     got = plan.evaluate_host(X)
     ref = onp.evaluate_batch(X[:40], P, objective)
     assert rel_err(got["z"][:40], ref["z"]) < TOL_VAL
