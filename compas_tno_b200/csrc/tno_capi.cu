@@ -446,7 +446,7 @@ int tno_plan_create(const tno_problem_desc* D, tno_plan** out_plan) {
     if ((rc = build_onchip(P, D))) return rc;
     if (P->onchip_ok) {
       P->kernel = TNO_KERNEL_ONCHIP;
-      I.smem_bytes = (int64_t)P->oc.smem_doubles * 8;
+      I.smem_bytes = (int64_t)P->oc.smem_bytes;
     } else if (D->kernel == TNO_KERNEL_ONCHIP) {
       return fail(TNO_EINVAL, "problem does not fit the on-chip kernel family (shared memory / 16-bit index limits)");
     }

@@ -1,19 +1,25 @@
 // Kernel family 2: "on-chip" -- one CTA per candidate, factor and right-hand-side panel resident in
-// shared memory, one fused launch for the whole evaluation (persistent grid-stride over candidates).
+// shared memory, ONE fused launch for the whole evaluation (persistent grid-stride over candidates).
 //
 // HBM traffic of a candidate is its algorithmic traffic only: x in; z, f, grad, g and the dense J out.
-// The numeric factor (nnz_l doubles) and the panel R (ni x W doubles) never leave the SM.  Pattern
-// indices are 16-bit streams shared by all candidates (L2 / L1 resident).
+// The numeric factor (nnz_l doubles) and the panel R (ni x W doubles) never leave the SM.
 //
-// Parallelism inside a candidate comes from the elimination tree: columns of one level set are
-// independent, so the factorisation (pull / "dot product" form of L D L^T) and both triangular solves
-// are level-synchronous sweeps; lanes of a sweep item run over right-hand-side columns (coalesced,
-// conflict-free panel rows), narrow levels at the top of the tree split one dot product over several
-// lanes and reduce with shuffles.
+// Parallelism inside a candidate comes from the elimination tree.  The plan orders the matrix by level
+// (height above the leaves), so the columns -- and rows -- of one level are contiguous and independent:
+//   * factorisation: pull ("dot product") form of L D L^T, one barrier per level; the (a, b, d) index
+//     triples of a level are streamed from L2 into the idle panel with cp.async two levels ahead, so no
+//     global-memory latency sits on the level-to-level critical path;
+//   * forward solve: pull form over the rows of a level, lanes = right-hand-side columns (conflict-free,
+//     contiguous panel rows), long rows split over sub-slots and reduced with shuffles;
+//   * backward solve: PUSH form over the same row-major storage -- a vertex has at most one ancestor per
+//     level, so the updates of one level never collide and a dense top row is spread over the whole CTA;
+//   * all solve indices (row pointers, 16-bit columns, level table) live in shared memory for the CTA's
+//     lifetime, shared by every candidate it processes.
 //
 // Math restated from the reference, same citations as tno_interleaved.cu.
 #include <algorithm>
 #include <cstdio>
+#include <cstring>
 
 #include "tno_plan.hpp"
 
@@ -33,6 +39,16 @@ struct OcArgs {
   int32_t* status;
   int64_t N;
 };
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gsrc));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
+}
 
 __device__ __forceinline__ void oc_envelope(const DevPlan& P, double x, double y, double t, double* ub, double* lb,
                                             double* dub, double* dlb) {
@@ -59,57 +75,71 @@ __device__ __forceinline__ void oc_envelope(const DevPlan& P, double x, double y
   }
 }
 
-// Level-synchronous L D L^T solve of `ncols` panel columns.  PHASE 1 columns: [0, n1) then x (W-2), y (W-1);
-// PHASE 2 columns: [c_q, c_q + ncols).  G lanes (power of two) cover the columns of one row.
-template <int PHASE>
-__device__ __forceinline__ void oc_solve(const DevPlan& P, const DevOnchip& O, const double* __restrict__ Lv,
-                                         double* __restrict__ R, int ncols, int G, int tid, int nthreads) {
+// L D L^T solve of the panel columns [c0, c0 + ncols) for all rows, level-synchronous.
+template <int THREADS>
+__device__ __forceinline__ void oc_solve(const DevOnchip& O, const OcLevel* __restrict__ levels,
+                                         const unsigned short* __restrict__ rowptr16, const unsigned short* __restrict__ rowcol16,
+                                         const double* __restrict__ Lv, double* __restrict__ R, int ni, int c0, int ncols, int tid) {
   const int W = O.W;
-  const int r = tid & (G - 1);
-  const int slot = tid / G;
-  const int nslots = nthreads / G;
+  int G = 1;
+  while (G < ncols && G < 32) G <<= 1;
   const int cgroups = (ncols + G - 1) / G;
-  auto colmap = [&](int cidx) -> int {
-    if (PHASE == 1) return cidx < O.n1 ? cidx : (W - 2 + (cidx - O.n1));
-    return O.c_q + cidx;
-  };
-  // forward: y_i = b_i - sum_j L_ij y_j   (unit lower, rows of one level are independent)
+  const int r = tid & (G - 1);
+  // ---- forward (unit lower, pull): y_i = b_i - sum_j L_ij y_j ----
   for (int lev = 1; lev < O.nlevels; ++lev) {
-    const int i0 = O.s_lev_ptr[lev], i1 = O.s_lev_ptr[lev + 1];
-    const int nitems = (i1 - i0) * cgroups;
-    for (int it = slot; it < nitems; it += nslots) {
-      const int ri = it / cgroups;
-      const int cidx = (it - ri * cgroups) * G + r;
-      if (cidx < ncols) {
-        const int row = O.s_row[i0 + ri];
-        const int col = colmap(cidx);
-        double acc = R[row * W + col];
-        const int t0 = O.rowptr[row], t1 = O.rowptr[row + 1];
-#pragma unroll 4
-        for (int t = t0; t < t1; ++t) {
-          const uint32_t pc = __ldg(O.row_pc + t);
-          acc = fma(-Lv[pc & 0xffffu], R[(pc >> 16) * W + col], acc);
-        }
-        R[row * W + col] = acc;
+    const OcLevel L = levels[lev];
+    const int nitems = (L.row1 - L.row0) * cgroups;
+    int S = 1;
+    while (S * 2 * G <= 32 && nitems * S * 2 * G <= THREADS) S <<= 1;
+    const int lpi = S * G;
+    const int sub = (tid & (lpi - 1)) / G;
+    const int per_pass = THREADS / lpi;
+    for (int base = 0; base < nitems; base += per_pass) {
+      const int it = base + tid / lpi;
+      const int rr = it / cgroups;
+      const int cidx = (it - rr * cgroups) * G + r;
+      const bool valid = it < nitems && cidx < ncols;
+      const int row = L.row0 + rr;
+      const int col = c0 + cidx;
+      double acc = 0.0;
+      if (valid) {
+        const int t1 = rowptr16[row + 1];
+        for (int t = rowptr16[row] + sub; t < t1; t += S) acc = fma(Lv[t], R[(int)rowcol16[t] * W + col], acc);
       }
+      for (int off = lpi >> 1; off >= G; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+      if (valid && sub == 0) R[row * W + col] -= acc;
     }
     __syncthreads();
   }
-  // backward: x_j = y_j / d_j - sum_{i > j} L_ij x_i
-  for (int lev = O.nlevels - 1; lev >= 0; --lev) {
-    const int i0 = O.s_lev_ptr[lev], i1 = O.s_lev_ptr[lev + 1];
-    const int nitems = (i1 - i0) * cgroups;
-    for (int it = slot; it < nitems; it += nslots) {
-      const int ri = it / cgroups;
-      const int cidx = (it - ri * cgroups) * G + r;
-      if (cidx < ncols) {
-        const int j = O.s_row[i0 + ri];
-        const int col = colmap(cidx);
-        const int p0 = P.colptr[j], p1 = P.colptr[j + 1];
-        double acc = R[j * W + col] * Lv[p0];
-#pragma unroll 4
-        for (int p = p0 + 1; p < p1; ++p) acc = fma(-Lv[p], R[(int)__ldg(O.rowidx16 + p) * W + col], acc);
-        R[j * W + col] = acc;
+  // ---- diagonal: y_i / d_i ----
+  for (int it = tid / G; it < ni * cgroups; it += THREADS / G) {
+    const int row = it / cgroups;
+    const int cidx = (it - row * cgroups) * G + r;
+    if (cidx < ncols) R[row * W + c0 + cidx] *= Lv[O.nlow + row];
+  }
+  __syncthreads();
+  // ---- backward (unit upper, push): x_i final -> x_j -= L_ij x_i for every j in row i ----
+  for (int lev = O.nlevels - 1; lev >= 1; --lev) {
+    const OcLevel L = levels[lev];
+    const int nitems = (L.row1 - L.row0) * cgroups;
+    int S = 1;
+    while (nitems * S * 2 * G <= THREADS) S <<= 1;
+    const int lpi = S * G;
+    const int sub = (tid & (lpi - 1)) / G;
+    const int per_pass = THREADS / lpi;
+    for (int base = 0; base < nitems; base += per_pass) {
+      const int it = base + tid / lpi;
+      const int rr = it / cgroups;
+      const int cidx = (it - rr * cgroups) * G + r;
+      if (it < nitems && cidx < ncols) {
+        const int row = L.row0 + rr;
+        const int col = c0 + cidx;
+        const double xi = R[row * W + col];
+        const int t1 = rowptr16[row + 1];
+        for (int t = rowptr16[row] + sub; t < t1; t += S) {
+          double* dst = R + (int)rowcol16[t] * W + col;
+          *dst = fma(-Lv[t], xi, *dst);
+        }
       }
     }
     __syncthreads();
@@ -119,24 +149,34 @@ __device__ __forceinline__ void oc_solve(const DevPlan& P, const DevOnchip& O, c
 template <int THREADS, int MINB>
 __global__ void __launch_bounds__(THREADS, MINB) k_onchip(const __grid_constant__ DevPlan P, const __grid_constant__ DevOnchip O,
                                                             const __grid_constant__ OcArgs A) {
-  extern __shared__ double sm[];
+  extern __shared__ __align__(16) unsigned char smraw[];
+  double* sm = reinterpret_cast<double*>(smraw);
   double* xs = sm + O.o_x;
   double* Lv = sm + O.o_l;
   double* R = sm + O.o_r;
   double* qs = R;  // q lives in the panel region until the matrix is assembled
-  double* qsup = sm + O.o_small + O.o_qsup;
-  double* react = sm + O.o_small + O.o_react;  // nb x 3
-  double* gxy = sm + O.o_small + O.o_gxy;      // 2 x nb x k : Cb^T U B, Cb^T V B
-  double* red = sm + O.o_small + O.o_red;      // THREADS / 32 + 2
-  double* envd = O.o_env >= 0 ? sm + O.o_env : nullptr;  // dub[n] | dlb[n]
+  double* qsup = sm + O.o_qsup;
+  double* react = sm + O.o_react;  // nb x 3
+  double* gxy = sm + O.o_gxy;      // Cb^T U B | Cb^T V B (nb x k each) | Cb^T U d0 | Cb^T V d0 (nb each)
+  double* azsup = sm + O.o_azsup;  // nsup x nb : dz/dzb at the neighbours of the supports
+  double* red = sm + O.o_red;
+  const unsigned short* rowptr16 = reinterpret_cast<const unsigned short*>(smraw + O.o_idx_bytes + O.idx_rowptr);
+  const unsigned short* rowcol16 = reinterpret_cast<const unsigned short*>(smraw + O.o_idx_bytes + O.idx_rowcol);
+  const OcLevel* levels = reinterpret_cast<const OcLevel*>(smraw + O.o_idx_bytes + O.idx_levels);
   __shared__ int s_flags;
 
   const int tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5;
   const int n = P.n, m = P.m, ni = P.ni, nb = P.nb, k = P.k, nvar = P.var.nvar, ng = P.con.ng, W = O.W;
+  const int nlow = O.nlow;
   const bool has_t = P.var.o_t >= 0;
   const bool want_thrust = (P.objective == TNO_OBJ_MIN || P.objective == TNO_OBJ_MAX);
   const bool want_reac = (P.constraints & TNO_CON_REAC_BOUNDS) != 0;
+
+  // index region: loaded once per CTA, reused by every candidate
+  for (int i = tid; i < O.idx_bytes / 16; i += THREADS)
+    reinterpret_cast<uint4*>(smraw + O.o_idx_bytes)[i] = reinterpret_cast<const uint4*>(O.idx_init)[i];
+  __syncthreads();
 
   for (int64_t cand = blockIdx.x; cand < A.N; cand += gridDim.x) {
     // ---- 0. variables ------------------------------------------------------------------------------
@@ -172,54 +212,73 @@ __global__ void __launch_bounds__(THREADS, MINB) k_onchip(const __grid_constant_
     // ---- 2. assemble -(Ci^T Q Ci) into the pattern of L; keep q of the support edges ----------------
     for (int p = tid; p < P.nnz_l; p += THREADS) {
       double acc = 0.0;
-      for (int t = P.asm_ptr[p]; t < P.asm_ptr[p + 1]; ++t) acc += (double)P.asm_coef[t] * qs[P.asm_edge[t]];
+      for (int t = O.asm_ptr[p]; t < O.asm_ptr[p + 1]; ++t) acc += (double)O.asm_coef[t] * qs[O.asm_edge[t]];
       Lv[p] = acc;
     }
     for (int t = tid; t < O.nsup; t += THREADS) qsup[t] = qs[O.sup_edge[t]];
-    __syncthreads();
+    __syncthreads();  // q consumed: the panel region is free for the factor stream
 
     // ---- 3. numeric L D L^T, level by level (off-diagonals stay unscaled until step 4) --------------
-    for (int lev = 0; lev < O.nlevels; ++lev) {
-      const int i0 = O.f_lev_ptr[lev], i1 = O.f_lev_ptr[lev + 1];
-      const int lpi = O.f_lev_lpi[lev];
-      const int sub = tid & (lpi - 1);
-      const int per_pass = THREADS / lpi;
-      const int npass = (i1 - i0 + per_pass - 1) / per_pass;
-      for (int ps = 0; ps < npass; ++ps) {
-        const int it = i0 + ps * per_pass + tid / lpi;
-        const bool valid = it < i1;
-        double acc = 0.0;
-        int pos = 0, j = 0;
-        if (valid) {
-          pos = O.f_item_pos[it];
-          j = O.f_item_col[it];
-          const int t0 = O.f_item_pptr[it], t1 = O.f_item_pptr[it + 1];
-          for (int t = t0 + sub; t < t1; t += lpi) {
-            const unsigned long long pr = __ldg(O.f_pairs + t);
-            const int a = (int)(pr & 0xffffu), b = (int)((pr >> 16) & 0xffffu), dp = (int)((pr >> 32) & 0xffffu);
-            acc = fma(Lv[a] * Lv[dp], Lv[b], acc);  // U_ic * (1/d_c) * U_jc
-          }
+    {
+      unsigned char* stage_base = reinterpret_cast<unsigned char*>(R);
+      const int seg_bytes = O.fseg_units * 16;
+      auto issue = [&](int lev) {
+        if (O.stage && lev < O.nlevels) {
+          const OcLevel L = levels[lev];
+          unsigned char* dst = stage_base + (lev % 3) * seg_bytes;
+          const uint4* src = O.f_stream + L.seg_off;
+          for (unsigned u = tid; u < L.seg_units; u += THREADS) cp_async16(dst + 16 * u, src + u);
         }
-        for (int off = lpi >> 1; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
-        if (valid && sub == 0) {
-          const double v = Lv[pos] - acc;
-          if (pos == P.colptr[j]) {
-            if (!(v > 0.0)) atomicOr(&s_flags, TNO_STATUS_NOT_PD);
-            Lv[pos] = 1.0 / v;
-          } else {
-            Lv[pos] = v;
+        cp_async_commit();
+      };
+      issue(0);
+      issue(1);
+      for (int lev = 0; lev < O.nlevels; ++lev) {
+        cp_async_wait<1>();
+        __syncthreads();
+        issue(lev + 2);
+        const OcLevel L = levels[lev];
+        const uint2* rec = O.stage ? reinterpret_cast<const uint2*>(stage_base + (lev % 3) * seg_bytes)
+                                   : reinterpret_cast<const uint2*>(O.f_stream + L.seg_off);
+        const unsigned long long* pairs = reinterpret_cast<const unsigned long long*>(rec + L.nitems + 1);
+        const int lpi = L.lpi;
+        const int sub = tid & (lpi - 1);
+        const int per_pass = THREADS / lpi;
+        for (int base = 0; base < L.nitems; base += per_pass) {
+          const int it = base + tid / lpi;
+          const bool valid = it < L.nitems;
+          double acc = 0.0;
+          unsigned pf = 0;
+          if (valid) {
+            const uint2 r0 = rec[it];
+            pf = r0.x;
+            const int t1 = rec[it + 1].y;
+            for (int t = r0.y + sub; t < t1; t += lpi) {
+              const unsigned long long pr = pairs[t];
+              const int a = (int)(pr & 0xffffu), b = (int)((pr >> 16) & 0xffffu), dp = (int)((pr >> 32) & 0xffffu);
+              acc = fma(Lv[a] * Lv[dp], Lv[b], acc);  // U_ic * (1/d_c) * U_jc
+            }
+          }
+          for (int off = lpi >> 1; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+          if (valid && sub == 0) {
+            const int pos = (int)(pf & 0xffffu);
+            const double v = Lv[pos] - acc;
+            if (pf >> 31) {
+              if (!(v > 0.0)) atomicOr(&s_flags, TNO_STATUS_NOT_PD);
+              Lv[pos] = 1.0 / v;
+            } else {
+              Lv[pos] = v;
+            }
           }
         }
       }
+      cp_async_wait<0>();
       __syncthreads();
     }
     // ---- 4. L_ij = U_ij / d_j ----------------------------------------------------------------------
-    for (int p = tid; p < P.nnz_l; p += THREADS) {
-      const int dp = O.ent_dp[p];
-      if (dp != p) Lv[p] *= Lv[dp];
-    }
-    // (the panel region is free from here on: q has been consumed)
-    // ---- 5. phase-1 right-hand sides ----------------------------------------------------------------
+    for (int p = tid; p < nlow; p += THREADS) Lv[p] *= Lv[nlow + (int)rowcol16[p]];
+
+    // ---- 5. phase-1 right-hand sides: z | z_lambdv | Az | x | y -------------------------------------
     for (int r = tid; r < ni; r += THREADS) {
       const int v = P.row_vertex[r];
       double px, py, pz;
@@ -234,8 +293,8 @@ __global__ void __launch_bounds__(THREADS, MINB) k_onchip(const __grid_constant_
       pz *= pzs;
       double bx = -px, by = -py, bz = -pz;
       double* row = R + r * W;
-      if (O.c_zb >= 0)
-        for (int b = 0; b < nb; ++b) row[O.c_zb + b] = 0.0;
+      if (O.c_az >= 0)
+        for (int b = 0; b < nb; ++b) row[O.c_az + b] = 0.0;
       for (int t = P.vadj_ptr[v]; t < P.vadj_ptr[v + 1]; ++t) {
         const int o = P.vadj_other[t];
         const int ro = P.vrow[o];
@@ -246,24 +305,19 @@ __global__ void __launch_bounds__(THREADS, MINB) k_onchip(const __grid_constant_
         bx = fma(-qe, P.X[3 * o + 0], bx);
         by = fma(-qe, P.X[3 * o + 1], by);
         bz = fma(-qe, zb, bz);
-        if (O.c_zb >= 0) row[O.c_zb + b] -= qe;
+        if (O.c_az >= 0) row[O.c_az + b] -= qe;
       }
-      row[W - 2] = bx;
-      row[W - 1] = by;
+      row[O.c_x] = bx;
+      row[O.c_y] = by;
       row[O.c_z] = bz;
       if (O.c_lambdv >= 0) row[O.c_lambdv] = -P.pzv[v];
     }
     __syncthreads();
 
-    // ---- 6. solve phase 1: z | Az | z_lambdv | x | y ------------------------------------------------
-    {
-      const int nc1 = O.n1 + 2;
-      int G = 1;
-      while (G < nc1 && G < 32) G <<= 1;
-      oc_solve<1>(P, O, Lv, R, nc1, G, tid, THREADS);
-    }
+    // ---- 6. solve phase 1 ---------------------------------------------------------------------------
+    oc_solve<THREADS>(O, levels, rowptr16, rowcol16, Lv, R, ni, 0, O.ncols1, tid);
 
-    // ---- 7. everything that needs x, y (transient columns) or only z --------------------------------
+    // ---- 7. everything that needs the transient columns (x, y, Az) or only z ------------------------
     auto zfix = [&](int b) -> double { return P.var.o_zb >= 0 ? xs[P.var.o_zb + b] : P.X[3 * P.fixed[b] + 2]; };
     auto zval = [&](int v) -> double {
       const int r = P.vrow[v];
@@ -271,7 +325,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_onchip(const __grid_constant_
     };
     auto xyval = [&](int v, int axis) -> double {
       const int r = P.vrow[v];
-      return r >= 0 ? R[r * W + W - 2 + axis] : P.X[3 * v + axis];
+      return r >= 0 ? R[r * W + O.c_x + axis] : P.X[3 * v + axis];
     };
     for (int v = tid; v < n; v += THREADS) {
       const double z = zval(v);
@@ -282,8 +336,10 @@ __global__ void __launch_bounds__(THREADS, MINB) k_onchip(const __grid_constant_
         if (has_t) {
           double dub, dlb;
           oc_envelope(P, xyval(v, 0), xyval(v, 1), xs[P.var.o_t], &ub, &lb, &dub, &dlb);
-          envd[v] = dub;
-          envd[n + v] = dlb;
+          if (Jout) {  // thickness column: [-dlb/dt ; +dub/dt]
+            Jout[(int64_t)(P.con.r_env + v) * nvar + P.var.o_t] = -dlb;
+            Jout[(int64_t)(P.con.r_env + n + v) * nvar + P.var.o_t] = dub;
+          }
         } else {
           ub = P.ub[v];
           lb = P.lb[v];
@@ -294,6 +350,16 @@ __global__ void __launch_bounds__(THREADS, MINB) k_onchip(const __grid_constant_
           gout[P.con.r_env + n + v] = g1;
         }
         gmin = fmin(gmin, fmin(g0, g1));
+      }
+    }
+    if (Jout && P.con.r_env >= 0 && P.var.o_zb >= 0) {
+      // dz/dzb block straight to the Jacobian (its panel columns are about to be reused)
+      for (int idx = tid; idx < n * nb; idx += THREADS) {
+        const int v = idx / nb, b = idx - v * nb;
+        const int r = P.vrow[v];
+        const double a = r >= 0 ? R[r * W + O.c_az + b] : ((-1 - r) == b ? 1.0 : 0.0);
+        Jout[(int64_t)(P.con.r_env + v) * nvar + P.var.o_zb + b] = a;
+        Jout[(int64_t)(P.con.r_env + n + v) * nvar + P.var.o_zb + b] = -a;
       }
     }
     if (want_thrust || want_reac) {
@@ -356,17 +422,24 @@ __global__ void __launch_bounds__(THREADS, MINB) k_onchip(const __grid_constant_
         gxy[it] = gx;
         gxy[nb * k + it] = gy;
       }
+      if (want_reac && O.c_az >= 0) {
+        for (int it = tid; it < O.nsup * nb; it += THREADS) {
+          const int t = it / nb, b = it - t * nb;
+          const int ro = P.vrow[O.sup_other[t]];
+          azsup[it] = ro >= 0 ? R[ro * W + O.c_az + b] : ((-1 - ro) == b ? 1.0 : 0.0);
+        }
+      }
     }
     __syncthreads();
 
     // ---- 8. phase-2 right-hand sides: Ci^T W B | Ci^T W d0 ------------------------------------------
-    const int nc2 = (O.c_q >= 0) ? (k + (O.c_lambdh >= 0 ? 1 : 0)) : 0;
-    if (nc2 > 0) {
+    if (O.ncols2 > 0) {
+      const int nc2 = O.ncols2;
       int G = 1;
       while (G < nc2 && G < 32) G <<= 1;
       const int cgroups = (nc2 + G - 1) / G;
-      const int r_ = tid & (G - 1), slot = tid / G, nslots = THREADS / G;
-      for (int it = slot; it < ni * cgroups; it += nslots) {
+      const int r_ = tid & (G - 1);
+      for (int it = tid / G; it < ni * cgroups; it += THREADS / G) {
         const int r = it / cgroups;
         const int cidx = (it - r * cgroups) * G + r_;
         if (cidx >= nc2) continue;
@@ -385,14 +458,13 @@ __global__ void __launch_bounds__(THREADS, MINB) k_onchip(const __grid_constant_
       }
       __syncthreads();
       // ---- 9. solve phase 2 ----
-      oc_solve<2>(P, O, Lv, R, nc2, G, tid, THREADS);
+      oc_solve<THREADS>(O, levels, rowptr16, rowcol16, Lv, R, ni, O.c_q, nc2, tid);
     }
 
     // ---- 10. reac_bounds rows, objective, gradient ---------------------------------------------------
     if (want_reac) {
       const bool has_env = (P.constraints & TNO_CON_ENVELOPE) != 0;
-      // one item per (support b, Jacobian column)
-      for (int it = tid; it < nb * nvar; it += THREADS) {
+      for (int it = tid; it < nb * nvar; it += THREADS) {  // one item per (support b, Jacobian column)
         const int b = it / nvar, col = it - b * nvar;
         const int vb = P.fixed[b];
         const double Rx = react[3 * b], Ry = react[3 * b + 1], Rz = react[3 * b + 2];
@@ -427,16 +499,14 @@ __global__ void __launch_bounds__(THREADS, MINB) k_onchip(const __grid_constant_
           vx = zb * sx * (-Rz * dRx + Rx * dRz) / rz2 / sz;
           vy = zb * sy * (-Rz * dRy + Ry * dRz) / rz2 / sz;
         } else if (P.var.o_zb >= 0 && col >= P.var.o_zb && col < P.var.o_zb + nb) {
+          // dRz/dzb = Cb^T Q C A ; the reference adds COLUMN b of it to row b (jacobian.py:222)
           const int cb = col - P.var.o_zb;
           double acc = 0.0;
           for (int t = O.sup_ptr[cb]; t < O.sup_ptr[cb + 1]; ++t) {
-            const int o = O.sup_other[t];
             const double sg = (double)O.sup_sign[t];
-            const double qe = qsup[t];
-            const int ro = P.vrow[o];
-            const double Ao = ro >= 0 ? R[ro * W + O.c_zb + b] : ((-1 - ro) == b ? 1.0 : 0.0);
+            const double Ao = azsup[t * nb + b];
             const double Ac = (cb == b) ? 1.0 : 0.0;
-            acc = fma(sg * qe, sg > 0 ? (Ac - Ao) : (Ao - Ac), acc);
+            acc = fma(sg * qsup[t], sg > 0 ? (Ac - Ao) : (Ao - Ac), acc);
           }
           vx = sz * zb * fabs(Rx) / rz2 * acc;
           vy = sz * zb * fabs(Ry) / rz2 * acc;
@@ -447,9 +517,8 @@ __global__ void __launch_bounds__(THREADS, MINB) k_onchip(const __grid_constant_
         } else if (col == P.var.o_lambdv) {
           double dRz = 0.0;
           for (int t = t0; t < t1; ++t) {
-            const int o = O.sup_other[t];
             const double sg = (double)O.sup_sign[t];
-            const int ro = P.vrow[o];
+            const int ro = P.vrow[O.sup_other[t]];
             if (ro >= 0) {
               const double dzo = R[ro * W + O.c_lambdv];
               dRz = fma(sg * qsup[t], sg > 0 ? -dzo : dzo, dRz);
@@ -526,19 +595,12 @@ __global__ void __launch_bounds__(THREADS, MINB) k_onchip(const __grid_constant_
         for (int e = tid; e < n * nvar; e += THREADS) {
           const int v = __umulhi((unsigned)e, O.nvar_magic);
           const int col = e - v * nvar;
-          const int r = P.vrow[v];
           const int src = O.colsrc[col];
-          double a, bneg;
-          if (src >= 0) {
-            a = r >= 0 ? R[r * W + src] : 0.0;
-            if (r < 0 && P.var.o_zb >= 0 && col == P.var.o_zb + (-1 - r)) a = 1.0;
-            bneg = -a;
-          } else {  // thickness column: [-dlb/dt ; +dub/dt]
-            a = -envd[n + v];
-            bneg = envd[v];
-          }
+          if (src == -1) continue;  // zb and thickness columns were written in step 7
+          const int r = P.vrow[v];
+          const double a = (src >= 0 && r >= 0) ? R[r * W + src] : 0.0;
           o1[e] = a;
-          o2[e] = bneg;
+          o2[e] = -a;
         }
       }
     }
@@ -568,27 +630,39 @@ int build_onchip(Plan* PL, const tno_problem_desc* D) {
   DevPlan& P = PL->dp;
   DevOnchip& O = PL->oc;
   PL->onchip_ok = false;
-  const int ni = P.ni, n = P.n, m = P.m, nb = P.nb, k = P.k, nvar = P.var.nvar;
+  const int ni = P.ni, m = P.m, nb = P.nb, k = P.k, nvar = P.var.nvar;
   const int nnz = P.nnz_l;
-  if (nnz >= 65536 || ni >= 65536) return TNO_OK;
+  const int nlow = nnz - ni;
+  if (nnz >= 65536 || ni >= 65535 || S.nlevels < 1) return TNO_OK;
+  const int THREADS = 256;
 
-  // panel columns: [z | Az | z_lambdv | Dq | z_lambdh], x and y transient in the last two columns
+  // panel columns
   int pos = 0;
   O.c_z = pos++;
-  O.c_zb = -1;
   O.c_lambdv = -1;
   O.c_q = -1;
   O.c_lambdh = -1;
-  if (P.var.o_zb >= 0) { O.c_zb = pos; pos += nb; }
-  if (P.var.o_lambdv >= 0) { O.c_lambdv = pos; pos += 1; }
-  O.n1 = pos;
+  if (P.var.o_lambdv >= 0) O.c_lambdv = pos++;
+  const int n_persist = pos;
+  O.ncols2 = 0;
   if (P.rhs.c_q >= 0) {
-    O.c_q = pos; pos += k;
-    if (P.var.o_lambdh >= 0) { O.c_lambdh = pos; pos += 1; }
+    O.c_q = pos;
+    O.ncols2 = k + (P.var.o_lambdh >= 0 ? 1 : 0);
+    if (P.var.o_lambdh >= 0) O.c_lambdh = O.c_q + k;
   }
-  O.W = std::max(pos, O.n1 + 2);
+  O.c_az = (P.var.o_zb >= 0) ? n_persist : -1;
+  O.c_x = n_persist + (P.var.o_zb >= 0 ? nb : 0);
+  O.c_y = O.c_x + 1;
+  O.ncols1 = O.c_y + 1;
+  O.W = std::max(O.ncols1, n_persist + O.ncols2);
   O.nlevels = S.nlevels;
+  O.nlow = nlow;
   O.nvar_magic = (uint32_t)((((uint64_t)1 << 32) + nvar - 1) / nvar);
+
+  // CSC position -> on-chip position (CSR order of the strictly lower part, diagonals last)
+  std::vector<int> newpos(nnz, -1);
+  for (int j = 0; j < ni; ++j) newpos[S.colptr[j]] = nlow + j;
+  for (int t = 0; t < nlow; ++t) newpos[S.rowpos[t]] = t;
 
   // support incidence
   std::vector<int> sup_ptr(nb + 1, 0), sup_edge, sup_other, edge_sup(m, -1);
@@ -596,7 +670,7 @@ int build_onchip(Plan* PL, const tno_problem_desc* D) {
   for (int b = 0; b < nb; ++b) {
     const int vb = PL->h_fixed[b];
     for (int t = PL->h_vadj_ptr[vb]; t < PL->h_vadj_ptr[vb + 1]; ++t) {
-      edge_sup[PL->h_vadj_edge[t]] = (int)sup_edge.size();  // an edge between two supports keeps the last index; q is the same
+      edge_sup[PL->h_vadj_edge[t]] = (int)sup_edge.size();
       sup_edge.push_back(PL->h_vadj_edge[t]);
       sup_other.push_back(PL->h_vadj_other[t]);
       sup_sign.push_back(PL->h_vadj_sign[t]);
@@ -605,97 +679,148 @@ int build_onchip(Plan* PL, const tno_problem_desc* D) {
   }
   O.nsup = (int)sup_edge.size();
 
-  // shared memory layout (doubles)
-  int off = 0;
-  O.o_x = off; off += (nvar + 3) / 4 * 4;
-  O.o_l = off; off += (nnz + 3) / 4 * 4;
-  O.o_r = off; off += std::max(ni * O.W, m);
-  off = (off + 3) / 4 * 4;
-  O.o_env = -1;
-  if (P.var.o_t >= 0) { O.o_env = off; off += 2 * n; }
-  O.o_small = off;
-  int so = 0;
-  O.o_qsup = so; so += O.nsup;
-  O.o_react = so; so += 3 * nb;
-  O.o_gxy = so; so += 2 * nb * k + 2 * nb;  // + (Cb^T U d0, Cb^T V d0) for the lambdh column
-  O.o_red = so; so += 40;
-  off += so;
-  O.smem_doubles = off;
-  const size_t smem_bytes = (size_t)off * 8;
-  int max_optin = 0;
-  TNO_CUDA_OK(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, PL->device));
-  if (smem_bytes > (size_t)max_optin) return TNO_OK;
-  int smem_sm = 0;
-  TNO_CUDA_OK(cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, PL->device));
-  PL->onchip_threads = 256;
-  PL->onchip_ctas_per_sm = std::max(1, std::min(8, (int)((size_t)smem_sm / (smem_bytes + 1024))));
-
-  // ---- factorisation items, level ordered ----
-  std::vector<int> f_lev_ptr(S.nlevels + 1, 0), f_lev_lpi(S.nlevels, 1), f_item_pptr(1, 0);
-  std::vector<unsigned long long> f_pairs;
-  std::vector<unsigned short> f_item_pos, f_item_col, ent_dp(nnz), s_row(ni), rowidx16(nnz);
-  std::vector<uint32_t> row_bd(S.rowpos.size()), row_pc(S.rowpos.size());
-  for (size_t t = 0; t < S.rowpos.size(); ++t) {
-    const int c = S.rowcol[t];
-    row_bd[t] = (uint32_t)S.rowpos[t] | ((uint32_t)S.colptr[c] << 16);
-    row_pc[t] = (uint32_t)S.rowpos[t] | ((uint32_t)c << 16);
-  }
-  for (int j = 0; j < ni; ++j)
-    for (int p = S.colptr[j]; p < S.colptr[j + 1]; ++p) {
-      ent_dp[p] = (unsigned short)S.colptr[j];
-      rowidx16[p] = (unsigned short)S.rowidx[p];
-    }
+  // ---- factor stream, one segment per level ----
+  std::vector<OcLevel> levels(S.nlevels);
+  std::vector<uint32_t> stream;  // 32-bit words; segments padded to 16 bytes
+  uint32_t max_units = 0;
   for (int lev = 0; lev < S.nlevels; ++lev) {
-    int64_t pairs = 0;
-    for (int ci = S.level_ptr[lev]; ci < S.level_ptr[lev + 1]; ++ci) {
-      const int j = S.level_cols[ci];
+    OcLevel& L = levels[lev];
+    std::memset(&L, 0, sizeof(L));
+    L.row0 = (unsigned short)S.level_ptr[lev];
+    L.row1 = (unsigned short)S.level_ptr[lev + 1];
+    std::vector<uint32_t> recs;
+    std::vector<unsigned long long> prs;
+    int nitems = 0;
+    for (int j = S.level_ptr[lev]; j < S.level_ptr[lev + 1]; ++j) {
+      if (S.level_cols[j] != j) {
+        set_error("internal: level ordering is not contiguous");
+        return TNO_EINVAL;
+      }
       for (int p = S.colptr[j]; p < S.colptr[j + 1]; ++p) {
-        f_item_pos.push_back((unsigned short)p);
-        f_item_col.push_back((unsigned short)j);
+        recs.push_back((uint32_t)newpos[p] | (p == S.colptr[j] ? 0x80000000u : 0u));
+        recs.push_back((uint32_t)prs.size());
         for (int64_t t = S.dot_ptr[p]; t < S.dot_ptr[p + 1]; ++t)
-          f_pairs.push_back((unsigned long long)S.dot_a[t] | ((unsigned long long)S.dot_b[t] << 16) |
-                            ((unsigned long long)S.colptr[S.dot_c[t]] << 32));
-        f_item_pptr.push_back((int)f_pairs.size());
-        pairs += S.dot_ptr[p + 1] - S.dot_ptr[p];
+          prs.push_back((unsigned long long)newpos[S.dot_a[t]] | ((unsigned long long)newpos[S.dot_b[t]] << 16) |
+                        ((unsigned long long)(nlow + S.dot_c[t]) << 32));
+        ++nitems;
       }
     }
-    f_lev_ptr[lev + 1] = (int)f_item_pos.size();
-    const int items = f_lev_ptr[lev + 1] - f_lev_ptr[lev];
+    recs.push_back(0);
+    recs.push_back((uint32_t)prs.size());
+    if (nitems >= 65536) return TNO_OK;
+    L.nitems = (unsigned short)nitems;
     int lpi = 1;
-    if (items > 0 && pairs / items >= 4)
-      while (lpi < 32 && items * lpi * 2 <= PL->onchip_threads) lpi <<= 1;
-    f_lev_lpi[lev] = lpi;
+    if (nitems > 0 && (int64_t)prs.size() / nitems >= 4)
+      while (lpi < 32 && nitems * lpi * 2 <= THREADS) lpi <<= 1;
+    L.lpi = (unsigned short)lpi;
+    L.seg_off = (uint32_t)(stream.size() / 4);
+    stream.insert(stream.end(), recs.begin(), recs.end());
+    for (unsigned long long pr : prs) {
+      stream.push_back((uint32_t)(pr & 0xffffffffu));
+      stream.push_back((uint32_t)(pr >> 32));
+    }
+    while (stream.size() % 4) stream.push_back(0);
+    L.seg_units = (uint32_t)(stream.size() / 4) - L.seg_off;
+    max_units = std::max(max_units, L.seg_units);
   }
-  for (int i = 0; i < ni; ++i) s_row[i] = (unsigned short)S.level_cols[i];
+  O.fseg_units = (int)max_units;
+
+  // ---- assembly gather lists in on-chip position order ----
+  std::vector<int> asm_ptr(nnz + 1, 0), asm_edge;
+  std::vector<float> asm_coef;
+  {
+    std::vector<std::vector<std::pair<int, float>>> contrib(nnz);
+    for (int e = 0; e < m; ++e) {
+      const int u = D->edges[2 * e], v = D->edges[2 * e + 1];
+      const int ru = PL->h_vrow[u], rv = PL->h_vrow[v];
+      if (ru >= 0) contrib[nlow + ru].push_back({e, -1.f});
+      if (rv >= 0) contrib[nlow + rv].push_back({e, -1.f});
+      if (ru >= 0 && rv >= 0) contrib[newpos[S.pos(std::max(ru, rv), std::min(ru, rv))]].push_back({e, +1.f});
+    }
+    for (int p = 0; p < nnz; ++p) {
+      for (auto& c : contrib[p]) {
+        asm_edge.push_back(c.first);
+        asm_coef.push_back(c.second);
+      }
+      asm_ptr[p + 1] = (int)asm_edge.size();
+    }
+  }
+
+  // ---- shared-memory index region image: rowptr16 | rowcol16 | levels ----
+  std::vector<unsigned char> idx;
+  auto align16 = [&]() {
+    while (idx.size() % 16) idx.push_back(0);
+  };
+  O.idx_rowptr = 0;
+  for (int i = 0; i <= ni; ++i) {
+    const unsigned short v = (unsigned short)S.rowptr[i];
+    idx.push_back((unsigned char)(v & 0xff));
+    idx.push_back((unsigned char)(v >> 8));
+  }
+  align16();
+  O.idx_rowcol = (int)idx.size();
+  for (int t = 0; t < nlow; ++t) {
+    const unsigned short v = (unsigned short)S.rowcol[t];
+    idx.push_back((unsigned char)(v & 0xff));
+    idx.push_back((unsigned char)(v >> 8));
+  }
+  align16();
+  O.idx_levels = (int)idx.size();
+  {
+    const unsigned char* lp = reinterpret_cast<const unsigned char*>(levels.data());
+    idx.insert(idx.end(), lp, lp + levels.size() * sizeof(OcLevel));
+  }
+  align16();
+  O.idx_bytes = (int)idx.size();
+
+  // ---- shared memory layout ----
+  int off = 0;  // doubles
+  auto take = [&](int count) {
+    const int o = off;
+    off += (count + 1) / 2 * 2;  // keep 16-byte alignment
+    return o;
+  };
+  O.o_x = take(nvar);
+  O.o_l = take(nnz);
+  const int panel = std::max(ni * O.W, m);
+  const int stage_doubles = 3 * O.fseg_units * 2;
+  O.stage = 1;
+  O.o_r = take(std::max(panel, stage_doubles));
+  O.o_env = -1;
+  O.o_qsup = take(O.nsup);
+  O.o_react = take(3 * nb);
+  O.o_gxy = take(2 * nb * k + 2 * nb);
+  O.o_azsup = take(((P.constraints & TNO_CON_REAC_BOUNDS) && P.var.o_zb >= 0) ? O.nsup * nb : 0);
+  O.o_red = take(40);
+  O.o_idx_bytes = off * 8;
+  O.smem_bytes = O.o_idx_bytes + O.idx_bytes;
+  int max_optin = 0, smem_sm = 0;
+  TNO_CUDA_OK(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, PL->device));
+  TNO_CUDA_OK(cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, PL->device));
+  if (O.smem_bytes > max_optin) return TNO_OK;
+  PL->onchip_threads = THREADS;
+  PL->onchip_ctas_per_sm = std::max(1, std::min(8, smem_sm / (O.smem_bytes + 1024)));
 
   std::vector<double> Bt((size_t)k * m);
   for (int e = 0; e < m; ++e)
     for (int j = 0; j < k; ++j) Bt[(size_t)j * m + e] = D->B[(size_t)e * k + j];
   std::vector<int> colsrc(nvar, -1);
   for (int j = 0; j < k; ++j) colsrc[j] = O.c_q >= 0 ? O.c_q + j : -2;
-  if (P.var.o_zb >= 0)
-    for (int b = 0; b < nb; ++b) colsrc[P.var.o_zb + b] = O.c_zb + b;
-  if (P.var.o_lambdh >= 0) colsrc[P.var.o_lambdh] = O.c_lambdh;
+  if (P.var.o_lambdh >= 0) colsrc[P.var.o_lambdh] = O.c_lambdh >= 0 ? O.c_lambdh : -2;
   if (P.var.o_lambdv >= 0) colsrc[P.var.o_lambdv] = O.c_lambdv;
-  if (P.var.o_t >= 0) colsrc[P.var.o_t] = -1;
 
   int rc;
+  const void* dptr = nullptr;
 #define UPO(field, hostvec) \
   if ((rc = upload_vec(PL, hostvec, &O.field))) return rc;
   UPO(Bt, Bt);
-  UPO(f_lev_ptr, f_lev_ptr);
-  UPO(f_lev_lpi, f_lev_lpi);
-  UPO(f_item_pos, f_item_pos);
-  UPO(f_item_col, f_item_col);
-  UPO(f_item_pptr, f_item_pptr);
-  UPO(f_pairs, f_pairs);
-  UPO(rowptr, S.rowptr);
-  UPO(row_bd, row_bd);
-  UPO(row_pc, row_pc);
-  UPO(ent_dp, ent_dp);
-  UPO(s_lev_ptr, S.level_ptr);
-  UPO(s_row, s_row);
-  UPO(rowidx16, rowidx16);
+  UPO(asm_ptr, asm_ptr);
+  UPO(asm_edge, asm_edge);
+  UPO(asm_coef, asm_coef);
+  if ((rc = upload_bytes(PL, stream.data(), stream.size() * 4, &dptr))) return rc;
+  O.f_stream = reinterpret_cast<const uint4*>(dptr);
+  if ((rc = upload_bytes(PL, idx.data(), idx.size(), &dptr))) return rc;
+  O.idx_init = reinterpret_cast<const unsigned char*>(dptr);
   UPO(edge_sup, edge_sup);
   UPO(sup_ptr, sup_ptr);
   UPO(sup_edge, sup_edge);
@@ -722,7 +847,7 @@ int run_onchip(Plan* PL, const double* x_dev, int64_t N, int64_t ldx, const tno_
   A.gmin = out->gmin;
   A.status = out->status;
   A.N = N;
-  const size_t smem = (size_t)PL->oc.smem_doubles * 8;
+  const size_t smem = (size_t)PL->oc.smem_bytes;
   const int grid = (int)std::min<int64_t>(N, (int64_t)PL->sm_count * PL->onchip_ctas_per_sm);
   auto kern = PL->onchip_ctas_per_sm >= 2 ? k_onchip<256, 2> : k_onchip<256, 1>;
   TNO_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

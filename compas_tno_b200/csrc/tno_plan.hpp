@@ -106,40 +106,45 @@ struct DevPlan {
 };
 
 // Device data of the on-chip kernel family (tno_onchip.cu): level-ordered index streams, all 16-bit.
+// One level set of the elimination tree (rows == columns are contiguous per level after the level ordering).
+struct OcLevel {
+  unsigned short row0, row1;   // rows / columns [row0, row1)
+  unsigned short nitems;       // entries of L in those columns (factorisation work items)
+  unsigned short lpi;          // lanes sharing one item's dot product (power of two <= 32)
+  uint32_t seg_off;            // factor stream segment: offset and length in 16-byte units
+  uint32_t seg_units;
+  uint32_t pad;
+};
+
+// Device data of the on-chip kernel family (tno_onchip.cu).
+// Value array Lv (shared memory): strictly-lower entries of L in CSR (row-major) order [0, nlow), then the ni
+// diagonal slots [nlow, nlow + ni) which hold 1 / d_j after the factorisation.
 struct DevOnchip {
-  int W;                 // columns of the shared-memory right-hand-side panel (= nrhs - 2: x, y are transient)
-  int n1;                // persistent phase-1 columns: z | Az | z_lambdv  -> panel columns [0, n1)
-  int c_z, c_zb, c_lambdv, c_q, c_lambdh;   // panel column of each block (-1 = absent); x -> W-2, y -> W-1 in phase 1
-  int nlevels;
-  int nsup;              // number of (support, incident edge) pairs
-  uint32_t nvar_magic;   // ceil(2^32 / nvar) for the flat index -> (row, col) split
-  // smem layout in doubles
-  int o_x, o_l, o_r, o_small, smem_doubles;
-  int o_qsup, o_react, o_gxy, o_red;   // inside the small region
-  const double* Bt;      // k x m (transposed B): coalesced over edges
-  // factorisation (pull form, L D L^T): items = entries of L ordered by level of their column
-  const int* f_lev_ptr;          // nlevels + 1
-  const int* f_lev_lpi;          // lanes per item in each level (power of two <= 32)
-  const unsigned short* f_item_pos;   // position of the entry in the CSC value array
-  const unsigned short* f_item_col;   // its column j
-  const unsigned long long* f_pairs;  // per pair: pos(i,c) | pos(j,c) << 16 | colptr[c] << 32, ordered by item
-  const int* f_item_pptr;        // items + 1 : pair range of each item
-  const int* rowptr;             // CSR of the strictly lower part of L (row j: columns c < j)
-  const uint32_t* row_bd;        // per CSR entry: pos(j, c) | colptr[c] << 16
-  const uint32_t* row_pc;        // per CSR entry: pos(j, c) | c << 16          (forward solve)
-  const unsigned short* ent_dp;  // per CSC position: position of the diagonal of its column
-  // solves: rows (= columns) ordered by level
-  const int* s_lev_ptr;          // nlevels + 1
-  const unsigned short* s_row;
-  const unsigned short* rowidx16;  // CSC row indices
-  // topology helpers
-  const int* edge_sup;           // m: index into the qsup array or -1
-  const int* sup_ptr;            // nb + 1 : ranges of (support, incident edge) pairs
-  const int* sup_edge;           // nsup
-  const int* sup_other;          // nsup: vertex at the other end
-  const float* sup_sign;         // nsup: C[e, support]
-  const int* colsrc;             // nvar: panel column feeding Jacobian column c (-1: thickness column)
-  int o_env;                     // smem offset of dub[n] | dlb[n] (thickness variable), else -1
+  int W;                 // panel columns: [z | z_lambdv | Dq (k) | z_lambdh]; Az, x, y transient in the Dq columns
+  int c_z, c_lambdv, c_q, c_lambdh;   // persistent panel columns (-1 = absent)
+  int c_az, c_x, c_y;    // transient phase-1 columns (overwritten by phase 2)
+  int ncols1, ncols2;    // columns solved in phase 1: [0, ncols1); in phase 2: [c_q, c_q + ncols2)
+  int nlevels, nlow, nsup;
+  uint32_t nvar_magic;   // ceil(2^32 / nvar): flat index -> (row, col)
+  // shared memory layout: offsets in doubles, o_idx in bytes
+  int o_x, o_l, o_r, o_env, o_qsup, o_react, o_gxy, o_azsup, o_red, o_idx_bytes;
+  int idx_rowptr, idx_rowcol, idx_levels;   // byte offsets inside the index region
+  int idx_bytes;
+  int smem_bytes;
+  int stage;             // 1: factor stream staged through the panel with cp.async (3 buffers of fseg_units)
+  int fseg_units;        // largest level segment, 16-byte units
+  const double* Bt;      // k x m (transposed B)
+  const int* asm_ptr;    // nnz_l + 1, assembly gather lists in Lv position order
+  const int* asm_edge;
+  const float* asm_coef;
+  const uint4* f_stream; // per level: (nitems + 1) records {pos | diag << 31, first pair} then pairs {a | b << 16 | dp << 32}
+  const unsigned char* idx_init;   // image of the shared-memory index region (rowptr16, rowcol16, levels)
+  const int* edge_sup;   // m: index of an edge in the support-incidence list or -1
+  const int* sup_ptr;    // nb + 1
+  const int* sup_edge;   // nsup
+  const int* sup_other;  // nsup: vertex at the other end
+  const float* sup_sign; // nsup: C[e, support]
+  const int* colsrc;     // nvar: panel column feeding Jacobian column c (-1: written in the phase-1 epilogue)
 };
 
 struct EmitTable {

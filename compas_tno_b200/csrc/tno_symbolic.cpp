@@ -223,6 +223,13 @@ void analyse(int ni, const std::vector<std::pair<int, int>>& edges, int ordering
         }
       }
     }
+    // ... then stable-sort the postorder by level (height above the leaves).  Children still precede
+    // parents, so fill and tree are unchanged, and every level set becomes a contiguous block of columns
+    // (and, row-wise, a contiguous block of rows): the level-synchronous kernels need no index lists.
+    std::vector<int> lvl(ni, 0);
+    for (int j = 0; j < ni; ++j)
+      if (parent[j] >= 0) lvl[parent[j]] = std::max(lvl[parent[j]], lvl[j] + 1);
+    std::stable_sort(post.begin(), post.end(), [&](int a, int b) { return lvl[a] < lvl[b]; });
     std::vector<int> neworder(ni);
     for (int r = 0; r < ni; ++r) neworder[r] = order[post[r]];
     order.swap(neworder);
