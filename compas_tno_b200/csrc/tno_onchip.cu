@@ -75,73 +75,136 @@ __device__ __forceinline__ void oc_envelope(const DevPlan& P, double x, double y
   }
 }
 
-// L D L^T solve of the panel columns [c0, c0 + ncols) for all rows, level-synchronous.
+// ---- level kernels of the triangular solves -----------------------------------------------------------
+// A "team" of NT threads (the whole CTA, or one warp for the narrow levels near the root) handles the rows
+// of one level.  G = 2^gshift lanes cover the columns of a row, TWO adjacent columns per lane (one 16-byte
+// shared-memory access), S = 2^sshift sub-slots split the entries of a row.
+
+// forward, pull form: y_i -= sum_j L_ij y_j ; sub-slot partial sums are combined with shuffles (S * G <= 32)
+template <int NT>
+__device__ __forceinline__ void oc_pull_level(const OcLevel& L, int sshift, int gshift, int tl, int c0, int ncols, int W,
+                                              const unsigned short* __restrict__ rowptr16,
+                                              const unsigned short* __restrict__ rowcol16, const double* __restrict__ Lv,
+                                              double* __restrict__ R) {
+  const int lshift = sshift + gshift;
+  const int rows = L.row1 - L.row0;
+  const int r = tl & ((1 << gshift) - 1);
+  const int sub = (tl >> gshift) & ((1 << sshift) - 1);
+  const int S = 1 << sshift;
+  const bool colok = 2 * r < ncols;
+  const int col = c0 + 2 * r;
+  for (int base = 0; base < rows; base += NT >> lshift) {
+    const int it = base + (tl >> lshift);
+    const bool valid = it < rows && colok;
+    const int row = L.row0 + it;
+    double ax = 0.0, ay = 0.0;
+    if (valid) {
+      const int t1 = rowptr16[row + 1];
+#pragma unroll 4
+      for (int t = rowptr16[row] + sub; t < t1; t += S) {
+        const double l = Lv[t];
+        const double2 y = *reinterpret_cast<const double2*>(R + (int)rowcol16[t] * W + col);
+        ax = fma(l, y.x, ax);
+        ay = fma(l, y.y, ay);
+      }
+    }
+    for (int off = (1 << lshift) >> 1; off >= (1 << gshift); off >>= 1) {
+      ax += __shfl_xor_sync(0xffffffffu, ax, off);
+      ay += __shfl_xor_sync(0xffffffffu, ay, off);
+    }
+    if (valid && sub == 0) {
+      double2* d = reinterpret_cast<double2*>(R + row * W + col);
+      double2 v = *d;
+      v.x -= ax;
+      v.y -= ay;
+      *d = v;
+    }
+  }
+}
+
+// backward, push form: x_i is final -> x_j -= L_ij x_i for every entry j of row i.  A vertex has at most one
+// ancestor per level, so the targets of one level are disjoint: no atomics, any number of sub-slots.
+template <int NT>
+__device__ __forceinline__ void oc_push_level(const OcLevel& L, int sshift, int gshift, int tl, int c0, int ncols, int W,
+                                              const unsigned short* __restrict__ rowptr16,
+                                              const unsigned short* __restrict__ rowcol16, const double* __restrict__ Lv,
+                                              double* __restrict__ R) {
+  const int lshift = sshift + gshift;
+  const int rows = L.row1 - L.row0;
+  const int r = tl & ((1 << gshift) - 1);
+  const int sub = (tl >> gshift) & ((1 << sshift) - 1);
+  const int S = 1 << sshift;
+  const bool colok = 2 * r < ncols;
+  const int col = c0 + 2 * r;
+  for (int base = 0; base < rows; base += NT >> lshift) {
+    const int it = base + (tl >> lshift);
+    if (it < rows && colok) {
+      const int row = L.row0 + it;
+      const double2 xi = *reinterpret_cast<const double2*>(R + row * W + col);
+      const int t1 = rowptr16[row + 1];
+#pragma unroll 4
+      for (int t = rowptr16[row] + sub; t < t1; t += S) {
+        const double l = Lv[t];
+        double2* d = reinterpret_cast<double2*>(R + (int)rowcol16[t] * W + col);
+        double2 v = *d;
+        v.x = fma(-l, xi.x, v.x);
+        v.y = fma(-l, xi.y, v.y);
+        *d = v;
+      }
+    }
+  }
+}
+
+// L D L^T solve of the panel columns [c0, c0 + ncols) (c0 even) for all rows.  Levels [1, lsplit) are wide and use the
+// whole CTA with one block barrier each; levels [lsplit, nlevels) fit one warp, which walks them with warp barriers
+// only while the other warps wait at a single block barrier.
 template <int THREADS>
-__device__ __forceinline__ void oc_solve(const DevOnchip& O, const OcLevel* __restrict__ levels,
+__device__ __forceinline__ void oc_solve(const DevOnchip& O, int phase, const OcLevel* __restrict__ levels,
                                          const unsigned short* __restrict__ rowptr16, const unsigned short* __restrict__ rowcol16,
                                          const double* __restrict__ Lv, double* __restrict__ R, int ni, int c0, int ncols, int tid) {
   const int W = O.W;
-  int G = 1;
-  while (G < ncols && G < 32) G <<= 1;
-  const int cgroups = (ncols + G - 1) / G;
-  const int r = tid & (G - 1);
-  // ---- forward (unit lower, pull): y_i = b_i - sum_j L_ij y_j ----
-  for (int lev = 1; lev < O.nlevels; ++lev) {
+  const int gshift = O.gshift[phase];
+  const int lsplit = O.lsplit[phase];
+  const int H = O.nlevels;
+  for (int lev = 1; lev < lsplit; ++lev) {
     const OcLevel L = levels[lev];
-    const int nitems = (L.row1 - L.row0) * cgroups;
-    int S = 1;
-    while (S * 2 * G <= 32 && nitems * S * 2 * G <= THREADS) S <<= 1;
-    const int lpi = S * G;
-    const int sub = (tid & (lpi - 1)) / G;
-    const int per_pass = THREADS / lpi;
-    for (int base = 0; base < nitems; base += per_pass) {
-      const int it = base + tid / lpi;
-      const int rr = it / cgroups;
-      const int cidx = (it - rr * cgroups) * G + r;
-      const bool valid = it < nitems && cidx < ncols;
-      const int row = L.row0 + rr;
-      const int col = c0 + cidx;
-      double acc = 0.0;
-      if (valid) {
-        const int t1 = rowptr16[row + 1];
-        for (int t = rowptr16[row] + sub; t < t1; t += S) acc = fma(Lv[t], R[(int)rowcol16[t] * W + col], acc);
-      }
-      for (int off = lpi >> 1; off >= G; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
-      if (valid && sub == 0) R[row * W + col] -= acc;
-    }
+    oc_pull_level<THREADS>(L, L.pull_s[phase][0], gshift, tid, c0, ncols, W, rowptr16, rowcol16, Lv, R);
     __syncthreads();
   }
-  // ---- diagonal: y_i / d_i ----
-  for (int it = tid / G; it < ni * cgroups; it += THREADS / G) {
-    const int row = it / cgroups;
-    const int cidx = (it - row * cgroups) * G + r;
-    if (cidx < ncols) R[row * W + c0 + cidx] *= Lv[O.nlow + row];
+  if (tid < 32) {
+    for (int lev = lsplit; lev < H; ++lev) {
+      const OcLevel L = levels[lev];
+      oc_pull_level<32>(L, L.pull_s[phase][1], gshift, tid, c0, ncols, W, rowptr16, rowcol16, Lv, R);
+      __syncwarp();
+    }
   }
   __syncthreads();
-  // ---- backward (unit upper, push): x_i final -> x_j -= L_ij x_i for every j in row i ----
-  for (int lev = O.nlevels - 1; lev >= 1; --lev) {
-    const OcLevel L = levels[lev];
-    const int nitems = (L.row1 - L.row0) * cgroups;
-    int S = 1;
-    while (nitems * S * 2 * G <= THREADS) S <<= 1;
-    const int lpi = S * G;
-    const int sub = (tid & (lpi - 1)) / G;
-    const int per_pass = THREADS / lpi;
-    for (int base = 0; base < nitems; base += per_pass) {
-      const int it = base + tid / lpi;
-      const int rr = it / cgroups;
-      const int cidx = (it - rr * cgroups) * G + r;
-      if (it < nitems && cidx < ncols) {
-        const int row = L.row0 + rr;
-        const int col = c0 + cidx;
-        const double xi = R[row * W + col];
-        const int t1 = rowptr16[row + 1];
-        for (int t = rowptr16[row] + sub; t < t1; t += S) {
-          double* dst = R + (int)rowcol16[t] * W + col;
-          *dst = fma(-Lv[t], xi, *dst);
-        }
+  // diagonal: y_i / d_i
+  {
+    const int r = tid & ((1 << gshift) - 1);
+    if (2 * r < ncols) {
+      for (int row = tid >> gshift; row < ni; row += THREADS >> gshift) {
+        double2* d = reinterpret_cast<double2*>(R + row * W + c0 + 2 * r);
+        const double s = Lv[O.nlow + row];
+        double2 v = *d;
+        v.x *= s;
+        v.y *= s;
+        *d = v;
       }
     }
+  }
+  __syncthreads();
+  if (tid < 32) {
+    for (int lev = H - 1; lev >= lsplit && lev >= 1; --lev) {
+      const OcLevel L = levels[lev];
+      oc_push_level<32>(L, L.push_s[phase][1], gshift, tid, c0, ncols, W, rowptr16, rowcol16, Lv, R);
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+  for (int lev = lsplit - 1; lev >= 1; --lev) {
+    const OcLevel L = levels[lev];
+    oc_push_level<THREADS>(L, L.push_s[phase][0], gshift, tid, c0, ncols, W, rowptr16, rowcol16, Lv, R);
     __syncthreads();
   }
 }
@@ -241,11 +304,11 @@ __global__ void __launch_bounds__(THREADS, MINB) k_onchip(const __grid_constant_
         const uint2* rec = O.stage ? reinterpret_cast<const uint2*>(stage_base + (lev % 3) * seg_bytes)
                                    : reinterpret_cast<const uint2*>(O.f_stream + L.seg_off);
         const unsigned long long* pairs = reinterpret_cast<const unsigned long long*>(rec + L.nitems + 1);
-        const int lpi = L.lpi;
+        const int lpi = 1 << L.lpi_shift;
         const int sub = tid & (lpi - 1);
-        const int per_pass = THREADS / lpi;
+        const int per_pass = THREADS >> L.lpi_shift;
         for (int base = 0; base < L.nitems; base += per_pass) {
-          const int it = base + tid / lpi;
+          const int it = base + (tid >> L.lpi_shift);
           const bool valid = it < L.nitems;
           double acc = 0.0;
           unsigned pf = 0;
@@ -293,8 +356,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_onchip(const __grid_constant_
       pz *= pzs;
       double bx = -px, by = -py, bz = -pz;
       double* row = R + r * W;
-      if (O.c_az >= 0)
-        for (int b = 0; b < nb; ++b) row[O.c_az + b] = 0.0;
+      for (int cc = 0; cc < ((O.ncols1 + 1) & ~1); ++cc) row[cc] = 0.0;  // incl. padding columns touched by 2-column lanes
       for (int t = P.vadj_ptr[v]; t < P.vadj_ptr[v + 1]; ++t) {
         const int o = P.vadj_other[t];
         const int ro = P.vrow[o];
@@ -315,7 +377,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_onchip(const __grid_constant_
     __syncthreads();
 
     // ---- 6. solve phase 1 ---------------------------------------------------------------------------
-    oc_solve<THREADS>(O, levels, rowptr16, rowcol16, Lv, R, ni, 0, O.ncols1, tid);
+    oc_solve<THREADS>(O, 0, levels, rowptr16, rowcol16, Lv, R, ni, 0, O.ncols1, tid);
 
     // ---- 7. everything that needs the transient columns (x, y, Az) or only z ------------------------
     auto zfix = [&](int b) -> double { return P.var.o_zb >= 0 ? xs[P.var.o_zb + b] : P.X[3 * P.fixed[b] + 2]; };
@@ -435,14 +497,10 @@ __global__ void __launch_bounds__(THREADS, MINB) k_onchip(const __grid_constant_
     // ---- 8. phase-2 right-hand sides: Ci^T W B | Ci^T W d0 ------------------------------------------
     if (O.ncols2 > 0) {
       const int nc2 = O.ncols2;
-      int G = 1;
-      while (G < nc2 && G < 32) G <<= 1;
-      const int cgroups = (nc2 + G - 1) / G;
-      const int r_ = tid & (G - 1);
-      for (int it = tid / G; it < ni * cgroups; it += THREADS / G) {
-        const int r = it / cgroups;
-        const int cidx = (it - r * cgroups) * G + r_;
-        if (cidx >= nc2) continue;
+      const int g2 = O.rhs2_shift;  // 2^g2 lanes walk the columns of one row
+      const int r_ = tid & ((1 << g2) - 1);
+      for (int r = tid >> g2; r < ni; r += THREADS >> g2)
+      for (int cidx = r_; cidx < nc2; cidx += 1 << g2) {
         const int v = P.row_vertex[r];
         const double zv = R[r * W + O.c_z];
         double acc = 0.0;
@@ -456,9 +514,11 @@ __global__ void __launch_bounds__(THREADS, MINB) k_onchip(const __grid_constant_
         }
         R[r * W + O.c_q + cidx] = acc;
       }
+      if (nc2 & 1)  // the spare column next to an odd column count takes part in the two-column accesses: keep it finite
+        for (int r = tid; r < ni; r += THREADS) R[r * W + O.c_q + nc2] = 0.0;
       __syncthreads();
       // ---- 9. solve phase 2 ----
-      oc_solve<THREADS>(O, levels, rowptr16, rowcol16, Lv, R, ni, O.c_q, nc2, tid);
+      oc_solve<THREADS>(O, 1, levels, rowptr16, rowcol16, Lv, R, ni, O.c_q, nc2, tid);
     }
 
     // ---- 10. reac_bounds rows, objective, gradient ---------------------------------------------------
@@ -643,6 +703,7 @@ int build_onchip(Plan* PL, const tno_problem_desc* D) {
   O.c_q = -1;
   O.c_lambdh = -1;
   if (P.var.o_lambdv >= 0) O.c_lambdv = pos++;
+  if (pos & 1) ++pos;  // phase-2 columns start on a 16-byte boundary (two columns per lane)
   const int n_persist = pos;
   O.ncols2 = 0;
   if (P.rhs.c_q >= 0) {
@@ -655,7 +716,24 @@ int build_onchip(Plan* PL, const tno_problem_desc* D) {
   O.c_y = O.c_x + 1;
   O.ncols1 = O.c_y + 1;
   O.W = std::max(O.ncols1, n_persist + O.ncols2);
+  O.W = (O.W + 2) / 2 * 2;  // even, and one spare column for the odd lane of a two-column access
   O.nlevels = S.nlevels;
+  for (int ph = 0; ph < 2; ++ph) {
+    const int ncols = ph == 0 ? O.ncols1 : O.ncols2;
+    const int lanes = std::max(1, (ncols + 1) / 2);
+    int g = 0;
+    while ((1 << g) < lanes) ++g;
+    if (g > 5) return TNO_OK;  // more than 64 columns per phase: not handled on chip
+    O.gshift[ph] = g;
+    if (ph == 1) {
+      int g2 = 0;
+      while ((1 << g2) < std::min(std::max(ncols, 1), 32)) ++g2;
+      O.rhs2_shift = g2;
+    }
+    int ls = S.nlevels;
+    while (ls > 1 && ((S.level_ptr[ls] - S.level_ptr[ls - 1]) << g) <= 32) --ls;
+    O.lsplit[ph] = ls;
+  }
   O.nlow = nlow;
   O.nvar_magic = (uint32_t)((((uint64_t)1 << 32) + nvar - 1) / nvar);
 
@@ -709,10 +787,25 @@ int build_onchip(Plan* PL, const tno_problem_desc* D) {
     recs.push_back((uint32_t)prs.size());
     if (nitems >= 65536) return TNO_OK;
     L.nitems = (unsigned short)nitems;
-    int lpi = 1;
+    int lpi_shift = 0;
     if (nitems > 0 && (int64_t)prs.size() / nitems >= 4)
-      while (lpi < 32 && nitems * lpi * 2 <= THREADS) lpi <<= 1;
-    L.lpi = (unsigned short)lpi;
+      while (lpi_shift < 5 && ((nitems << (lpi_shift + 1)) * 2) <= THREADS * 2 && (nitems << (lpi_shift + 1)) <= THREADS) ++lpi_shift;
+    L.lpi_shift = (unsigned char)lpi_shift;
+    {
+      const int rows = S.level_ptr[lev + 1] - S.level_ptr[lev];
+      for (int ph = 0; ph < 2; ++ph) {
+        const int g = O.gshift[ph];
+        for (int team = 0; team < 2; ++team) {
+          const int NT = team == 0 ? THREADS : 32;
+          int sp = 0;  // pull: S * G <= 32 (shuffle reduction) and rows * S * G <= NT
+          while (sp + 1 + g <= 5 && (rows << (sp + 1 + g)) <= NT) ++sp;
+          int sq = 0;  // push: rows * S * G <= NT
+          while (sq < 5 && (rows << (sq + 1 + g)) <= NT) ++sq;
+          L.pull_s[ph][team] = (unsigned char)sp;
+          L.push_s[ph][team] = (unsigned char)sq;
+        }
+      }
+    }
     L.seg_off = (uint32_t)(stream.size() / 4);
     stream.insert(stream.end(), recs.begin(), recs.end());
     for (unsigned long long pr : prs) {

@@ -110,10 +110,13 @@ struct DevPlan {
 struct OcLevel {
   unsigned short row0, row1;   // rows / columns [row0, row1)
   unsigned short nitems;       // entries of L in those columns (factorisation work items)
-  unsigned short lpi;          // lanes sharing one item's dot product (power of two <= 32)
+  unsigned char lpi_shift;     // log2 of the lanes sharing one item's dot product in the factorisation
+  unsigned char pad0;
   uint32_t seg_off;            // factor stream segment: offset and length in 16-byte units
   uint32_t seg_units;
-  uint32_t pad;
+  // log2 of the sub-slots splitting one row, [phase 0/1][team: 0 = whole CTA, 1 = one warp]
+  unsigned char pull_s[2][2];  // forward solve (pull): S * G <= 32
+  unsigned char push_s[2][2];  // backward solve (push)
 };
 
 // Device data of the on-chip kernel family (tno_onchip.cu).
@@ -124,6 +127,9 @@ struct DevOnchip {
   int c_z, c_lambdv, c_q, c_lambdh;   // persistent panel columns (-1 = absent)
   int c_az, c_x, c_y;    // transient phase-1 columns (overwritten by phase 2)
   int ncols1, ncols2;    // columns solved in phase 1: [0, ncols1); in phase 2: [c_q, c_q + ncols2)
+  int rhs2_shift;        // log2 of the lanes walking the phase-2 right-hand-side columns of one row
+  int gshift[2];         // log2 of the lanes covering the columns of one row (two columns per lane), per phase
+  int lsplit[2];         // first level handled by a single warp (rows * G <= 32 from there to the root), per phase
   int nlevels, nlow, nsup;
   uint32_t nvar_magic;   // ceil(2^32 / nvar): flat index -> (row, col)
   // shared memory layout: offsets in doubles, o_idx in bytes
