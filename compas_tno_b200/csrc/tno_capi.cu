@@ -2,6 +2,7 @@
 // and the batched evaluation entry points.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <new>
@@ -187,7 +188,8 @@ int tno_plan_create(const tno_problem_desc* D, tno_plan** out_plan) {
   }
   Symbolic& S = P->sym;
   try {
-    analyse(ni, aedges, D->ordering, coords.data(), true, true, &S);
+    const char* cw = getenv("TNO_CHAIN_WIDTH");  // developer knob: 0 disables the chain partition
+    analyse(ni, aedges, D->ordering, coords.data(), true, true, &S, cw ? atoi(cw) : 8);
   } catch (const std::exception& ex) {
     return fail(TNO_EINVAL, std::string("symbolic analysis failed: ") + ex.what());
   }
@@ -448,7 +450,7 @@ int tno_plan_create(const tno_problem_desc* D, tno_plan** out_plan) {
       P->kernel = TNO_KERNEL_ONCHIP;
       I.smem_bytes = (int64_t)P->oc.smem_bytes;
     } else if (D->kernel == TNO_KERNEL_ONCHIP) {
-      return fail(TNO_EINVAL, "problem does not fit the on-chip kernel family (shared memory / 16-bit index limits)");
+      return fail(TNO_EINVAL, std::string("problem does not fit the on-chip kernel family: ") + tno_last_error());
     }
   }
   I.kernel = P->kernel;

@@ -19,7 +19,9 @@
 // Math restated from the reference, same citations as tno_interleaved.cu.
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <map>
 
 #include "tno_plan.hpp"
 
@@ -38,6 +40,7 @@ struct OcArgs {
   double* gmin;
   int32_t* status;
   int64_t N;
+  long long* phase_clocks;  // optional (TNO_PHASE_CLOCKS=1): clock64() of CTA 0 at the phase boundaries of its first candidate
 };
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
@@ -75,19 +78,19 @@ __device__ __forceinline__ void oc_envelope(const DevPlan& P, double x, double y
   }
 }
 
-// ---- level kernels of the triangular solves -----------------------------------------------------------
-// A "team" of NT threads (the whole CTA, or one warp for the narrow levels near the root) handles the rows
-// of one level.  G = 2^gshift lanes cover the columns of a row, TWO adjacent columns per lane (one 16-byte
-// shared-memory access), S = 2^sshift sub-slots split the entries of a row.
+// ---- kernels of the triangular solves ----------------------------------------------------------------
+// G = 2^gshift lanes cover the columns of a row, TWO adjacent columns per lane (one 16-byte shared-memory
+// access), S = 2^sshift sub-slots split the entries of a row.  Rows [row0, row1) are mutually independent.
 
-// forward, pull form: y_i -= sum_j L_ij y_j ; sub-slot partial sums are combined with shuffles (S * G <= 32)
+// forward, pull form: y_i -= sum_j L_ij y_j over the CSR entries of row i; sub-slot partial sums are combined
+// with shuffles (S * G <= 32)
 template <int NT>
-__device__ __forceinline__ void oc_pull_level(const OcLevel& L, int sshift, int gshift, int tl, int c0, int ncols, int W,
-                                              const unsigned short* __restrict__ rowptr16,
-                                              const unsigned short* __restrict__ rowcol16, const double* __restrict__ Lv,
-                                              double* __restrict__ R) {
+__device__ __forceinline__ void oc_pull_rows(int row0, int row1, int sshift, int gshift, int tl, int c0, int ncols, int W,
+                                             const unsigned short* __restrict__ rowptr16,
+                                             const unsigned short* __restrict__ rowcol16, const double* __restrict__ V,
+                                             double* __restrict__ R) {
   const int lshift = sshift + gshift;
-  const int rows = L.row1 - L.row0;
+  const int rows = row1 - row0;
   const int r = tl & ((1 << gshift) - 1);
   const int sub = (tl >> gshift) & ((1 << sshift) - 1);
   const int S = 1 << sshift;
@@ -96,13 +99,13 @@ __device__ __forceinline__ void oc_pull_level(const OcLevel& L, int sshift, int 
   for (int base = 0; base < rows; base += NT >> lshift) {
     const int it = base + (tl >> lshift);
     const bool valid = it < rows && colok;
-    const int row = L.row0 + it;
+    const int row = row0 + it;
     double ax = 0.0, ay = 0.0;
     if (valid) {
       const int t1 = rowptr16[row + 1];
 #pragma unroll 4
       for (int t = rowptr16[row] + sub; t < t1; t += S) {
-        const double l = Lv[t];
+        const double l = V[t];
         const double2 y = *reinterpret_cast<const double2*>(R + (int)rowcol16[t] * W + col);
         ax = fma(l, y.x, ax);
         ay = fma(l, y.y, ay);
@@ -122,15 +125,15 @@ __device__ __forceinline__ void oc_pull_level(const OcLevel& L, int sshift, int 
   }
 }
 
-// backward, push form: x_i is final -> x_j -= L_ij x_i for every entry j of row i.  A vertex has at most one
-// ancestor per level, so the targets of one level are disjoint: no atomics, any number of sub-slots.
+// backward, push form: x_i is final -> x_j -= L_ij x_i for every CSR entry j of row i.  A vertex has at most one
+// ancestor per level (and per chain level), so the targets of independent rows are disjoint: no atomics.
 template <int NT>
-__device__ __forceinline__ void oc_push_level(const OcLevel& L, int sshift, int gshift, int tl, int c0, int ncols, int W,
-                                              const unsigned short* __restrict__ rowptr16,
-                                              const unsigned short* __restrict__ rowcol16, const double* __restrict__ Lv,
-                                              double* __restrict__ R) {
+__device__ __forceinline__ void oc_push_rows(int row0, int row1, int sshift, int gshift, int tl, int c0, int ncols, int W,
+                                             const unsigned short* __restrict__ rowptr16,
+                                             const unsigned short* __restrict__ rowcol16, const double* __restrict__ V,
+                                             double* __restrict__ R) {
   const int lshift = sshift + gshift;
-  const int rows = L.row1 - L.row0;
+  const int rows = row1 - row0;
   const int r = tl & ((1 << gshift) - 1);
   const int sub = (tl >> gshift) & ((1 << sshift) - 1);
   const int S = 1 << sshift;
@@ -139,12 +142,12 @@ __device__ __forceinline__ void oc_push_level(const OcLevel& L, int sshift, int 
   for (int base = 0; base < rows; base += NT >> lshift) {
     const int it = base + (tl >> lshift);
     if (it < rows && colok) {
-      const int row = L.row0 + it;
+      const int row = row0 + it;
       const double2 xi = *reinterpret_cast<const double2*>(R + row * W + col);
       const int t1 = rowptr16[row + 1];
 #pragma unroll 4
       for (int t = rowptr16[row] + sub; t < t1; t += S) {
-        const double l = Lv[t];
+        const double l = V[t];
         double2* d = reinterpret_cast<double2*>(R + (int)rowcol16[t] * W + col);
         double2 v = *d;
         v.x = fma(-l, xi.x, v.x);
@@ -155,37 +158,91 @@ __device__ __forceinline__ void oc_push_level(const OcLevel& L, int sshift, int 
   }
 }
 
-// L D L^T solve of the panel columns [c0, c0 + ncols) (c0 even) for all rows.  Levels [1, lsplit) are wide and use the
-// whole CTA with one block barrier each; levels [lsplit, nlevels) fit one warp, which walks them with warp barriers
-// only while the other warps wait at a single block barrier.
-template <int THREADS>
-__device__ __forceinline__ void oc_solve(const DevOnchip& O, int phase, const OcLevel* __restrict__ levels,
-                                         const unsigned short* __restrict__ rowptr16, const unsigned short* __restrict__ rowcol16,
-                                         const double* __restrict__ Lv, double* __restrict__ R, int ni, int c0, int ncols, int tid) {
-  const int W = O.W;
-  const int gshift = O.gshift[phase];
-  const int lsplit = O.lsplit[phase];
-  const int H = O.nlevels;
-  for (int lev = 1; lev < lsplit; ++lev) {
-    const OcLevel L = levels[lev];
-    oc_pull_level<THREADS>(L, L.pull_s[phase][0], gshift, tid, c0, ncols, W, rowptr16, rowcol16, Lv, R);
+// Dense part of a chain level: y_C = Z_C r_C (forward, TRANSPOSED = false) or x_C = Z_C^T y_C (backward), Z unit lower
+// triangular stored packed in V.  All rows of the level are computed into registers first, then written back.
+constexpr int OC_ZPASS = 4;
+template <int NT, bool TRANSPOSED>
+__device__ __forceinline__ void oc_chain_apply(const OcRange& L, const OcChain* __restrict__ chains,
+                                               const unsigned char* __restrict__ rowchain, int wide_rows, int gshift, int tl, int c0,
+                                               int ncols, int W, const double* __restrict__ V, double* __restrict__ R) {
+  const int rows = L.row1 - L.row0;
+  const int r = tl & ((1 << gshift) - 1);
+  const bool colok = 2 * r < ncols;
+  const int col = c0 + 2 * r;
+  const int B = OC_ZPASS * (NT >> gshift);  // rows per batch
+  // forward results only depend on LOWER rows of the chain, so batches run from the top rows down (and the other way
+  // round for the transposed product): a batch never reads what an earlier batch has overwritten.
+  for (int done = 0; done < rows; done += B) {
+    const int lo = TRANSPOSED ? done : max(0, rows - done - B);
+    const int hi = TRANSPOSED ? min(rows, done + B) : rows - done;
+    double2 res[OC_ZPASS];
+#pragma unroll
+    for (int ps = 0; ps < OC_ZPASS; ++ps) {
+      const int it = lo + ps * (NT >> gshift) + (tl >> gshift);
+      res[ps] = make_double2(0.0, 0.0);
+      if (it < hi && colok) {
+        const int row = L.row0 + it;
+        const OcChain C = chains[L.chain0 + rowchain[row - wide_rows]];
+        const int il = row - C.row0;
+        double2 acc = *reinterpret_cast<const double2*>(R + row * W + col);
+        if (!TRANSPOSED) {
+          const double* z = V + C.zoff + (il * (il - 1)) / 2;
+#pragma unroll 4
+          for (int j = 0; j < il; ++j) {
+            const double2 y = *reinterpret_cast<const double2*>(R + (C.row0 + j) * W + col);
+            acc.x = fma(z[j], y.x, acc.x);
+            acc.y = fma(z[j], y.y, acc.y);
+          }
+        } else {
+#pragma unroll 4
+          for (int i = il + 1; i < C.T; ++i) {
+            const double zz = V[C.zoff + (i * (i - 1)) / 2 + il];
+            const double2 y = *reinterpret_cast<const double2*>(R + (C.row0 + i) * W + col);
+            acc.x = fma(zz, y.x, acc.x);
+            acc.y = fma(zz, y.y, acc.y);
+          }
+        }
+        res[ps] = acc;
+      }
+    }
     __syncthreads();
-  }
-  if (tid < 32) {
-    for (int lev = lsplit; lev < H; ++lev) {
-      const OcLevel L = levels[lev];
-      oc_pull_level<32>(L, L.pull_s[phase][1], gshift, tid, c0, ncols, W, rowptr16, rowcol16, Lv, R);
-      __syncwarp();
+#pragma unroll
+    for (int ps = 0; ps < OC_ZPASS; ++ps) {
+      const int it = lo + ps * (NT >> gshift) + (tl >> gshift);
+      if (it < hi && colok) *reinterpret_cast<double2*>(R + (L.row0 + it) * W + col) = res[ps];
     }
   }
-  __syncthreads();
-  // diagonal: y_i / d_i
+}
+
+// L D L^T solve of the panel columns [c0, c0 + ncols) (c0 even) for all rows.
+template <int THREADS>
+__device__ __forceinline__ void oc_solve(const DevOnchip& O, int phase, const OcRange* __restrict__ wide,
+                                         const OcRange* __restrict__ clev, const OcChain* __restrict__ chains,
+                                         const unsigned char* __restrict__ rowchain, const unsigned short* __restrict__ rowptr16,
+                                         const unsigned short* __restrict__ rowcol16, const double* __restrict__ V,
+                                         double* __restrict__ R, int ni, int c0, int ncols, int tid) {
+  const int W = O.W;
+  const int gshift = O.gshift[phase];
+  // ---- forward ----
+  for (int lev = 1; lev < O.nwide; ++lev) {
+    const OcRange L = wide[lev];
+    oc_pull_rows<THREADS>(L.row0, L.row1, L.pull_s[phase], gshift, tid, c0, ncols, W, rowptr16, rowcol16, V, R);
+    __syncthreads();
+  }
+  for (int cl = 0; cl < O.nclev; ++cl) {
+    const OcRange L = clev[cl];
+    oc_pull_rows<THREADS>(L.row0, L.row1, L.pull_s[phase], gshift, tid, c0, ncols, W, rowptr16, rowcol16, V, R);
+    __syncthreads();
+    oc_chain_apply<THREADS, false>(L, chains, rowchain, O.wide_rows, gshift, tid, c0, ncols, W, V, R);
+    __syncthreads();
+  }
+  // ---- diagonal: y_i / d_i ----
   {
     const int r = tid & ((1 << gshift) - 1);
     if (2 * r < ncols) {
       for (int row = tid >> gshift; row < ni; row += THREADS >> gshift) {
         double2* d = reinterpret_cast<double2*>(R + row * W + c0 + 2 * r);
-        const double s = Lv[O.nlow + row];
+        const double s = V[O.nlo + row];
         double2 v = *d;
         v.x *= s;
         v.y *= s;
@@ -194,20 +251,93 @@ __device__ __forceinline__ void oc_solve(const DevOnchip& O, int phase, const Oc
     }
   }
   __syncthreads();
-  if (tid < 32) {
-    for (int lev = H - 1; lev >= lsplit && lev >= 1; --lev) {
-      const OcLevel L = levels[lev];
-      oc_push_level<32>(L, L.push_s[phase][1], gshift, tid, c0, ncols, W, rowptr16, rowcol16, Lv, R);
-      __syncwarp();
+  // ---- backward ----
+  for (int cl = O.nclev - 1; cl >= 0; --cl) {
+    const OcRange L = clev[cl];
+    oc_chain_apply<THREADS, true>(L, chains, rowchain, O.wide_rows, gshift, tid, c0, ncols, W, V, R);
+    __syncthreads();
+    // the rows of one chain share their descendants, so their updates are gathered per outside column ("target")
+    // instead of pushed per row: x_j -= sum_{i in chain} L_ij x_i.  Targets of one chain level are disjoint.
+    {
+      const int r = tid & ((1 << gshift) - 1);
+      const int col = c0 + 2 * r;
+      if (2 * r < ncols) {
+        for (int t = L.tgt0 + (tid >> gshift); t < L.tgt1; t += THREADS >> gshift) {
+          const int e1 = __ldg(O.ct_ptr + t + 1);
+          double ax = 0.0, ay = 0.0;
+#pragma unroll 4
+          for (int e = __ldg(O.ct_ptr + t); e < e1; ++e) {
+            const uint32_t w = __ldg(O.ct_ent + e);
+            const double l = V[w & 0xffffu];
+            const double2 x = *reinterpret_cast<const double2*>(R + (int)(w >> 16) * W + col);
+            ax = fma(l, x.x, ax);
+            ay = fma(l, x.y, ay);
+          }
+          double2* d = reinterpret_cast<double2*>(R + (int)__ldg(O.ct_col + t) * W + col);
+          double2 v = *d;
+          v.x -= ax;
+          v.y -= ay;
+          *d = v;
+        }
+      }
     }
+    __syncthreads();
   }
-  __syncthreads();
-  for (int lev = lsplit - 1; lev >= 1; --lev) {
-    const OcLevel L = levels[lev];
-    oc_push_level<THREADS>(L, L.push_s[phase][0], gshift, tid, c0, ncols, W, rowptr16, rowcol16, Lv, R);
+  for (int lev = O.nwide - 1; lev >= 1; --lev) {
+    const OcRange L = wide[lev];
+    oc_push_rows<THREADS>(L.row0, L.row1, L.push_s[phase], gshift, tid, c0, ncols, W, rowptr16, rowcol16, V, R);
     __syncthreads();
   }
 }
+
+// Dense work of the chains [c0, c1) of one chain level, one warp per chain:
+//   (B) in-place L D L^T of the dense triangle S_C (diagonal in the diagonal slots, which end up holding 1 / d),
+//   (C) in-place inversion of the unit lower triangular L_C  ->  Z_C.
+// Lane = row of the chain (rows beyond 32 wrap around).
+__device__ __forceinline__ void oc_chain_dense(const OcChain* __restrict__ chains, int c0, int c1, int nlo, double* __restrict__ V,
+                                               int* s_flags, int warp, int lane, int nwarps) {
+  for (int c = c0 + warp; c < c1; c += nwarps) {
+    const OcChain C = chains[c];
+    const int T = C.T;
+    double* dg = V + nlo + C.row0;
+    double* Z = V + C.zoff;
+    // ---- (B) L D L^T ----
+    for (int j = 0; j < T; ++j) {
+      const double d = dg[j];
+      if (lane == 0 && !(d > 0.0)) atomicOr(s_flags, TNO_STATUS_NOT_PD);
+      const double inv = 1.0 / d;
+      for (int i = j + 1 + lane; i < T; i += 32) {
+        const double* zi = Z + (i * (i - 1)) / 2;
+        const double uij = zi[j] * inv;  // l_ij
+        double* zw = Z + (i * (i - 1)) / 2;
+#pragma unroll 4
+        for (int kk = j + 1; kk < i; ++kk) zw[kk] = fma(-uij, Z[(kk * (kk - 1)) / 2 + j], zw[kk]);
+        dg[i] = fma(-uij, zi[j], dg[i]);
+      }
+      __syncwarp();
+      for (int i = j + 1 + lane; i < T; i += 32) Z[(i * (i - 1)) / 2 + j] *= inv;
+      if (lane == 0) dg[j] = inv;
+      __syncwarp();
+    }
+    // ---- (C) Z = L_C^-1, columns from right to left ----
+    for (int j = T - 2; j >= 0; --j) {
+      double acc[2] = {0.0, 0.0};
+      int cnt = 0;
+      for (int i = j + 1 + lane; i < T; i += 32, ++cnt) {
+        const double* zi = Z + (i * (i - 1)) / 2;
+        double a = zi[j];
+#pragma unroll 4
+        for (int kk = j + 1; kk < i; ++kk) a = fma(zi[kk], Z[(kk * (kk - 1)) / 2 + j], a);
+        acc[cnt & 1] = a;
+      }
+      __syncwarp();
+      cnt = 0;
+      for (int i = j + 1 + lane; i < T; i += 32, ++cnt) Z[(i * (i - 1)) / 2 + j] = -acc[cnt & 1];
+      __syncwarp();
+    }
+  }
+}
+
 
 template <int THREADS, int MINB>
 __global__ void __launch_bounds__(THREADS, MINB) k_onchip(const __grid_constant__ DevPlan P, const __grid_constant__ DevOnchip O,
@@ -215,7 +345,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_onchip(const __grid_constant_
   extern __shared__ __align__(16) unsigned char smraw[];
   double* sm = reinterpret_cast<double*>(smraw);
   double* xs = sm + O.o_x;
-  double* Lv = sm + O.o_l;
+  double* V = sm + O.o_v;
   double* R = sm + O.o_r;
   double* qs = R;  // q lives in the panel region until the matrix is assembled
   double* qsup = sm + O.o_qsup;
@@ -223,15 +353,21 @@ __global__ void __launch_bounds__(THREADS, MINB) k_onchip(const __grid_constant_
   double* gxy = sm + O.o_gxy;      // Cb^T U B | Cb^T V B (nb x k each) | Cb^T U d0 | Cb^T V d0 (nb each)
   double* azsup = sm + O.o_azsup;  // nsup x nb : dz/dzb at the neighbours of the supports
   double* red = sm + O.o_red;
+  double* pers = sm + O.o_pers;    // ni x npers : z (, z_lambdv) after phase 1
   const unsigned short* rowptr16 = reinterpret_cast<const unsigned short*>(smraw + O.o_idx_bytes + O.idx_rowptr);
   const unsigned short* rowcol16 = reinterpret_cast<const unsigned short*>(smraw + O.o_idx_bytes + O.idx_rowcol);
-  const OcLevel* levels = reinterpret_cast<const OcLevel*>(smraw + O.o_idx_bytes + O.idx_levels);
+  const OcRange* wide = reinterpret_cast<const OcRange*>(smraw + O.o_idx_bytes + O.idx_wide);
+  const OcRange* clev = reinterpret_cast<const OcRange*>(smraw + O.o_idx_bytes + O.idx_clev);
+  const OcChain* chains = reinterpret_cast<const OcChain*>(smraw + O.o_idx_bytes + O.idx_chains);
+  const unsigned char* rowchain = smraw + O.o_idx_bytes + O.idx_rowchain;
+  const OcChunk* chunks = reinterpret_cast<const OcChunk*>(smraw + O.o_idx_bytes + O.idx_chunks);
+  const OcOp* ops = reinterpret_cast<const OcOp*>(smraw + O.o_idx_bytes + O.idx_ops);
   __shared__ int s_flags;
 
   const int tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5;
   const int n = P.n, m = P.m, ni = P.ni, nb = P.nb, k = P.k, nvar = P.var.nvar, ng = P.con.ng, W = O.W;
-  const int nlow = O.nlow;
+  const int nlo = O.nlo;
   const bool has_t = P.var.o_t >= 0;
   const bool want_thrust = (P.objective == TNO_OBJ_MIN || P.objective == TNO_OBJ_MAX);
   const bool want_reac = (P.constraints & TNO_CON_REAC_BOUNDS) != 0;
@@ -242,6 +378,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_onchip(const __grid_constant_
   __syncthreads();
 
   for (int64_t cand = blockIdx.x; cand < A.N; cand += gridDim.x) {
+    if (A.phase_clocks && blockIdx.x == 0 && tid == 0 && cand == (int64_t)(A.N > 4 * gridDim.x ? 4 * gridDim.x : 0)) A.phase_clocks[0] = clock64();
     // ---- 0. variables ------------------------------------------------------------------------------
     if (tid < nvar) xs[tid] = A.x[cand * A.ldx + tid];
     if (tid == 0) s_flags = 0;
@@ -254,9 +391,11 @@ __global__ void __launch_bounds__(THREADS, MINB) k_onchip(const __grid_constant_
     double* gout = A.g ? A.g + cand * ng : nullptr;
     double* Jout = A.J ? A.J + cand * (int64_t)ng * nvar : nullptr;
 
+    if (A.phase_clocks && blockIdx.x == 0 && tid == 0 && cand == (int64_t)(A.N > 4 * gridDim.x ? 4 * gridDim.x : 0)) A.phase_clocks[1] = clock64();
     // ---- 1. q = B q_ind + lambdh d ; funicular rows of g -------------------------------------------
     for (int e = tid; e < m; e += THREADS) {
       double acc = lamh * P.d[e];
+#pragma unroll 8
       for (int j = 0; j < k; ++j) acc = fma(__ldg(O.Bt + (int64_t)j * m + e), xs[j], acc);
       qs[e] = acc;
       if (A.q) A.q[cand * m + e] = acc;
@@ -272,75 +411,114 @@ __global__ void __launch_bounds__(THREADS, MINB) k_onchip(const __grid_constant_
     }
     __syncthreads();
 
+    if (A.phase_clocks && blockIdx.x == 0 && tid == 0 && cand == (int64_t)(A.N > 4 * gridDim.x ? 4 * gridDim.x : 0)) A.phase_clocks[2] = clock64();
     // ---- 2. assemble -(Ci^T Q Ci) into the pattern of L; keep q of the support edges ----------------
-    for (int p = tid; p < P.nnz_l; p += THREADS) {
-      double acc = 0.0;
-      for (int t = O.asm_ptr[p]; t < O.asm_ptr[p + 1]; ++t) acc += (double)O.asm_coef[t] * qs[O.asm_edge[t]];
-      Lv[p] = acc;
+    if (O.simple_asm) {
+      // off-diagonal positions: one edge or fill; diagonals: minus the sum over the incident edges
+      for (int p = tid; p < nlo; p += THREADS) {
+        const unsigned e = __ldg(O.asm_e16 + p);
+        V[p] = e == 0xffffu ? 0.0 : qs[e];
+      }
+      for (int p = tid; p < O.nz; p += THREADS) {
+        const unsigned e = __ldg(O.asm_z16 + p);
+        V[nlo + ni + p] = e == 0xffffu ? 0.0 : qs[e];
+      }
+      for (int r = tid; r < ni; r += THREADS) {
+        double acc = 0.0;
+        const int t1 = O.radj_ptr[r + 1];
+#pragma unroll 4
+        for (int t = O.radj_ptr[r]; t < t1; ++t) acc -= qs[__ldg(O.radj + t) >> 16];
+        V[nlo + r] = acc;
+      }
+    } else {
+      for (int p = tid; p < O.nv; p += THREADS) {
+        double acc = 0.0;
+        for (int t = O.asm_ptr[p]; t < O.asm_ptr[p + 1]; ++t) acc += (double)O.asm_coef[t] * qs[O.asm_edge[t]];
+        V[p] = acc;
+      }
     }
+    if (tid == 0) V[O.pos_m1] = -1.0;
     for (int t = tid; t < O.nsup; t += THREADS) qsup[t] = qs[O.sup_edge[t]];
     __syncthreads();  // q consumed: the panel region is free for the factor stream
 
-    // ---- 3. numeric L D L^T, level by level (off-diagonals stay unscaled until step 4) --------------
+    if (A.phase_clocks && blockIdx.x == 0 && tid == 0 && cand == (int64_t)(A.N > 4 * gridDim.x ? 4 * gridDim.x : 0)) A.phase_clocks[3] = clock64();
+    // ---- 3. numeric L D L^T: a short program of staged pull chunks (wide levels, chain S-steps, rectangular
+    //         chain rows) and dense chain ops.  Off-diagonal CSR entries stay unscaled (U = L D) until step 4.
     {
       unsigned char* stage_base = reinterpret_cast<unsigned char*>(R);
+      double* tmpbuf = R + O.o_tmp_doubles;
       const int seg_bytes = O.fseg_units * 16;
-      auto issue = [&](int lev) {
-        if (O.stage && lev < O.nlevels) {
-          const OcLevel L = levels[lev];
-          unsigned char* dst = stage_base + (lev % 3) * seg_bytes;
-          const uint4* src = O.f_stream + L.seg_off;
-          for (unsigned u = tid; u < L.seg_units; u += THREADS) cp_async16(dst + 16 * u, src + u);
+      auto issue = [&](int c) {
+        if (c < O.nchunks) {
+          const OcChunk K = chunks[c];
+          unsigned char* dst = stage_base + (c % 3) * seg_bytes;
+          const uint4* src = O.f_stream + K.seg_off;
+          for (unsigned u = tid; u < K.seg_units; u += THREADS) cp_async16(dst + 16 * u, src + u);
         }
         cp_async_commit();
       };
       issue(0);
       issue(1);
-      for (int lev = 0; lev < O.nlevels; ++lev) {
+      for (int op = 0; op < O.nops; ++op) {
+        const OcOp OP = ops[op];
+        if (OP.type == OC_OP_DENSE) {
+          __syncthreads();
+          oc_chain_dense(chains, OP.a, OP.b, nlo, V, &s_flags, warp, lane, THREADS / 32);
+          continue;
+        }
+        const int c = OP.a;
         cp_async_wait<1>();
         __syncthreads();
-        issue(lev + 2);
-        const OcLevel L = levels[lev];
-        const uint2* rec = O.stage ? reinterpret_cast<const uint2*>(stage_base + (lev % 3) * seg_bytes)
-                                   : reinterpret_cast<const uint2*>(O.f_stream + L.seg_off);
-        const unsigned long long* pairs = reinterpret_cast<const unsigned long long*>(rec + L.nitems + 1);
-        const int lpi = 1 << L.lpi_shift;
+        issue(c + 2);
+        const OcChunk K = chunks[c];
+        const uint2* rec = reinterpret_cast<const uint2*>(stage_base + (c % 3) * seg_bytes);
+        const unsigned long long* pairs = reinterpret_cast<const unsigned long long*>(rec + K.nitems + 1);
+        const int lpi = 1 << K.lpi_shift;
         const int sub = tid & (lpi - 1);
-        const int per_pass = THREADS >> L.lpi_shift;
-        for (int base = 0; base < L.nitems; base += per_pass) {
-          const int it = base + (tid >> L.lpi_shift);
-          const bool valid = it < L.nitems;
+        const int per_pass = THREADS >> K.lpi_shift;
+        for (int base = 0; base < K.nitems; base += per_pass) {
+          const int it = base + (tid >> K.lpi_shift);
+          const bool valid = it < K.nitems;
           double acc = 0.0;
           unsigned pf = 0;
           if (valid) {
             const uint2 r0 = rec[it];
             pf = r0.x;
             const int t1 = rec[it + 1].y;
+#pragma unroll 2
             for (int t = r0.y + sub; t < t1; t += lpi) {
               const unsigned long long pr = pairs[t];
               const int a = (int)(pr & 0xffffu), b = (int)((pr >> 16) & 0xffffu), dp = (int)((pr >> 32) & 0xffffu);
-              acc = fma(Lv[a] * Lv[dp], Lv[b], acc);  // U_ic * (1/d_c) * U_jc
+              acc = fma(V[a] * V[dp], V[b], acc);  // U_ic * (1 / d_c) * U_jc   (rectangular rows: S_ic * (-1) * Z_jc)
             }
           }
           for (int off = lpi >> 1; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
           if (valid && sub == 0) {
             const int pos = (int)(pf & 0xffffu);
-            const double v = Lv[pos] - acc;
-            if (pf >> 31) {
+            const double v = V[pos] - acc;
+            if (K.kind == 1) {
+              tmpbuf[it] = v;
+            } else if (pf >> 31) {
               if (!(v > 0.0)) atomicOr(&s_flags, TNO_STATUS_NOT_PD);
-              Lv[pos] = 1.0 / v;
+              V[pos] = 1.0 / v;
             } else {
-              Lv[pos] = v;
+              V[pos] = v;
             }
           }
+        }
+        if (K.kind == 1) {  // rectangular chain rows read each other's S values: write back after everyone has read
+          __syncthreads();
+          for (int it = tid; it < K.nitems; it += THREADS) V[(int)(rec[it].x & 0xffffu)] = tmpbuf[it];
         }
       }
       cp_async_wait<0>();
       __syncthreads();
     }
-    // ---- 4. L_ij = U_ij / d_j ----------------------------------------------------------------------
-    for (int p = tid; p < nlow; p += THREADS) Lv[p] *= Lv[nlow + (int)rowcol16[p]];
+    if (A.phase_clocks && blockIdx.x == 0 && tid == 0 && cand == (int64_t)(A.N > 4 * gridDim.x ? 4 * gridDim.x : 0)) A.phase_clocks[4] = clock64();
+    // ---- 4. L_ij = U_ij / d_j for the CSR entries (the dense chain blocks are already final) ---------
+    for (int p = tid; p < nlo; p += THREADS) V[p] *= V[nlo + (int)rowcol16[p]];
 
+    if (A.phase_clocks && blockIdx.x == 0 && tid == 0 && cand == (int64_t)(A.N > 4 * gridDim.x ? 4 * gridDim.x : 0)) A.phase_clocks[5] = clock64();
     // ---- 5. phase-1 right-hand sides: z | z_lambdv | Az | x | y -------------------------------------
     for (int r = tid; r < ni; r += THREADS) {
       const int v = P.row_vertex[r];
@@ -376,14 +554,23 @@ __global__ void __launch_bounds__(THREADS, MINB) k_onchip(const __grid_constant_
     }
     __syncthreads();
 
+    if (A.phase_clocks && blockIdx.x == 0 && tid == 0 && cand == (int64_t)(A.N > 4 * gridDim.x ? 4 * gridDim.x : 0)) A.phase_clocks[6] = clock64();
     // ---- 6. solve phase 1 ---------------------------------------------------------------------------
-    oc_solve<THREADS>(O, 0, levels, rowptr16, rowcol16, Lv, R, ni, 0, O.ncols1, tid);
+    oc_solve<THREADS>(O, 0, wide, clev, chains, rowchain, rowptr16, rowcol16, V, R, ni, 0, O.ncols1, tid);
 
+    if (A.phase_clocks && blockIdx.x == 0 && tid == 0 && cand == (int64_t)(A.N > 4 * gridDim.x ? 4 * gridDim.x : 0)) A.phase_clocks[7] = clock64();
     // ---- 7. everything that needs the transient columns (x, y, Az) or only z ------------------------
     auto zfix = [&](int b) -> double { return P.var.o_zb >= 0 ? xs[P.var.o_zb + b] : P.X[3 * P.fixed[b] + 2]; };
+    // persistent phase-1 results leave the panel: phase 2 reuses all of its columns
+    for (int it = tid; it < ni * O.npers; it += THREADS) {
+      const int r = O.npers == 1 ? it : (it >> 1);
+      const int c = O.npers == 1 ? 0 : (it & 1);
+      pers[it] = R[r * W + (c == 0 ? O.c_z : O.c_lambdv)];
+    }
+    __syncthreads();
     auto zval = [&](int v) -> double {
       const int r = P.vrow[v];
-      return r >= 0 ? R[r * W + O.c_z] : zfix(-1 - r);
+      return r >= 0 ? pers[r * O.npers] : zfix(-1 - r);
     };
     auto xyval = [&](int v, int axis) -> double {
       const int r = P.vrow[v];
@@ -494,6 +681,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_onchip(const __grid_constant_
     }
     __syncthreads();
 
+    if (A.phase_clocks && blockIdx.x == 0 && tid == 0 && cand == (int64_t)(A.N > 4 * gridDim.x ? 4 * gridDim.x : 0)) A.phase_clocks[8] = clock64();
     // ---- 8. phase-2 right-hand sides: Ci^T W B | Ci^T W d0 ------------------------------------------
     if (O.ncols2 > 0) {
       const int nc2 = O.ncols2;
@@ -501,26 +689,41 @@ __global__ void __launch_bounds__(THREADS, MINB) k_onchip(const __grid_constant_
       const int r_ = tid & ((1 << g2) - 1);
       for (int r = tid >> g2; r < ni; r += THREADS >> g2)
       for (int cidx = r_; cidx < nc2; cidx += 1 << g2) {
-        const int v = P.row_vertex[r];
-        const double zv = R[r * W + O.c_z];
+        const double zv = pers[r * O.npers];
         double acc = 0.0;
-        for (int t = P.vadj_ptr[v]; t < P.vadj_ptr[v + 1]; ++t) {
-          const double zo = zval(P.vadj_other[t]);
-          const double sg = (double)P.vadj_sign[t];
-          const double w = sg > 0 ? (zv - zo) : (zo - zv);
-          const int e = P.vadj_edge[t];
-          const double coef = cidx < k ? P.B[(int64_t)e * k + cidx] : P.d[e];
-          acc = fma(sg * w, coef, acc);
+        if (O.adj_deg > 0) {
+          // padded adjacency: a fixed number of independent record loads, then independent B loads
+          const uint32_t* rp = O.radj_pad + r * O.adj_deg;
+#pragma unroll 8
+          for (int t = 0; t < O.adj_deg; ++t) {
+            const uint32_t rec = __ldg(rp + t);
+            const int e = (int)(rec >> 16);
+            const double zo = (rec & 0x8000u) ? zfix((int)(rec & 0x7fffu)) : pers[(int)(rec & 0x7fffu) * O.npers];
+            const double coef = cidx < k ? __ldg(P.B + (int64_t)e * k + cidx) : P.d[e];
+            acc = fma(zv - zo, coef, acc);
+          }
+        } else {
+          const int t1 = O.radj_ptr[r + 1];
+#pragma unroll 4
+          for (int t = O.radj_ptr[r]; t < t1; ++t) {
+            const uint32_t rec = __ldg(O.radj + t);
+            const int e = (int)(rec >> 16);
+            const double zo = (rec & 0x8000u) ? zfix((int)(rec & 0x7fffu)) : pers[(int)(rec & 0x7fffu) * O.npers];
+            const double coef = cidx < k ? __ldg(P.B + (int64_t)e * k + cidx) : P.d[e];
+            acc = fma(zv - zo, coef, acc);  // C[e, v] * (C z)_e = z_v - z_other exactly
+          }
         }
         R[r * W + O.c_q + cidx] = acc;
       }
       if (nc2 & 1)  // the spare column next to an odd column count takes part in the two-column accesses: keep it finite
         for (int r = tid; r < ni; r += THREADS) R[r * W + O.c_q + nc2] = 0.0;
       __syncthreads();
+      if (A.phase_clocks && blockIdx.x == 0 && tid == 0 && cand == (int64_t)(A.N > 4 * gridDim.x ? 4 * gridDim.x : 0)) A.phase_clocks[9] = clock64();
       // ---- 9. solve phase 2 ----
-      oc_solve<THREADS>(O, 1, levels, rowptr16, rowcol16, Lv, R, ni, O.c_q, nc2, tid);
+      oc_solve<THREADS>(O, 1, wide, clev, chains, rowchain, rowptr16, rowcol16, V, R, ni, O.c_q, nc2, tid);
     }
 
+    if (A.phase_clocks && blockIdx.x == 0 && tid == 0 && cand == (int64_t)(A.N > 4 * gridDim.x ? 4 * gridDim.x : 0)) A.phase_clocks[10] = clock64();
     // ---- 10. reac_bounds rows, objective, gradient ---------------------------------------------------
     if (want_reac) {
       const bool has_env = (P.constraints & TNO_CON_ENVELOPE) != 0;
@@ -580,7 +783,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_onchip(const __grid_constant_
             const double sg = (double)O.sup_sign[t];
             const int ro = P.vrow[O.sup_other[t]];
             if (ro >= 0) {
-              const double dzo = R[ro * W + O.c_lambdv];
+              const double dzo = pers[ro * O.npers + 1];
               dRz = fma(sg * qsup[t], sg > 0 ? -dzo : dzo, dRz);
             }
           }
@@ -632,23 +835,9 @@ __global__ void __launch_bounds__(THREADS, MINB) k_onchip(const __grid_constant_
       if (A.f) A.f[cand] = fval;
     }
 
+    if (A.phase_clocks && blockIdx.x == 0 && tid == 0 && cand == (int64_t)(A.N > 4 * gridDim.x ? 4 * gridDim.x : 0)) A.phase_clocks[11] = clock64();
     // ---- 11. dense Jacobian: funicular block from B, envelope block from the panel -------------------
     if (Jout) {
-      if (P.con.r_fun >= 0) {
-        double* o1 = Jout + (int64_t)P.con.r_fun * nvar;
-        double* o2 = o1 + (int64_t)m * nvar;
-        for (int e = tid; e < m * nvar; e += THREADS) {
-          const int row = __umulhi((unsigned)e, O.nvar_magic);
-          const int col = e - row * nvar;
-          double v = 0.0;
-          if (col < k)
-            v = __ldg(P.B + (int64_t)row * k + col);
-          else if (col == P.var.o_lambdh)
-            v = P.d[row];
-          o1[e] = v;
-          o2[e] = -v;
-        }
-      }
       if (P.con.r_env >= 0) {
         double* o1 = Jout + (int64_t)P.con.r_env * nvar;
         double* o2 = o1 + (int64_t)n * nvar;
@@ -658,13 +847,15 @@ __global__ void __launch_bounds__(THREADS, MINB) k_onchip(const __grid_constant_
           const int src = O.colsrc[col];
           if (src == -1) continue;  // zb and thickness columns were written in step 7
           const int r = P.vrow[v];
-          const double a = (src >= 0 && r >= 0) ? R[r * W + src] : 0.0;
+          double a = 0.0;
+          if (r >= 0) a = src >= 0 ? R[r * W + src] : (src == -3 ? pers[r * O.npers + 1] : 0.0);
           o1[e] = a;
           o2[e] = -a;
         }
       }
     }
 
+    if (A.phase_clocks && blockIdx.x == 0 && tid == 0 && cand == (int64_t)(A.N > 4 * gridDim.x ? 4 * gridDim.x : 0)) A.phase_clocks[12] = clock64();
     // ---- 12. feasibility margin and status -----------------------------------------------------------
     for (int off = 16; off > 0; off >>= 1) gmin = fmin(gmin, __shfl_xor_sync(0xffffffffu, gmin, off));
     const unsigned anybad = __ballot_sync(0xffffffffu, bad);
@@ -680,7 +871,23 @@ __global__ void __launch_bounds__(THREADS, MINB) k_onchip(const __grid_constant_
       if (A.status) A.status[cand] = s_flags;
     }
     __syncthreads();  // panel, flags and small arrays are reused by the next candidate
+    if (A.phase_clocks && blockIdx.x == 0 && tid == 0 && cand == (int64_t)(A.N > 4 * gridDim.x ? 4 * gridDim.x : 0)) A.phase_clocks[13] = clock64();
   }
+}
+
+// The funicular rows of J ([B 0; -B 0] plus the d0 column) do not depend on the candidate: a pure streaming
+// kernel replicates the precomputed block.  Each thread keeps one 16-byte chunk in registers and writes it to
+// CPB candidates, so the block is read once per CPB candidates (L2) and the stores run at HBM speed.
+constexpr int FILL_CPB = 16;
+__global__ void __launch_bounds__(256) k_fill_funicular(const double2* __restrict__ src, int64_t chunks, double* __restrict__ J,
+                                                        int64_t cand_stride, int64_t row_off, int64_t N) {
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= chunks) return;
+  const double2 v = src[c];
+  const int64_t c0 = (int64_t)blockIdx.y * FILL_CPB;
+  const int64_t c1 = c0 + FILL_CPB < N ? c0 + FILL_CPB : N;
+  for (int64_t cand = c0; cand < c1; ++cand)
+    reinterpret_cast<double2*>(J + cand * cand_stride + row_off)[c] = v;
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -692,57 +899,97 @@ int build_onchip(Plan* PL, const tno_problem_desc* D) {
   PL->onchip_ok = false;
   const int ni = P.ni, m = P.m, nb = P.nb, k = P.k, nvar = P.var.nvar;
   const int nnz = P.nnz_l;
-  const int nlow = nnz - ni;
-  if (nnz >= 65536 || ni >= 65535 || S.nlevels < 1) return TNO_OK;
+  if (nnz >= 60000 || ni >= 32768 || S.nlevels < 1 || m >= 65535) { set_error("on-chip family not applicable: nnz >= 60000 || ni >= 32768 || S.nlevels < 1 || m >= 65535"); return TNO_OK; }
   const int THREADS = 256;
 
-  // panel columns
+  // ---- panel columns.  phase 1: [z | z_lambdv | Az (nb) | x | y]   phase 2: [Dq (k) | z_lambdh] -------------
   int pos = 0;
   O.c_z = pos++;
   O.c_lambdv = -1;
   O.c_q = -1;
   O.c_lambdh = -1;
   if (P.var.o_lambdv >= 0) O.c_lambdv = pos++;
-  if (pos & 1) ++pos;  // phase-2 columns start on a 16-byte boundary (two columns per lane)
-  const int n_persist = pos;
-  O.ncols2 = 0;
-  if (P.rhs.c_q >= 0) {
-    O.c_q = pos;
-    O.ncols2 = k + (P.var.o_lambdh >= 0 ? 1 : 0);
-    if (P.var.o_lambdh >= 0) O.c_lambdh = O.c_q + k;
-  }
-  O.c_az = (P.var.o_zb >= 0) ? n_persist : -1;
-  O.c_x = n_persist + (P.var.o_zb >= 0 ? nb : 0);
+  O.npers = pos;
+  O.c_az = (P.var.o_zb >= 0) ? pos : -1;
+  O.c_x = pos + (P.var.o_zb >= 0 ? nb : 0);
   O.c_y = O.c_x + 1;
   O.ncols1 = O.c_y + 1;
-  O.W = std::max(O.ncols1, n_persist + O.ncols2);
-  O.W = (O.W + 2) / 2 * 2;  // even, and one spare column for the odd lane of a two-column access
-  O.nlevels = S.nlevels;
+  O.ncols2 = 0;
+  if (P.rhs.c_q >= 0) {
+    O.c_q = 0;
+    O.ncols2 = k + (P.var.o_lambdh >= 0 ? 1 : 0);
+    if (P.var.o_lambdh >= 0) O.c_lambdh = k;
+  }
+  O.W = (std::max(O.ncols1, O.ncols2) + 1) / 2 * 2;
+  O.nvar_magic = (uint32_t)((((uint64_t)1 << 32) + nvar - 1) / nvar);
+  O.rhs2_shift = 0;
   for (int ph = 0; ph < 2; ++ph) {
     const int ncols = ph == 0 ? O.ncols1 : O.ncols2;
     const int lanes = std::max(1, (ncols + 1) / 2);
     int g = 0;
     while ((1 << g) < lanes) ++g;
-    if (g > 5) return TNO_OK;  // more than 64 columns per phase: not handled on chip
+    if (g > 5) { set_error("on-chip family not applicable: g > 5"); return TNO_OK; }  // more than 64 columns per phase: not handled on chip
     O.gshift[ph] = g;
     if (ph == 1) {
       int g2 = 0;
       while ((1 << g2) < std::min(std::max(ncols, 1), 32)) ++g2;
       O.rhs2_shift = g2;
     }
-    int ls = S.nlevels;
-    while (ls > 1 && ((S.level_ptr[ls] - S.level_ptr[ls - 1]) << g) <= 32) --ls;
-    O.lsplit[ph] = ls;
   }
-  O.nlow = nlow;
-  O.nvar_magic = (uint32_t)((((uint64_t)1 << 32) + nvar - 1) / nvar);
 
-  // CSC position -> on-chip position (CSR order of the strictly lower part, diagonals last)
+  // ---- chains -------------------------------------------------------------------------------------------
+  const int nch = (int)S.chain_clevel.size();
+  const int ncl = (int)S.clevel_ptr.size() - 1;
+  const int wide_rows = S.wide_rows;
+  const int nwide = nch > 0 ? S.wide_levels : S.nlevels;
+  std::vector<int> chain_of(ni, -1), zoff_rel(std::max(nch, 1), 0);
+  int nz = 0;
+  for (int c = 0; c < nch; ++c) {
+    const int T = S.chain_ptr[c + 1] - S.chain_ptr[c];
+    if (T > 64) { set_error("on-chip family not applicable: T > 64"); return TNO_OK; }
+    for (int r = S.chain_ptr[c]; r < S.chain_ptr[c + 1]; ++r) chain_of[r] = c;
+    zoff_rel[c] = nz;
+    nz += T * (T - 1) / 2;
+  }
+  // outside CSR
+  std::vector<int> rowptr_o(ni + 1, 0), rowcol_o, csr_of_t(S.rowcol.size(), -1);
+  for (int i = 0; i < ni; ++i) {
+    for (int t = S.rowptr[i]; t < S.rowptr[i + 1]; ++t) {
+      const int j = S.rowcol[t];
+      if (chain_of[i] >= 0 && chain_of[i] == chain_of[j]) continue;
+      csr_of_t[t] = (int)rowcol_o.size();
+      rowcol_o.push_back(j);
+    }
+    rowptr_o[i + 1] = (int)rowcol_o.size();
+  }
+  const int nlo = (int)rowcol_o.size();
+  const int nv = nlo + ni + nz + 1;
+  if (nv >= 65535) { set_error("on-chip family not applicable: nv >= 65535"); return TNO_OK; }
+  O.nlo = nlo;
+  O.nz = nz;
+  O.nv = nv - 1;
+  O.pos_m1 = nv - 1;
+  O.wide_rows = wide_rows;
+  O.nwide = nwide;
+  O.nclev = nch > 0 ? ncl : 0;
+  O.nchains = nch;
+  auto zpos = [&](int i, int j) {  // i > j, same chain
+    const int c = chain_of[i];
+    const int il = i - S.chain_ptr[c], jl = j - S.chain_ptr[c];
+    return nlo + ni + zoff_rel[c] + il * (il - 1) / 2 + jl;
+  };
+  // CSC position -> V position
   std::vector<int> newpos(nnz, -1);
-  for (int j = 0; j < ni; ++j) newpos[S.colptr[j]] = nlow + j;
-  for (int t = 0; t < nlow; ++t) newpos[S.rowpos[t]] = t;
+  for (int j = 0; j < ni; ++j) newpos[S.colptr[j]] = nlo + j;
+  for (size_t t = 0; t < S.rowpos.size(); ++t) {
+    int i = 0;  // row of CSR entry t
+    (void)i;
+  }
+  for (int i = 0; i < ni; ++i)
+    for (int t = S.rowptr[i]; t < S.rowptr[i + 1]; ++t)
+      newpos[S.rowpos[t]] = csr_of_t[t] >= 0 ? csr_of_t[t] : zpos(i, S.rowcol[t]);
 
-  // support incidence
+  // ---- support incidence ----
   std::vector<int> sup_ptr(nb + 1, 0), sup_edge, sup_other, edge_sup(m, -1);
   std::vector<float> sup_sign;
   for (int b = 0; b < nb; ++b) {
@@ -757,80 +1004,194 @@ int build_onchip(Plan* PL, const tno_problem_desc* D) {
   }
   O.nsup = (int)sup_edge.size();
 
-  // ---- factor stream, one segment per level ----
-  std::vector<OcLevel> levels(S.nlevels);
-  std::vector<uint32_t> stream;  // 32-bit words; segments padded to 16 bytes
+  // ---- factorisation program ----------------------------------------------------------------------------
+  struct Item {
+    uint32_t pf;                          // V position | diagonal flag
+    std::vector<unsigned long long> prs;  // a | b << 16 | dp << 32
+  };
+  std::vector<OcChunk> chunks;
+  std::vector<OcOp> ops;
+  std::vector<uint32_t> stream;
   uint32_t max_units = 0;
-  for (int lev = 0; lev < S.nlevels; ++lev) {
-    OcLevel& L = levels[lev];
-    std::memset(&L, 0, sizeof(L));
-    L.row0 = (unsigned short)S.level_ptr[lev];
-    L.row1 = (unsigned short)S.level_ptr[lev + 1];
-    std::vector<uint32_t> recs;
-    std::vector<unsigned long long> prs;
-    int nitems = 0;
+  int max_tmp_items = 0;
+  const size_t CHUNK_BYTES = 12 * 1024;
+  auto emit_step = [&](const std::vector<Item>& items, int kind) {
+    size_t i0 = 0;
+    while (i0 < items.size()) {
+      size_t i1 = i0, bytes = 8;
+      while (i1 < items.size()) {
+        const size_t add = 8 + 8 * items[i1].prs.size();
+        if (i1 > i0 && bytes + add > CHUNK_BYTES) break;
+        bytes += add;
+        ++i1;
+      }
+      OcChunk K;
+      std::memset(&K, 0, sizeof(K));
+      K.seg_off = (uint32_t)(stream.size() / 4);
+      K.nitems = (unsigned short)(i1 - i0);
+      K.kind = (unsigned char)kind;
+      size_t npairs = 0;
+      for (size_t i = i0; i < i1; ++i) {
+        stream.push_back(items[i].pf);
+        stream.push_back((uint32_t)npairs);
+        npairs += items[i].prs.size();
+      }
+      stream.push_back(0);
+      stream.push_back((uint32_t)npairs);
+      for (size_t i = i0; i < i1; ++i)
+        for (unsigned long long pr : items[i].prs) {
+          stream.push_back((uint32_t)(pr & 0xffffffffu));
+          stream.push_back((uint32_t)(pr >> 32));
+        }
+      while (stream.size() % 4) stream.push_back(0);
+      K.seg_units = (uint32_t)(stream.size() / 4) - K.seg_off;
+      const int nitems = (int)(i1 - i0);
+      int lpi_shift = 0;
+      if (nitems > 0 && npairs / nitems >= 4)
+        while (lpi_shift < 5 && (nitems << (lpi_shift + 1)) <= THREADS) ++lpi_shift;
+      K.lpi_shift = (unsigned char)lpi_shift;
+      max_units = std::max(max_units, K.seg_units);
+      if (kind == 1) max_tmp_items = std::max(max_tmp_items, nitems);
+      OcOp OP;
+      std::memset(&OP, 0, sizeof(OP));
+      OP.type = OC_OP_CHUNK;
+      OP.a = (unsigned short)chunks.size();
+      ops.push_back(OP);
+      chunks.push_back(K);
+      i0 = i1;
+    }
+  };
+  auto make_item = [&](int p, bool diag_flag, int col_limit) {
+    // pairs over common columns c < col_limit (all common columns when col_limit < 0)
+    Item it;
+    it.pf = (uint32_t)newpos[p] | (diag_flag ? 0x80000000u : 0u);
+    for (int64_t t = S.dot_ptr[p]; t < S.dot_ptr[p + 1]; ++t) {
+      if (col_limit >= 0 && S.dot_c[t] >= col_limit) continue;
+      it.prs.push_back((unsigned long long)newpos[S.dot_a[t]] | ((unsigned long long)newpos[S.dot_b[t]] << 16) |
+                       ((unsigned long long)(nlo + S.dot_c[t]) << 32));
+    }
+    return it;
+  };
+  for (int lev = 0; lev < nwide; ++lev) {
+    std::vector<Item> items;
     for (int j = S.level_ptr[lev]; j < S.level_ptr[lev + 1]; ++j) {
       if (S.level_cols[j] != j) {
         set_error("internal: level ordering is not contiguous");
         return TNO_EINVAL;
       }
-      for (int p = S.colptr[j]; p < S.colptr[j + 1]; ++p) {
-        recs.push_back((uint32_t)newpos[p] | (p == S.colptr[j] ? 0x80000000u : 0u));
-        recs.push_back((uint32_t)prs.size());
-        for (int64_t t = S.dot_ptr[p]; t < S.dot_ptr[p + 1]; ++t)
-          prs.push_back((unsigned long long)newpos[S.dot_a[t]] | ((unsigned long long)newpos[S.dot_b[t]] << 16) |
-                        ((unsigned long long)(nlow + S.dot_c[t]) << 32));
-        ++nitems;
-      }
+      for (int p = S.colptr[j]; p < S.colptr[j + 1]; ++p) items.push_back(make_item(p, p == S.colptr[j], -1));
     }
-    recs.push_back(0);
-    recs.push_back((uint32_t)prs.size());
-    if (nitems >= 65536) return TNO_OK;
-    L.nitems = (unsigned short)nitems;
-    int lpi_shift = 0;
-    if (nitems > 0 && (int64_t)prs.size() / nitems >= 4)
-      while (lpi_shift < 5 && ((nitems << (lpi_shift + 1)) * 2) <= THREADS * 2 && (nitems << (lpi_shift + 1)) <= THREADS) ++lpi_shift;
-    L.lpi_shift = (unsigned char)lpi_shift;
-    {
-      const int rows = S.level_ptr[lev + 1] - S.level_ptr[lev];
-      for (int ph = 0; ph < 2; ++ph) {
-        const int g = O.gshift[ph];
-        for (int team = 0; team < 2; ++team) {
-          const int NT = team == 0 ? THREADS : 32;
-          int sp = 0;  // pull: S * G <= 32 (shuffle reduction) and rows * S * G <= NT
-          while (sp + 1 + g <= 5 && (rows << (sp + 1 + g)) <= NT) ++sp;
-          int sq = 0;  // push: rows * S * G <= NT
-          while (sq < 5 && (rows << (sq + 1 + g)) <= NT) ++sq;
-          L.pull_s[ph][team] = (unsigned char)sp;
-          L.push_s[ph][team] = (unsigned char)sq;
-        }
-      }
-    }
-    L.seg_off = (uint32_t)(stream.size() / 4);
-    stream.insert(stream.end(), recs.begin(), recs.end());
-    for (unsigned long long pr : prs) {
-      stream.push_back((uint32_t)(pr & 0xffffffffu));
-      stream.push_back((uint32_t)(pr >> 32));
-    }
-    while (stream.size() % 4) stream.push_back(0);
-    L.seg_units = (uint32_t)(stream.size() / 4) - L.seg_off;
-    max_units = std::max(max_units, L.seg_units);
+    emit_step(items, 0);
   }
+  for (int cl = 0; cl < O.nclev; ++cl) {
+    const int c0 = S.clevel_ptr[cl], c1 = S.clevel_ptr[cl + 1];
+    std::vector<Item> sitems, ritems;
+    for (int c = c0; c < c1; ++c) {
+      const int r0 = S.chain_ptr[c], r1 = S.chain_ptr[c + 1];
+      for (int j = r0; j < r1; ++j)
+        for (int p = S.colptr[j]; p < S.colptr[j + 1]; ++p) sitems.push_back(make_item(p, false, r0));  // S = A - outside pairs
+      // rectangular rows, columns in descending order:  U_ij = S_ij + sum_{c < j in chain, (i, c) present} S_ic Z_jc
+      for (int j = r1 - 1; j >= r0; --j)
+        for (int p = S.colptr[j] + 1; p < S.colptr[j + 1]; ++p) {
+          const int i = S.rowidx[p];
+          if (i < r1) continue;  // triangle entry
+          Item it;
+          it.pf = (uint32_t)newpos[p];
+          for (int cc = r0; cc < j; ++cc) {
+            const int pic = S.pos(i, cc);
+            if (pic < 0) continue;
+            it.prs.push_back((unsigned long long)newpos[pic] | ((unsigned long long)zpos(j, cc) << 16) |
+                             ((unsigned long long)O.pos_m1 << 32));
+          }
+          ritems.push_back(it);
+        }
+    }
+    emit_step(sitems, 0);
+    OcOp OP;
+    std::memset(&OP, 0, sizeof(OP));
+    OP.type = OC_OP_DENSE;
+    OP.a = (unsigned short)c0;
+    OP.b = (unsigned short)c1;
+    ops.push_back(OP);
+    if (!ritems.empty()) emit_step(ritems, 1);
+  }
+  O.nchunks = (int)chunks.size();
+  O.nops = (int)ops.size();
   O.fseg_units = (int)max_units;
+  if (chunks.size() >= 65535) { set_error("on-chip family not applicable: chunks.size() >= 65535"); return TNO_OK; }
 
-  // ---- assembly gather lists in on-chip position order ----
-  std::vector<int> asm_ptr(nnz + 1, 0), asm_edge;
+  // ---- solve ranges ----
+  auto make_range = [&](int row0, int row1, int chain0, int chain1) {
+    OcRange L;
+    std::memset(&L, 0, sizeof(L));
+    L.row0 = (unsigned short)row0;
+    L.row1 = (unsigned short)row1;
+    L.chain0 = (unsigned short)chain0;
+    L.chain1 = (unsigned short)chain1;
+    const int rows = row1 - row0;
+    for (int ph = 0; ph < 2; ++ph) {
+      const int g = O.gshift[ph];
+      int sp = 0;
+      while (sp + 1 + g <= 5 && (rows << (sp + 1 + g)) <= THREADS) ++sp;
+      int sq = 0;
+      while (sq < 5 && (rows << (sq + 1 + g)) <= THREADS) ++sq;
+      L.pull_s[ph] = (unsigned char)sp;
+      L.push_s[ph] = (unsigned char)sq;
+    }
+    return L;
+  };
+  std::vector<OcRange> wide_r, clev_r;
+  for (int lev = 0; lev < nwide; ++lev) wide_r.push_back(make_range(S.level_ptr[lev], S.level_ptr[lev + 1], 0, 0));
+  std::vector<OcChain> chain_r(std::max(nch, 1));
+  std::memset(chain_r.data(), 0, chain_r.size() * sizeof(OcChain));
+  std::vector<unsigned char> rowchain(std::max(ni - wide_rows, 1), 0);
+  for (int cl = 0; cl < O.nclev; ++cl) {
+    const int c0 = S.clevel_ptr[cl], c1 = S.clevel_ptr[cl + 1];
+    if (c1 - c0 > 255) { set_error("on-chip family not applicable: c1 - c0 > 255"); return TNO_OK; }
+    clev_r.push_back(make_range(S.chain_ptr[c0], S.chain_ptr[c1], c0, c1));
+    for (int c = c0; c < c1; ++c) {
+      chain_r[c].row0 = (unsigned short)S.chain_ptr[c];
+      chain_r[c].T = (unsigned short)(S.chain_ptr[c + 1] - S.chain_ptr[c]);
+      chain_r[c].zoff = (uint32_t)(nlo + ni + zoff_rel[c]);
+      for (int r = S.chain_ptr[c]; r < S.chain_ptr[c + 1]; ++r) rowchain[r - wide_rows] = (unsigned char)(c - c0);
+    }
+  }
+  std::vector<int> ct_ptr(1, 0);
+  std::vector<unsigned short> ct_col;
+  std::vector<uint32_t> ct_ent;
+  for (int cl = 0; cl < O.nclev; ++cl) {
+    const int c0 = S.clevel_ptr[cl], c1 = S.clevel_ptr[cl + 1];
+    clev_r[cl].tgt0 = (unsigned short)ct_col.size();
+    for (int c = c0; c < c1; ++c) {
+      std::map<int, std::vector<uint32_t>> by_col;  // outside column -> entries of this chain's rows
+      for (int i = S.chain_ptr[c]; i < S.chain_ptr[c + 1]; ++i)
+        for (int t = rowptr_o[i]; t < rowptr_o[i + 1]; ++t) by_col[rowcol_o[t]].push_back((uint32_t)t | ((uint32_t)i << 16));
+      for (auto& kv : by_col) {
+        ct_col.push_back((unsigned short)kv.first);
+        ct_ent.insert(ct_ent.end(), kv.second.begin(), kv.second.end());
+        ct_ptr.push_back((int)ct_ent.size());
+      }
+    }
+    clev_r[cl].tgt1 = (unsigned short)ct_col.size();
+  }
+  if (ct_col.size() >= 65535) { set_error("on-chip family not applicable: ct_col.size() >= 65535"); return TNO_OK; }
+  if (ct_col.empty()) ct_col.push_back(0);
+  if (ct_ent.empty()) ct_ent.push_back(0);
+  if (clev_r.empty()) clev_r.push_back(make_range(0, 0, 0, 0));
+
+  // ---- assembly maps in V position order ----
+  std::vector<int> asm_ptr(nv, 0), asm_edge;
   std::vector<float> asm_coef;
   {
-    std::vector<std::vector<std::pair<int, float>>> contrib(nnz);
+    std::vector<std::vector<std::pair<int, float>>> contrib(nv - 1);
     for (int e = 0; e < m; ++e) {
       const int u = D->edges[2 * e], v = D->edges[2 * e + 1];
       const int ru = PL->h_vrow[u], rv = PL->h_vrow[v];
-      if (ru >= 0) contrib[nlow + ru].push_back({e, -1.f});
-      if (rv >= 0) contrib[nlow + rv].push_back({e, -1.f});
+      if (ru >= 0) contrib[nlo + ru].push_back({e, -1.f});
+      if (rv >= 0) contrib[nlo + rv].push_back({e, -1.f});
       if (ru >= 0 && rv >= 0) contrib[newpos[S.pos(std::max(ru, rv), std::min(ru, rv))]].push_back({e, +1.f});
     }
-    for (int p = 0; p < nnz; ++p) {
+    for (int p = 0; p < nv - 1; ++p) {
       for (auto& c : contrib[p]) {
         asm_edge.push_back(c.first);
         asm_coef.push_back(c.second);
@@ -838,31 +1199,83 @@ int build_onchip(Plan* PL, const tno_problem_desc* D) {
       asm_ptr[p + 1] = (int)asm_edge.size();
     }
   }
+  std::vector<unsigned short> asm_e16(std::max(nlo, 1), 0xffff), asm_z16(std::max(nz, 1), 0xffff);
+  O.simple_asm = 1;
+  for (int p = 0; p < nv - 1 && O.simple_asm; ++p) {
+    if (p >= nlo && p < nlo + ni) continue;
+    const int cnt = asm_ptr[p + 1] - asm_ptr[p];
+    if (cnt > 1 || (cnt == 1 && asm_coef[asm_ptr[p]] != 1.f)) O.simple_asm = 0;
+    if (cnt == 1) (p < nlo ? asm_e16[p] : asm_z16[p - nlo - ni]) = (unsigned short)asm_edge[asm_ptr[p]];
+  }
 
-  // ---- shared-memory index region image: rowptr16 | rowcol16 | levels ----
+  // ---- row adjacency records ----
+  std::vector<int> radj_ptr(ni + 1, 0);
+  std::vector<uint32_t> radj, radj_pad;
+  int maxdeg = 0;
+  {
+    std::vector<int> row_vertex(ni, -1);
+    for (int v = 0; v < P.n; ++v)
+      if (PL->h_vrow[v] >= 0) row_vertex[PL->h_vrow[v]] = v;
+    for (int r = 0; r < ni; ++r) {
+      const int v = row_vertex[r];
+      for (int t = PL->h_vadj_ptr[v]; t < PL->h_vadj_ptr[v + 1]; ++t) {
+        const int ro = PL->h_vrow[PL->h_vadj_other[t]];
+        const uint32_t other = ro >= 0 ? (uint32_t)ro : (0x8000u | (uint32_t)(-1 - ro));
+        radj.push_back(other | ((uint32_t)PL->h_vadj_edge[t] << 16));
+      }
+      radj_ptr[r + 1] = (int)radj.size();
+      maxdeg = std::max(maxdeg, radj_ptr[r + 1] - radj_ptr[r]);
+    }
+    O.adj_deg = maxdeg <= 8 ? maxdeg : 0;
+    if (O.adj_deg > 0) {
+      radj_pad.assign((size_t)ni * O.adj_deg, 0);
+      for (int r = 0; r < ni; ++r)
+        for (int t = 0; t < O.adj_deg; ++t) {
+          const int src = radj_ptr[r] + t;
+          // padding: "other end" = the row itself (z_v - z_v = 0), any valid edge
+          radj_pad[(size_t)r * O.adj_deg + t] = src < radj_ptr[r + 1] ? radj[src] : ((uint32_t)r | (radj[radj_ptr[r]] & 0xffff0000u));
+        }
+    } else {
+      radj_pad.assign(1, 0);
+    }
+  }
+
+  // ---- shared-memory index region image ----
   std::vector<unsigned char> idx;
   auto align16 = [&]() {
     while (idx.size() % 16) idx.push_back(0);
   };
-  O.idx_rowptr = 0;
-  for (int i = 0; i <= ni; ++i) {
-    const unsigned short v = (unsigned short)S.rowptr[i];
+  auto put16 = [&](int v) {
     idx.push_back((unsigned char)(v & 0xff));
-    idx.push_back((unsigned char)(v >> 8));
-  }
+    idx.push_back((unsigned char)((v >> 8) & 0xff));
+  };
+  auto put_bytes = [&](const void* ptr, size_t bytes) {
+    const unsigned char* bp = reinterpret_cast<const unsigned char*>(ptr);
+    idx.insert(idx.end(), bp, bp + bytes);
+  };
+  O.idx_rowptr = 0;
+  for (int i = 0; i <= ni; ++i) put16(rowptr_o[i]);
   align16();
   O.idx_rowcol = (int)idx.size();
-  for (int t = 0; t < nlow; ++t) {
-    const unsigned short v = (unsigned short)S.rowcol[t];
-    idx.push_back((unsigned char)(v & 0xff));
-    idx.push_back((unsigned char)(v >> 8));
-  }
+  for (int t = 0; t < nlo; ++t) put16(rowcol_o[t]);
   align16();
-  O.idx_levels = (int)idx.size();
-  {
-    const unsigned char* lp = reinterpret_cast<const unsigned char*>(levels.data());
-    idx.insert(idx.end(), lp, lp + levels.size() * sizeof(OcLevel));
-  }
+  O.idx_wide = (int)idx.size();
+  put_bytes(wide_r.data(), wide_r.size() * sizeof(OcRange));
+  align16();
+  O.idx_clev = (int)idx.size();
+  put_bytes(clev_r.data(), clev_r.size() * sizeof(OcRange));
+  align16();
+  O.idx_chains = (int)idx.size();
+  put_bytes(chain_r.data(), chain_r.size() * sizeof(OcChain));
+  align16();
+  O.idx_rowchain = (int)idx.size();
+  put_bytes(rowchain.data(), rowchain.size());
+  align16();
+  O.idx_chunks = (int)idx.size();
+  put_bytes(chunks.data(), chunks.size() * sizeof(OcChunk));
+  align16();
+  O.idx_ops = (int)idx.size();
+  put_bytes(ops.data(), ops.size() * sizeof(OcOp));
   align16();
   O.idx_bytes = (int)idx.size();
 
@@ -874,12 +1287,12 @@ int build_onchip(Plan* PL, const tno_problem_desc* D) {
     return o;
   };
   O.o_x = take(nvar);
-  O.o_l = take(nnz);
+  O.o_v = take(nv);
   const int panel = std::max(ni * O.W, m);
   const int stage_doubles = 3 * O.fseg_units * 2;
-  O.stage = 1;
-  O.o_r = take(std::max(panel, stage_doubles));
-  O.o_env = -1;
+  O.o_tmp_doubles = stage_doubles;
+  O.o_r = take(std::max(panel, stage_doubles + max_tmp_items + 2));
+  O.o_pers = take(ni * O.npers);
   O.o_qsup = take(O.nsup);
   O.o_react = take(3 * nb);
   O.o_gxy = take(2 * nb * k + 2 * nb);
@@ -890,7 +1303,7 @@ int build_onchip(Plan* PL, const tno_problem_desc* D) {
   int max_optin = 0, smem_sm = 0;
   TNO_CUDA_OK(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, PL->device));
   TNO_CUDA_OK(cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, PL->device));
-  if (O.smem_bytes > max_optin) return TNO_OK;
+  if (O.smem_bytes > max_optin) { set_error("on-chip family not applicable: O.smem_bytes > max_optin"); return TNO_OK; }
   PL->onchip_threads = THREADS;
   PL->onchip_ctas_per_sm = std::max(1, std::min(8, smem_sm / (O.smem_bytes + 1024)));
 
@@ -900,7 +1313,21 @@ int build_onchip(Plan* PL, const tno_problem_desc* D) {
   std::vector<int> colsrc(nvar, -1);
   for (int j = 0; j < k; ++j) colsrc[j] = O.c_q >= 0 ? O.c_q + j : -2;
   if (P.var.o_lambdh >= 0) colsrc[P.var.o_lambdh] = O.c_lambdh >= 0 ? O.c_lambdh : -2;
-  if (P.var.o_lambdv >= 0) colsrc[P.var.o_lambdv] = O.c_lambdv;
+  if (P.var.o_lambdv >= 0) colsrc[P.var.o_lambdv] = -3;  // from the persistent copy
+  std::vector<double> Jfun;
+  if (P.con.r_fun >= 0) {
+    Jfun.assign((size_t)2 * m * nvar, 0.0);
+    for (int e = 0; e < m; ++e) {
+      for (int j = 0; j < k; ++j) {
+        Jfun[(size_t)e * nvar + j] = D->B[(size_t)e * k + j];
+        Jfun[(size_t)(m + e) * nvar + j] = -D->B[(size_t)e * k + j];
+      }
+      if (P.var.o_lambdh >= 0) {
+        Jfun[(size_t)e * nvar + P.var.o_lambdh] = D->d[e];
+        Jfun[(size_t)(m + e) * nvar + P.var.o_lambdh] = -D->d[e];
+      }
+    }
+  }
 
   int rc;
   const void* dptr = nullptr;
@@ -910,6 +1337,8 @@ int build_onchip(Plan* PL, const tno_problem_desc* D) {
   UPO(asm_ptr, asm_ptr);
   UPO(asm_edge, asm_edge);
   UPO(asm_coef, asm_coef);
+  UPO(asm_e16, asm_e16);
+  UPO(asm_z16, asm_z16);
   if ((rc = upload_bytes(PL, stream.data(), stream.size() * 4, &dptr))) return rc;
   O.f_stream = reinterpret_cast<const uint4*>(dptr);
   if ((rc = upload_bytes(PL, idx.data(), idx.size(), &dptr))) return rc;
@@ -920,6 +1349,13 @@ int build_onchip(Plan* PL, const tno_problem_desc* D) {
   UPO(sup_other, sup_other);
   UPO(sup_sign, sup_sign);
   UPO(colsrc, colsrc);
+  UPO(radj_ptr, radj_ptr);
+  UPO(radj, radj);
+  UPO(radj_pad, radj_pad);
+  UPO(ct_ptr, ct_ptr);
+  UPO(ct_col, ct_col);
+  UPO(ct_ent, ct_ent);
+  UPO(Jfun, Jfun);
 #undef UPO
   PL->onchip_ok = true;
   return TNO_OK;
@@ -940,15 +1376,43 @@ int run_onchip(Plan* PL, const double* x_dev, int64_t N, int64_t ldx, const tno_
   A.gmin = out->gmin;
   A.status = out->status;
   A.N = N;
+  A.phase_clocks = nullptr;
+  static const bool want_clocks = getenv("TNO_PHASE_CLOCKS") != nullptr;
+  if (want_clocks) {
+    TNO_CUDA_OK(cudaMalloc((void**)&A.phase_clocks, 16 * sizeof(long long)));
+    TNO_CUDA_OK(cudaMemsetAsync(A.phase_clocks, 0, 16 * sizeof(long long), stream));
+  }
   const size_t smem = (size_t)PL->oc.smem_bytes;
   const int grid = (int)std::min<int64_t>(N, (int64_t)PL->sm_count * PL->onchip_ctas_per_sm);
   auto kern = PL->onchip_ctas_per_sm >= 2 ? k_onchip<256, 2> : k_onchip<256, 1>;
   TNO_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (out->J && PL->dp.con.r_fun >= 0) {
+    const int64_t count = (int64_t)2 * PL->dp.m * PL->dp.var.nvar;  // even
+    const int64_t chunks = count / 2;
+    const int64_t cand_stride = (int64_t)PL->dp.con.ng * PL->dp.var.nvar;
+    dim3 g((unsigned)((chunks + 255) / 256), (unsigned)((N + FILL_CPB - 1) / FILL_CPB), 1);
+    PL->prof_begin(KK_EMIT_J, stream);
+    k_fill_funicular<<<g, 256, 0, stream>>>(reinterpret_cast<const double2*>(PL->oc.Jfun), chunks, out->J, cand_stride,
+                                            (int64_t)PL->dp.con.r_fun * PL->dp.var.nvar, N);
+    PL->prof_end(stream);
+    PL->launches += 1;
+  }
   PL->prof_begin(KK_ONCHIP, stream);
   kern<<<grid, 256, smem, stream>>>(PL->dp, PL->oc, A);
   PL->prof_end(stream);
   PL->launches += 1;
   TNO_CUDA_OK(cudaGetLastError());
+  if (want_clocks) {
+    long long h[16];
+    TNO_CUDA_OK(cudaStreamSynchronize(stream));
+    TNO_CUDA_OK(cudaMemcpy(h, A.phase_clocks, sizeof(h), cudaMemcpyDeviceToHost));
+    cudaFree(A.phase_clocks);
+    static const char* names[13] = {"x", "q", "assemble", "factor", "scale", "rhs1", "solve1", "post1", "rhs2", "solve2",
+                                    "reac/obj", "emitJ", "final"};
+    fprintf(stderr, "[tno phase clocks] N=%lld grid=%d total=%lld :", (long long)N, grid, h[13] - h[0]);
+    for (int i = 0; i < 13; ++i) fprintf(stderr, " %s=%lld", names[i], h[i + 1] - h[i]);
+    fprintf(stderr, "\n");
+  }
   return TNO_OK;
 }
 

@@ -105,52 +105,83 @@ struct DevPlan {
   const double* pz0;
 };
 
-// Device data of the on-chip kernel family (tno_onchip.cu): level-ordered index streams, all 16-bit.
-// One level set of the elimination tree (rows == columns are contiguous per level after the level ordering).
-struct OcLevel {
-  unsigned short row0, row1;   // rows / columns [row0, row1)
-  unsigned short nitems;       // entries of L in those columns (factorisation work items)
-  unsigned char lpi_shift;     // log2 of the lanes sharing one item's dot product in the factorisation
-  unsigned char pad0;
-  uint32_t seg_off;            // factor stream segment: offset and length in 16-byte units
-  uint32_t seg_units;
-  // log2 of the sub-slots splitting one row, [phase 0/1][team: 0 = whole CTA, 1 = one warp]
-  unsigned char pull_s[2][2];  // forward solve (pull): S * G <= 32
-  unsigned char push_s[2][2];  // backward solve (push)
+// ---- on-chip kernel family (tno_onchip.cu) -----------------------------------------------------------
+// Row ranges of one solve step: a wide level (rows are independent) or a chain level (the rows of all chains
+// of one depth of the chain tree).  Sub-slot counts are log2, [phase 0/1].
+struct OcRange {
+  unsigned short row0, row1;
+  unsigned char pull_s[2];   // forward (pull) sub-slots per row: S * G <= 32 (shuffle reduction)
+  unsigned char push_s[2];   // backward (push) sub-slots per row: any power of two
+  unsigned short chain0, chain1;   // chain levels only: chains [chain0, chain1)
+  unsigned short tgt0, tgt1;       // chain levels only: outside columns reached by those chains, [tgt0, tgt1) in ct_*
+};
+struct OcChain {
+  unsigned short row0, T;    // rows [row0, row0 + T)
+  uint32_t zoff;             // position (in the value array) of its dense strictly-lower block, (i, j) at i(i-1)/2 + j
+};
+// One staged piece of the factorisation stream.
+struct OcChunk {
+  uint32_t seg_off, seg_units;   // 16-byte units inside f_stream
+  unsigned short nitems;
+  unsigned char lpi_shift;       // log2 lanes sharing one item's dot product
+  unsigned char kind;            // 0: result written in place; 1: via the temp buffer (rectangular chain rows)
+};
+// Factorisation program: a short list of ops executed in order by the whole CTA.
+enum { OC_OP_CHUNK = 0, OC_OP_DENSE = 1 };
+struct OcOp {
+  unsigned short type;
+  unsigned short a, b;   // CHUNK: a = chunk id.  DENSE: chains [a, b)
+  unsigned short pad;
 };
 
-// Device data of the on-chip kernel family (tno_onchip.cu).
-// Value array Lv (shared memory): strictly-lower entries of L in CSR (row-major) order [0, nlow), then the ni
-// diagonal slots [nlow, nlow + ni) which hold 1 / d_j after the factorisation.
+// Device data of the on-chip kernel family.
+// Value array V (shared memory, 16-bit positions):
+//   [0, nlo)            strictly-lower entries of L OUTSIDE the chain blocks, CSR (row-major) order
+//   [nlo, nlo + ni)     diagonal slots; hold 1 / d_j after the factorisation
+//   [nlo + ni, .. + nz) dense strictly-lower chain blocks: S, then L_C, finally Z_C = L_C^-1
+//   [pos_m1]            the constant -1
 struct DevOnchip {
-  int W;                 // panel columns: [z | z_lambdv | Dq (k) | z_lambdh]; Az, x, y transient in the Dq columns
-  int c_z, c_lambdv, c_q, c_lambdh;   // persistent panel columns (-1 = absent)
-  int c_az, c_x, c_y;    // transient phase-1 columns (overwritten by phase 2)
-  int ncols1, ncols2;    // columns solved in phase 1: [0, ncols1); in phase 2: [c_q, c_q + ncols2)
-  int rhs2_shift;        // log2 of the lanes walking the phase-2 right-hand-side columns of one row
-  int gshift[2];         // log2 of the lanes covering the columns of one row (two columns per lane), per phase
-  int lsplit[2];         // first level handled by a single warp (rows * G <= 32 from there to the root), per phase
-  int nlevels, nlow, nsup;
-  uint32_t nvar_magic;   // ceil(2^32 / nvar): flat index -> (row, col)
-  // shared memory layout: offsets in doubles, o_idx in bytes
-  int o_x, o_l, o_r, o_env, o_qsup, o_react, o_gxy, o_azsup, o_red, o_idx_bytes;
-  int idx_rowptr, idx_rowcol, idx_levels;   // byte offsets inside the index region
-  int idx_bytes;
-  int smem_bytes;
-  int stage;             // 1: factor stream staged through the panel with cp.async (3 buffers of fseg_units)
-  int fseg_units;        // largest level segment, 16-byte units
+  int W;                 // panel columns (even).  phase 1: [z | z_lambdv | Az (nb) | x | y], phase 2: [Dq (k) | z_lambdh]
+  int c_z, c_lambdv, c_q, c_lambdh;
+  int c_az, c_x, c_y;
+  int npers;             // persistent phase-1 results kept outside the panel: z (, z_lambdv)
+  int ncols1, ncols2;
+  int rhs2_shift;        // log2 lanes walking the phase-2 right-hand-side columns of one row
+  int gshift[2];         // log2 lanes covering the columns of one row (two columns per lane), per phase
+  int nlo, nz, nv, pos_m1;
+  int wide_rows, nwide, nclev, nchains, nchunks, nops, nsup;
+  int adj_deg;           // padded adjacency width (0: use the pointer lists)
+  uint32_t nvar_magic;   // ceil(2^32 / nvar)
+  // shared memory layout: offsets in doubles, index region in bytes
+  int o_x, o_v, o_r, o_pers, o_qsup, o_react, o_gxy, o_azsup, o_red, o_idx_bytes;
+  int idx_rowptr, idx_rowcol, idx_wide, idx_clev, idx_chains, idx_rowchain, idx_chunks, idx_ops;
+  int idx_bytes, smem_bytes;
+  int fseg_units;        // staging buffer size, 16-byte units (3 buffers)
+  int o_tmp_doubles;     // offset (doubles, inside the panel region) of the temp buffer of kind-1 chunks
+  int simple_asm;
   const double* Bt;      // k x m (transposed B)
-  const int* asm_ptr;    // nnz_l + 1, assembly gather lists in Lv position order
+  const int* asm_ptr;    // generic assembly gather lists in V position order (nlo + ni entries)
   const int* asm_edge;
   const float* asm_coef;
-  const uint4* f_stream; // per level: (nitems + 1) records {pos | diag << 31, first pair} then pairs {a | b << 16 | dp << 32}
-  const unsigned char* idx_init;   // image of the shared-memory index region (rowptr16, rowcol16, levels)
-  const int* edge_sup;   // m: index of an edge in the support-incidence list or -1
+  const unsigned short* asm_e16;  // nlo: the edge feeding each CSR position, 0xFFFF for fill / chain-side entries
+  const unsigned short* asm_z16;  // nz : the edge feeding each dense chain position, 0xFFFF for none
+  const uint4* f_stream;
+  const unsigned char* idx_init;  // image of the shared-memory index region
+  const int* edge_sup;   // m
   const int* sup_ptr;    // nb + 1
   const int* sup_edge;   // nsup
-  const int* sup_other;  // nsup: vertex at the other end
-  const float* sup_sign; // nsup: C[e, support]
-  const int* colsrc;     // nvar: panel column feeding Jacobian column c (-1: written in the phase-1 epilogue)
+  const int* sup_other;  // nsup
+  const float* sup_sign; // nsup
+  const int* colsrc;     // nvar
+  const int* radj_ptr;   // ni + 1
+  const uint32_t* radj;  // other end (row, or 0x8000 | support index) | edge << 16
+  const uint32_t* radj_pad;  // ni x adj_deg, padded with self references (zero contribution)
+  // column-wise view of the chain rows' outside entries (backward solve): for every outside column ("target")
+  // reached by the chains of one chain level, the entries (value position | row << 16) of the chain rows in it
+  const int* ct_ptr;
+  const unsigned short* ct_col;
+  const uint32_t* ct_ent;
+  const double* Jfun;    // 2m x nvar
 };
 
 struct EmitTable {

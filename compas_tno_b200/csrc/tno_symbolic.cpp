@@ -169,7 +169,7 @@ int Symbolic::pos(int row, int col) const {
 }
 
 void analyse(int ni, const std::vector<std::pair<int, int>>& edges, int ordering, const double* coords,
-             bool build_update_lists, bool build_dot_lists, Symbolic* S) {
+             bool build_update_lists, bool build_dot_lists, Symbolic* S, int chain_width) {
   S->ni = ni;
   Adj adj = build_adjacency(ni, edges);
   S->nnz_a = ni;
@@ -235,6 +235,84 @@ void analyse(int ni, const std::vector<std::pair<int, int>>& edges, int ordering
     order.swap(neworder);
   }
   symbolic_factor(permuted_adj(order), &cols, &parent);
+
+  // ---- chain partition of the narrow top of the tree ------------------------------------------------
+  // Levels whose width drops to <= chain_width form the "narrow region".  Inside it a chain is a maximal
+  // tree path v1 -> v2 -> ... where v(i+1) = parent(v(i)) and v(i) is the ONLY child of v(i+1) inside the
+  // region.  The rows of a chain only reach (a) columns outside the region or in descendant chains and
+  // (b) earlier columns of the same chain, so a chain is processed as one dense triangular block.
+  // Chains are renumbered contiguously, ordered by their depth in the tree of chains ("chain level").
+  S->wide_levels = 0;
+  S->wide_rows = ni;
+  S->chain_ptr.assign(1, ni);
+  S->chain_clevel.clear();
+  S->clevel_ptr.assign(1, 0);
+  if (chain_width > 0 && ni > 0) {
+    std::vector<int> lvl(ni, 0);
+    for (int j = 0; j < ni; ++j)
+      if (parent[j] >= 0) lvl[parent[j]] = std::max(lvl[parent[j]], lvl[j] + 1);
+    const int nlev = *std::max_element(lvl.begin(), lvl.end()) + 1;
+    std::vector<int> width(nlev, 0);
+    for (int j = 0; j < ni; ++j) width[lvl[j]]++;
+    int Lc = nlev;
+    for (int l = 1; l < nlev; ++l)
+      if (width[l] <= chain_width) {
+        Lc = l;
+        break;
+      }
+    int wide_rows = 0;
+    for (int l = 0; l < Lc; ++l) wide_rows += width[l];
+    if (Lc < nlev) {
+      // nodes are level sorted: the region is [wide_rows, ni)
+      std::vector<int> nchild(ni, 0), only_child(ni, -1);
+      for (int j = wide_rows; j < ni; ++j)
+        if (parent[j] >= 0) {
+          nchild[parent[j]]++;
+          only_child[parent[j]] = j;
+        }
+      std::vector<int> chain_of(ni, -1), chain_first, chain_len, clev;
+      for (int j = wide_rows; j < ni; ++j) {  // ascending = children first
+        if (nchild[j] == 1) {
+          const int c = chain_of[only_child[j]];
+          chain_of[j] = c;
+          chain_len[c]++;
+        } else {
+          int cl = 0;
+          // chain level = 1 + max over the chains of the in-region children
+          for (int c2 = wide_rows; c2 < j; ++c2)
+            if (parent[c2] == j) cl = std::max(cl, clev[chain_of[c2]] + 1);
+          chain_of[j] = (int)chain_first.size();
+          chain_first.push_back(j);
+          chain_len.push_back(1);
+          clev.push_back(cl);
+        }
+      }
+      const int nch = (int)chain_first.size();
+      std::vector<int> corder(nch);
+      std::iota(corder.begin(), corder.end(), 0);
+      std::stable_sort(corder.begin(), corder.end(), [&](int a, int b) { return clev[a] < clev[b]; });
+      // members of each chain in path order (ascending node index within a chain is path order)
+      std::vector<std::vector<int>> members(nch);
+      for (int j = wide_rows; j < ni; ++j) members[chain_of[j]].push_back(j);
+      std::vector<int> neworder(order.begin(), order.begin() + wide_rows);
+      S->chain_ptr.clear();
+      S->chain_clevel.clear();
+      for (int ci : corder) {
+        S->chain_ptr.push_back((int)neworder.size());
+        S->chain_clevel.push_back(clev[ci]);
+        for (int j : members[ci]) neworder.push_back(order[j]);
+      }
+      S->chain_ptr.push_back((int)neworder.size());
+      const int ncl = S->chain_clevel.empty() ? 0 : S->chain_clevel.back() + 1;
+      S->clevel_ptr.assign(ncl + 1, 0);
+      for (int cl : S->chain_clevel) S->clevel_ptr[cl + 1]++;
+      for (int l = 0; l < ncl; ++l) S->clevel_ptr[l + 1] += S->clevel_ptr[l];
+      S->wide_levels = Lc;
+      S->wide_rows = wide_rows;
+      order.swap(neworder);
+      symbolic_factor(permuted_adj(order), &cols, &parent);
+    }
+  }
 
   S->perm = order;
   S->iperm.assign(ni, 0);

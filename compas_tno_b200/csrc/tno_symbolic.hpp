@@ -24,6 +24,11 @@ struct Symbolic {
   std::vector<int> level_ptr;    // nlevels+1
   std::vector<int> level_cols;   // columns sorted by level
   int nlevels = 0;
+  // chain partition of the narrow top of the tree (see tno_symbolic.cpp).  Rows [0, wide_rows) belong to the
+  // wide levels [0, wide_levels) and are level ordered; rows of chain c are [chain_ptr[c], chain_ptr[c+1]),
+  // chains are sorted by chain level, clevel_ptr indexes chains.
+  int wide_levels = 0, wide_rows = 0;
+  std::vector<int> chain_ptr, chain_clevel, clevel_ptr;
   int nnz_a = 0;                 // lower triangle incl. diagonal
   int max_colcount = 0;
   int64_t factor_flops = 0;      // sum_j c_j^2 (c_j = off-diagonal count + 1)
@@ -46,6 +51,6 @@ struct Symbolic {
 // adjacency given as an edge list between free positions (duplicates and self loops tolerated).
 // coords (2 per free position) are only used by the nested-dissection ordering and may be null.
 void analyse(int ni, const std::vector<std::pair<int, int>>& edges, int ordering, const double* coords,
-             bool build_update_lists, bool build_dot_lists, Symbolic* out);
+             bool build_update_lists, bool build_dot_lists, Symbolic* out, int chain_width = 8);
 
 }  // namespace tno
