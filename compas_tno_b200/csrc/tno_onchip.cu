@@ -290,54 +290,88 @@ __device__ __forceinline__ void oc_solve(const DevOnchip& O, int phase, const Oc
   }
 }
 
-// Dense work of the chains [c0, c1) of one chain level, one warp per chain:
-//   (B) in-place L D L^T of the dense triangle S_C (diagonal in the diagonal slots, which end up holding 1 / d),
-//   (C) in-place inversion of the unit lower triangular L_C  ->  Z_C.
-// Lane = row of the chain (rows beyond 32 wrap around).
-__device__ __forceinline__ void oc_chain_dense(const OcChain* __restrict__ chains, int c0, int c1, int nlo, double* __restrict__ V,
-                                               int* s_flags, int warp, int lane, int nwarps) {
-  for (int c = c0 + warp; c < c1; c += nwarps) {
-    const OcChain C = chains[c];
-    const int T = C.T;
-    double* dg = V + nlo + C.row0;
-    double* Z = V + C.zoff;
-    // ---- (B) L D L^T ----
-    for (int j = 0; j < T; ++j) {
-      const double d = dg[j];
-      if (lane == 0 && !(d > 0.0)) atomicOr(s_flags, TNO_STATUS_NOT_PD);
-      const double inv = 1.0 / d;
-      for (int i = j + 1 + lane; i < T; i += 32) {
-        const double* zi = Z + (i * (i - 1)) / 2;
-        const double uij = zi[j] * inv;  // l_ij
-        double* zw = Z + (i * (i - 1)) / 2;
-#pragma unroll 4
-        for (int kk = j + 1; kk < i; ++kk) zw[kk] = fma(-uij, Z[(kk * (kk - 1)) / 2 + j], zw[kk]);
-        dg[i] = fma(-uij, zi[j], dg[i]);
+// Dense work of one chain level, whole CTA, all chains of the level at once:
+//   (B) right-looking L D L^T of every dense triangle, ONE barrier per column step: element (i, k) subtracts
+//       u_ij u_kj / d_j for every j < k; the owner of a diagonal inverts it as soon as it is final, so the
+//       division overlaps the other threads' updates.  Columns are scaled to L = U D^-1 afterwards.
+//   (C) Z = L^-1: one thread per column solves L z = e_c by forward substitution into a second buffer
+//       (columns are independent, no barriers), then the blocks are copied back over L.
+template <int THREADS>
+__device__ __forceinline__ void oc_chain_dense(const DevOnchip& O, const OcDense& DN, double* __restrict__ V,
+                                               double* __restrict__ tmpz, int* s_flags, int tid) {
+  const int zbase = O.nlo + (O.nv - O.nlo - O.nz);  // first dense position (= nlo + ni)
+  // ---- (B) ----
+  // every thread keeps its (up to OC_DE) element descriptors in registers for the whole factorisation of the level
+  constexpr int OC_DE = 4;
+  uint4 dsc[OC_DE];
+  const int nde = (int)(DN.de1 - DN.de0);
+#pragma unroll
+  for (int q = 0; q < OC_DE; ++q) {
+    const int e = q * THREADS + tid;
+    dsc[q] = e < nde ? __ldg(O.de + DN.de0 + e) : make_uint4(0u, 0u, 0x00ffu, 0u);  // k = 255 > i = 0: never active
+  }
+  const bool in_regs = nde <= OC_DE * THREADS;
+  auto step_elem = [&](const uint4 d, int j) {
+    const int kk = (int)(d.z & 0xffu), ii = (int)((d.z >> 8) & 0xffu);
+    if (kk > j && kk <= ii) {
+      const int sp = (int)(d.y & 0xffffu);
+      const double inv = V[(int)(d.y >> 16) + j];
+      const double uij = V[(int)(d.x & 0xffffu) + j];
+      const double ukj = V[(int)(d.x >> 16) + j];
+      double sv = fma(-uij * inv, ukj, V[sp]);
+      if (kk == ii && j == ii - 1) {  // diagonal just became final
+        if (!(sv > 0.0)) atomicOr(s_flags, TNO_STATUS_NOT_PD);
+        sv = 1.0 / sv;
       }
-      __syncwarp();
-      for (int i = j + 1 + lane; i < T; i += 32) Z[(i * (i - 1)) / 2 + j] *= inv;
-      if (lane == 0) dg[j] = inv;
-      __syncwarp();
+      V[sp] = sv;
     }
-    // ---- (C) Z = L_C^-1, columns from right to left ----
-    for (int j = T - 2; j >= 0; --j) {
-      double acc[2] = {0.0, 0.0};
-      int cnt = 0;
-      for (int i = j + 1 + lane; i < T; i += 32, ++cnt) {
-        const double* zi = Z + (i * (i - 1)) / 2;
-        double a = zi[j];
-#pragma unroll 4
-        for (int kk = j + 1; kk < i; ++kk) a = fma(zi[kk], Z[(kk * (kk - 1)) / 2 + j], a);
-        acc[cnt & 1] = a;
-      }
-      __syncwarp();
-      cnt = 0;
-      for (int i = j + 1 + lane; i < T; i += 32, ++cnt) Z[(i * (i - 1)) / 2 + j] = -acc[cnt & 1];
-      __syncwarp();
+  };
+  for (uint32_t e = DN.de0 + tid; e < DN.de1; e += THREADS) {
+    const uint4 d = __ldg(O.de + e);
+    if ((d.z & 0xffffu) == 0u) {  // element (0, 0): final after the S-step
+      const int sp = (int)(d.y & 0xffffu);
+      const double v = V[sp];
+      if (!(v > 0.0)) atomicOr(s_flags, TNO_STATUS_NOT_PD);
+      V[sp] = 1.0 / v;
     }
   }
+  __syncthreads();
+  for (int j = 0; j + 1 < (int)DN.tmax; ++j) {
+    if (in_regs) {
+      // elements are sorted by descending k: once a thread's first element is inactive, all of them are
+      if ((int)(dsc[0].z & 0xffu) > j && (int)(dsc[0].z & 0xffu) != 0xff) {
+#pragma unroll
+        for (int q = 0; q < OC_DE; ++q) step_elem(dsc[q], j);
+      }
+    } else {
+      for (uint32_t e = DN.de0 + tid; e < DN.de1; e += THREADS) step_elem(__ldg(O.de + e), j);
+    }
+    __syncthreads();
+  }
+  for (uint32_t e = DN.de0 + tid; e < DN.de1; e += THREADS) {
+    const uint4 d = __ldg(O.de + e);
+    const int kk = (int)(d.z & 0xffu), ii = (int)((d.z >> 8) & 0xffu);
+    if (kk < ii) V[(int)(d.y & 0xffffu)] *= V[(int)(d.y >> 16) + kk];  // l_ik = u_ik / d_k
+  }
+  __syncthreads();
+  // ---- (C) ----
+  for (uint32_t cidx = DN.dc0 + tid; cidx < DN.dc1; cidx += THREADS) {
+    const uint32_t w = __ldg(O.dc + cidx);
+    const int zoff = (int)(w & 0xffffu), T = (int)((w >> 16) & 0xffu), c = (int)(w >> 24);
+    const double* Lz = V + zoff;
+    double* Zt = tmpz + (zoff - zbase);
+    for (int i = c + 1; i < T; ++i) {
+      const int rb = (i * (i - 1)) / 2;
+      double a = Lz[rb + c];
+#pragma unroll 4
+      for (int kk = c + 1; kk < i; ++kk) a = fma(Lz[rb + kk], Zt[(kk * (kk - 1)) / 2 + c], a);
+      Zt[rb + c] = -a;
+    }
+  }
+  __syncthreads();
+  for (uint32_t p = DN.zlo + tid; p < DN.zhi; p += THREADS) V[p] = tmpz[p - zbase];
+  __syncthreads();
 }
-
 
 template <int THREADS, int MINB>
 __global__ void __launch_bounds__(THREADS, MINB) k_onchip(const __grid_constant__ DevPlan P, const __grid_constant__ DevOnchip O,
@@ -353,7 +387,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_onchip(const __grid_constant_
   double* gxy = sm + O.o_gxy;      // Cb^T U B | Cb^T V B (nb x k each) | Cb^T U d0 | Cb^T V d0 (nb each)
   double* azsup = sm + O.o_azsup;  // nsup x nb : dz/dzb at the neighbours of the supports
   double* red = sm + O.o_red;
-  double* pers = sm + O.o_pers;    // ni x npers : z (, z_lambdv) after phase 1
+  double* pers = sm + O.o_pers;    // z_lambdv of the free rows after phase 1 (lambdv variable only)
   const unsigned short* rowptr16 = reinterpret_cast<const unsigned short*>(smraw + O.o_idx_bytes + O.idx_rowptr);
   const unsigned short* rowcol16 = reinterpret_cast<const unsigned short*>(smraw + O.o_idx_bytes + O.idx_rowcol);
   const OcRange* wide = reinterpret_cast<const OcRange*>(smraw + O.o_idx_bytes + O.idx_wide);
@@ -362,6 +396,8 @@ __global__ void __launch_bounds__(THREADS, MINB) k_onchip(const __grid_constant_
   const unsigned char* rowchain = smraw + O.o_idx_bytes + O.idx_rowchain;
   const OcChunk* chunks = reinterpret_cast<const OcChunk*>(smraw + O.o_idx_bytes + O.idx_chunks);
   const OcOp* ops = reinterpret_cast<const OcOp*>(smraw + O.o_idx_bytes + O.idx_ops);
+  const OcDense* dense = reinterpret_cast<const OcDense*>(smraw + O.o_idx_bytes + O.idx_dense);
+  double* zs = sm + O.o_zs;        // z of the free rows (after phase 1) followed by zb of the supports
   __shared__ int s_flags;
 
   const int tid = threadIdx.x;
@@ -459,16 +495,23 @@ __global__ void __launch_bounds__(THREADS, MINB) k_onchip(const __grid_constant_
       };
       issue(0);
       issue(1);
+      const bool clk = A.phase_clocks && blockIdx.x == 0 && tid == 0 && cand == (int64_t)(A.N > 4 * gridDim.x ? 4 * gridDim.x : 0);
+      long long t_dense = 0, t_wait = 0, t_last = clk ? clock64() : 0;
       for (int op = 0; op < O.nops; ++op) {
         const OcOp OP = ops[op];
         if (OP.type == OC_OP_DENSE) {
           __syncthreads();
-          oc_chain_dense(chains, OP.a, OP.b, nlo, V, &s_flags, warp, lane, THREADS / 32);
+          const long long t0 = clk ? clock64() : 0;
+          oc_chain_dense<THREADS>(O, dense[OP.a], V, R + O.o_tmpz_doubles, &s_flags, tid);
+          __syncthreads();
+          if (clk) t_dense += clock64() - t0;
           continue;
         }
         const int c = OP.a;
+        const long long tw0 = clk ? clock64() : 0;
         cp_async_wait<1>();
         __syncthreads();
+        if (clk) t_wait += clock64() - tw0;
         issue(c + 2);
         const OcChunk K = chunks[c];
         const uint2* rec = reinterpret_cast<const uint2*>(stage_base + (c % 3) * seg_bytes);
@@ -513,6 +556,10 @@ __global__ void __launch_bounds__(THREADS, MINB) k_onchip(const __grid_constant_
       }
       cp_async_wait<0>();
       __syncthreads();
+      if (clk) {
+        A.phase_clocks[14] = t_dense;
+        A.phase_clocks[15] = t_wait;
+      }
     }
     if (A.phase_clocks && blockIdx.x == 0 && tid == 0 && cand == (int64_t)(A.N > 4 * gridDim.x ? 4 * gridDim.x : 0)) A.phase_clocks[4] = clock64();
     // ---- 4. L_ij = U_ij / d_j for the CSR entries (the dense chain blocks are already final) ---------
@@ -562,15 +609,15 @@ __global__ void __launch_bounds__(THREADS, MINB) k_onchip(const __grid_constant_
     // ---- 7. everything that needs the transient columns (x, y, Az) or only z ------------------------
     auto zfix = [&](int b) -> double { return P.var.o_zb >= 0 ? xs[P.var.o_zb + b] : P.X[3 * P.fixed[b] + 2]; };
     // persistent phase-1 results leave the panel: phase 2 reuses all of its columns
-    for (int it = tid; it < ni * O.npers; it += THREADS) {
-      const int r = O.npers == 1 ? it : (it >> 1);
-      const int c = O.npers == 1 ? 0 : (it & 1);
-      pers[it] = R[r * W + (c == 0 ? O.c_z : O.c_lambdv)];
+    for (int r = tid; r < ni; r += THREADS) {
+      zs[r] = R[r * W + O.c_z];
+      if (O.npers > 1) pers[r] = R[r * W + O.c_lambdv];
     }
+    if (tid < nb) zs[ni + tid] = zfix(tid);
     __syncthreads();
-    auto zval = [&](int v) -> double {
+    auto zval = [&](int v) -> double {  // branch-free: free rows first, supports behind them
       const int r = P.vrow[v];
-      return r >= 0 ? pers[r * O.npers] : zfix(-1 - r);
+      return zs[r >= 0 ? r : ni - 1 - r];
     };
     auto xyval = [&](int v, int axis) -> double {
       const int r = P.vrow[v];
@@ -689,28 +736,34 @@ __global__ void __launch_bounds__(THREADS, MINB) k_onchip(const __grid_constant_
       const int r_ = tid & ((1 << g2) - 1);
       for (int r = tid >> g2; r < ni; r += THREADS >> g2)
       for (int cidx = r_; cidx < nc2; cidx += 1 << g2) {
-        const double zv = pers[r * O.npers];
+        const double zv = zs[r];
+        // coefficient column: B[:, cidx] for the q_ind columns, d0 for the lambdh column (branch-free addressing)
+        const double* cbase = cidx < k ? P.B + cidx : P.d;
+        const int cstride = cidx < k ? k : 1;
         double acc = 0.0;
         if (O.adj_deg > 0) {
-          // padded adjacency: a fixed number of independent record loads, then independent B loads
+          // padded adjacency: all record loads first, then all coefficient loads, then the arithmetic
           const uint32_t* rp = O.radj_pad + r * O.adj_deg;
-#pragma unroll 8
-          for (int t = 0; t < O.adj_deg; ++t) {
-            const uint32_t rec = __ldg(rp + t);
-            const int e = (int)(rec >> 16);
-            const double zo = (rec & 0x8000u) ? zfix((int)(rec & 0x7fffu)) : pers[(int)(rec & 0x7fffu) * O.npers];
-            const double coef = cidx < k ? __ldg(P.B + (int64_t)e * k + cidx) : P.d[e];
-            acc = fma(zv - zo, coef, acc);
+          uint32_t rec[8];
+          double cf[8];
+#pragma unroll
+          for (int t = 0; t < 8; ++t) rec[t] = t < O.adj_deg ? __ldg(rp + t) : (uint32_t)r;
+#pragma unroll
+          for (int t = 0; t < 8; ++t) cf[t] = t < O.adj_deg ? __ldg(cbase + (int64_t)(rec[t] >> 16) * cstride) : 0.0;
+#pragma unroll
+          for (int t = 0; t < 8; ++t) {
+            const int o = (int)(rec[t] & 0x7fffu);
+            const double zo = zs[(rec[t] & 0x8000u) ? ni + o : o];
+            acc = fma(zv - zo, cf[t], acc);  // C[e, v] * (C z)_e = z_v - z_other exactly
           }
         } else {
           const int t1 = O.radj_ptr[r + 1];
 #pragma unroll 4
           for (int t = O.radj_ptr[r]; t < t1; ++t) {
             const uint32_t rec = __ldg(O.radj + t);
-            const int e = (int)(rec >> 16);
-            const double zo = (rec & 0x8000u) ? zfix((int)(rec & 0x7fffu)) : pers[(int)(rec & 0x7fffu) * O.npers];
-            const double coef = cidx < k ? __ldg(P.B + (int64_t)e * k + cidx) : P.d[e];
-            acc = fma(zv - zo, coef, acc);  // C[e, v] * (C z)_e = z_v - z_other exactly
+            const int o = (int)(rec & 0x7fffu);
+            const double zo = zs[(rec & 0x8000u) ? ni + o : o];
+            acc = fma(zv - zo, __ldg(cbase + (int64_t)(rec >> 16) * cstride), acc);
           }
         }
         R[r * W + O.c_q + cidx] = acc;
@@ -783,7 +836,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_onchip(const __grid_constant_
             const double sg = (double)O.sup_sign[t];
             const int ro = P.vrow[O.sup_other[t]];
             if (ro >= 0) {
-              const double dzo = pers[ro * O.npers + 1];
+              const double dzo = pers[ro];
               dRz = fma(sg * qsup[t], sg > 0 ? -dzo : dzo, dRz);
             }
           }
@@ -848,7 +901,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_onchip(const __grid_constant_
           if (src == -1) continue;  // zb and thickness columns were written in step 7
           const int r = P.vrow[v];
           double a = 0.0;
-          if (r >= 0) a = src >= 0 ? R[r * W + src] : (src == -3 ? pers[r * O.npers + 1] : 0.0);
+          if (r >= 0) a = src >= 0 ? R[r * W + src] : (src == -3 ? pers[r] : 0.0);
           o1[e] = a;
           o2[e] = -a;
         }
@@ -1011,6 +1064,9 @@ int build_onchip(Plan* PL, const tno_problem_desc* D) {
   };
   std::vector<OcChunk> chunks;
   std::vector<OcOp> ops;
+  std::vector<OcDense> dense_r;
+  std::vector<uint4> de;
+  std::vector<uint32_t> dc;
   std::vector<uint32_t> stream;
   uint32_t max_units = 0;
   int max_tmp_items = 0;
@@ -1110,9 +1166,38 @@ int build_onchip(Plan* PL, const tno_problem_desc* D) {
     OcOp OP;
     std::memset(&OP, 0, sizeof(OP));
     OP.type = OC_OP_DENSE;
-    OP.a = (unsigned short)c0;
-    OP.b = (unsigned short)c1;
+    OP.a = (unsigned short)cl;
     ops.push_back(OP);
+    {
+      OcDense DN;
+      std::memset(&DN, 0, sizeof(DN));
+      DN.de0 = (uint32_t)de.size();
+      DN.dc0 = (uint32_t)dc.size();
+      DN.zlo = (uint32_t)(nlo + ni + zoff_rel[c0]);
+      for (int c = c0; c < c1; ++c) {
+        const int r0 = S.chain_ptr[c], T = S.chain_ptr[c + 1] - r0;
+        const int zoff = nlo + ni + zoff_rel[c];
+        DN.tmax = std::max<uint32_t>(DN.tmax, (uint32_t)T);
+        DN.zhi = (uint32_t)(zoff + T * (T - 1) / 2);
+        for (int i = 0; i < T; ++i)
+          for (int kk = 0; kk <= i; ++kk) {
+            const uint32_t rb_i = (uint32_t)(zoff + i * (i - 1) / 2), rb_k = (uint32_t)(zoff + kk * (kk - 1) / 2);
+            const uint32_t self = kk == i ? (uint32_t)(nlo + r0 + i) : rb_i + (uint32_t)kk;
+            uint4 d;
+            d.x = rb_i | (rb_k << 16);
+            d.y = self | ((uint32_t)(nlo + r0) << 16);
+            d.z = (uint32_t)kk | ((uint32_t)i << 8);
+            d.w = 0;
+            de.push_back(d);
+          }
+        for (int cc = 0; cc + 1 < T; ++cc) dc.push_back((uint32_t)zoff | ((uint32_t)T << 16) | ((uint32_t)cc << 24));
+      }
+      std::stable_sort(de.begin() + DN.de0, de.end(),
+                       [](const uint4& a, const uint4& b) { return (a.z & 0xffu) > (b.z & 0xffu); });
+      DN.de1 = (uint32_t)de.size();
+      DN.dc1 = (uint32_t)dc.size();
+      dense_r.push_back(DN);
+    }
     if (!ritems.empty()) emit_step(ritems, 1);
   }
   O.nchunks = (int)chunks.size();
@@ -1277,6 +1362,10 @@ int build_onchip(Plan* PL, const tno_problem_desc* D) {
   O.idx_ops = (int)idx.size();
   put_bytes(ops.data(), ops.size() * sizeof(OcOp));
   align16();
+  O.idx_dense = (int)idx.size();
+  if (dense_r.empty()) dense_r.resize(1);
+  put_bytes(dense_r.data(), dense_r.size() * sizeof(OcDense));
+  align16();
   O.idx_bytes = (int)idx.size();
 
   // ---- shared memory layout ----
@@ -1291,8 +1380,10 @@ int build_onchip(Plan* PL, const tno_problem_desc* D) {
   const int panel = std::max(ni * O.W, m);
   const int stage_doubles = 3 * O.fseg_units * 2;
   O.o_tmp_doubles = stage_doubles;
-  O.o_r = take(std::max(panel, stage_doubles + max_tmp_items + 2));
-  O.o_pers = take(ni * O.npers);
+  O.o_tmpz_doubles = (stage_doubles + max_tmp_items + 2) / 2 * 2;
+  O.o_r = take(std::max(panel, O.o_tmpz_doubles + nz + 2));
+  O.o_zs = take(ni + nb);
+  O.o_pers = take(O.npers > 1 ? ni : 0);
   O.o_qsup = take(O.nsup);
   O.o_react = take(3 * nb);
   O.o_gxy = take(2 * nb * k + 2 * nb);
@@ -1355,6 +1446,10 @@ int build_onchip(Plan* PL, const tno_problem_desc* D) {
   UPO(ct_ptr, ct_ptr);
   UPO(ct_col, ct_col);
   UPO(ct_ent, ct_ent);
+  if (de.empty()) de.push_back(uint4{0, 0, 0, 0});
+  if (dc.empty()) dc.push_back(0);
+  UPO(de, de);
+  UPO(dc, dc);
   UPO(Jfun, Jfun);
 #undef UPO
   PL->onchip_ok = true;
@@ -1411,6 +1506,7 @@ int run_onchip(Plan* PL, const double* x_dev, int64_t N, int64_t ldx, const tno_
                                     "reac/obj", "emitJ", "final"};
     fprintf(stderr, "[tno phase clocks] N=%lld grid=%d total=%lld :", (long long)N, grid, h[13] - h[0]);
     for (int i = 0; i < 13; ++i) fprintf(stderr, " %s=%lld", names[i], h[i + 1] - h[i]);
+    fprintf(stderr, " | factor: dense=%lld chunk-wait=%lld", h[14], h[15]);
     fprintf(stderr, "\n");
   }
   return TNO_OK;

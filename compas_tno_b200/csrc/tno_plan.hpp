@@ -126,11 +126,18 @@ struct OcChunk {
   unsigned char lpi_shift;       // log2 lanes sharing one item's dot product
   unsigned char kind;            // 0: result written in place; 1: via the temp buffer (rectangular chain rows)
 };
+// Dense work of one chain level (all its chains at once, whole CTA).
+struct OcDense {
+  uint32_t de0, de1;     // triangle elements (diagonal included) in de[]
+  uint32_t dc0, dc1;     // chain columns in dc[]
+  uint32_t zlo, zhi;     // value positions of the dense blocks of this chain level
+  uint32_t tmax;         // longest chain
+};
 // Factorisation program: a short list of ops executed in order by the whole CTA.
 enum { OC_OP_CHUNK = 0, OC_OP_DENSE = 1 };
 struct OcOp {
   unsigned short type;
-  unsigned short a, b;   // CHUNK: a = chunk id.  DENSE: chains [a, b)
+  unsigned short a, b;   // CHUNK: a = chunk id.  DENSE: a = chain level
   unsigned short pad;
 };
 
@@ -158,6 +165,11 @@ struct DevOnchip {
   int idx_bytes, smem_bytes;
   int fseg_units;        // staging buffer size, 16-byte units (3 buffers)
   int o_tmp_doubles;     // offset (doubles, inside the panel region) of the temp buffer of kind-1 chunks
+  int o_tmpz_doubles;    // offset (doubles, inside the panel region) of the nz-double buffer used by the block inversion
+  int idx_dense;         // byte offset of the OcDense table inside the index region
+  const uint4* de;       // element descriptors: x = rowbase_i | rowbase_k << 16, y = selfpos | dgbase << 16, z = k | i << 8
+  const uint32_t* dc;    // column descriptors: zoff | T << 16 | c << 24
+  int o_zs;              // smem offset (doubles) of zs[ni + nb]: z of the free rows, then zb of the supports
   int simple_asm;
   const double* Bt;      // k x m (transposed B)
   const int* asm_ptr;    // generic assembly gather lists in V position order (nlo + ni entries)
