@@ -20,7 +20,7 @@ STATUS_OK, STATUS_NOT_PD, STATUS_NONFINITE = 0, 1, 2
 EXPORTS = [
     "tno_abi_version", "tno_last_error", "tno_plan_create", "tno_plan_destroy", "tno_plan_query",
     "tno_plan_symbolic", "tno_eval_batch", "tno_eval_batch_host", "tno_plan_launch_count",
-    "tno_plan_profile", "tno_plan_profile_read",
+    "tno_plan_profile", "tno_plan_profile_read", "tno_symbolic_analyse",
 ]
 
 _dp = C.POINTER(C.c_double)
@@ -96,6 +96,9 @@ def load():
     lib.tno_plan_profile.restype = C.c_int
     lib.tno_plan_profile_read.argtypes = [C.c_void_p, C.c_int32, C.c_char_p, _dp, C.POINTER(C.c_int64)]
     lib.tno_plan_profile_read.restype = C.c_int
+    lib.tno_symbolic_analyse.argtypes = [C.c_int32, C.c_int32, _ip, C.c_int32, C.c_int32, _ip, _ip, _ip, C.c_int32, _ip, _ip,
+                                         C.c_int32, _ip]
+    lib.tno_symbolic_analyse.restype = C.c_int
     if lib.tno_abi_version() != ABI_VERSION:
         raise RuntimeError("libtno_b200.so ABI %d != binding ABI %d" % (lib.tno_abi_version(), ABI_VERSION))
     _lib = lib
@@ -112,3 +115,23 @@ def check(rc):
         if rc == -1:
             raise NotImplementedError("tno_b200: " + msg)  # mirrors the reference's NotImplementedError
         raise TnoError("tno_b200 error %d: %s" % (rc, msg))
+
+
+def symbolic_analyse(n_free, edges, ordering=0, chain_width=4):
+    """Host-only symbolic analysis (no GPU needed): dict(perm, colptr, rowidx, parent, chain_ptr, info)."""
+    import numpy as np
+    lib = load()
+    e = np.ascontiguousarray(np.asarray(edges, dtype=np.int32).reshape(-1, 2))
+    info = np.zeros(8, np.int32)
+    p = lambda a: a.ctypes.data_as(_ip)  # noqa: E731
+    check(lib.tno_symbolic_analyse(n_free, len(e), p(e), ordering, chain_width, None, None, None, 0, None, None, 0, p(info)))
+    perm = np.zeros(n_free, np.int32)
+    colptr = np.zeros(n_free + 1, np.int32)
+    rowidx = np.zeros(int(info[0]), np.int32)
+    parent = np.zeros(n_free, np.int32)
+    chain_ptr = np.zeros(int(info[5]) + 1, np.int32)
+    check(lib.tno_symbolic_analyse(n_free, len(e), p(e), ordering, chain_width, p(perm), p(colptr), p(rowidx), len(rowidx),
+                                   p(parent), p(chain_ptr), len(chain_ptr), p(info)))
+    keys = ("nnz_l", "etree_height", "max_colcount", "wide_levels", "wide_rows", "chains", "chain_levels", "factor_flops")
+    return dict(perm=perm, colptr=colptr, rowidx=rowidx, parent=parent, chain_ptr=chain_ptr,
+                info=dict(zip(keys, (int(v) for v in info))))

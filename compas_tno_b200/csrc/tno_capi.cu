@@ -189,7 +189,7 @@ int tno_plan_create(const tno_problem_desc* D, tno_plan** out_plan) {
   Symbolic& S = P->sym;
   try {
     const char* cw = getenv("TNO_CHAIN_WIDTH");  // developer knob: 0 disables the chain partition
-    analyse(ni, aedges, D->ordering, coords.data(), true, true, &S, cw ? atoi(cw) : 8);
+    analyse(ni, aedges, D->ordering, coords.data(), true, true, &S, cw ? atoi(cw) : 4);
   } catch (const std::exception& ex) {
     return fail(TNO_EINVAL, std::string("symbolic analysis failed: ") + ex.what());
   }
@@ -475,6 +475,46 @@ int tno_plan_symbolic(const tno_plan* plan, int32_t* perm, int32_t* colptr, int3
   if (rowidx) std::copy(S.rowidx.begin(), S.rowidx.end(), rowidx);
   if (parent) std::copy(S.parent.begin(), S.parent.end(), parent);
   if (level) std::copy(S.level.begin(), S.level.end(), level);
+  return TNO_OK;
+}
+
+int tno_symbolic_analyse(int32_t n_free, int32_t n_edges, const int32_t* edges, int32_t ordering, int32_t chain_width,
+                         int32_t* perm, int32_t* colptr, int32_t* rowidx, int32_t rowidx_capacity, int32_t* parent,
+                         int32_t* chain_ptr, int32_t chain_capacity, int32_t* info) {
+  if (n_free <= 0 || n_edges < 0 || (n_edges > 0 && !edges) || !info) return fail(TNO_EINVAL, "bad argument");
+  std::vector<std::pair<int, int>> e;
+  for (int i = 0; i < n_edges; ++i) {
+    const int a = edges[2 * i], b = edges[2 * i + 1];
+    if (a < 0 || a >= n_free || b < 0 || b >= n_free) return fail(TNO_EINVAL, "edge endpoint out of range");
+    e.push_back({a, b});
+  }
+  Symbolic S;
+  try {
+    analyse(n_free, e, ordering, nullptr, true, true, &S, chain_width);
+  } catch (const std::exception& ex) {
+    return fail(TNO_EINVAL, std::string("symbolic analysis failed: ") + ex.what());
+  }
+  const int nnz = (int)S.rowidx.size();
+  const int nch = (int)S.chain_clevel.size();
+  info[0] = nnz;
+  info[1] = S.nlevels;
+  info[2] = S.max_colcount;
+  info[3] = S.wide_levels;
+  info[4] = S.wide_rows;
+  info[5] = nch;
+  info[6] = (int)S.clevel_ptr.size() - 1;
+  info[7] = (int)S.factor_flops;
+  if (perm) std::copy(S.perm.begin(), S.perm.end(), perm);
+  if (colptr) std::copy(S.colptr.begin(), S.colptr.end(), colptr);
+  if (parent) std::copy(S.parent.begin(), S.parent.end(), parent);
+  if (rowidx) {
+    if (rowidx_capacity < nnz) return fail(TNO_EINVAL, "rowidx capacity too small");
+    std::copy(S.rowidx.begin(), S.rowidx.end(), rowidx);
+  }
+  if (chain_ptr) {
+    if (chain_capacity < nch + 1) return fail(TNO_EINVAL, "chain capacity too small");
+    std::copy(S.chain_ptr.begin(), S.chain_ptr.end(), chain_ptr);
+  }
   return TNO_OK;
 }
 

@@ -170,6 +170,14 @@ int tno_plan_query(const tno_plan* plan, tno_plan_info* info);
 int tno_plan_symbolic(const tno_plan* plan, int32_t* perm, int32_t* colptr, int32_t* rowidx,
                       int32_t* parent, int32_t* level);
 
+/* Host-only entry to the symbolic analysis (no CUDA device needed; used by the CPU test-suite).  The matrix pattern is
+ * given as an edge list between n_free rows.  ordering as in tno_problem_desc; chain_width = widest level still
+ * handled as dense chains by the on-chip kernels (0 = none).  Outputs may be NULL; info[8] receives
+ * { nnz_l, etree height, max column count, wide levels, wide rows, chains, chain levels, factor flops }. */
+int tno_symbolic_analyse(int32_t n_free, int32_t n_edges, const int32_t* edges, int32_t ordering, int32_t chain_width,
+                         int32_t* perm, int32_t* colptr, int32_t* rowidx, int32_t rowidx_capacity, int32_t* parent,
+                         int32_t* chain_ptr, int32_t chain_capacity, int32_t* info);
+
 /* Evaluate N candidates.  x_dev: device pointer, candidate j at x_dev + j * ldx (ldx >= nvar).
  * `cuda_stream` is a cudaStream_t (NULL = default stream).  Asynchronous. */
 int tno_eval_batch(tno_plan* plan, const double* x_dev, int64_t n_candidates, int64_t ldx,
