@@ -220,21 +220,34 @@ __device__ __forceinline__ void oc_solve(const DevOnchip& O, int phase, const Oc
                                          const OcRange* __restrict__ clev, const OcChain* __restrict__ chains,
                                          const unsigned char* __restrict__ rowchain, const unsigned short* __restrict__ rowptr16,
                                          const unsigned short* __restrict__ rowcol16, const double* __restrict__ V,
-                                         double* __restrict__ R, int ni, int c0, int ncols, int tid) {
+                                         double* __restrict__ R, int ni, int c0, int ncols, int tid,
+                                         const unsigned short* ct_ptr, const unsigned short* ct_col, const uint32_t* ct_ent,
+                                         long long* tc = nullptr) {
   const int W = O.W;
   const int gshift = O.gshift[phase];
+  long long tq = tc ? clock64() : 0;
+  auto lap = [&](int slot) {
+    if (tc) {
+      const long long now = clock64();
+      tc[slot] += now - tq;
+      tq = now;
+    }
+  };
   // ---- forward ----
   for (int lev = 1; lev < O.nwide; ++lev) {
     const OcRange L = wide[lev];
     oc_pull_rows<THREADS>(L.row0, L.row1, L.pull_s[phase], gshift, tid, c0, ncols, W, rowptr16, rowcol16, V, R);
     __syncthreads();
   }
+  lap(0);
   for (int cl = 0; cl < O.nclev; ++cl) {
     const OcRange L = clev[cl];
     oc_pull_rows<THREADS>(L.row0, L.row1, L.pull_s[phase], gshift, tid, c0, ncols, W, rowptr16, rowcol16, V, R);
     __syncthreads();
+    lap(1);
     oc_chain_apply<THREADS, false>(L, chains, rowchain, O.wide_rows, gshift, tid, c0, ncols, W, V, R);
     __syncthreads();
+    lap(2);
   }
   // ---- diagonal: y_i / d_i ----
   {
@@ -251,11 +264,13 @@ __device__ __forceinline__ void oc_solve(const DevOnchip& O, int phase, const Oc
     }
   }
   __syncthreads();
+  lap(3);
   // ---- backward ----
   for (int cl = O.nclev - 1; cl >= 0; --cl) {
     const OcRange L = clev[cl];
     oc_chain_apply<THREADS, true>(L, chains, rowchain, O.wide_rows, gshift, tid, c0, ncols, W, V, R);
     __syncthreads();
+    lap(4);
     // the rows of one chain share their descendants, so their updates are gathered per outside column ("target")
     // instead of pushed per row: x_j -= sum_{i in chain} L_ij x_i.  Targets of one chain level are disjoint.
     {
@@ -263,17 +278,17 @@ __device__ __forceinline__ void oc_solve(const DevOnchip& O, int phase, const Oc
       const int col = c0 + 2 * r;
       if (2 * r < ncols) {
         for (int t = L.tgt0 + (tid >> gshift); t < L.tgt1; t += THREADS >> gshift) {
-          const int e1 = __ldg(O.ct_ptr + t + 1);
+          const int e1 = ct_ptr[t + 1];
           double ax = 0.0, ay = 0.0;
 #pragma unroll 4
-          for (int e = __ldg(O.ct_ptr + t); e < e1; ++e) {
-            const uint32_t w = __ldg(O.ct_ent + e);
+          for (int e = ct_ptr[t]; e < e1; ++e) {
+            const uint32_t w = ct_ent[e];
             const double l = V[w & 0xffffu];
             const double2 x = *reinterpret_cast<const double2*>(R + (int)(w >> 16) * W + col);
             ax = fma(l, x.x, ax);
             ay = fma(l, x.y, ay);
           }
-          double2* d = reinterpret_cast<double2*>(R + (int)__ldg(O.ct_col + t) * W + col);
+          double2* d = reinterpret_cast<double2*>(R + (int)ct_col[t] * W + col);
           double2 v = *d;
           v.x -= ax;
           v.y -= ay;
@@ -282,12 +297,14 @@ __device__ __forceinline__ void oc_solve(const DevOnchip& O, int phase, const Oc
       }
     }
     __syncthreads();
+    lap(5);
   }
   for (int lev = O.nwide - 1; lev >= 1; --lev) {
     const OcRange L = wide[lev];
     oc_push_rows<THREADS>(L.row0, L.row1, L.push_s[phase], gshift, tid, c0, ncols, W, rowptr16, rowcol16, V, R);
     __syncthreads();
   }
+  lap(6);
 }
 
 // Dense work of one chain level, whole CTA, all chains of the level at once:
@@ -298,7 +315,8 @@ __device__ __forceinline__ void oc_solve(const DevOnchip& O, int phase, const Oc
 //       (columns are independent, no barriers), then the blocks are copied back over L.
 template <int THREADS>
 __device__ __forceinline__ void oc_chain_dense(const DevOnchip& O, const OcDense& DN, double* __restrict__ V,
-                                               double* __restrict__ tmpz, int* s_flags, int tid) {
+                                               double* __restrict__ tmpz, int* s_flags, int tid, long long* t_b) {
+  const long long tb0 = t_b ? clock64() : 0;
   const int zbase = O.nlo + (O.nv - O.nlo - O.nz);  // first dense position (= nlo + ni)
   // ---- (B) ----
   // every thread keeps its (up to OC_DE) element descriptors in registers for the whole factorisation of the level
@@ -354,6 +372,7 @@ __device__ __forceinline__ void oc_chain_dense(const DevOnchip& O, const OcDense
     if (kk < ii) V[(int)(d.y & 0xffffu)] *= V[(int)(d.y >> 16) + kk];  // l_ik = u_ik / d_k
   }
   __syncthreads();
+  if (t_b) *t_b += clock64() - tb0;
   // ---- (C) ----
   for (uint32_t cidx = DN.dc0 + tid; cidx < DN.dc1; cidx += THREADS) {
     const uint32_t w = __ldg(O.dc + cidx);
@@ -398,6 +417,9 @@ __global__ void __launch_bounds__(THREADS, MINB) k_onchip(const __grid_constant_
   const OcOp* ops = reinterpret_cast<const OcOp*>(smraw + O.o_idx_bytes + O.idx_ops);
   const OcDense* dense = reinterpret_cast<const OcDense*>(smraw + O.o_idx_bytes + O.idx_dense);
   double* zs = sm + O.o_zs;        // z of the free rows (after phase 1) followed by zb of the supports
+  const unsigned short* ct_ptr = O.ct_in_smem ? reinterpret_cast<const unsigned short*>(smraw + O.o_idx_bytes + O.idx_ct_ptr) : O.ct_ptr;
+  const unsigned short* ct_col = O.ct_in_smem ? reinterpret_cast<const unsigned short*>(smraw + O.o_idx_bytes + O.idx_ct_col) : O.ct_col;
+  const uint32_t* ct_ent = O.ct_in_smem ? reinterpret_cast<const uint32_t*>(smraw + O.o_idx_bytes + O.idx_ct_ent) : O.ct_ent;
   __shared__ int s_flags;
 
   const int tid = threadIdx.x;
@@ -496,13 +518,13 @@ __global__ void __launch_bounds__(THREADS, MINB) k_onchip(const __grid_constant_
       issue(0);
       issue(1);
       const bool clk = A.phase_clocks && blockIdx.x == 0 && tid == 0 && cand == (int64_t)(A.N > 4 * gridDim.x ? 4 * gridDim.x : 0);
-      long long t_dense = 0, t_wait = 0, t_last = clk ? clock64() : 0;
+      long long t_dense = 0, t_wait = 0, t_ldl = 0, t_last = clk ? clock64() : 0;
       for (int op = 0; op < O.nops; ++op) {
         const OcOp OP = ops[op];
         if (OP.type == OC_OP_DENSE) {
           __syncthreads();
           const long long t0 = clk ? clock64() : 0;
-          oc_chain_dense<THREADS>(O, dense[OP.a], V, R + O.o_tmpz_doubles, &s_flags, tid);
+          oc_chain_dense<THREADS>(O, dense[OP.a], V, R + O.o_tmpz_doubles, &s_flags, tid, clk ? &t_ldl : nullptr);
           __syncthreads();
           if (clk) t_dense += clock64() - t0;
           continue;
@@ -558,7 +580,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_onchip(const __grid_constant_
       __syncthreads();
       if (clk) {
         A.phase_clocks[14] = t_dense;
-        A.phase_clocks[15] = t_wait;
+        A.phase_clocks[15] = t_ldl;
       }
     }
     if (A.phase_clocks && blockIdx.x == 0 && tid == 0 && cand == (int64_t)(A.N > 4 * gridDim.x ? 4 * gridDim.x : 0)) A.phase_clocks[4] = clock64();
@@ -603,7 +625,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_onchip(const __grid_constant_
 
     if (A.phase_clocks && blockIdx.x == 0 && tid == 0 && cand == (int64_t)(A.N > 4 * gridDim.x ? 4 * gridDim.x : 0)) A.phase_clocks[6] = clock64();
     // ---- 6. solve phase 1 ---------------------------------------------------------------------------
-    oc_solve<THREADS>(O, 0, wide, clev, chains, rowchain, rowptr16, rowcol16, V, R, ni, 0, O.ncols1, tid);
+    oc_solve<THREADS>(O, 0, wide, clev, chains, rowchain, rowptr16, rowcol16, V, R, ni, 0, O.ncols1, tid, ct_ptr, ct_col, ct_ent);
 
     if (A.phase_clocks && blockIdx.x == 0 && tid == 0 && cand == (int64_t)(A.N > 4 * gridDim.x ? 4 * gridDim.x : 0)) A.phase_clocks[7] = clock64();
     // ---- 7. everything that needs the transient columns (x, y, Az) or only z ------------------------
@@ -773,7 +795,14 @@ __global__ void __launch_bounds__(THREADS, MINB) k_onchip(const __grid_constant_
       __syncthreads();
       if (A.phase_clocks && blockIdx.x == 0 && tid == 0 && cand == (int64_t)(A.N > 4 * gridDim.x ? 4 * gridDim.x : 0)) A.phase_clocks[9] = clock64();
       // ---- 9. solve phase 2 ----
-      oc_solve<THREADS>(O, 1, wide, clev, chains, rowchain, rowptr16, rowcol16, V, R, ni, O.c_q, nc2, tid);
+      {
+        const bool clk2 = A.phase_clocks && blockIdx.x == 0 && tid == 0 && cand == (int64_t)(A.N > 4 * gridDim.x ? 4 * gridDim.x : 0);
+        long long tcs[7] = {0, 0, 0, 0, 0, 0, 0};
+        oc_solve<THREADS>(O, 1, wide, clev, chains, rowchain, rowptr16, rowcol16, V, R, ni, O.c_q, nc2, tid, ct_ptr, ct_col, ct_ent,
+                          clk2 ? tcs : nullptr);
+        if (clk2)
+          for (int q = 0; q < 7; ++q) A.phase_clocks[16 + q] = tcs[q];
+      }
     }
 
     if (A.phase_clocks && blockIdx.x == 0 && tid == 0 && cand == (int64_t)(A.N > 4 * gridDim.x ? 4 * gridDim.x : 0)) A.phase_clocks[10] = clock64();
@@ -1241,7 +1270,7 @@ int build_onchip(Plan* PL, const tno_problem_desc* D) {
       for (int r = S.chain_ptr[c]; r < S.chain_ptr[c + 1]; ++r) rowchain[r - wide_rows] = (unsigned char)(c - c0);
     }
   }
-  std::vector<int> ct_ptr(1, 0);
+  std::vector<unsigned short> ct_ptr(1, 0);
   std::vector<unsigned short> ct_col;
   std::vector<uint32_t> ct_ent;
   for (int cl = 0; cl < O.nclev; ++cl) {
@@ -1254,12 +1283,12 @@ int build_onchip(Plan* PL, const tno_problem_desc* D) {
       for (auto& kv : by_col) {
         ct_col.push_back((unsigned short)kv.first);
         ct_ent.insert(ct_ent.end(), kv.second.begin(), kv.second.end());
-        ct_ptr.push_back((int)ct_ent.size());
+        ct_ptr.push_back((unsigned short)ct_ent.size());
       }
     }
     clev_r[cl].tgt1 = (unsigned short)ct_col.size();
   }
-  if (ct_col.size() >= 65535) { set_error("on-chip family not applicable: ct_col.size() >= 65535"); return TNO_OK; }
+  if (ct_col.size() >= 65535 || ct_ent.size() >= 65535) { set_error("on-chip family not applicable: ct_col.size() >= 65535"); return TNO_OK; }
   if (ct_col.empty()) ct_col.push_back(0);
   if (ct_ent.empty()) ct_ent.push_back(0);
   if (clev_r.empty()) clev_r.push_back(make_range(0, 0, 0, 0));
@@ -1366,7 +1395,18 @@ int build_onchip(Plan* PL, const tno_problem_desc* D) {
   if (dense_r.empty()) dense_r.resize(1);
   put_bytes(dense_r.data(), dense_r.size() * sizeof(OcDense));
   align16();
+  const int idx_bytes_core = (int)idx.size();
+  O.idx_ct_ptr = (int)idx.size();
+  put_bytes(ct_ptr.data(), ct_ptr.size() * 2);
+  align16();
+  O.idx_ct_col = (int)idx.size();
+  put_bytes(ct_col.data(), ct_col.size() * 2);
+  align16();
+  O.idx_ct_ent = (int)idx.size();
+  put_bytes(ct_ent.data(), ct_ent.size() * 4);
+  align16();
   O.idx_bytes = (int)idx.size();
+  O.ct_in_smem = 1;
 
   // ---- shared memory layout ----
   int off = 0;  // doubles
@@ -1390,10 +1430,19 @@ int build_onchip(Plan* PL, const tno_problem_desc* D) {
   O.o_azsup = take(((P.constraints & TNO_CON_REAC_BOUNDS) && P.var.o_zb >= 0) ? O.nsup * nb : 0);
   O.o_red = take(40);
   O.o_idx_bytes = off * 8;
-  O.smem_bytes = O.o_idx_bytes + O.idx_bytes;
   int max_optin = 0, smem_sm = 0;
   TNO_CUDA_OK(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, PL->device));
   TNO_CUDA_OK(cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, PL->device));
+  {
+    // keep the column-wise chain index in shared memory only if that does not cost a resident CTA
+    const int with_ct = O.o_idx_bytes + O.idx_bytes, without_ct = O.o_idx_bytes + idx_bytes_core;
+    auto ctas = [&](int bytes) { return bytes > max_optin ? 0 : smem_sm / (bytes + 1024); };
+    if (ctas(with_ct) < ctas(without_ct) || with_ct > max_optin) {
+      O.ct_in_smem = 0;
+      O.idx_bytes = idx_bytes_core;
+    }
+  }
+  O.smem_bytes = O.o_idx_bytes + O.idx_bytes;
   if (O.smem_bytes > max_optin) { set_error("on-chip family not applicable: O.smem_bytes > max_optin"); return TNO_OK; }
   PL->onchip_threads = THREADS;
   PL->onchip_ctas_per_sm = std::max(1, std::min(8, smem_sm / (O.smem_bytes + 1024)));
@@ -1474,11 +1523,13 @@ int run_onchip(Plan* PL, const double* x_dev, int64_t N, int64_t ldx, const tno_
   A.phase_clocks = nullptr;
   static const bool want_clocks = getenv("TNO_PHASE_CLOCKS") != nullptr;
   if (want_clocks) {
-    TNO_CUDA_OK(cudaMalloc((void**)&A.phase_clocks, 16 * sizeof(long long)));
-    TNO_CUDA_OK(cudaMemsetAsync(A.phase_clocks, 0, 16 * sizeof(long long), stream));
+    TNO_CUDA_OK(cudaMalloc((void**)&A.phase_clocks, 24 * sizeof(long long)));
+    TNO_CUDA_OK(cudaMemsetAsync(A.phase_clocks, 0, 24 * sizeof(long long), stream));
   }
   const size_t smem = (size_t)PL->oc.smem_bytes;
-  const int grid = (int)std::min<int64_t>(N, (int64_t)PL->sm_count * PL->onchip_ctas_per_sm);
+  static const char* force_ctas = getenv("TNO_CTAS_PER_SM");  // developer knob
+  const int ctas = force_ctas ? std::max(1, atoi(force_ctas)) : PL->onchip_ctas_per_sm;
+  const int grid = (int)std::min<int64_t>(N, (int64_t)PL->sm_count * ctas);
   auto kern = PL->onchip_ctas_per_sm >= 2 ? k_onchip<256, 2> : k_onchip<256, 1>;
   TNO_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   if (out->J && PL->dp.con.r_fun >= 0) {
@@ -1498,7 +1549,7 @@ int run_onchip(Plan* PL, const double* x_dev, int64_t N, int64_t ldx, const tno_
   PL->launches += 1;
   TNO_CUDA_OK(cudaGetLastError());
   if (want_clocks) {
-    long long h[16];
+    long long h[24];
     TNO_CUDA_OK(cudaStreamSynchronize(stream));
     TNO_CUDA_OK(cudaMemcpy(h, A.phase_clocks, sizeof(h), cudaMemcpyDeviceToHost));
     cudaFree(A.phase_clocks);
@@ -1506,7 +1557,9 @@ int run_onchip(Plan* PL, const double* x_dev, int64_t N, int64_t ldx, const tno_
                                     "reac/obj", "emitJ", "final"};
     fprintf(stderr, "[tno phase clocks] N=%lld grid=%d total=%lld :", (long long)N, grid, h[13] - h[0]);
     for (int i = 0; i < 13; ++i) fprintf(stderr, " %s=%lld", names[i], h[i + 1] - h[i]);
-    fprintf(stderr, " | factor: dense=%lld chunk-wait=%lld", h[14], h[15]);
+    fprintf(stderr, " | factor: dense=%lld (LDL^T part %lld)", h[14], h[15]);
+    fprintf(stderr, " | solve2: pull-wide=%lld pull-chain=%lld Z=%lld diag=%lld Zt=%lld gather=%lld push-wide=%lld", h[16], h[17], h[18],
+            h[19], h[20], h[21], h[22]);
     fprintf(stderr, "\n");
   }
   return TNO_OK;

@@ -190,9 +190,11 @@ struct DevOnchip {
   const uint32_t* radj_pad;  // ni x adj_deg, padded with self references (zero contribution)
   // column-wise view of the chain rows' outside entries (backward solve): for every outside column ("target")
   // reached by the chains of one chain level, the entries (value position | row << 16) of the chain rows in it
-  const int* ct_ptr;
+  const unsigned short* ct_ptr;
   const unsigned short* ct_col;
   const uint32_t* ct_ent;
+  int ct_in_smem;        // 1: the three arrays live in the shared-memory index region at idx_ct_*
+  int idx_ct_ptr, idx_ct_col, idx_ct_ent;
   const double* Jfun;    // 2m x nvar
 };
 
