@@ -221,8 +221,8 @@ __device__ __forceinline__ void oc_solve(const DevOnchip& O, int phase, const Oc
                                          const unsigned char* __restrict__ rowchain, const unsigned short* __restrict__ rowptr16,
                                          const unsigned short* __restrict__ rowcol16, const double* __restrict__ V,
                                          double* __restrict__ R, int ni, int c0, int ncols, int tid,
-                                         const unsigned short* ct_ptr, const unsigned short* ct_col, const uint32_t* ct_ent,
-                                         long long* tc = nullptr) {
+                                         const unsigned short* ct_ptr, const unsigned short* ct_col, const unsigned short* ct_ent,
+                                         const unsigned char* ct_row, long long* tc = nullptr) {
   const int W = O.W;
   const int gshift = O.gshift[phase];
   long long tq = tc ? clock64() : 0;
@@ -282,9 +282,8 @@ __device__ __forceinline__ void oc_solve(const DevOnchip& O, int phase, const Oc
           double ax = 0.0, ay = 0.0;
 #pragma unroll 4
           for (int e = ct_ptr[t]; e < e1; ++e) {
-            const uint32_t w = ct_ent[e];
-            const double l = V[w & 0xffffu];
-            const double2 x = *reinterpret_cast<const double2*>(R + (int)(w >> 16) * W + col);
+            const double l = V[ct_ent[e]];
+            const double2 x = *reinterpret_cast<const double2*>(R + (L.row0 + (int)ct_row[e]) * W + col);
             ax = fma(l, x.x, ax);
             ay = fma(l, x.y, ay);
           }
@@ -416,10 +415,20 @@ __global__ void __launch_bounds__(THREADS, MINB) k_onchip(const __grid_constant_
   const OcChunk* chunks = reinterpret_cast<const OcChunk*>(smraw + O.o_idx_bytes + O.idx_chunks);
   const OcOp* ops = reinterpret_cast<const OcOp*>(smraw + O.o_idx_bytes + O.idx_ops);
   const OcDense* dense = reinterpret_cast<const OcDense*>(smraw + O.o_idx_bytes + O.idx_dense);
+  const short* vrow_s = reinterpret_cast<const short*>(smraw + O.o_idx_bytes + O.idx_vrow);
+  const short* rowv_s = reinterpret_cast<const short*>(smraw + O.o_idx_bytes + O.idx_rowv);
+  const int* ecptr_s = reinterpret_cast<const int*>(smraw + O.o_idx_bytes + O.idx_ecptr);
+  const int* colsrc_s = reinterpret_cast<const int*>(smraw + O.o_idx_bytes + O.idx_colsrc);
+  const int* supptr_s = reinterpret_cast<const int*>(smraw + O.o_idx_bytes + O.idx_supptr);
+  const int* supother_s = reinterpret_cast<const int*>(smraw + O.o_idx_bytes + O.idx_supother);
+  const int* supedge_s = reinterpret_cast<const int*>(smraw + O.o_idx_bytes + O.idx_supedge);
+  const float* supsign_s = reinterpret_cast<const float*>(smraw + O.o_idx_bytes + O.idx_supsign);
+  const int* fixed_s = reinterpret_cast<const int*>(smraw + O.o_idx_bytes + O.idx_fixed);
   double* zs = sm + O.o_zs;        // z of the free rows (after phase 1) followed by zb of the supports
   const unsigned short* ct_ptr = O.ct_in_smem ? reinterpret_cast<const unsigned short*>(smraw + O.o_idx_bytes + O.idx_ct_ptr) : O.ct_ptr;
   const unsigned short* ct_col = O.ct_in_smem ? reinterpret_cast<const unsigned short*>(smraw + O.o_idx_bytes + O.idx_ct_col) : O.ct_col;
-  const uint32_t* ct_ent = O.ct_in_smem ? reinterpret_cast<const uint32_t*>(smraw + O.o_idx_bytes + O.idx_ct_ent) : O.ct_ent;
+  const unsigned short* ct_ent = O.ct_in_smem ? reinterpret_cast<const unsigned short*>(smraw + O.o_idx_bytes + O.idx_ct_ent) : O.ct_ent;
+  const unsigned char* ct_row = O.ct_in_smem ? smraw + O.o_idx_bytes + O.idx_ct_row : O.ct_row;
   __shared__ int s_flags;
 
   const int tid = threadIdx.x;
@@ -451,10 +460,24 @@ __global__ void __launch_bounds__(THREADS, MINB) k_onchip(const __grid_constant_
 
     if (A.phase_clocks && blockIdx.x == 0 && tid == 0 && cand == (int64_t)(A.N > 4 * gridDim.x ? 4 * gridDim.x : 0)) A.phase_clocks[1] = clock64();
     // ---- 1. q = B q_ind + lambdh d ; funicular rows of g -------------------------------------------
-    for (int e = tid; e < m; e += THREADS) {
-      double acc = lamh * P.d[e];
-#pragma unroll 8
-      for (int j = 0; j < k; ++j) acc = fma(__ldg(O.Bt + (int64_t)j * m + e), xs[j], acc);
+    for (int e0 = tid; e0 < m; e0 += 4 * THREADS) {
+      // four edges per thread at once: 4 x unroll independent loads of B in flight
+      double acc4[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc4[i] = (e0 + i * THREADS < m) ? lamh * P.d[e0 + i * THREADS] : 0.0;
+#pragma unroll 4
+      for (int j = 0; j < k; ++j) {
+        const double xj = xs[j];
+        const double* bj = O.Bt + (int64_t)j * m + e0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          if (e0 + i * THREADS < m) acc4[i] = fma(__ldg(bj + i * THREADS), xj, acc4[i]);
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+      const int e = e0 + i * THREADS;
+      if (e >= m) continue;
+      const double acc = acc4[i];
       qs[e] = acc;
       if (A.q) A.q[cand * m + e] = acc;
       if (P.con.r_fun >= 0) {
@@ -466,6 +489,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_onchip(const __grid_constant_
         gmin = fmin(gmin, fmin(g0, g1));
       }
       bad |= !isfinite(acc);
+      }
     }
     __syncthreads();
 
@@ -496,7 +520,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_onchip(const __grid_constant_
       }
     }
     if (tid == 0) V[O.pos_m1] = -1.0;
-    for (int t = tid; t < O.nsup; t += THREADS) qsup[t] = qs[O.sup_edge[t]];
+    for (int t = tid; t < O.nsup; t += THREADS) qsup[t] = qs[supedge_s[t]];
     __syncthreads();  // q consumed: the panel region is free for the factor stream
 
     if (A.phase_clocks && blockIdx.x == 0 && tid == 0 && cand == (int64_t)(A.N > 4 * gridDim.x ? 4 * gridDim.x : 0)) A.phase_clocks[3] = clock64();
@@ -590,7 +614,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_onchip(const __grid_constant_
     if (A.phase_clocks && blockIdx.x == 0 && tid == 0 && cand == (int64_t)(A.N > 4 * gridDim.x ? 4 * gridDim.x : 0)) A.phase_clocks[5] = clock64();
     // ---- 5. phase-1 right-hand sides: z | z_lambdv | Az | x | y -------------------------------------
     for (int r = tid; r < ni; r += THREADS) {
-      const int v = P.row_vertex[r];
+      const int v = rowv_s[r];
       double px, py, pz;
       if (P.var.o_lambdh >= 0) {
         px = lamh * P.px0[v];
@@ -606,7 +630,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_onchip(const __grid_constant_
       for (int cc = 0; cc < ((O.ncols1 + 1) & ~1); ++cc) row[cc] = 0.0;  // incl. padding columns touched by 2-column lanes
       for (int t = P.vadj_ptr[v]; t < P.vadj_ptr[v + 1]; ++t) {
         const int o = P.vadj_other[t];
-        const int ro = P.vrow[o];
+        const int ro = vrow_s[o];
         if (ro >= 0) continue;
         const int b = -1 - ro;
         const double qe = qsup[O.edge_sup[P.vadj_edge[t]]];
@@ -625,11 +649,11 @@ __global__ void __launch_bounds__(THREADS, MINB) k_onchip(const __grid_constant_
 
     if (A.phase_clocks && blockIdx.x == 0 && tid == 0 && cand == (int64_t)(A.N > 4 * gridDim.x ? 4 * gridDim.x : 0)) A.phase_clocks[6] = clock64();
     // ---- 6. solve phase 1 ---------------------------------------------------------------------------
-    oc_solve<THREADS>(O, 0, wide, clev, chains, rowchain, rowptr16, rowcol16, V, R, ni, 0, O.ncols1, tid, ct_ptr, ct_col, ct_ent);
+    oc_solve<THREADS>(O, 0, wide, clev, chains, rowchain, rowptr16, rowcol16, V, R, ni, 0, O.ncols1, tid, ct_ptr, ct_col, ct_ent, ct_row);
 
     if (A.phase_clocks && blockIdx.x == 0 && tid == 0 && cand == (int64_t)(A.N > 4 * gridDim.x ? 4 * gridDim.x : 0)) A.phase_clocks[7] = clock64();
     // ---- 7. everything that needs the transient columns (x, y, Az) or only z ------------------------
-    auto zfix = [&](int b) -> double { return P.var.o_zb >= 0 ? xs[P.var.o_zb + b] : P.X[3 * P.fixed[b] + 2]; };
+    auto zfix = [&](int b) -> double { return P.var.o_zb >= 0 ? xs[P.var.o_zb + b] : P.X[3 * fixed_s[b] + 2]; };
     // persistent phase-1 results leave the panel: phase 2 reuses all of its columns
     for (int r = tid; r < ni; r += THREADS) {
       zs[r] = R[r * W + O.c_z];
@@ -638,11 +662,11 @@ __global__ void __launch_bounds__(THREADS, MINB) k_onchip(const __grid_constant_
     if (tid < nb) zs[ni + tid] = zfix(tid);
     __syncthreads();
     auto zval = [&](int v) -> double {  // branch-free: free rows first, supports behind them
-      const int r = P.vrow[v];
+      const int r = vrow_s[v];
       return zs[r >= 0 ? r : ni - 1 - r];
     };
     auto xyval = [&](int v, int axis) -> double {
-      const int r = P.vrow[v];
+      const int r = vrow_s[v];
       return r >= 0 ? R[r * W + O.c_x + axis] : P.X[3 * v + axis];
     };
     for (int v = tid; v < n; v += THREADS) {
@@ -674,7 +698,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_onchip(const __grid_constant_
       // dz/dzb block straight to the Jacobian (its panel columns are about to be reused)
       for (int idx = tid; idx < n * nb; idx += THREADS) {
         const int v = idx / nb, b = idx - v * nb;
-        const int r = P.vrow[v];
+        const int r = vrow_s[v];
         const double a = r >= 0 ? R[r * W + O.c_az + b] : ((-1 - r) == b ? 1.0 : 0.0);
         Jout[(int64_t)(P.con.r_env + v) * nvar + P.var.o_zb + b] = a;
         Jout[(int64_t)(P.con.r_env + n + v) * nvar + P.var.o_zb + b] = -a;
@@ -683,12 +707,12 @@ __global__ void __launch_bounds__(THREADS, MINB) k_onchip(const __grid_constant_
     if (want_thrust || want_reac) {
       // R_b = Cb^T Q C X - P_b
       for (int b = tid; b < nb; b += THREADS) {
-        const int vb = P.fixed[b];
+        const int vb = fixed_s[b];
         const double xb = P.X[3 * vb + 0], yb = P.X[3 * vb + 1], zb = zfix(b);
         double Rx = 0.0, Ry = 0.0, Rz = 0.0, ud0 = 0.0, vd0 = 0.0;
-        for (int t = O.sup_ptr[b]; t < O.sup_ptr[b + 1]; ++t) {
-          const int o = O.sup_other[t];
-          const double sg = (double)O.sup_sign[t];
+        for (int t = supptr_s[b]; t < supptr_s[b + 1]; ++t) {
+          const int o = supother_s[t];
+          const double sg = (double)supsign_s[t];
           const double qe = qsup[t];
           const double xo = xyval(o, 0), yo = xyval(o, 1), zo = zval(o);
           const double u = sg > 0 ? (xb - xo) : (xo - xb);
@@ -698,7 +722,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_onchip(const __grid_constant_
           Ry = fma(sg * qe, vv, Ry);
           Rz = fma(sg * qe, w, Rz);
           if (P.var.o_lambdh >= 0) {
-            const double d0 = P.d[O.sup_edge[t]];
+            const double d0 = P.d[supedge_s[t]];
             ud0 = fma(sg * u, d0, ud0);
             vd0 = fma(sg * vv, d0, vd0);
           }
@@ -724,16 +748,16 @@ __global__ void __launch_bounds__(THREADS, MINB) k_onchip(const __grid_constant_
       // (Cb^T U B)[b, j], (Cb^T V B)[b, j]
       for (int it = tid; it < nb * k; it += THREADS) {
         const int b = it / k, j = it - b * k;
-        const int vb = P.fixed[b];
+        const int vb = fixed_s[b];
         const double xb = P.X[3 * vb + 0], yb = P.X[3 * vb + 1];
         double gx = 0.0, gy = 0.0;
-        for (int t = O.sup_ptr[b]; t < O.sup_ptr[b + 1]; ++t) {
-          const int o = O.sup_other[t];
-          const double sg = (double)O.sup_sign[t];
+        for (int t = supptr_s[b]; t < supptr_s[b + 1]; ++t) {
+          const int o = supother_s[t];
+          const double sg = (double)supsign_s[t];
           const double xo = xyval(o, 0), yo = xyval(o, 1);
           const double u = sg > 0 ? (xb - xo) : (xo - xb);
           const double vv = sg > 0 ? (yb - yo) : (yo - yb);
-          const double Bej = P.B[(int64_t)O.sup_edge[t] * k + j];
+          const double Bej = P.B[(int64_t)supedge_s[t] * k + j];
           gx = fma(sg * u, Bej, gx);
           gy = fma(sg * vv, Bej, gy);
         }
@@ -743,7 +767,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_onchip(const __grid_constant_
       if (want_reac && O.c_az >= 0) {
         for (int it = tid; it < O.nsup * nb; it += THREADS) {
           const int t = it / nb, b = it - t * nb;
-          const int ro = P.vrow[O.sup_other[t]];
+          const int ro = vrow_s[supother_s[t]];
           azsup[it] = ro >= 0 ? R[ro * W + O.c_az + b] : ((-1 - ro) == b ? 1.0 : 0.0);
         }
       }
@@ -756,49 +780,60 @@ __global__ void __launch_bounds__(THREADS, MINB) k_onchip(const __grid_constant_
       const int nc2 = O.ncols2;
       const int g2 = O.rhs2_shift;  // 2^g2 lanes walk the columns of one row
       const int r_ = tid & ((1 << g2) - 1);
-      for (int r = tid >> g2; r < ni; r += THREADS >> g2)
-      for (int cidx = r_; cidx < nc2; cidx += 1 << g2) {
-        const double zv = zs[r];
-        // coefficient column: B[:, cidx] for the q_ind columns, d0 for the lambdh column (branch-free addressing)
-        const double* cbase = cidx < k ? P.B + cidx : P.d;
-        const int cstride = cidx < k ? k : 1;
-        double acc = 0.0;
-        if (O.adj_deg > 0) {
-          // padded adjacency: all record loads first, then all coefficient loads, then the arithmetic
-          const uint32_t* rp = O.radj_pad + r * O.adj_deg;
-          uint32_t rec[8];
-          double cf[8];
+      // Edge-wise accumulation: B is read exactly once per candidate (coalesced rows in colour order) and every edge
+      // updates the panel rows of its two end points.  Edges of one colour share no free vertex, so the updates of a
+      // colour never collide; one barrier per colour.
+      for (int it = tid; it < ni * (W >> 1); it += THREADS) reinterpret_cast<double2*>(R)[it] = make_double2(0.0, 0.0);
+      __syncthreads();
+      // every colour holds at most 8 edges per thread slot (the plan splits larger colours): the records and
+      // coefficients of the NEXT colour are loaded into registers while the current colour is accumulated, so the
+      // L2 round trip is off the critical path
+      {
+        const int ept = THREADS >> g2;  // edges per pass
+        for (int cb = 0; cb < nc2; cb += 1 << g2) {   // uniform trip count: every thread reaches every barrier
+          const int cidx = cb + r_;
+          const bool cok = cidx < nc2;
+          uint32_t rec[8], recn[8];
+          double cf[8], cfn[8];
+          auto fetch = [&](int color, uint32_t (&rc)[8], double (&cc)[8]) {
+            const int p0 = ecptr_s[color], p1 = ecptr_s[color + 1];
 #pragma unroll
-          for (int t = 0; t < 8; ++t) rec[t] = t < O.adj_deg ? __ldg(rp + t) : (uint32_t)r;
+            for (int u = 0; u < 8; ++u) {
+              const int e = p0 + (tid >> g2) + u * ept;
+              const bool ok = cok && e < p1;
+              rc[u] = ok ? __ldg(O.ec_rec + e) : 0xffffffffu;
+              cc[u] = ok ? __ldg(O.Bc + (int64_t)e * O.bc_stride + cidx) : 0.0;
+            }
+          };
+          fetch(0, rec, cf);
+          for (int color = 0; color < O.ncolors; ++color) {
+            if (color + 1 < O.ncolors) fetch(color + 1, recn, cfn);
 #pragma unroll
-          for (int t = 0; t < 8; ++t) cf[t] = t < O.adj_deg ? __ldg(cbase + (int64_t)(rec[t] >> 16) * cstride) : 0.0;
+            for (int u = 0; u < 8; ++u) {
+              if (rec[u] != 0xffffffffu) {
+                const int hv = (int)(rec[u] & 0xffffu), tv = (int)(rec[u] >> 16);
+                const double zh = zs[(hv & 0x8000) ? ni + (hv & 0x7fff) : hv];
+                const double zt = zs[(tv & 0x8000) ? ni + (tv & 0x7fff) : tv];
+                const double wc = (zh - zt) * cf[u];  // (C z)_e B[e, j]
+                if (!(hv & 0x8000)) R[hv * W + O.c_q + cidx] += wc;   // C[e, head] = +1
+                if (!(tv & 0x8000)) R[tv * W + O.c_q + cidx] -= wc;   // C[e, tail] = -1
+              }
+            }
+            __syncthreads();
 #pragma unroll
-          for (int t = 0; t < 8; ++t) {
-            const int o = (int)(rec[t] & 0x7fffu);
-            const double zo = zs[(rec[t] & 0x8000u) ? ni + o : o];
-            acc = fma(zv - zo, cf[t], acc);  // C[e, v] * (C z)_e = z_v - z_other exactly
-          }
-        } else {
-          const int t1 = O.radj_ptr[r + 1];
-#pragma unroll 4
-          for (int t = O.radj_ptr[r]; t < t1; ++t) {
-            const uint32_t rec = __ldg(O.radj + t);
-            const int o = (int)(rec & 0x7fffu);
-            const double zo = zs[(rec & 0x8000u) ? ni + o : o];
-            acc = fma(zv - zo, __ldg(cbase + (int64_t)(rec >> 16) * cstride), acc);
+            for (int u = 0; u < 8; ++u) {
+              rec[u] = recn[u];
+              cf[u] = cfn[u];
+            }
           }
         }
-        R[r * W + O.c_q + cidx] = acc;
       }
-      if (nc2 & 1)  // the spare column next to an odd column count takes part in the two-column accesses: keep it finite
-        for (int r = tid; r < ni; r += THREADS) R[r * W + O.c_q + nc2] = 0.0;
-      __syncthreads();
       if (A.phase_clocks && blockIdx.x == 0 && tid == 0 && cand == (int64_t)(A.N > 4 * gridDim.x ? 4 * gridDim.x : 0)) A.phase_clocks[9] = clock64();
       // ---- 9. solve phase 2 ----
       {
         const bool clk2 = A.phase_clocks && blockIdx.x == 0 && tid == 0 && cand == (int64_t)(A.N > 4 * gridDim.x ? 4 * gridDim.x : 0);
         long long tcs[7] = {0, 0, 0, 0, 0, 0, 0};
-        oc_solve<THREADS>(O, 1, wide, clev, chains, rowchain, rowptr16, rowcol16, V, R, ni, O.c_q, nc2, tid, ct_ptr, ct_col, ct_ent,
+        oc_solve<THREADS>(O, 1, wide, clev, chains, rowchain, rowptr16, rowcol16, V, R, ni, O.c_q, nc2, tid, ct_ptr, ct_col, ct_ent, ct_row,
                           clk2 ? tcs : nullptr);
         if (clk2)
           for (int q = 0; q < 7; ++q) A.phase_clocks[16 + q] = tcs[q];
@@ -811,27 +846,27 @@ __global__ void __launch_bounds__(THREADS, MINB) k_onchip(const __grid_constant_
       const bool has_env = (P.constraints & TNO_CON_ENVELOPE) != 0;
       for (int it = tid; it < nb * nvar; it += THREADS) {  // one item per (support b, Jacobian column)
         const int b = it / nvar, col = it - b * nvar;
-        const int vb = P.fixed[b];
+        const int vb = fixed_s[b];
         const double Rx = react[3 * b], Ry = react[3 * b + 1], Rz = react[3 * b + 2];
         const double sx = Rx < 0 ? -1.0 : 1.0, sy = Ry < 0 ? -1.0 : 1.0, sz = Rz < 0 ? -1.0 : 1.0;
         const double rz2 = Rz * Rz;
         const double zb = zfix(b);
         double vx = 0.0, vy = 0.0;
-        const int t0 = O.sup_ptr[b], t1 = O.sup_ptr[b + 1];
+        const int t0 = supptr_s[b], t1 = supptr_s[b + 1];
         if (col < k || col == P.var.o_lambdh) {
           const bool isq = col < k;
           const int pcol = isq ? (O.c_q + col) : O.c_lambdh;
           double dRx = isq ? gxy[b * k + col] : 0.0, dRy = isq ? gxy[nb * k + b * k + col] : 0.0, dRz = 0.0;
           for (int t = t0; t < t1; ++t) {
-            const int o = O.sup_other[t];
-            const int e = O.sup_edge[t];
-            const double sg = (double)O.sup_sign[t];
+            const int o = supother_s[t];
+            const int e = supedge_s[t];
+            const double sg = (double)supsign_s[t];
             const double qe = qsup[t];
             const double zo = zval(o);
             const double w = sg > 0 ? (zb - zo) : (zo - zb);
             const double coef = isq ? P.B[(int64_t)e * k + col] : P.d[e];
             dRz = fma(sg * w, coef, dRz);
-            const int ro = P.vrow[o];
+            const int ro = vrow_s[o];
             if ((has_env || !isq) && ro >= 0) {
               const double dzo = R[ro * W + pcol];
               dRz = fma(sg * qe, sg > 0 ? -dzo : dzo, dRz);
@@ -847,8 +882,8 @@ __global__ void __launch_bounds__(THREADS, MINB) k_onchip(const __grid_constant_
           // dRz/dzb = Cb^T Q C A ; the reference adds COLUMN b of it to row b (jacobian.py:222)
           const int cb = col - P.var.o_zb;
           double acc = 0.0;
-          for (int t = O.sup_ptr[cb]; t < O.sup_ptr[cb + 1]; ++t) {
-            const double sg = (double)O.sup_sign[t];
+          for (int t = supptr_s[cb]; t < supptr_s[cb + 1]; ++t) {
+            const double sg = (double)supsign_s[t];
             const double Ao = azsup[t * nb + b];
             const double Ac = (cb == b) ? 1.0 : 0.0;
             acc = fma(sg * qsup[t], sg > 0 ? (Ac - Ao) : (Ao - Ac), acc);
@@ -862,8 +897,8 @@ __global__ void __launch_bounds__(THREADS, MINB) k_onchip(const __grid_constant_
         } else if (col == P.var.o_lambdv) {
           double dRz = 0.0;
           for (int t = t0; t < t1; ++t) {
-            const double sg = (double)O.sup_sign[t];
-            const int ro = P.vrow[O.sup_other[t]];
+            const double sg = (double)supsign_s[t];
+            const int ro = vrow_s[supother_s[t]];
             if (ro >= 0) {
               const double dzo = pers[ro];
               dRz = fma(sg * qsup[t], sg > 0 ? -dzo : dzo, dRz);
@@ -926,9 +961,9 @@ __global__ void __launch_bounds__(THREADS, MINB) k_onchip(const __grid_constant_
         for (int e = tid; e < n * nvar; e += THREADS) {
           const int v = __umulhi((unsigned)e, O.nvar_magic);
           const int col = e - v * nvar;
-          const int src = O.colsrc[col];
+          const int src = colsrc_s[col];
           if (src == -1) continue;  // zb and thickness columns were written in step 7
-          const int r = P.vrow[v];
+          const int r = vrow_s[v];
           double a = 0.0;
           if (r >= 0) a = src >= 0 ? R[r * W + src] : (src == -3 ? pers[r] : 0.0);
           o1[e] = a;
@@ -1272,7 +1307,9 @@ int build_onchip(Plan* PL, const tno_problem_desc* D) {
   }
   std::vector<unsigned short> ct_ptr(1, 0);
   std::vector<unsigned short> ct_col;
-  std::vector<uint32_t> ct_ent;
+  std::vector<unsigned short> ct_ent;
+  std::vector<unsigned char> ct_row;
+  bool ct_rows_fit = true;
   for (int cl = 0; cl < O.nclev; ++cl) {
     const int c0 = S.clevel_ptr[cl], c1 = S.clevel_ptr[cl + 1];
     clev_r[cl].tgt0 = (unsigned short)ct_col.size();
@@ -1282,15 +1319,22 @@ int build_onchip(Plan* PL, const tno_problem_desc* D) {
         for (int t = rowptr_o[i]; t < rowptr_o[i + 1]; ++t) by_col[rowcol_o[t]].push_back((uint32_t)t | ((uint32_t)i << 16));
       for (auto& kv : by_col) {
         ct_col.push_back((unsigned short)kv.first);
-        ct_ent.insert(ct_ent.end(), kv.second.begin(), kv.second.end());
+        for (uint32_t w : kv.second) {
+          const int rel = (int)(w >> 16) - S.chain_ptr[c0];
+          if (rel > 255) ct_rows_fit = false;
+          ct_ent.push_back((unsigned short)(w & 0xffffu));
+          ct_row.push_back((unsigned char)(rel & 0xff));
+        }
         ct_ptr.push_back((unsigned short)ct_ent.size());
       }
     }
     clev_r[cl].tgt1 = (unsigned short)ct_col.size();
   }
+  if (!ct_rows_fit) { set_error("on-chip family not applicable: a chain level has more than 256 rows"); return TNO_OK; }
   if (ct_col.size() >= 65535 || ct_ent.size() >= 65535) { set_error("on-chip family not applicable: ct_col.size() >= 65535"); return TNO_OK; }
   if (ct_col.empty()) ct_col.push_back(0);
   if (ct_ent.empty()) ct_ent.push_back(0);
+  if (ct_row.empty()) ct_row.push_back(0);
   if (clev_r.empty()) clev_r.push_back(make_range(0, 0, 0, 0));
 
   // ---- assembly maps in V position order ----
@@ -1354,6 +1398,60 @@ int build_onchip(Plan* PL, const tno_problem_desc* D) {
     }
   }
 
+  // ---- edge colouring for the phase-2 right-hand sides ----
+  std::vector<int> ec_ptr;
+  std::vector<uint32_t> ec_rec;
+  std::vector<double> Bc;
+  {
+    const int stride = k + (P.var.o_lambdh >= 0 ? 1 : 0);
+    O.bc_stride = stride;
+    std::vector<int> color(m, -1);
+    std::vector<std::vector<char>> used;  // used[c][row]
+    int ncol = 0;
+    for (int e = 0; e < m; ++e) {
+      const int ru = PL->h_vrow[D->edges[2 * e]], rv = PL->h_vrow[D->edges[2 * e + 1]];
+      if (ru < 0 && rv < 0) continue;  // support-to-support edge: no free row to update
+      int c = 0;
+      for (;; ++c) {
+        if (c == ncol) {
+          used.push_back(std::vector<char>(ni, 0));
+          ++ncol;
+        }
+        if ((ru < 0 || !used[c][ru]) && (rv < 0 || !used[c][rv])) break;
+      }
+      color[e] = c;
+      if (ru >= 0) used[c][ru] = 1;
+      if (rv >= 0) used[c][rv] = 1;
+    }
+    const int max_per_color = 8 * (THREADS >> O.rhs2_shift);
+    ec_ptr.assign(1, 0);
+    for (int c = 0; c < ncol; ++c) {
+      int in_piece = 0;
+      for (int e = 0; e < m; ++e) {
+        if (color[e] != c) continue;
+        if (in_piece == max_per_color) {  // a subset of a colour is conflict free too
+          ec_ptr.push_back((int)ec_rec.size());
+          in_piece = 0;
+        }
+        ++in_piece;
+        const int ru = PL->h_vrow[D->edges[2 * e]], rv = PL->h_vrow[D->edges[2 * e + 1]];
+        const uint32_t tail = ru >= 0 ? (uint32_t)ru : (0x8000u | (uint32_t)(-1 - ru));   // C[e, u] = -1
+        const uint32_t head = rv >= 0 ? (uint32_t)rv : (0x8000u | (uint32_t)(-1 - rv));   // C[e, v] = +1
+        ec_rec.push_back(head | (tail << 16));
+        for (int j = 0; j < k; ++j) Bc.push_back(D->B[(size_t)e * k + j]);
+        if (P.var.o_lambdh >= 0) Bc.push_back(D->d[e]);
+      }
+      ec_ptr.push_back((int)ec_rec.size());
+    }
+    O.ncolors = (int)ec_ptr.size() - 1;
+    if (ec_rec.empty()) ec_rec.push_back(0);
+    if (Bc.empty()) Bc.push_back(0.0);
+  }
+
+  std::vector<int> colsrc(nvar, -1);
+  for (int j = 0; j < k; ++j) colsrc[j] = O.c_q >= 0 ? O.c_q + j : -2;
+  if (P.var.o_lambdh >= 0) colsrc[P.var.o_lambdh] = O.c_lambdh >= 0 ? O.c_lambdh : -2;
+  if (P.var.o_lambdv >= 0) colsrc[P.var.o_lambdv] = -3;  // from the persistent copy
   // ---- shared-memory index region image ----
   std::vector<unsigned char> idx;
   auto align16 = [&]() {
@@ -1395,6 +1493,26 @@ int build_onchip(Plan* PL, const tno_problem_desc* D) {
   if (dense_r.empty()) dense_r.resize(1);
   put_bytes(dense_r.data(), dense_r.size() * sizeof(OcDense));
   align16();
+  {
+    std::vector<int> row_vertex(ni, -1);
+    for (int v = 0; v < P.n; ++v)
+      if (PL->h_vrow[v] >= 0) row_vertex[PL->h_vrow[v]] = v;
+    auto put_table = [&](int* off, const void* ptr, size_t bytes) {
+      *off = (int)idx.size();
+      put_bytes(ptr, bytes);
+      align16();
+    };
+    std::vector<short> vrow16(PL->h_vrow.begin(), PL->h_vrow.end()), rowv16(row_vertex.begin(), row_vertex.end());
+    put_table(&O.idx_vrow, vrow16.data(), vrow16.size() * 2);
+    put_table(&O.idx_rowv, rowv16.data(), rowv16.size() * 2);
+    put_table(&O.idx_ecptr, ec_ptr.data(), ec_ptr.size() * 4);
+    put_table(&O.idx_colsrc, colsrc.data(), colsrc.size() * 4);
+    put_table(&O.idx_supptr, sup_ptr.data(), sup_ptr.size() * 4);
+    put_table(&O.idx_supother, sup_other.data(), std::max<size_t>(sup_other.size(), 1) * 4);
+    put_table(&O.idx_supedge, sup_edge.data(), std::max<size_t>(sup_edge.size(), 1) * 4);
+    put_table(&O.idx_supsign, sup_sign.data(), std::max<size_t>(sup_sign.size(), 1) * 4);
+    put_table(&O.idx_fixed, PL->h_fixed.data(), PL->h_fixed.size() * 4);
+  }
   const int idx_bytes_core = (int)idx.size();
   O.idx_ct_ptr = (int)idx.size();
   put_bytes(ct_ptr.data(), ct_ptr.size() * 2);
@@ -1403,7 +1521,10 @@ int build_onchip(Plan* PL, const tno_problem_desc* D) {
   put_bytes(ct_col.data(), ct_col.size() * 2);
   align16();
   O.idx_ct_ent = (int)idx.size();
-  put_bytes(ct_ent.data(), ct_ent.size() * 4);
+  put_bytes(ct_ent.data(), ct_ent.size() * 2);
+  align16();
+  O.idx_ct_row = (int)idx.size();
+  put_bytes(ct_row.data(), ct_row.size());
   align16();
   O.idx_bytes = (int)idx.size();
   O.ct_in_smem = 1;
@@ -1450,10 +1571,6 @@ int build_onchip(Plan* PL, const tno_problem_desc* D) {
   std::vector<double> Bt((size_t)k * m);
   for (int e = 0; e < m; ++e)
     for (int j = 0; j < k; ++j) Bt[(size_t)j * m + e] = D->B[(size_t)e * k + j];
-  std::vector<int> colsrc(nvar, -1);
-  for (int j = 0; j < k; ++j) colsrc[j] = O.c_q >= 0 ? O.c_q + j : -2;
-  if (P.var.o_lambdh >= 0) colsrc[P.var.o_lambdh] = O.c_lambdh >= 0 ? O.c_lambdh : -2;
-  if (P.var.o_lambdv >= 0) colsrc[P.var.o_lambdv] = -3;  // from the persistent copy
   std::vector<double> Jfun;
   if (P.con.r_fun >= 0) {
     Jfun.assign((size_t)2 * m * nvar, 0.0);
@@ -1492,9 +1609,13 @@ int build_onchip(Plan* PL, const tno_problem_desc* D) {
   UPO(radj_ptr, radj_ptr);
   UPO(radj, radj);
   UPO(radj_pad, radj_pad);
+  UPO(ec_ptr, ec_ptr);
+  UPO(ec_rec, ec_rec);
+  UPO(Bc, Bc);
   UPO(ct_ptr, ct_ptr);
   UPO(ct_col, ct_col);
   UPO(ct_ent, ct_ent);
+  UPO(ct_row, ct_row);
   if (de.empty()) de.push_back(uint4{0, 0, 0, 0});
   if (dc.empty()) dc.push_back(0);
   UPO(de, de);
@@ -1555,6 +1676,8 @@ int run_onchip(Plan* PL, const double* x_dev, int64_t N, int64_t ldx, const tno_
     cudaFree(A.phase_clocks);
     static const char* names[13] = {"x", "q", "assemble", "factor", "scale", "rhs1", "solve1", "post1", "rhs2", "solve2",
                                     "reac/obj", "emitJ", "final"};
+    fprintf(stderr, "[tno smem] total=%d idx=%d ct_in_smem=%d V=%d panel=%d doubles\n", PL->oc.smem_bytes, PL->oc.idx_bytes,
+            PL->oc.ct_in_smem, PL->oc.nv, PL->oc.o_zs - PL->oc.o_r);
     fprintf(stderr, "[tno phase clocks] N=%lld grid=%d total=%lld :", (long long)N, grid, h[13] - h[0]);
     for (int i = 0; i < 13; ++i) fprintf(stderr, " %s=%lld", names[i], h[i + 1] - h[i]);
     fprintf(stderr, " | factor: dense=%lld (LDL^T part %lld)", h[14], h[15]);
