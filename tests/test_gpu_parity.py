@@ -143,3 +143,65 @@ def test_dropin_callbacks_slsqp(tno):
     assert out_gpu[2] == out_cpu[2]                       # same number of iterations
     assert rel_err(out_gpu[0], out_cpu[0]) < 1e-6         # same iterate after 12 SLSQP steps
     assert abs(out_gpu[1] - out_cpu[1]) < 1e-6 * max(1.0, abs(out_cpu[1]))
+
+
+@pytest.mark.parametrize("kernel", ["interleaved", "onchip"])
+def test_edge_cases_batch_sizes_and_subsets(tno, kernel):
+    """Empty batch, batch of one, ragged sizes around the warp / CTA / grid granularity, output subsets."""
+    from compas_tno_b200.plan import TnoPlan
+    P, objective, xs, exp = load_case("cross14_q_zb_min")
+    plan = TnoPlan(P, objective=objective, kernel=kernel)
+    rng = np.random.default_rng(7)
+    Xall = xs[0] * (1.0 + 0.03 * rng.uniform(-1, 1, size=(700, xs.shape[1])))
+    full = plan.evaluate_host(Xall)
+    assert plan.evaluate_host(np.zeros((0, plan.nvar)))["f"].shape == (0,)
+    for N in (1, 31, 33, 297, 700):
+        got = plan.evaluate_host(Xall[:N], outputs=("f", "z", "gmin", "status"))
+        assert set(got) == {"f", "z", "gmin", "status"}
+        for key in got:
+            assert np.array_equal(got[key], full[key][:N]), (N, key)      # results do not depend on the batch size
+    only_J = plan.evaluate_host(Xall[:5], outputs=("J",))
+    assert np.array_equal(only_J["J"], full["J"][:5])
+    with pytest.raises(ValueError):
+        plan.evaluate_host(np.zeros((3, plan.nvar + 1)))
+
+
+@pytest.mark.parametrize("kernel", ["interleaved", "onchip"])
+def test_pz_scale_matches_oracle_with_scaled_loads(tno, kernel):
+    """Monte-Carlo self-weight input: pz_scale[j] multiplies the vertical loads of candidate j."""
+    import copy
+    from compas_tno_b200.plan import TnoPlan
+    from oracle import callbacks_np as onp
+    P, objective, xs, _ = load_case("dome_q_zb_reac_min")
+    plan = TnoPlan(P, objective=objective, kernel=kernel)
+    scale = np.array([0.8, 1.0, 1.2])
+    got = plan.evaluate_host(xs[:3], pz_scale=scale)
+    for j in range(3):
+        Pj = copy.copy(P)
+        Pj.P = P.P.copy()
+        Pj.P[:, 2] *= scale[j]
+        ref = onp.evaluate_batch(xs[j:j + 1], Pj, objective)
+        assert rel_err(got["z"][j], ref["z"][0]) < TOL_VAL
+        assert rel_err(got["g"][j], ref["g"][0]) < TOL_VAL
+        assert rel_err(got["J"][j], ref["J"][0]) < TOL_JAC
+        assert abs(got["f"][j] - ref["f"][0]) < TOL_VAL * abs(ref["f"][0])
+
+
+def test_synthetic_benchmark_workloads_against_oracle(tno):
+    """The exact workloads bench.py times (disc-20 cross vault, 16 x 20 dome) are parity-checked too."""
+    from compas_tno_b200 import workloads as W
+    from compas_tno_b200.plan import TnoPlan
+    from oracle import callbacks_np as onp
+    for build, kw, objective in ((W.crossvault_problem, dict(n_div=20), "min"),
+                                 (W.dome_problem, dict(constraints=("funicular", "envelope", "reac_bounds")), "max")):
+        P, xstar = build(**kw)
+        X = W.sample_candidates(P, xstar, 6, seed=11, basis=P.candidate_basis)
+        plan = TnoPlan(P, objective=objective)
+        got = plan.evaluate_host(X)
+        ref = onp.evaluate_batch(X, P, objective)
+        assert np.all(got["status"] == 0)
+        assert rel_err(got["z"], ref["z"]) < TOL_VAL
+        assert rel_err(got["g"], ref["g"]) < TOL_VAL
+        assert rel_err(got["f"], ref["f"]) < TOL_VAL
+        assert rel_err(got["grad"], ref["grad"]) < TOL_JAC
+        assert rel_err(got["J"], ref["J"]) < TOL_JAC
