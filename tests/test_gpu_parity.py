@@ -205,3 +205,23 @@ def test_synthetic_benchmark_workloads_against_oracle(tno):
         assert rel_err(got["f"], ref["f"]) < TOL_VAL
         assert rel_err(got["grad"], ref["grad"]) < TOL_JAC
         assert rel_err(got["J"], ref["J"]) < TOL_JAC
+
+
+def test_disc40_interleaved_family_against_oracle(tno):
+    """BASELINE config 4 geometry (cross vault discretisation 40, 3360 edges): too large for shared memory, so the
+    interleaved family must pick it up automatically; two candidates against the oracle (its m-RHS solve is slow)."""
+    from compas_tno_b200 import workloads as W
+    from compas_tno_b200.plan import TnoPlan
+    from oracle import callbacks_np as onp
+    P, xstar = W.crossvault_problem(40, n_states=3)
+    X = W.sample_candidates(P, xstar, 2, seed=5, basis=P.candidate_basis)
+    plan = TnoPlan(P, objective="min")                 # kernel="auto"
+    assert plan.info["kernel"] == 1
+    got = plan.evaluate_host(X, pz_scale=np.array([1.0, 1.1]))
+    ref0 = onp.evaluate_batch(X[:1], P, "min")
+    assert np.all(got["status"] == 0)
+    assert rel_err(got["z"][0], ref0["z"][0]) < TOL_VAL
+    assert rel_err(got["g"][0], ref0["g"][0]) < TOL_VAL
+    assert abs(got["f"][0] - ref0["f"][0]) < TOL_VAL * abs(ref0["f"][0])
+    assert rel_err(got["grad"][0], ref0["grad"][0]) < TOL_JAC
+    assert rel_err(got["J"][0], ref0["J"][0]) < TOL_JAC
