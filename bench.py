@@ -279,8 +279,15 @@ def run_ours(args):
                 ent["bytes_per_eval"] = kbytes[kname]
                 ent["GB/s"] = kbytes[kname] * N * args.steps / (ms_k * 1e-3) / 1e9
             per_kernel[kname] = ent
+        traffic = None   # DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
+            if args.workload == "crossvault_disc20" and name in tj:
+                traffic = tj[name]["dram_bytes_per_candidate"] * evals_per_launch
+        except Exception:
+            traffic = None
         roofline = {"bound": "hbm", "kernel": name, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "traffic": None, "peak_source": peak_src, "kernel_share_of_step": kms / total_kernel_ms,
+                    "traffic": traffic, "peak_source": peak_src, "kernel_share_of_step": kms / total_kernel_ms,
                     "bytes_per_eval": bytes_per_eval, "evals_per_launch": evals_per_launch,
                     "whole_step": {"bytes_per_eval": B_alg, "achieved": value / world * B_alg / 1e9,
                                    "frac": value / world * B_alg / 1e9 / peak},
