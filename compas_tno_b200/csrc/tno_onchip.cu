@@ -613,6 +613,9 @@ __global__ void __launch_bounds__(THREADS, MINB) k_onchip(const __grid_constant_
 
     if (A.phase_clocks && blockIdx.x == 0 && tid == 0 && cand == (int64_t)(A.N > 4 * gridDim.x ? 4 * gridDim.x : 0)) A.phase_clocks[5] = clock64();
     // ---- 5. phase-1 right-hand sides: z | z_lambdv | Az | x | y -------------------------------------
+    // (the scale pass above only touches V; the panel is cleared with coalesced 16-byte stores first)
+    for (int it = tid; it < ni * (W >> 1); it += THREADS) reinterpret_cast<double2*>(R)[it] = make_double2(0.0, 0.0);
+    __syncthreads();
     for (int r = tid; r < ni; r += THREADS) {
       const int v = rowv_s[r];
       double px, py, pz;
@@ -627,7 +630,6 @@ __global__ void __launch_bounds__(THREADS, MINB) k_onchip(const __grid_constant_
       pz *= pzs;
       double bx = -px, by = -py, bz = -pz;
       double* row = R + r * W;
-      for (int cc = 0; cc < ((O.ncols1 + 1) & ~1); ++cc) row[cc] = 0.0;  // incl. padding columns touched by 2-column lanes
       for (int t = P.vadj_ptr[v]; t < P.vadj_ptr[v + 1]; ++t) {
         const int o = P.vadj_other[t];
         const int ro = vrow_s[o];
