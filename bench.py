@@ -342,6 +342,31 @@ def run_ours(args):
                "sample": "%d candidates of %s through oracle/callbacks_np.py (reference call order: constr_wrapper, "
                          "sensitivities_wrapper, objective, gradient), one process per core" % (ns, args.workload)}
 
+    # ---- sweep wall-times of the other BASELINE configurations that fit one GPU (N = 1 only; short) ----
+    sweeps = None
+    if rank == 0 and world == 1 and not args.no_sweeps:
+        sweeps = {}
+        for wname, wbatch, label in (("dome_16x20", 4096, "config 2: dome, radial form, max thrust + reac_bounds, 4096 multi-start"),):
+            Pw, xw, objw = build_workload(wname, n_states=6)
+            planw = TnoPlan(Pw, objective=objw, device=local)
+            Xw = torch.from_numpy(candidates(Pw, xw, wbatch, seed=20261019 + 2)).to(dev)
+            namesw = ("f", "grad", "g", "J", "z", "gmin", "status")
+            outw = {k: torch.empty(planw._shape(k, wbatch), device=dev, dtype=torch.int32 if k == "status" else torch.float64) for k in namesw}
+            for _ in range(3):
+                planw.evaluate_device(Xw, namesw, out=outw)
+            torch.cuda.synchronize()
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record()
+            for _ in range(5):
+                planw.evaluate_device(Xw, namesw, out=outw)
+            a1.record()
+            torch.cuda.synchronize()
+            msw = a0.elapsed_time(a1) / 5
+            sweeps[wname] = {"what": label, "candidates": wbatch, "wall_ms_per_sweep": msw, "evals_per_s": wbatch / (msw * 1e-3),
+                             "kernel_family": {1: "interleaved", 2: "onchip"}.get(planw.info["kernel"]), "nvar": planw.nvar, "ng": planw.ng,
+                             "bytes_per_eval": planw.bytes_per_eval, "status_nonzero": int((outw["status"] != 0).sum().item())}
+            planw.close()
+
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -353,7 +378,7 @@ def run_ours(args):
                        "kernel_family": {1: "interleaved", 2: "onchip"}.get(info["kernel"], str(info["kernel"])),
                        "l2_policy": "outputs per step (%.2f GB) exceed the 126 MB L2; inputs re-read each step" % (N * B_alg / 1e9),
                        "parallelism": "candidates sharded, plan replicated, all_gather(f, status)" if world > 1 else "single GPU"},
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "sweeps": sweeps,
             "status_nonzero": status_bad,
         }
         print(json.dumps(line))
@@ -373,6 +398,7 @@ def main():
     ap.add_argument("--kernel", default="auto", choices=["auto", "interleaved", "onchip"])
     ap.add_argument("--cpu-evals-per-core", type=int, default=24)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-sweeps", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -1011,7 +1011,29 @@ __global__ void __launch_bounds__(256) k_fill_funicular(const double2* __restric
 
 // ------------------------------------------------------------------------------------------------------
 // host: schedule construction
+static int build_onchip_impl(Plan* PL, const tno_problem_desc* D, const int THREADS);
+
+// Builds the on-chip schedule for 256-thread CTAs first; when only one CTA fits per SM anyway (large panels: dome,
+// fan), rebuilds it for 512-thread CTAs so that the wide phases get twice the threads.
 int build_onchip(Plan* PL, const tno_problem_desc* D) {
+  const size_t mark = PL->dev_allocs.size();
+  int rc = build_onchip_impl(PL, D, 256);
+  if (rc != TNO_OK || !PL->onchip_ok) return rc;
+  if (PL->onchip_ctas_per_sm == 1 && !getenv("TNO_ONCHIP_256")) {
+    for (size_t i = mark; i < PL->dev_allocs.size(); ++i) cudaFree(PL->dev_allocs[i]);
+    PL->dev_allocs.resize(mark);
+    rc = build_onchip_impl(PL, D, 512);
+    if (rc != TNO_OK) return rc;
+    if (!PL->onchip_ok) {  // should not happen (same memory footprint); fall back to the 256-thread schedule
+      for (size_t i = mark; i < PL->dev_allocs.size(); ++i) cudaFree(PL->dev_allocs[i]);
+      PL->dev_allocs.resize(mark);
+      rc = build_onchip_impl(PL, D, 256);
+    }
+  }
+  return rc;
+}
+
+static int build_onchip_impl(Plan* PL, const tno_problem_desc* D, const int THREADS) {
   const Symbolic& S = PL->sym;
   DevPlan& P = PL->dp;
   DevOnchip& O = PL->oc;
@@ -1019,7 +1041,6 @@ int build_onchip(Plan* PL, const tno_problem_desc* D) {
   const int ni = P.ni, m = P.m, nb = P.nb, k = P.k, nvar = P.var.nvar;
   const int nnz = P.nnz_l;
   if (nnz >= 60000 || ni >= 32768 || S.nlevels < 1 || m >= 65535) { set_error("on-chip family not applicable: nnz >= 60000 || ni >= 32768 || S.nlevels < 1 || m >= 65535"); return TNO_OK; }
-  const int THREADS = 256;
 
   // ---- panel columns.  phase 1: [z | z_lambdv | Az (nb) | x | y]   phase 2: [Dq (k) | z_lambdh] -------------
   int pos = 0;
@@ -1569,6 +1590,7 @@ int build_onchip(Plan* PL, const tno_problem_desc* D) {
   if (O.smem_bytes > max_optin) { set_error("on-chip family not applicable: O.smem_bytes > max_optin"); return TNO_OK; }
   PL->onchip_threads = THREADS;
   PL->onchip_ctas_per_sm = std::max(1, std::min(8, smem_sm / (O.smem_bytes + 1024)));
+  if (THREADS == 512) PL->onchip_ctas_per_sm = 1;
 
   std::vector<double> Bt((size_t)k * m);
   for (int e = 0; e < m; ++e)
@@ -1653,7 +1675,8 @@ int run_onchip(Plan* PL, const double* x_dev, int64_t N, int64_t ldx, const tno_
   static const char* force_ctas = getenv("TNO_CTAS_PER_SM");  // developer knob
   const int ctas = force_ctas ? std::max(1, atoi(force_ctas)) : PL->onchip_ctas_per_sm;
   const int grid = (int)std::min<int64_t>(N, (int64_t)PL->sm_count * ctas);
-  auto kern = PL->onchip_ctas_per_sm >= 2 ? k_onchip<256, 2> : k_onchip<256, 1>;
+  const int threads = PL->onchip_threads;
+  auto kern = threads == 512 ? k_onchip<512, 1> : (PL->onchip_ctas_per_sm >= 2 ? k_onchip<256, 2> : k_onchip<256, 1>);
   TNO_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   if (out->J && PL->dp.con.r_fun >= 0) {
     const int64_t count = (int64_t)2 * PL->dp.m * PL->dp.var.nvar;  // even
@@ -1667,7 +1690,7 @@ int run_onchip(Plan* PL, const double* x_dev, int64_t N, int64_t ldx, const tno_
     PL->launches += 1;
   }
   PL->prof_begin(KK_ONCHIP, stream);
-  kern<<<grid, 256, smem, stream>>>(PL->dp, PL->oc, A);
+  kern<<<grid, threads, smem, stream>>>(PL->dp, PL->oc, A);
   PL->prof_end(stream);
   PL->launches += 1;
   TNO_CUDA_OK(cudaGetLastError());
