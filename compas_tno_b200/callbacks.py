@@ -21,7 +21,7 @@ from .plan import TnoPlan
 __all__ = [
     "accelerate", "constr_wrapper", "sensitivities_wrapper", "f_min_thrust", "f_max_thrust", "gradient_fmin",
     "gradient_fmax", "f_reduce_thk", "gradient_reduce_thk", "f_tight_crosssection", "gradient_tight_crosssection",
-    "objective_selector", "evaluate_batch",
+    "f_bestfit", "gradient_bestfit", "f_constant", "gradient_feasibility", "objective_selector", "evaluate_batch",
 ]
 
 _ATTR = "_tno_b200_state"
@@ -87,6 +87,8 @@ f_min_thrust, gradient_fmin = _objective("min")
 f_max_thrust, gradient_fmax = _objective("max")
 f_reduce_thk, gradient_reduce_thk = _objective("t")
 f_tight_crosssection, gradient_tight_crosssection = _objective("n")
+f_bestfit, gradient_bestfit = _objective("bestfit")
+f_constant, gradient_feasibility = _objective("feasibility")
 
 _SELECT = {
     "min": (f_min_thrust, gradient_fmin),
@@ -95,6 +97,9 @@ _SELECT = {
     "s": (f_tight_crosssection, gradient_tight_crosssection),
     "n": (f_tight_crosssection, gradient_tight_crosssection),
     "max_load": (f_tight_crosssection, gradient_tight_crosssection),
+    "bestfit": (f_bestfit, gradient_bestfit),
+    "target": (f_bestfit, gradient_bestfit),
+    "feasibility": (f_constant, gradient_feasibility),
 }
 
 
@@ -112,7 +117,7 @@ def accelerate(problem, objective="min", device=0, kernel="auto"):
     problem._tno_b200_kernel = kernel
     if hasattr(problem, _ATTR):
         delattr(problem, _ATTR)
-    objective = {"s": "n", "max_load": "n"}.get(objective, objective)
+    objective = {"s": "n", "max_load": "n", "target": "bestfit"}.get(objective, objective)
     fobj, fgrad = objective_selector(objective)
     _state(problem, objective)
     problem.fobj, problem.fgrad = fobj, fgrad
@@ -122,5 +127,5 @@ def accelerate(problem, objective="min", device=0, kernel="auto"):
 
 def evaluate_batch(problem, xs, objective="min", outputs=("f", "grad", "g", "J", "z", "status"), device=0):
     """The batched entry point the reference does not have: all callbacks for every row of xs."""
-    st, problem = _state(problem, {"s": "n", "max_load": "n"}.get(objective, objective))
+    st, problem = _state(problem, {"s": "n", "max_load": "n", "target": "bestfit"}.get(objective, objective))
     return st.plan.evaluate_host(xs, outputs)

@@ -470,9 +470,33 @@ __global__ void k_epilogue(DevPlan P, double* __restrict__ ws, int64_t NC, int64
     }
   }
 
+  if (P.objective == TNO_OBJ_BESTFIT) {
+    // f = sum_v (z_v - s_v)^2 ;  grad = (2 (z - s))^T [dz/dq_ind | dz/dzb]   (objectives.py:170-200, derivatives.py:355-413)
+    f = 0.0;
+    for (int v = 0; v < n; ++v) {
+      const double dz = zval(P, ws, NC, c, v) - P.s[v];
+      f = fma(dz, dz, f);
+    }
+    const int ncol = P.k + (P.var.o_zb >= 0 ? nb : 0);
+    for (int j = 0; j < ncol; ++j) {
+      const bool isq = j < P.k;
+      const int pc = isq ? P.rhs.c_q + j : P.rhs.c_zb + (j - P.k);
+      double acc = 0.0;
+      if (!isq) {
+        const int b = j - P.k;
+        acc = 2.0 * (zfixed(P, ws, NC, c, b) - P.s[P.fixed[b]]);
+      }
+      for (int r = 0; r < P.ni; ++r) {
+        const double w = 2.0 * (WS(P.slot.s_r + r * nrhs + P.rhs.cz) - P.s[P.row_vertex[r]]);
+        acc = fma(w, WS(P.slot.s_r + r * nrhs + pc), acc);
+      }
+      WS(P.slot.s_grad + (isq ? j : P.var.o_zb + (j - P.k))) = acc;
+    }
+  }
   if (P.objective == TNO_OBJ_MAX) f = -f;
   if (P.objective == TNO_OBJ_T) f = WS(P.slot.s_x + nvar - 1);
   if (P.objective == TNO_OBJ_NEG_LAST) f = -WS(P.slot.s_x + nvar - 1);
+  if (P.objective == TNO_OBJ_FEASIBILITY) f = 1.0;
   bad |= !isfinite(f);
   if (f_out) f_out[c] = f;
   if (gmin_out) gmin_out[c] = gmin;
@@ -551,7 +575,9 @@ int run_interleaved(Plan* PL, const double* x_dev, int64_t N, int64_t ldx, const
     LAUNCH(KK_RHS1, k_rhs1, grid1(nc, TB, gyr), TB, P, ws, NC, nc, rtile);
     constexpr int RB = 4;
     LAUNCH(KK_SOLVE1, k_solve<RB>, grid1(nc, TB, (P.rhs.nrhs1 + RB - 1) / RB), TB, P, ws, NC, nc, 0, P.rhs.nrhs1);
-    if (P.rhs.nrhs2 > 0) {
+    // the dz/dq_ind columns only feed the Jacobian and the bestfit gradient
+    const bool need2 = P.rhs.nrhs2 > 0 && (out->J != nullptr || (P.objective == TNO_OBJ_BESTFIT && out->grad != nullptr));
+    if (need2) {
       LAUNCH(KK_RHS2, k_rhs2, grid1(nc, TB, gyr), TB, P, ws, NC, nc, rtile);
       LAUNCH(KK_SOLVE2, k_solve<RB>, grid1(nc, TB, (P.rhs.nrhs2 + RB - 1) / RB), TB, P, ws, NC, nc, P.rhs.nrhs1, P.rhs.nrhs2);
     }

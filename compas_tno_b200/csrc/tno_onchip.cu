@@ -406,6 +406,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_onchip(const __grid_constant_
   double* azsup = sm + O.o_azsup;  // nsup x nb : dz/dzb at the neighbours of the supports
   double* red = sm + O.o_red;
   double* pers = sm + O.o_pers;    // z_lambdv of the free rows after phase 1 (lambdv variable only)
+  double* bf = sm + O.o_bf;        // bestfit objective: per-warp partial column sums (THREADS / 32 x 16)
   const unsigned short* rowptr16 = reinterpret_cast<const unsigned short*>(smraw + O.o_idx_bytes + O.idx_rowptr);
   const unsigned short* rowcol16 = reinterpret_cast<const unsigned short*>(smraw + O.o_idx_bytes + O.idx_rowcol);
   const OcRange* wide = reinterpret_cast<const OcRange*>(smraw + O.o_idx_bytes + O.idx_wide);
@@ -438,6 +439,9 @@ __global__ void __launch_bounds__(THREADS, MINB) k_onchip(const __grid_constant_
   const bool has_t = P.var.o_t >= 0;
   const bool want_thrust = (P.objective == TNO_OBJ_MIN || P.objective == TNO_OBJ_MAX);
   const bool want_reac = (P.constraints & TNO_CON_REAC_BOUNDS) != 0;
+  const bool want_bestfit = P.objective == TNO_OBJ_BESTFIT;
+  // the dz/dq_ind panel is only needed by the Jacobian and by the bestfit gradient
+  const bool need2 = O.ncols2 > 0 && (A.J != nullptr || (want_bestfit && A.grad != nullptr));
 
   // index region: loaded once per CTA, reused by every candidate
   for (int i = tid; i < O.idx_bytes / 16; i += THREADS)
@@ -454,6 +458,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_onchip(const __grid_constant_
     const double lamv = P.var.o_lambdv >= 0 ? xs[P.var.o_lambdv] : 1.0;
     const double pzs = A.pzs ? A.pzs[cand] : 1.0;
     double gmin = 1e300;
+    double fpart = 0.0;
     bool bad = false;
     double* gout = A.g ? A.g + cand * ng : nullptr;
     double* Jout = A.J ? A.J + cand * (int64_t)ng * nvar : nullptr;
@@ -675,6 +680,10 @@ __global__ void __launch_bounds__(THREADS, MINB) k_onchip(const __grid_constant_
       const double z = zval(v);
       if (A.z) A.z[cand * n + v] = z;
       bad |= !isfinite(z);
+      if (want_bestfit) {
+        const double dz = z - __ldg(P.s + v);
+        fpart = fma(dz, dz, fpart);
+      }
       if (P.con.r_env >= 0) {
         double ub, lb;
         if (has_t) {
@@ -696,6 +705,32 @@ __global__ void __launch_bounds__(THREADS, MINB) k_onchip(const __grid_constant_
         gmin = fmin(gmin, fmin(g0, g1));
       }
     }
+    // bestfit gradient: dst[c] = sum_r 2 (z_r - s_r) R[r, col0 + c]  (+ the identity rows of the supports).
+    // Half-warps walk 16 consecutive panel columns of one row (conflict-free), rows are spread over the
+    // 2 * THREADS / 32 half-warps; fixed reduction order, so results are reproducible run to run.
+    auto wcolsum = [&](int col0, int ncols, double* dst, bool add_fixed) {
+      constexpr int NW = THREADS / 32;
+      const int csub = lane & 15, rsub = lane >> 4;
+      for (int cb = 0; cb < ncols; cb += 16) {
+        const bool cok = cb + csub < ncols;
+        double acc = 0.0;
+        for (int r = warp * 2 + rsub; r < ni; r += 2 * NW) {
+          const double w = 2.0 * (zs[r] - __ldg(P.s + rowv_s[r]));
+          if (cok) acc = fma(w, R[r * W + col0 + cb + csub], acc);
+        }
+        acc += __shfl_xor_sync(0xffffffffu, acc, 16);
+        if (lane < 16) bf[warp * 16 + lane] = acc;
+        __syncthreads();
+        if (tid < 16 && cb + tid < ncols) {
+          double sum = 0.0;
+          for (int w = 0; w < NW; ++w) sum += bf[w * 16 + tid];
+          if (add_fixed) sum += 2.0 * (zs[ni + cb + tid] - __ldg(P.s + fixed_s[cb + tid]));
+          dst[cb + tid] = sum;
+        }
+        __syncthreads();
+      }
+    };
+    if (want_bestfit && A.grad && P.var.o_zb >= 0) wcolsum(O.c_az, nb, A.grad + cand * nvar + P.var.o_zb, true);
     if (Jout && P.con.r_env >= 0 && P.var.o_zb >= 0) {
       // dz/dzb block straight to the Jacobian (its panel columns are about to be reused)
       for (int idx = tid; idx < n * nb; idx += THREADS) {
@@ -778,7 +813,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_onchip(const __grid_constant_
 
     if (A.phase_clocks && blockIdx.x == 0 && tid == 0 && cand == (int64_t)(A.N > 4 * gridDim.x ? 4 * gridDim.x : 0)) A.phase_clocks[8] = clock64();
     // ---- 8. phase-2 right-hand sides: Ci^T W B | Ci^T W d0 ------------------------------------------
-    if (O.ncols2 > 0) {
+    if (need2) {
       const int nc2 = O.ncols2;
       const int g2 = O.rhs2_shift;  // 2^g2 lanes walk the columns of one row
       const int r_ = tid & ((1 << g2) - 1);
@@ -944,10 +979,20 @@ __global__ void __launch_bounds__(THREADS, MINB) k_onchip(const __grid_constant_
         for (int b = 0; b < nb; ++b) fval += sqrt(react[3 * b] * react[3 * b] + react[3 * b + 1] * react[3 * b + 1]);
         fval *= osign;
       }
+    } else if (want_bestfit) {
+      if (A.grad) wcolsum(O.c_q, k, A.grad + cand * nvar, false);
+      for (int off = 16; off > 0; off >>= 1) fpart += __shfl_xor_sync(0xffffffffu, fpart, off);
+      if (lane == 0) red[warp] = fpart;
+      __syncthreads();
+      if (tid == 0)
+        for (int w = 0; w < THREADS / 32; ++w) fval += red[w];
+      __syncthreads();  // red is reused by the feasibility reduction below
     } else {
       if (tid < nvar && A.grad)
         A.grad[cand * nvar + tid] = (tid == nvar - 1) ? (P.objective == TNO_OBJ_T ? 1.0 : (P.objective == TNO_OBJ_NEG_LAST ? -1.0 : 0.0)) : 0.0;
-      if (tid == 0) fval = P.objective == TNO_OBJ_T ? xs[nvar - 1] : (P.objective == TNO_OBJ_NEG_LAST ? -xs[nvar - 1] : 0.0);
+      if (tid == 0)
+        fval = P.objective == TNO_OBJ_T ? xs[nvar - 1]
+               : (P.objective == TNO_OBJ_NEG_LAST ? -xs[nvar - 1] : (P.objective == TNO_OBJ_FEASIBILITY ? 1.0 : 0.0));
     }
     if (tid == 0) {
       bad |= !isfinite(fval);
@@ -1573,6 +1618,7 @@ static int build_onchip_impl(Plan* PL, const tno_problem_desc* D, const int THRE
   O.o_gxy = take(2 * nb * k + 2 * nb);
   O.o_azsup = take(((P.constraints & TNO_CON_REAC_BOUNDS) && P.var.o_zb >= 0) ? O.nsup * nb : 0);
   O.o_red = take(40);
+  O.o_bf = take(P.objective == TNO_OBJ_BESTFIT ? (THREADS / 32) * 16 : 0);
   O.o_idx_bytes = off * 8;
   int max_optin = 0, smem_sm = 0;
   TNO_CUDA_OK(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, PL->device));

@@ -64,6 +64,9 @@ extern "C" {
 #define TNO_OBJ_MAX 2        /* f_max_thrust  / gradient_fmax */
 #define TNO_OBJ_T 3          /* f_reduce_thk  / gradient_reduce_thk          f = +x[-1] */
 #define TNO_OBJ_NEG_LAST 4   /* f_tight_crosssection ('n','s','max_load')    f = -x[-1] */
+#define TNO_OBJ_BESTFIT 5    /* f_bestfit     / gradient_bestfit   ('bestfit','target'; variables q [, zb]; needs s)
+                                problems/objectives.py:170-200, problems/derivatives.py:355-413 */
+#define TNO_OBJ_FEASIBILITY 6 /* f_constant   / gradient_feasibility   f = 1, grad = 0  (objectives.py:395-412) */
 
 /* parametric envelopes (arithmetic lives in the un-vendored compas_tna; closed forms recovered from
  * the reference fixtures) */

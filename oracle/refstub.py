@@ -104,6 +104,10 @@ def load_reference():
         f_max_thrust=prb.f_max_thrust,
         gradient_fmin=prb.gradient_fmin,
         gradient_fmax=prb.gradient_fmax,
+        f_constant=prb.f_constant,
+        gradient_feasibility=prb.gradient_feasibility,
+        f_bestfit=prb.f_bestfit,
+        gradient_bestfit=prb.gradient_bestfit,
         f_reduce_thk=prb.f_reduce_thk,
         gradient_reduce_thk=prb.gradient_reduce_thk,
         f_tight_crosssection=prb.f_tight_crosssection,

@@ -158,6 +158,9 @@ def main():
     xs = sample_points(rng, P, form, 4, none)
     run_case(ref, "cross14_q_zb_min", form, P, ["q", "zb"], ["funicular", "envelope"], "min", xs, 0.5)
 
+    run_case(ref, "cross14_q_zb_bestfit", form, P, ["q", "zb"], ["funicular", "envelope"], "bestfit", xs[:3], 0.5)
+    run_case(ref, "cross14_q_zb_feasibility", form, P, ["q", "zb"], ["funicular", "envelope"], "feasibility", xs[:2], 0.5)
+
     # ---- B: cross vault, thickness variable -------------------------------------------------
     env = CrossVaultEnvelopeNP((0.0, 10.0), (0.0, 10.0), 0.5)
     tail = lambda j, rng: np.array([0.5 if j == 0 else rng.uniform(0.3, 0.5)])  # noqa: E731
@@ -179,6 +182,8 @@ def main():
     xs = sample_points(rng, P, form, 3, none)
     run_case(ref, "dome_q_zb_reac_min", form, P, ["q", "zb"], ["funicular", "envelope", "reac_bounds"], "min",
              xs, thk, extra={"b": form["b"]})
+
+    run_case(ref, "dome_q_zb_bestfit", form, P, ["q", "zb"], ["funicular", "envelope"], "bestfit", xs[:2], thk)
 
     # ---- E: dome, thickness variable, x* = stored optimum -----------------------------------
     env = DomeEnvelopeNP((5.0, 5.0), 5.0, thk)

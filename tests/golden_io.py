@@ -19,6 +19,8 @@ CASES = [
     "dome_q_zb_lambdh_reac",
     "dome_q_zb_lambdv",
     "freeform_q_zb_min",
+    "cross14_q_zb_bestfit", "cross14_q_zb_feasibility",
+    "dome_q_zb_bestfit",
 ]
 
 
@@ -77,7 +79,7 @@ def load_case(name, envelope_factory=None):
             c = var_offset(P.variables, k, nb, "t")
             neg[:, c] = z["J_dub"][j]
         J.append(np.vstack([fun, env, neg, z["J_reac"][j]]))
-    expected = dict(g=z["g"], J=np.array(J), f=z["f"], grad=z["grad"], X=z["X"], q=z["q"], mineig=z["mineig"])
+    expected = dict(g=z["g"], J=np.array(J), f=np.asarray(z["f"]).reshape(len(z["x"])), grad=z["grad"], X=z["X"], q=z["q"], mineig=z["mineig"])
     return P, objective, xs, expected
 
 

@@ -167,6 +167,47 @@ def test_edge_cases_batch_sizes_and_subsets(tno, kernel):
 
 
 @pytest.mark.parametrize("kernel", ["interleaved", "onchip"])
+@pytest.mark.parametrize("name", ["cross14_q_zb_bestfit", "dome_q_zb_bestfit", "dome_q_zb_reac_min"])
+def test_output_subsets_skip_the_sensitivity_solve(tno, name, kernel):
+    """Without J (and, for bestfit, without grad) the dz/dq_ind solve is skipped: every other output is unchanged."""
+    from compas_tno_b200.plan import TnoPlan
+    from oracle import callbacks_np as onp
+    P, objective, xs, exp = load_case(name)
+    plan = TnoPlan(P, objective=objective, kernel=kernel)
+    rng = np.random.default_rng(11)
+    X = xs[0] * (1.0 + 0.02 * rng.uniform(-1, 1, size=(67, xs.shape[1])))
+    full = plan.evaluate_host(X)
+    light = plan.evaluate_host(X, outputs=("f", "g", "z", "q", "gmin", "status"))
+    for key in light:
+        assert np.array_equal(light[key], full[key]), key
+    only_grad = plan.evaluate_host(X, outputs=("grad",))
+    assert np.array_equal(only_grad["grad"], full["grad"])
+    ref = onp.evaluate_batch(X[:4], P, objective)
+    assert rel_err(full["f"][:4], ref["f"]) < 1e-10
+    assert rel_err(full["grad"][:4], ref["grad"]) < 1e-8
+
+
+def test_dropin_bestfit_and_feasibility_callbacks(tno):
+    """f_bestfit / gradient_bestfit / f_constant / gradient_feasibility keep the reference's callable protocol."""
+    import compas_tno_b200 as tb
+    from compas_tno_b200 import callbacks as cb
+    P, objective, xs, exp = load_case("cross14_q_zb_bestfit")
+    fobj, fgrad = cb.objective_selector("target")
+    assert (fobj, fgrad) == (cb.f_bestfit, cb.gradient_bestfit)
+    M = P
+    tb.accelerate(M, "bestfit")
+    f = M.fobj(xs[1], M)
+    g = M.fgrad(xs[1], M)
+    assert isinstance(f, float) and g.shape == (xs.shape[1],)
+    assert abs(f - exp["f"][1]) < 1e-10 * abs(exp["f"][1])
+    assert rel_err(g, exp["grad"][1]) < 1e-8
+    M2 = load_case("cross14_q_zb_feasibility")[0]
+    tb.accelerate(M2, "feasibility")
+    assert M2.fobj(xs[0], M2) == 1.0
+    assert np.array_equal(M2.fgrad(xs[0], M2), np.zeros(xs.shape[1]))
+
+
+@pytest.mark.parametrize("kernel", ["interleaved", "onchip"])
 def test_pz_scale_matches_oracle_with_scaled_loads(tno, kernel):
     """Monte-Carlo self-weight input: pz_scale[j] multiplies the vertical loads of candidate j."""
     import copy
