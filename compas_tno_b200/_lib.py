@@ -12,7 +12,7 @@ ABI_VERSION = 1
 # masks / enums (mirror include/tno_b200.h)
 VAR_Q, VAR_ZB, VAR_T, VAR_LAMBDH, VAR_LAMBDV = 1, 2, 4, 8, 16
 CON_FUNICULAR, CON_ENVELOPE, CON_REAC_BOUNDS = 1, 2, 4
-OBJ_NONE, OBJ_MIN, OBJ_MAX, OBJ_T, OBJ_NEG_LAST, OBJ_BESTFIT, OBJ_FEASIBILITY = 0, 1, 2, 3, 4, 5, 6
+OBJ_NONE, OBJ_MIN, OBJ_MAX, OBJ_T, OBJ_NEG_LAST, OBJ_BESTFIT, OBJ_FEASIBILITY, OBJ_LOADPATH = 0, 1, 2, 3, 4, 5, 6, 7
 ENV_FIXED, ENV_DOME, ENV_CROSSVAULT = 0, 1, 2
 KERNEL_AUTO, KERNEL_INTERLEAVED, KERNEL_ONCHIP = 0, 1, 2
 STATUS_OK, STATUS_NOT_PD, STATUS_NONFINITE = 0, 1, 2

@@ -21,7 +21,7 @@ from .plan import TnoPlan
 __all__ = [
     "accelerate", "constr_wrapper", "sensitivities_wrapper", "f_min_thrust", "f_max_thrust", "gradient_fmin",
     "gradient_fmax", "f_reduce_thk", "gradient_reduce_thk", "f_tight_crosssection", "gradient_tight_crosssection",
-    "f_bestfit", "gradient_bestfit", "f_constant", "gradient_feasibility", "objective_selector", "evaluate_batch",
+    "f_bestfit", "gradient_bestfit", "f_loadpath_general", "gradient_loadpath", "f_constant", "gradient_feasibility", "objective_selector", "evaluate_batch",
 ]
 
 _ATTR = "_tno_b200_state"
@@ -89,6 +89,7 @@ f_reduce_thk, gradient_reduce_thk = _objective("t")
 f_tight_crosssection, gradient_tight_crosssection = _objective("n")
 f_bestfit, gradient_bestfit = _objective("bestfit")
 f_constant, gradient_feasibility = _objective("feasibility")
+f_loadpath_general, gradient_loadpath = _objective("loadpath")
 
 _SELECT = {
     "min": (f_min_thrust, gradient_fmin),
@@ -100,6 +101,7 @@ _SELECT = {
     "bestfit": (f_bestfit, gradient_bestfit),
     "target": (f_bestfit, gradient_bestfit),
     "feasibility": (f_constant, gradient_feasibility),
+    "loadpath": (f_loadpath_general, gradient_loadpath),
 }
 
 

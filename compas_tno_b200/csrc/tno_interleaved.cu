@@ -493,6 +493,41 @@ __global__ void k_epilogue(DevPlan P, double* __restrict__ ws, int64_t NC, int64
       WS(P.slot.s_grad + (isq ? j : P.var.o_zb + (j - P.k))) = acc;
     }
   }
+  if (P.objective == TNO_OBJ_LOADPATH) {
+    // f = sum_e |q_e| l_e^2 ;  grad_q = B^T (sign(q) l^2) + omega^T dz/dq_ind,  grad_zb = omega^T dz/dzb  with
+    // omega = 2 C^T (|q| o w)  (objectives.py:240-275, derivatives.py:640-718; the dx/dq, dy/dq terms of the
+    // reference vanish on a fixed plan because B spans the null space of the horizontal equilibrium)
+    f = 0.0;
+    for (int j = 0; j < nvar; ++j) WS(P.slot.s_grad + j) = 0.0;
+    for (int e = 0; e < m; ++e) {
+      const int a = P.edge_u[e], b = P.edge_v[e];
+      const double u = xval(P, ws, NC, c, b, 0) - xval(P, ws, NC, c, a, 0);
+      const double v = xval(P, ws, NC, c, b, 1) - xval(P, ws, NC, c, a, 1);
+      const double w = zval(P, ws, NC, c, b) - zval(P, ws, NC, c, a);
+      const double l2 = u * u + v * v + w * w;
+      const double qe = WS(P.slot.s_q + e);
+      f = fma(fabs(qe), l2, f);
+      const double sl = qe > 0.0 ? l2 : (qe < 0.0 ? -l2 : 0.0);
+      for (int j = 0; j < k; ++j) WS(P.slot.s_grad + j) = fma(sl, P.B[(int64_t)e * k + j], WS(P.slot.s_grad + j));
+    }
+    for (int v = 0; v < n; ++v) {
+      const double zv = zval(P, ws, NC, c, v);
+      double om = 0.0;
+      for (int t = P.vadj_ptr[v]; t < P.vadj_ptr[v + 1]; ++t)
+        om = fma(fabs(WS(P.slot.s_q + P.vadj_edge[t])), zv - zval(P, ws, NC, c, P.vadj_other[t]), om);
+      om *= 2.0;
+      const int r = P.vrow[v];
+      if (r >= 0) {
+        for (int j = 0; j < k; ++j)
+          WS(P.slot.s_grad + j) = fma(om, WS(P.slot.s_r + r * nrhs + P.rhs.c_q + j), WS(P.slot.s_grad + j));
+        if (P.var.o_zb >= 0)
+          for (int b = 0; b < nb; ++b)
+            WS(P.slot.s_grad + P.var.o_zb + b) = fma(om, WS(P.slot.s_r + r * nrhs + P.rhs.c_zb + b), WS(P.slot.s_grad + P.var.o_zb + b));
+      } else if (P.var.o_zb >= 0) {
+        WS(P.slot.s_grad + P.var.o_zb + (-1 - r)) += om;
+      }
+    }
+  }
   if (P.objective == TNO_OBJ_MAX) f = -f;
   if (P.objective == TNO_OBJ_T) f = WS(P.slot.s_x + nvar - 1);
   if (P.objective == TNO_OBJ_NEG_LAST) f = -WS(P.slot.s_x + nvar - 1);
@@ -576,7 +611,7 @@ int run_interleaved(Plan* PL, const double* x_dev, int64_t N, int64_t ldx, const
     constexpr int RB = 4;
     LAUNCH(KK_SOLVE1, k_solve<RB>, grid1(nc, TB, (P.rhs.nrhs1 + RB - 1) / RB), TB, P, ws, NC, nc, 0, P.rhs.nrhs1);
     // the dz/dq_ind columns only feed the Jacobian and the bestfit gradient
-    const bool need2 = P.rhs.nrhs2 > 0 && (out->J != nullptr || (P.objective == TNO_OBJ_BESTFIT && out->grad != nullptr));
+    const bool need2 = P.rhs.nrhs2 > 0 && (out->J != nullptr || ((P.objective == TNO_OBJ_BESTFIT || P.objective == TNO_OBJ_LOADPATH) && out->grad != nullptr));
     if (need2) {
       LAUNCH(KK_RHS2, k_rhs2, grid1(nc, TB, gyr), TB, P, ws, NC, nc, rtile);
       LAUNCH(KK_SOLVE2, k_solve<RB>, grid1(nc, TB, (P.rhs.nrhs2 + RB - 1) / RB), TB, P, ws, NC, nc, P.rhs.nrhs1, P.rhs.nrhs2);

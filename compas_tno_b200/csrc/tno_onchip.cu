@@ -406,7 +406,10 @@ __global__ void __launch_bounds__(THREADS, MINB) k_onchip(const __grid_constant_
   double* azsup = sm + O.o_azsup;  // nsup x nb : dz/dzb at the neighbours of the supports
   double* red = sm + O.o_red;
   double* pers = sm + O.o_pers;    // z_lambdv of the free rows after phase 1 (lambdv variable only)
-  double* bf = sm + O.o_bf;        // bestfit objective: per-warp partial column sums (THREADS / 32 x 16)
+  double* bf = sm + O.o_bf;        // bestfit / loadpath objectives: per-warp partial column sums (THREADS / 32 x 16)
+  double* lpe = sm + O.o_lpe;      // loadpath objective: sign(q_e) l_e^2 per edge (m)
+  double* lpa = sm + O.o_lpa;      //                     |q_e| w_e per edge (m), then the direct gradient term (k)
+  double* lpw = sm + O.o_lpw;      //                     omega = 2 C^T (|q| o w) per free row, then per support (ni + nb)
   const unsigned short* rowptr16 = reinterpret_cast<const unsigned short*>(smraw + O.o_idx_bytes + O.idx_rowptr);
   const unsigned short* rowcol16 = reinterpret_cast<const unsigned short*>(smraw + O.o_idx_bytes + O.idx_rowcol);
   const OcRange* wide = reinterpret_cast<const OcRange*>(smraw + O.o_idx_bytes + O.idx_wide);
@@ -440,8 +443,10 @@ __global__ void __launch_bounds__(THREADS, MINB) k_onchip(const __grid_constant_
   const bool want_thrust = (P.objective == TNO_OBJ_MIN || P.objective == TNO_OBJ_MAX);
   const bool want_reac = (P.constraints & TNO_CON_REAC_BOUNDS) != 0;
   const bool want_bestfit = P.objective == TNO_OBJ_BESTFIT;
-  // the dz/dq_ind panel is only needed by the Jacobian and by the bestfit gradient
-  const bool need2 = O.ncols2 > 0 && (A.J != nullptr || (want_bestfit && A.grad != nullptr));
+  const bool want_loadpath = P.objective == TNO_OBJ_LOADPATH;
+  const bool want_wsum = want_bestfit || want_loadpath;  // gradient = weighted column sums of the sensitivity panels
+  // the dz/dq_ind panel is only needed by the Jacobian and by the bestfit / loadpath gradients
+  const bool need2 = O.ncols2 > 0 && (A.J != nullptr || (want_wsum && A.grad != nullptr));
 
   // index region: loaded once per CTA, reused by every candidate
   for (int i = tid; i < O.idx_bytes / 16; i += THREADS)
@@ -705,18 +710,67 @@ __global__ void __launch_bounds__(THREADS, MINB) k_onchip(const __grid_constant_
         gmin = fmin(gmin, fmin(g0, g1));
       }
     }
-    // bestfit gradient: dst[c] = sum_r 2 (z_r - s_r) R[r, col0 + c]  (+ the identity rows of the supports).
-    // Half-warps walk 16 consecutive panel columns of one row (conflict-free), rows are spread over the
+    if (want_loadpath) {
+      // f = sum_e |q_e| l_e^2 ;  grad_q = B^T (sign(q) l^2) + omega^T dz/dq_ind ,  grad_zb = omega^T dz/dzb  with
+      // omega = 2 C^T (|q| o w)   (objectives.py:240-275, derivatives.py:640-718; the reference's dx/dq, dy/dq terms
+      // vanish on a fixed plan because B spans the null space of the horizontal equilibrium).
+      // q left the panel when the matrix was assembled: it is recomputed here, bit for bit as in step 1.
+      for (int e = tid; e < m; e += THREADS) {
+        double qe = lamh * P.d[e];
+#pragma unroll 4
+        for (int j = 0; j < k; ++j) qe = fma(__ldg(O.Bt + (int64_t)j * m + e), xs[j], qe);
+        const int a = __ldg(P.edge_u + e), b = __ldg(P.edge_v + e);
+        const double u = xyval(b, 0) - xyval(a, 0), v = xyval(b, 1) - xyval(a, 1), w = zval(b) - zval(a);
+        const double l2 = u * u + v * v + w * w;
+        fpart = fma(fabs(qe), l2, fpart);
+        lpe[e] = qe > 0.0 ? l2 : (qe < 0.0 ? -l2 : 0.0);
+        lpa[e] = fabs(qe) * w;
+      }
+      __syncthreads();
+      for (int v = tid; v < n; v += THREADS) {
+        double om = 0.0;
+        for (int t = __ldg(P.vadj_ptr + v); t < __ldg(P.vadj_ptr + v + 1); ++t)
+          om = fma((double)__ldg(P.vadj_sign + t), lpa[__ldg(P.vadj_edge + t)], om);
+        const int r = vrow_s[v];
+        lpw[r >= 0 ? r : ni - 1 - r] = 2.0 * om;
+      }
+      __syncthreads();
+      if (A.grad) {
+        // direct term: lpa[j] = sum_e lpe[e] B[e, j]; half-warps read 16 consecutive doubles of one row of B
+        constexpr int NW = THREADS / 32;
+        const int csub = lane & 15, rsub = lane >> 4;
+        for (int cb = 0; cb < k; cb += 16) {
+          const bool cok = cb + csub < k;
+          double acc = 0.0;
+          if (cok)
+            for (int e = warp * 2 + rsub; e < m; e += 2 * NW) acc = fma(lpe[e], __ldg(P.B + (int64_t)e * k + cb + csub), acc);
+          acc += __shfl_xor_sync(0xffffffffu, acc, 16);
+          if (lane < 16) bf[warp * 16 + lane] = acc;
+          __syncthreads();
+          if (tid < 16 && cb + tid < k) {
+            double sum = 0.0;
+            for (int w = 0; w < NW; ++w) sum += bf[w * 16 + tid];
+            lpa[cb + tid] = sum;
+          }
+          __syncthreads();
+        }
+      }
+    }
+    // bestfit / loadpath gradients: dst[c] = addend[c] + sum_r wgt(r) R[r, col0 + c]  (+ the identity rows of the
+    // supports).  Half-warps walk 16 consecutive panel columns of one row (conflict-free), rows are spread over the
     // 2 * THREADS / 32 half-warps; fixed reduction order, so results are reproducible run to run.
-    auto wcolsum = [&](int col0, int ncols, double* dst, bool add_fixed) {
+    auto wgt = [&](int i) -> double {  // i < ni: free row, else support i - ni
+      if (want_loadpath) return lpw[i];
+      return 2.0 * (zs[i] - __ldg(P.s + (i < ni ? (int)rowv_s[i] : fixed_s[i - ni])));
+    };
+    auto wcolsum = [&](int col0, int ncols, double* dst, const double* addend, bool add_fixed) {
       constexpr int NW = THREADS / 32;
       const int csub = lane & 15, rsub = lane >> 4;
       for (int cb = 0; cb < ncols; cb += 16) {
         const bool cok = cb + csub < ncols;
         double acc = 0.0;
         for (int r = warp * 2 + rsub; r < ni; r += 2 * NW) {
-          const double w = 2.0 * (zs[r] - __ldg(P.s + rowv_s[r]));
-          if (cok) acc = fma(w, R[r * W + col0 + cb + csub], acc);
+          if (cok) acc = fma(wgt(r), R[r * W + col0 + cb + csub], acc);
         }
         acc += __shfl_xor_sync(0xffffffffu, acc, 16);
         if (lane < 16) bf[warp * 16 + lane] = acc;
@@ -724,13 +778,14 @@ __global__ void __launch_bounds__(THREADS, MINB) k_onchip(const __grid_constant_
         if (tid < 16 && cb + tid < ncols) {
           double sum = 0.0;
           for (int w = 0; w < NW; ++w) sum += bf[w * 16 + tid];
-          if (add_fixed) sum += 2.0 * (zs[ni + cb + tid] - __ldg(P.s + fixed_s[cb + tid]));
+          if (add_fixed) sum += wgt(ni + cb + tid);
+          if (addend) sum += addend[cb + tid];
           dst[cb + tid] = sum;
         }
         __syncthreads();
       }
     };
-    if (want_bestfit && A.grad && P.var.o_zb >= 0) wcolsum(O.c_az, nb, A.grad + cand * nvar + P.var.o_zb, true);
+    if (want_wsum && A.grad && P.var.o_zb >= 0) wcolsum(O.c_az, nb, A.grad + cand * nvar + P.var.o_zb, nullptr, true);
     if (Jout && P.con.r_env >= 0 && P.var.o_zb >= 0) {
       // dz/dzb block straight to the Jacobian (its panel columns are about to be reused)
       for (int idx = tid; idx < n * nb; idx += THREADS) {
@@ -979,8 +1034,8 @@ __global__ void __launch_bounds__(THREADS, MINB) k_onchip(const __grid_constant_
         for (int b = 0; b < nb; ++b) fval += sqrt(react[3 * b] * react[3 * b] + react[3 * b + 1] * react[3 * b + 1]);
         fval *= osign;
       }
-    } else if (want_bestfit) {
-      if (A.grad) wcolsum(O.c_q, k, A.grad + cand * nvar, false);
+    } else if (want_wsum) {
+      if (A.grad) wcolsum(O.c_q, k, A.grad + cand * nvar, want_loadpath ? lpa : nullptr, false);
       for (int off = 16; off > 0; off >>= 1) fpart += __shfl_xor_sync(0xffffffffu, fpart, off);
       if (lane == 0) red[warp] = fpart;
       __syncthreads();
@@ -1618,7 +1673,11 @@ static int build_onchip_impl(Plan* PL, const tno_problem_desc* D, const int THRE
   O.o_gxy = take(2 * nb * k + 2 * nb);
   O.o_azsup = take(((P.constraints & TNO_CON_REAC_BOUNDS) && P.var.o_zb >= 0) ? O.nsup * nb : 0);
   O.o_red = take(40);
-  O.o_bf = take(P.objective == TNO_OBJ_BESTFIT ? (THREADS / 32) * 16 : 0);
+  const bool lp = P.objective == TNO_OBJ_LOADPATH;
+  O.o_bf = take((P.objective == TNO_OBJ_BESTFIT || lp) ? (THREADS / 32) * 16 : 0);
+  O.o_lpe = take(lp ? m : 0);
+  O.o_lpa = take(lp ? std::max(m, k) : 0);
+  O.o_lpw = take(lp ? ni + P.nb : 0);
   O.o_idx_bytes = off * 8;
   int max_optin = 0, smem_sm = 0;
   TNO_CUDA_OK(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, PL->device));

@@ -160,7 +160,7 @@ struct DevOnchip {
   int adj_deg;           // padded adjacency width (0: use the pointer lists)
   uint32_t nvar_magic;   // ceil(2^32 / nvar)
   // shared memory layout: offsets in doubles, index region in bytes
-  int o_x, o_v, o_r, o_pers, o_qsup, o_react, o_gxy, o_azsup, o_red, o_bf, o_idx_bytes;
+  int o_x, o_v, o_r, o_pers, o_qsup, o_react, o_gxy, o_azsup, o_red, o_bf, o_lpe, o_lpa, o_lpw, o_idx_bytes;
   int idx_rowptr, idx_rowcol, idx_wide, idx_clev, idx_chains, idx_rowchain, idx_chunks, idx_ops;
   int idx_bytes, smem_bytes;
   int fseg_units;        // staging buffer size, 16-byte units (3 buffers)

@@ -20,7 +20,8 @@ _VAR_BITS = {"q": _lib.VAR_Q, "zb": _lib.VAR_ZB, "t": _lib.VAR_T, "n": _lib.VAR_
 _CON_BITS = {"funicular": _lib.CON_FUNICULAR, "envelope": _lib.CON_ENVELOPE, "reac_bounds": _lib.CON_REAC_BOUNDS}
 _OBJ = {None: _lib.OBJ_NONE, "none": _lib.OBJ_NONE, "min": _lib.OBJ_MIN, "max": _lib.OBJ_MAX, "t": _lib.OBJ_T,
         "n": _lib.OBJ_NEG_LAST, "s": _lib.OBJ_NEG_LAST, "max_load": _lib.OBJ_NEG_LAST,
-        "bestfit": _lib.OBJ_BESTFIT, "target": _lib.OBJ_BESTFIT, "feasibility": _lib.OBJ_FEASIBILITY}
+        "bestfit": _lib.OBJ_BESTFIT, "target": _lib.OBJ_BESTFIT, "feasibility": _lib.OBJ_FEASIBILITY,
+        "loadpath": _lib.OBJ_LOADPATH}
 _KERNELS = {"auto": _lib.KERNEL_AUTO, "interleaved": _lib.KERNEL_INTERLEAVED, "onchip": _lib.KERNEL_ONCHIP}
 _ORDERINGS = {"auto": 0, "natural": 1, "mindeg": 2, "nested": 3}
 

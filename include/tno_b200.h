@@ -67,6 +67,8 @@ extern "C" {
 #define TNO_OBJ_BESTFIT 5    /* f_bestfit     / gradient_bestfit   ('bestfit','target'; variables q [, zb]; needs s)
                                 problems/objectives.py:170-200, problems/derivatives.py:355-413 */
 #define TNO_OBJ_FEASIBILITY 6 /* f_constant   / gradient_feasibility   f = 1, grad = 0  (objectives.py:395-412) */
+#define TNO_OBJ_LOADPATH 7   /* f_loadpath_general / gradient_loadpath  f = sum |q| l^2  (variables q [, zb])
+                                problems/objectives.py:240-275, problems/derivatives.py:640-718 */
 
 /* parametric envelopes (arithmetic lives in the un-vendored compas_tna; closed forms recovered from
  * the reference fixtures) */

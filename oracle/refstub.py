@@ -106,6 +106,8 @@ def load_reference():
         gradient_fmax=prb.gradient_fmax,
         f_constant=prb.f_constant,
         gradient_feasibility=prb.gradient_feasibility,
+        f_loadpath_general=prb.f_loadpath_general,
+        gradient_loadpath=prb.gradient_loadpath,
         f_bestfit=prb.f_bestfit,
         gradient_bestfit=prb.gradient_bestfit,
         f_reduce_thk=prb.f_reduce_thk,

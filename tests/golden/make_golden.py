@@ -159,6 +159,7 @@ def main():
     run_case(ref, "cross14_q_zb_min", form, P, ["q", "zb"], ["funicular", "envelope"], "min", xs, 0.5)
 
     run_case(ref, "cross14_q_zb_bestfit", form, P, ["q", "zb"], ["funicular", "envelope"], "bestfit", xs[:3], 0.5)
+    run_case(ref, "cross14_q_zb_loadpath", form, P, ["q", "zb"], ["funicular", "envelope"], "loadpath", xs[:3], 0.5)
     run_case(ref, "cross14_q_zb_feasibility", form, P, ["q", "zb"], ["funicular", "envelope"], "feasibility", xs[:2], 0.5)
 
     # ---- B: cross vault, thickness variable -------------------------------------------------
@@ -183,6 +184,7 @@ def main():
     run_case(ref, "dome_q_zb_reac_min", form, P, ["q", "zb"], ["funicular", "envelope", "reac_bounds"], "min",
              xs, thk, extra={"b": form["b"]})
 
+    run_case(ref, "dome_q_zb_loadpath", form, P, ["q", "zb"], ["funicular", "envelope"], "loadpath", xs[:2], thk)
     run_case(ref, "dome_q_zb_bestfit", form, P, ["q", "zb"], ["funicular", "envelope"], "bestfit", xs[:2], thk)
 
     # ---- E: dome, thickness variable, x* = stored optimum -----------------------------------

@@ -19,7 +19,7 @@ CASES = [
     "dome_q_zb_lambdh_reac",
     "dome_q_zb_lambdv",
     "freeform_q_zb_min",
-    "cross14_q_zb_bestfit", "cross14_q_zb_feasibility",
+    "cross14_q_zb_bestfit", "cross14_q_zb_feasibility", "cross14_q_zb_loadpath", "dome_q_zb_loadpath",
     "dome_q_zb_bestfit",
 ]
 
