@@ -7,12 +7,13 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libtno_b200.so")
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 # masks / enums (mirror include/tno_b200.h)
 VAR_Q, VAR_ZB, VAR_T, VAR_LAMBDH, VAR_LAMBDV = 1, 2, 4, 8, 16
 CON_FUNICULAR, CON_ENVELOPE, CON_REAC_BOUNDS = 1, 2, 4
 OBJ_NONE, OBJ_MIN, OBJ_MAX, OBJ_T, OBJ_NEG_LAST, OBJ_BESTFIT, OBJ_FEASIBILITY, OBJ_LOADPATH = 0, 1, 2, 3, 4, 5, 6, 7
+OBJ_ECOMP_LINEAR, OBJ_ECOMP_NONLINEAR = 8, 9
 ENV_FIXED, ENV_DOME, ENV_CROSSVAULT = 0, 1, 2
 KERNEL_AUTO, KERNEL_INTERLEAVED, KERNEL_ONCHIP = 0, 1, 2
 STATUS_OK, STATUS_NOT_PD, STATUS_NONFINITE = 0, 1, 2
@@ -36,6 +37,7 @@ class ProblemDesc(C.Structure):
         ("variables", C.c_uint32), ("constraints", C.c_uint32), ("objective", C.c_int32),
         ("envelope_kind", C.c_int32), ("env_params", C.c_double * 8), ("thk", C.c_double),
         ("device", C.c_int32), ("kernel", C.c_int32), ("ordering", C.c_int32), ("reserved", C.c_int32),
+        ("dXb", _dp), ("stiff", _dp),
     ]
 
 

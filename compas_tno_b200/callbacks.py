@@ -21,7 +21,8 @@ from .plan import TnoPlan
 __all__ = [
     "accelerate", "constr_wrapper", "sensitivities_wrapper", "f_min_thrust", "f_max_thrust", "gradient_fmin",
     "gradient_fmax", "f_reduce_thk", "gradient_reduce_thk", "f_tight_crosssection", "gradient_tight_crosssection",
-    "f_bestfit", "gradient_bestfit", "f_loadpath_general", "gradient_loadpath", "f_constant", "gradient_feasibility", "objective_selector", "evaluate_batch",
+    "f_bestfit", "gradient_bestfit", "f_loadpath_general", "gradient_loadpath", "f_complementary_energy", "gradient_complementary_energy",
+    "f_complementary_energy_nonlinear", "gradient_complementary_energy_nonlinear", "f_constant", "gradient_feasibility", "objective_selector", "evaluate_batch",
 ]
 
 _ATTR = "_tno_b200_state"
@@ -90,6 +91,8 @@ f_tight_crosssection, gradient_tight_crosssection = _objective("n")
 f_bestfit, gradient_bestfit = _objective("bestfit")
 f_constant, gradient_feasibility = _objective("feasibility")
 f_loadpath_general, gradient_loadpath = _objective("loadpath")
+f_complementary_energy, gradient_complementary_energy = _objective("Ecomp-linear")
+f_complementary_energy_nonlinear, gradient_complementary_energy_nonlinear = _objective("Ecomp-nonlinear")
 
 _SELECT = {
     "min": (f_min_thrust, gradient_fmin),
@@ -102,6 +105,8 @@ _SELECT = {
     "target": (f_bestfit, gradient_bestfit),
     "feasibility": (f_constant, gradient_feasibility),
     "loadpath": (f_loadpath_general, gradient_loadpath),
+    "Ecomp-linear": (f_complementary_energy, gradient_complementary_energy),
+    "Ecomp-nonlinear": (f_complementary_energy_nonlinear, gradient_complementary_energy_nonlinear),
 }
 
 

@@ -134,12 +134,16 @@ int tno_plan_create(const tno_problem_desc* D, tno_plan** out_plan) {
   if ((D->constraints & TNO_CON_REAC_BOUNDS) && !D->b) return fail(TNO_EINVAL, "reac_bounds needs b");
   if ((D->variables & TNO_VAR_LAMBDH) && (!D->px0 || !D->py0)) return fail(TNO_EINVAL, "lambdh needs px0 / py0");
   if ((D->variables & TNO_VAR_LAMBDV) && (!D->pzv || !D->pz0)) return fail(TNO_EINVAL, "lambdv needs pzv / pz0");
-  if (D->objective < TNO_OBJ_NONE || D->objective > TNO_OBJ_LOADPATH) return fail(TNO_EINVAL, "bad objective");
-  if (D->objective == TNO_OBJ_BESTFIT || D->objective == TNO_OBJ_LOADPATH) {
-    // gradient_bestfit / gradient_loadpath (derivatives.py:355-413, 640-718) only know the q and zb blocks
+  if (D->objective < TNO_OBJ_NONE || D->objective > TNO_OBJ_ECOMP_NONLINEAR) return fail(TNO_EINVAL, "bad objective");
+  const bool ecomp = D->objective == TNO_OBJ_ECOMP_LINEAR || D->objective == TNO_OBJ_ECOMP_NONLINEAR;
+  if (D->objective == TNO_OBJ_BESTFIT || D->objective == TNO_OBJ_LOADPATH || ecomp) {
+    // gradient_bestfit / gradient_loadpath / gradient_complementary_energy (derivatives.py:355-413, 640-718, 503-620):
+    // of the variables this library supports they only know the q and zb blocks
     if (D->variables & ~(TNO_VAR_Q | TNO_VAR_ZB))
-      return fail(TNO_EINVAL, "bestfit / loadpath objectives support the variables q and zb only");
+      return fail(TNO_EINVAL, "bestfit / loadpath / Ecomp objectives support the variables q and zb only");
     if (D->objective == TNO_OBJ_BESTFIT && !D->s) return fail(TNO_EINVAL, "bestfit objective needs the target surface s");
+    if (ecomp && !D->dXb) return fail(TNO_EINVAL, "Ecomp objectives need the support displacements dXb");
+    if (D->objective == TNO_OBJ_ECOMP_NONLINEAR && !D->stiff) return fail(TNO_EINVAL, "Ecomp-nonlinear needs stiff");
   }
 
   int ndev = 0;
@@ -281,7 +285,7 @@ int tno_plan_create(const tno_problem_desc* D, tno_plan** out_plan) {
   if (V.o_lambdv >= 0) { R.c_lambdv = pos; pos += 1; }
   R.nrhs1 = pos;
   const bool need_dq = (D->constraints & (TNO_CON_ENVELOPE | TNO_CON_REAC_BOUNDS)) != 0 || D->objective == TNO_OBJ_BESTFIT ||
-                       D->objective == TNO_OBJ_LOADPATH;
+                       D->objective == TNO_OBJ_LOADPATH || ecomp;
   if (need_dq) {
     R.c_q = pos; pos += k;
     if (V.o_lambdh >= 0) { R.c_lambdh = pos; pos += 1; }
@@ -335,6 +339,8 @@ int tno_plan_create(const tno_problem_desc* D, tno_plan** out_plan) {
   UP(py0, vec(D->py0, (size_t)n));
   UP(pzv, vec(D->pzv, (size_t)n));
   UP(pz0, vec(D->pz0, (size_t)n));
+  UP(dXb, vec(D->dXb, (size_t)nb * 3));
+  UP(stiff, vec(D->stiff, (size_t)m));
 #undef UP
 
   // ---- emit tables (user-facing row-major layouts as affine gathers of the scratch slots) --
@@ -375,7 +381,7 @@ int tno_plan_create(const tno_problem_desc* D, tno_plan** out_plan) {
     std::vector<EmitDesc2> t((size_t)nvar, cst(0.0));
     if (D->objective == TNO_OBJ_MIN || D->objective == TNO_OBJ_MAX)
       for (int j = 0; j < k; ++j) t[j] = one(SL.s_grad + j, +1.f);
-    else if (D->objective == TNO_OBJ_BESTFIT || D->objective == TNO_OBJ_LOADPATH)
+    else if (D->objective == TNO_OBJ_BESTFIT || D->objective == TNO_OBJ_LOADPATH || ecomp)
       for (int j = 0; j < nvar; ++j) t[j] = one(SL.s_grad + j, +1.f);
     else if (D->objective == TNO_OBJ_T)
       t[nvar - 1] = cst(1.0);

@@ -528,6 +528,57 @@ __global__ void k_epilogue(DevPlan P, double* __restrict__ ws, int64_t NC, int64
       }
     }
   }
+  if (P.objective == TNO_OBJ_ECOMP_LINEAR || P.objective == TNO_OBJ_ECOMP_NONLINEAR) {
+    // f = -sum(R o dXb), R = Cb^T Q C X - P_b ;  grad = -sum_b dXb[b] . dR_b/dx   (objectives.py:278-340,
+    // derivatives.py:503-620; dx/dq_ind, dy/dq_ind vanish on a fixed plan).  'simplified' quadratic term: sum stiff q^2.
+    f = 0.0;
+    for (int j = 0; j < nvar; ++j) WS(P.slot.s_grad + j) = 0.0;
+    for (int b = 0; b < nb; ++b) {
+      const int vb = P.fixed[b];
+      const int a0 = P.vadj_ptr[vb], a1 = P.vadj_ptr[vb + 1];
+      const double xb = P.X[3 * vb + 0], yb = P.X[3 * vb + 1], zb = zfixed(P, ws, NC, c, b);
+      const double dx = P.dXb[3 * b + 0], dy = P.dXb[3 * b + 1], dz = P.dXb[3 * b + 2];
+      double Rx = -P.P[3 * vb + 0], Ry = -P.P[3 * vb + 1], Rz = -pzs * P.P[3 * vb + 2];
+      for (int t = a0; t < a1; ++t) {
+        const int o = P.vadj_other[t];
+        const double qe = WS(P.slot.s_q + P.vadj_edge[t]);  // C[e, vb] (C X)_e = X_b - X_o whichever end the support is
+        Rx = fma(qe, xb - xval(P, ws, NC, c, o, 0), Rx);
+        Ry = fma(qe, yb - xval(P, ws, NC, c, o, 1), Ry);
+        Rz = fma(qe, zb - zval(P, ws, NC, c, o), Rz);
+      }
+      f -= Rx * dx + Ry * dy + Rz * dz;
+      for (int j = 0; j < k; ++j) {
+        double dRx = 0.0, dRy = 0.0, dRz = 0.0;
+        for (int t = a0; t < a1; ++t) {
+          const int o = P.vadj_other[t];
+          const int e = P.vadj_edge[t];
+          const double Bej = P.B[(int64_t)e * k + j];
+          dRx = fma(xb - xval(P, ws, NC, c, o, 0), Bej, dRx);
+          dRy = fma(yb - xval(P, ws, NC, c, o, 1), Bej, dRy);
+          dRz = fma(zb - zval(P, ws, NC, c, o), Bej, dRz);
+          const int ro = P.vrow[o];
+          if (ro >= 0) dRz = fma(-WS(P.slot.s_q + e), WS(P.slot.s_r + ro * nrhs + P.rhs.c_q + j), dRz);
+        }
+        WS(P.slot.s_grad + j) -= dx * dRx + dy * dRy + dz * dRz;
+      }
+      if (P.var.o_zb >= 0)
+        for (int cb = 0; cb < nb; ++cb) {
+          double acc = 0.0;
+          for (int t = a0; t < a1; ++t) {
+            const int ro = P.vrow[P.vadj_other[t]];
+            const double Ao = ro >= 0 ? WS(P.slot.s_r + ro * nrhs + P.rhs.c_zb + cb) : ((-1 - ro) == cb ? 1.0 : 0.0);
+            acc = fma(WS(P.slot.s_q + P.vadj_edge[t]), (cb == b ? 1.0 : 0.0) - Ao, acc);
+          }
+          WS(P.slot.s_grad + P.var.o_zb + cb) -= dz * acc;
+        }
+    }
+    if (P.objective == TNO_OBJ_ECOMP_NONLINEAR)
+      for (int e = 0; e < m; ++e) {
+        const double qe = WS(P.slot.s_q + e), se = P.stiff[e];
+        f = fma(se * qe, qe, f);
+        for (int j = 0; j < k; ++j) WS(P.slot.s_grad + j) = fma(2.0 * se * qe, P.B[(int64_t)e * k + j], WS(P.slot.s_grad + j));
+      }
+  }
   if (P.objective == TNO_OBJ_MAX) f = -f;
   if (P.objective == TNO_OBJ_T) f = WS(P.slot.s_x + nvar - 1);
   if (P.objective == TNO_OBJ_NEG_LAST) f = -WS(P.slot.s_x + nvar - 1);
@@ -611,7 +662,7 @@ int run_interleaved(Plan* PL, const double* x_dev, int64_t N, int64_t ldx, const
     constexpr int RB = 4;
     LAUNCH(KK_SOLVE1, k_solve<RB>, grid1(nc, TB, (P.rhs.nrhs1 + RB - 1) / RB), TB, P, ws, NC, nc, 0, P.rhs.nrhs1);
     // the dz/dq_ind columns only feed the Jacobian and the bestfit gradient
-    const bool need2 = P.rhs.nrhs2 > 0 && (out->J != nullptr || ((P.objective == TNO_OBJ_BESTFIT || P.objective == TNO_OBJ_LOADPATH) && out->grad != nullptr));
+    const bool need2 = P.rhs.nrhs2 > 0 && (out->J != nullptr || (P.objective >= TNO_OBJ_BESTFIT && P.objective != TNO_OBJ_FEASIBILITY && out->grad != nullptr));
     if (need2) {
       LAUNCH(KK_RHS2, k_rhs2, grid1(nc, TB, gyr), TB, P, ws, NC, nc, rtile);
       LAUNCH(KK_SOLVE2, k_solve<RB>, grid1(nc, TB, (P.rhs.nrhs2 + RB - 1) / RB), TB, P, ws, NC, nc, P.rhs.nrhs1, P.rhs.nrhs2);

@@ -444,9 +444,11 @@ __global__ void __launch_bounds__(THREADS, MINB) k_onchip(const __grid_constant_
   const bool want_reac = (P.constraints & TNO_CON_REAC_BOUNDS) != 0;
   const bool want_bestfit = P.objective == TNO_OBJ_BESTFIT;
   const bool want_loadpath = P.objective == TNO_OBJ_LOADPATH;
+  const bool want_ecomp = P.objective == TNO_OBJ_ECOMP_LINEAR || P.objective == TNO_OBJ_ECOMP_NONLINEAR;
+  const bool want_ecomp_nl = P.objective == TNO_OBJ_ECOMP_NONLINEAR;
   const bool want_wsum = want_bestfit || want_loadpath;  // gradient = weighted column sums of the sensitivity panels
   // the dz/dq_ind panel is only needed by the Jacobian and by the bestfit / loadpath gradients
-  const bool need2 = O.ncols2 > 0 && (A.J != nullptr || (want_wsum && A.grad != nullptr));
+  const bool need2 = O.ncols2 > 0 && (A.J != nullptr || ((want_wsum || want_ecomp) && A.grad != nullptr));
 
   // index region: loaded once per CTA, reused by every candidate
   for (int i = tid; i < O.idx_bytes / 16; i += THREADS)
@@ -489,6 +491,11 @@ __global__ void __launch_bounds__(THREADS, MINB) k_onchip(const __grid_constant_
       if (e >= m) continue;
       const double acc = acc4[i];
       qs[e] = acc;
+      if (want_ecomp_nl) {  // 'simplified' quadratic energy sum stiff q^2 and the weight of its gradient B^T (2 stiff q)
+        const double se = __ldg(P.stiff + e);
+        fpart = fma(se * acc, acc, fpart);
+        lpe[e] = 2.0 * se * acc;
+      }
       if (A.q) A.q[cand * m + e] = acc;
       if (P.con.r_fun >= 0) {
         const double g0 = acc - P.qmin[e], g1 = P.qmax[e] - acc;
@@ -735,7 +742,9 @@ __global__ void __launch_bounds__(THREADS, MINB) k_onchip(const __grid_constant_
         lpw[r >= 0 ? r : ni - 1 - r] = 2.0 * om;
       }
       __syncthreads();
-      if (A.grad) {
+    }
+    if ((want_loadpath || want_ecomp_nl) && A.grad) {
+      {
         // direct term: lpa[j] = sum_e lpe[e] B[e, j]; half-warps read 16 consecutive doubles of one row of B
         constexpr int NW = THREADS / 32;
         const int csub = lane & 15, rsub = lane >> 4;
@@ -796,7 +805,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_onchip(const __grid_constant_
         Jout[(int64_t)(P.con.r_env + n + v) * nvar + P.var.o_zb + b] = -a;
       }
     }
-    if (want_thrust || want_reac) {
+    if (want_thrust || want_reac || want_ecomp) {
       // R_b = Cb^T Q C X - P_b
       for (int b = tid; b < nb; b += THREADS) {
         const int vb = fixed_s[b];
@@ -856,7 +865,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_onchip(const __grid_constant_
         gxy[it] = gx;
         gxy[nb * k + it] = gy;
       }
-      if (want_reac && O.c_az >= 0) {
+      if ((want_reac || want_ecomp) && O.c_az >= 0) {
         for (int it = tid; it < O.nsup * nb; it += THREADS) {
           const int t = it / nb, b = it - t * nb;
           const int ro = vrow_s[supother_s[t]];
@@ -1034,6 +1043,46 @@ __global__ void __launch_bounds__(THREADS, MINB) k_onchip(const __grid_constant_
         for (int b = 0; b < nb; ++b) fval += sqrt(react[3 * b] * react[3 * b] + react[3 * b + 1] * react[3 * b + 1]);
         fval *= osign;
       }
+    } else if (want_ecomp) {
+      // f = -sum(R o dXb) [+ sum stiff q^2] ;  grad = -sum_b dXb[b] . dR_b/dx [+ B^T (2 stiff q)]
+      // (objectives.py:278-340, derivatives.py:503-620; dx/dq_ind and dy/dq_ind vanish on a fixed plan)
+      if (A.grad)
+        for (int col = tid; col < nvar; col += THREADS) {
+          double gsum = 0.0;
+          if (col < k) {
+            for (int b = 0; b < nb; ++b) {
+              const double zb = zfix(b);
+              double dRz = 0.0;
+              for (int t = supptr_s[b]; t < supptr_s[b + 1]; ++t) {
+                const int o = supother_s[t];
+                const int e = supedge_s[t];
+                dRz = fma(zb - zval(o), __ldg(P.B + (int64_t)e * k + col), dRz);  // C[e, b] (C z)_e = z_b - z_o
+                const int ro = vrow_s[o];
+                if (ro >= 0) dRz = fma(-qsup[t], R[ro * W + O.c_q + col], dRz);
+              }
+              gsum -= __ldg(P.dXb + 3 * b) * gxy[b * k + col] + __ldg(P.dXb + 3 * b + 1) * gxy[nb * k + b * k + col] +
+                      __ldg(P.dXb + 3 * b + 2) * dRz;
+            }
+            if (want_ecomp_nl) gsum += lpa[col];
+          } else {
+            const int cb = col - P.var.o_zb;
+            for (int b = 0; b < nb; ++b) {
+              double acc = 0.0;
+              for (int t = supptr_s[b]; t < supptr_s[b + 1]; ++t) acc = fma(qsup[t], (cb == b ? 1.0 : 0.0) - azsup[t * nb + cb], acc);
+              gsum -= __ldg(P.dXb + 3 * b + 2) * acc;
+            }
+          }
+          A.grad[cand * nvar + col] = gsum;
+        }
+      for (int off = 16; off > 0; off >>= 1) fpart += __shfl_xor_sync(0xffffffffu, fpart, off);
+      if (lane == 0) red[warp] = fpart;
+      __syncthreads();
+      if (tid == 0) {
+        for (int w = 0; w < THREADS / 32; ++w) fval += red[w];
+        for (int b = 0; b < nb; ++b)
+          fval -= react[3 * b] * P.dXb[3 * b] + react[3 * b + 1] * P.dXb[3 * b + 1] + react[3 * b + 2] * P.dXb[3 * b + 2];
+      }
+      __syncthreads();  // red is reused by the feasibility reduction below
     } else if (want_wsum) {
       if (A.grad) wcolsum(O.c_q, k, A.grad + cand * nvar, want_loadpath ? lpa : nullptr, false);
       for (int off = 16; off > 0; off >>= 1) fpart += __shfl_xor_sync(0xffffffffu, fpart, off);
@@ -1671,12 +1720,13 @@ static int build_onchip_impl(Plan* PL, const tno_problem_desc* D, const int THRE
   O.o_qsup = take(O.nsup);
   O.o_react = take(3 * nb);
   O.o_gxy = take(2 * nb * k + 2 * nb);
-  O.o_azsup = take(((P.constraints & TNO_CON_REAC_BOUNDS) && P.var.o_zb >= 0) ? O.nsup * nb : 0);
+  O.o_azsup = take((((P.constraints & TNO_CON_REAC_BOUNDS) || P.objective == TNO_OBJ_ECOMP_LINEAR || P.objective == TNO_OBJ_ECOMP_NONLINEAR) &&
+                     P.var.o_zb >= 0) ? O.nsup * nb : 0);
   O.o_red = take(40);
-  const bool lp = P.objective == TNO_OBJ_LOADPATH;
-  O.o_bf = take((P.objective == TNO_OBJ_BESTFIT || lp) ? (THREADS / 32) * 16 : 0);
-  O.o_lpe = take(lp ? m : 0);
-  O.o_lpa = take(lp ? std::max(m, k) : 0);
+  const bool lp = P.objective == TNO_OBJ_LOADPATH, enl = P.objective == TNO_OBJ_ECOMP_NONLINEAR;
+  O.o_bf = take((P.objective == TNO_OBJ_BESTFIT || lp || enl) ? (THREADS / 32) * 16 : 0);
+  O.o_lpe = take((lp || enl) ? m : 0);
+  O.o_lpa = take(lp ? std::max(m, k) : (enl ? k : 0));
   O.o_lpw = take(lp ? ni + P.nb : 0);
   O.o_idx_bytes = off * 8;
   int max_optin = 0, smem_sm = 0;

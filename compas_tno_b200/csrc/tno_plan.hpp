@@ -103,6 +103,8 @@ struct DevPlan {
   const double* py0;
   const double* pzv;
   const double* pz0;
+  const double* dXb;        // nb x 3 (complementary-energy objectives)
+  const double* stiff;      // m (Ecomp-nonlinear)
 };
 
 // ---- on-chip kernel family (tno_onchip.cu) -----------------------------------------------------------

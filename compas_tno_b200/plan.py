@@ -21,7 +21,8 @@ _CON_BITS = {"funicular": _lib.CON_FUNICULAR, "envelope": _lib.CON_ENVELOPE, "re
 _OBJ = {None: _lib.OBJ_NONE, "none": _lib.OBJ_NONE, "min": _lib.OBJ_MIN, "max": _lib.OBJ_MAX, "t": _lib.OBJ_T,
         "n": _lib.OBJ_NEG_LAST, "s": _lib.OBJ_NEG_LAST, "max_load": _lib.OBJ_NEG_LAST,
         "bestfit": _lib.OBJ_BESTFIT, "target": _lib.OBJ_BESTFIT, "feasibility": _lib.OBJ_FEASIBILITY,
-        "loadpath": _lib.OBJ_LOADPATH}
+        "loadpath": _lib.OBJ_LOADPATH, "Ecomp-linear": _lib.OBJ_ECOMP_LINEAR,
+        "Ecomp-nonlinear": _lib.OBJ_ECOMP_NONLINEAR}
 _KERNELS = {"auto": _lib.KERNEL_AUTO, "interleaved": _lib.KERNEL_INTERLEAVED, "onchip": _lib.KERNEL_ONCHIP}
 _ORDERINGS = {"auto": 0, "natural": 1, "mindeg": 2, "nested": 3}
 
@@ -118,6 +119,12 @@ class TnoPlan:
         D.py0 = dptr(getattr(M, "py0", None), (n,)) if "lambdh" in variables else None
         D.pzv = dptr(getattr(M, "pzv", None), (n,)) if "lambdv" in variables else None
         D.pz0 = dptr(getattr(M, "pz0", None), (n,)) if "lambdv" in variables else None
+        if objective in ("Ecomp-linear", "Ecomp-nonlinear"):
+            D.dXb = dptr(getattr(M, "dXb", None), (nb, 3))
+        if objective == "Ecomp-nonlinear":
+            if getattr(M, "Ecomp_method", "simplified") != "simplified":
+                raise NotImplementedError("Ecomp_method 'complete' is not available (neither in problems/setup.py:156)")
+            D.stiff = dptr(getattr(M, "stiff", None), (m,))
         D.variables = sum({_VAR_BITS[v] for v in variables})
         D.constraints = sum({_CON_BITS[c] for c in constraints})
         D.objective = _OBJ[objective]

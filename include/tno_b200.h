@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define TNO_ABI_VERSION 1
+#define TNO_ABI_VERSION 2
 
 /* error codes */
 #define TNO_OK 0
@@ -69,6 +69,10 @@ extern "C" {
 #define TNO_OBJ_FEASIBILITY 6 /* f_constant   / gradient_feasibility   f = 1, grad = 0  (objectives.py:395-412) */
 #define TNO_OBJ_LOADPATH 7   /* f_loadpath_general / gradient_loadpath  f = sum |q| l^2  (variables q [, zb])
                                 problems/objectives.py:240-275, problems/derivatives.py:640-718 */
+#define TNO_OBJ_ECOMP_LINEAR 8    /* f_complementary_energy / gradient_complementary_energy   ('Ecomp-linear'; needs dXb)
+                                     problems/objectives.py:278-312, problems/derivatives.py:503-582 */
+#define TNO_OBJ_ECOMP_NONLINEAR 9 /* f_complementary_energy_nonlinear / its gradient, method 'simplified'
+                                     ('Ecomp-nonlinear'; needs dXb and stiff)  objectives.py:315-340, derivatives.py:585-620 */
 
 /* parametric envelopes (arithmetic lives in the un-vendored compas_tna; closed forms recovered from
  * the reference fixtures) */
@@ -122,6 +126,8 @@ typedef struct tno_problem_desc {
   int32_t kernel;       /* TNO_KERNEL_* */
   int32_t ordering;     /* 0 = auto (minimum degree), 1 = natural, 2 = minimum degree, 3 = nested dissection */
   int32_t reserved;
+  const double* dXb;    /* nb x 3 prescribed support displacements (Ecomp objectives only)   Problem.dXb   */
+  const double* stiff;  /* m   0.5 l^2 / k per edge (Ecomp-nonlinear only)                   Problem.stiff */
 } tno_problem_desc;
 
 /* What the symbolic analysis found; all sizes a caller needs to allocate outputs. */

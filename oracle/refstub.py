@@ -108,6 +108,10 @@ def load_reference():
         gradient_feasibility=prb.gradient_feasibility,
         f_loadpath_general=prb.f_loadpath_general,
         gradient_loadpath=prb.gradient_loadpath,
+        f_complementary_energy=prb.f_complementary_energy,
+        gradient_complementary_energy=prb.gradient_complementary_energy,
+        f_complementary_energy_nonlinear=prb.f_complementary_energy_nonlinear,
+        gradient_complementary_energy_nonlinear=prb.gradient_complementary_energy_nonlinear,
         f_bestfit=prb.f_bestfit,
         gradient_bestfit=prb.gradient_bestfit,
         f_reduce_thk=prb.f_reduce_thk,

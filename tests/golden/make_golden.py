@@ -50,6 +50,8 @@ def reference_problem(ref, P, variables, constraints, thk, envelope=None, extra=
     M.envelope = envelope
     for key, val in (extra or {}).items():
         setattr(M, key, np.array(val, dtype=np.float64, copy=True))
+    if extra and "stiff" in extra:
+        M.Ecomp_method = "simplified"      # the only method set-up accepts (problems/setup.py:146-157)
     return M
 
 
@@ -160,6 +162,13 @@ def main():
 
     run_case(ref, "cross14_q_zb_bestfit", form, P, ["q", "zb"], ["funicular", "envelope"], "bestfit", xs[:3], 0.5)
     run_case(ref, "cross14_q_zb_loadpath", form, P, ["q", "zb"], ["funicular", "envelope"], "loadpath", xs[:3], 0.5)
+    centre = form["xyz"][:, :2].mean(axis=0)
+    out = form["xyz"][P.fixed, :2] - centre
+    dXb = np.column_stack([out / np.linalg.norm(out, axis=1, keepdims=True), -0.5 * np.ones(P.nb)])
+    dXb[1] *= 0.3                        # not symmetric on purpose
+    stiff = np.random.default_rng(SEED + 77).uniform(0.01, 0.05, size=(P.m, 1))
+    run_case(ref, "cross14_q_zb_ecomp_nonlinear", form, P, ["q", "zb"], ["funicular", "envelope"], "Ecomp-nonlinear", xs[:3], 0.5,
+             extra={"dXb": dXb, "stiff": stiff})
     run_case(ref, "cross14_q_zb_feasibility", form, P, ["q", "zb"], ["funicular", "envelope"], "feasibility", xs[:2], 0.5)
 
     # ---- B: cross vault, thickness variable -------------------------------------------------
@@ -185,6 +194,10 @@ def main():
              xs, thk, extra={"b": form["b"]})
 
     run_case(ref, "dome_q_zb_loadpath", form, P, ["q", "zb"], ["funicular", "envelope"], "loadpath", xs[:2], thk)
+    out = form["xyz"][P.fixed, :2] - np.array([5.0, 5.0])
+    dXb = np.column_stack([out / np.linalg.norm(out, axis=1, keepdims=True), np.linspace(-0.4, 0.2, P.nb)])
+    run_case(ref, "dome_q_zb_ecomp_linear", form, P, ["q", "zb"], ["funicular", "envelope"], "Ecomp-linear", xs[:2], thk,
+             extra={"dXb": dXb})
     run_case(ref, "dome_q_zb_bestfit", form, P, ["q", "zb"], ["funicular", "envelope"], "bestfit", xs[:2], thk)
 
     # ---- E: dome, thickness variable, x* = stored optimum -----------------------------------

@@ -20,6 +20,7 @@ CASES = [
     "dome_q_zb_lambdv",
     "freeform_q_zb_min",
     "cross14_q_zb_bestfit", "cross14_q_zb_feasibility", "cross14_q_zb_loadpath", "dome_q_zb_loadpath",
+    "cross14_q_zb_ecomp_nonlinear", "dome_q_zb_ecomp_linear",
     "dome_q_zb_bestfit",
 ]
 
@@ -52,6 +53,8 @@ def load_case(name, envelope_factory=None):
             val = z[key]
             attr = key[len("extra_"):]
             setattr(P, attr, val.copy())
+    if "extra_stiff" in z.files:
+        P.Ecomp_method = "simplified"
     if "envelope" in z.files:
         kind = str(z["envelope"])
         if envelope_factory is None:

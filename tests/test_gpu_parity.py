@@ -168,7 +168,7 @@ def test_edge_cases_batch_sizes_and_subsets(tno, kernel):
 
 @pytest.mark.parametrize("kernel", ["interleaved", "onchip"])
 @pytest.mark.parametrize("name", ["cross14_q_zb_bestfit", "dome_q_zb_bestfit", "cross14_q_zb_loadpath", "dome_q_zb_loadpath",
-                                  "dome_q_zb_reac_min"])
+                                  "cross14_q_zb_ecomp_nonlinear", "dome_q_zb_ecomp_linear", "dome_q_zb_reac_min"])
 def test_output_subsets_skip_the_sensitivity_solve(tno, name, kernel):
     """Without J (and, for bestfit, without grad) the dz/dq_ind solve is skipped: every other output is unchanged."""
     from compas_tno_b200.plan import TnoPlan
@@ -207,6 +207,12 @@ def test_dropin_bestfit_and_feasibility_callbacks(tno):
     tb.accelerate(Pl, "loadpath")
     assert abs(Pl.fobj(xl[0], Pl) - el["f"][0]) < 1e-10 * abs(el["f"][0])
     assert rel_err(Pl.fgrad(xl[0], Pl), el["grad"][0]) < 1e-8
+    for case, name in (("dome_q_zb_ecomp_linear", "Ecomp-linear"), ("cross14_q_zb_ecomp_nonlinear", "Ecomp-nonlinear")):
+        Pe, obj, xe, ee = load_case(case)
+        assert obj == name
+        tb.accelerate(Pe, name)
+        assert abs(Pe.fobj(xe[1], Pe) - ee["f"][1]) < 1e-10 * abs(ee["f"][1])
+        assert rel_err(Pe.fgrad(xe[1], Pe), ee["grad"][1]) < 1e-8
     M2 = load_case("cross14_q_zb_feasibility")[0]
     tb.accelerate(M2, "feasibility")
     assert M2.fobj(xs[0], M2) == 1.0
