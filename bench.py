@@ -51,6 +51,58 @@ def candidates(P, xs, N, seed):
     return W.sample_candidates(P, xs, N, seed=seed, basis=getattr(P, "candidate_basis", None))
 
 
+def sweep_specs():
+    """The BASELINE configurations 2-5 as single-GPU sweeps (per-GPU share where the configuration names 8 GPUs)."""
+    import numpy as np
+    from compas_tno_b200 import workloads as W
+    FULL = ("f", "grad", "g", "J", "z", "gmin", "status")
+    LIGHT = ("f", "gmin", "status")
+
+    def dome_multistart():
+        P, xs, obj = build_workload("dome_16x20", n_states=6)
+        return P, candidates(P, xs, 4096, seed=20261019 + 2), obj, FULL, None
+
+    def fan_thickness():
+        # fan form diagram of the reference fixture (tests/golden/fan_q_zb_max.npz carries its arrays) under the
+        # closed-form cross-vault envelope the fixture's lb / ub follow; the pavilion-vault envelope of the
+        # configuration is not pinned by any fixture (SURVEY.md section 8c), so the cross vault stands in for it
+        from compas_tno_b200.envelopes import CrossVaultEnvelope
+        from compas_tno_b200.problems import FixedProblem
+        z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "tests", "golden", "fan_q_zb_max.npz"))
+        P = FixedProblem.from_arrays(z["xyz"], z["edges"], z["fixed"], z["loads"], z["lb"], z["ub"], z["target"], z["q_form"],
+                                     ind=z["ind"])
+        P.B, P.d = z["B"].copy(), z["d"].reshape(-1, 1).copy()
+        P.variables, P.constraints, P.features = ["q", "zb", "t"], ["funicular", "envelope"], ["fixed"]
+        P.thk, P.envelope = 0.5, CrossVaultEnvelope((0.0, 10.0), (0.0, 10.0), 0.5)
+        x0 = z["x"][0]
+        X = np.repeat(np.concatenate([x0, [0.5]])[None, :], 256, axis=0)
+        X[:, -1] = 0.50 - np.arange(256) * (0.45 / 255.0)
+        return P, np.ascontiguousarray(X), "t", FULL, None
+
+    def disc40_montecarlo():
+        P, xs, obj = build_workload("crossvault_disc40", n_states=6)
+        N = 8192
+        X = np.repeat(np.asarray(xs, dtype=np.float64)[None, :], N, axis=0)
+        pzs = np.clip(np.random.default_rng(20261019 + 4).normal(1.0, 0.05, size=N), 0.8, 1.2)
+        return P, np.ascontiguousarray(X), obj, LIGHT, np.ascontiguousarray(pzs)
+
+    def dome_lambdh():
+        P, xs = W.dome_lambdh_problem(20, 16, n_states=6)
+        return P, W.lambdh_candidates(P, xs, 8192, seed=20261019 + 5), "max_load", FULL, None
+
+    return [
+        {"name": "dome_16x20", "what": "config 2: dome, radial form, max thrust + reac_bounds, 4096 multi-start", "build": dome_multistart},
+        {"name": "fan_thickness", "what": "config 3: fan form diagram (reference fixture), thickness sweep 0.50 -> 0.05 m in 256 steps, "
+                                          "objective t; cross-vault closed-form envelope (pavilion envelope unpinned)", "build": fan_thickness},
+        {"name": "crossvault_disc40_mc", "what": "config 4: cross vault disc 40, Monte-Carlo self-weight scale N(1, 0.05^2) clipped to "
+                                                 "[0.8, 1.2]; 8192 candidates = one GPU's share of 65,536 over 8; objectives + feasibility only",
+         "build": disc40_montecarlo, "reps": 2},
+        {"name": "dome_lambdh", "what": "config 5: dome, horizontal-load multiplier lambdh as a variable + reac_bounds, 8192 candidates with "
+                                        "batched Jacobians; one load direction per plan (per-candidate directions: one plan per direction)",
+         "build": dome_lambdh, "reps": 3},
+    ]
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe).
     The sampler is started before the warm-up (nvidia-smi needs ~0.1 s to start); only samples whose time stamp falls
@@ -360,30 +412,37 @@ def run_ours(args):
                "sample": "%d candidates of %s through oracle/callbacks_np.py (reference call order: constr_wrapper, "
                          "sensitivities_wrapper, objective, gradient), one process per core" % (ns, args.workload)}
 
-    # ---- sweep wall-times of the other BASELINE configurations that fit one GPU (N = 1 only; short) ----
+    # ---- sweep wall-times of the other BASELINE configurations (N = 1 only; each a few launches) ----
     sweeps = None
     if rank == 0 and world == 1 and not args.no_sweeps:
         sweeps = {}
-        for wname, wbatch, label in (("dome_16x20", 4096, "config 2: dome, radial form, max thrust + reac_bounds, 4096 multi-start"),):
-            Pw, xw, objw = build_workload(wname, n_states=6)
+        for spec in sweep_specs():
+            Pw, Xw_host, objw, namesw, pzs_host = spec["build"]()
+            wbatch = len(Xw_host)
             planw = TnoPlan(Pw, objective=objw, device=local)
-            Xw = torch.from_numpy(candidates(Pw, xw, wbatch, seed=20261019 + 2)).to(dev)
-            namesw = ("f", "grad", "g", "J", "z", "gmin", "status")
+            Xw = torch.from_numpy(Xw_host).to(dev)
+            pzsw = torch.from_numpy(pzs_host).to(dev) if pzs_host is not None else None
             outw = {k: torch.empty(planw._shape(k, wbatch), device=dev, dtype=torch.int32 if k == "status" else torch.float64) for k in namesw}
-            for _ in range(3):
-                planw.evaluate_device(Xw, namesw, out=outw)
+            for _ in range(2):
+                planw.evaluate_device(Xw, namesw, out=outw, pz_scale=pzsw)
             torch.cuda.synchronize()
             a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            reps = spec.get("reps", 5)
             a0.record()
-            for _ in range(5):
-                planw.evaluate_device(Xw, namesw, out=outw)
+            for _ in range(reps):
+                planw.evaluate_device(Xw, namesw, out=outw, pz_scale=pzsw)
             a1.record()
             torch.cuda.synchronize()
-            msw = a0.elapsed_time(a1) / 5
-            sweeps[wname] = {"what": label, "candidates": wbatch, "wall_ms_per_sweep": msw, "evals_per_s": wbatch / (msw * 1e-3),
-                             "kernel_family": {1: "interleaved", 2: "onchip"}.get(planw.info["kernel"]), "nvar": planw.nvar, "ng": planw.ng,
-                             "bytes_per_eval": planw.bytes_per_eval, "status_nonzero": int((outw["status"] != 0).sum().item())}
+            msw = a0.elapsed_time(a1) / reps
+            sweeps[spec["name"]] = {
+                "what": spec["what"], "candidates": wbatch, "outputs": list(namesw), "wall_ms_per_sweep": msw,
+                "evals_per_s": wbatch / (msw * 1e-3), "kernel_family": {1: "interleaved", 2: "onchip"}.get(planw.info["kernel"]),
+                "nvar": planw.nvar, "ng": planw.ng, "bytes_per_eval": planw.bytes_per_eval,
+                "status_nonzero": int((outw["status"] != 0).sum().item()),
+                "feasible": int((outw["gmin"] >= -1e-9).sum().item()) if "gmin" in outw else None}
             planw.close()
+            del outw, Xw
+            torch.cuda.empty_cache()
 
     if rank == 0:
         line = {

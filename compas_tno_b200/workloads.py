@@ -140,6 +140,53 @@ def dome_problem(n_hoops: int = 20, n_parallels: int = 16, thk: float = 0.5, rad
     return _finish(P, zb, mid.ravel(), variables, thk, n_states)
 
 
+def dome_lambdh_problem(n_hoops: int = 20, n_parallels: int = 16, thk: float = 0.5, radius: float = 5.0, rho: float = 20.0,
+                        theta: float = 0.3, lambd: float = 0.02, constraints=("funicular", "envelope", "reac_bounds"),
+                        n_states: int = 12):
+    """Dome under a horizontal load multiplier: px0, py0 = (cos, sin)(theta) x |pz|, q = B q_ind + lambdh d0
+    (variables q, zb, lambdh).  The compressive basis is that of the vertically loaded dome (d = 0); x* carries
+    lambdh = ``lambd``.  Returns (problem, x_star)."""
+    P0, x0 = dome_problem(n_hoops, n_parallels, thk, radius, rho, ("q", "zb"), constraints, n_states)
+    w = np.abs(P0.P[:, 2])
+    loads = P0.P.copy()
+    loads[:, 0], loads[:, 1] = np.cos(theta) * w, np.sin(theta) * w
+    Ph = FixedProblem.from_arrays(P0.X, _edges_of(P0), P0.fixed, loads, P0.lb.ravel(), P0.ub.ravel(), P0.s.ravel(), ind=P0.ind)
+    Ph.variables, Ph.constraints, Ph.features = ["q", "zb", "lambdh"], list(constraints), ["fixed"]
+    Ph.thk, Ph.envelope = thk, P0.envelope
+    Ph.px0, Ph.py0 = loads[:, [0]].copy(), loads[:, [1]].copy()
+    if getattr(P0, "b", None) is not None:
+        Ph.b = P0.b
+    Ph.candidate_basis = P0.candidate_basis
+    # d0 (zero on the independent edges, problems.py:516-528) is a poor equilibrium state on its own; candidates
+    # use q_ind = y - lambdh * shift, i.e. q = B y + lambdh * (d0 - B B^+ d0): the minimum-norm particular solution
+    Ph.lambdh_shift = np.linalg.lstsq(Ph.B, Ph.d0.ravel(), rcond=None)[0]
+    xq = x0[: Ph.k] - lambd * Ph.lambdh_shift
+    Ph.q = Ph.B @ xq.reshape(-1, 1) + lambd * Ph.d0
+    return Ph, np.concatenate([xq, x0[Ph.k:], [lambd]])
+
+
+def lambdh_candidates(problem, x_star, N: int, seed: int = SEED, sigma: float = 0.05):
+    """sample_candidates for a lambdh problem: convex combinations of the compressive basis, lambdh perturbed by
+    sigma, and the q_ind shift that goes with each candidate's lambdh."""
+    k = problem.k
+    x0 = np.asarray(x_star, dtype=np.float64).copy()
+    x0[:k] += x0[-1] * problem.lambdh_shift
+    X = sample_candidates(problem, x0, N, seed=seed, sigma=sigma, basis=problem.candidate_basis)
+    X[:, :k] -= X[:, [-1]] * problem.lambdh_shift[None, :]
+    return np.ascontiguousarray(X)
+
+
+def _edges_of(P):
+    """(m, 2) vertex pairs (u, v) of the connectivity matrix rows: C[e, u] = -1, C[e, v] = +1."""
+    C = P.C.tocsr()
+    out = np.zeros((C.shape[0], 2), dtype=np.int64)
+    for e in range(C.shape[0]):
+        cols = C.indices[C.indptr[e]: C.indptr[e + 1]]
+        vals = C.data[C.indptr[e]: C.indptr[e + 1]]
+        out[e, 0], out[e, 1] = cols[vals < 0][0], cols[vals > 0][0]
+    return out
+
+
 def _finish(P, zb, mid, variables, thk, n_states):
     """Basis of compressive states, each scaled so that its highest node touches the middle surface's crown
     (heights above the supports scale like 1 / |q|); x* = their mean.  Stores the basis on the problem."""
