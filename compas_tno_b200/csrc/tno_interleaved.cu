@@ -15,6 +15,7 @@
 // The matrix is negative definite on this branch (compression = negative q), so we factor
 // -(Ci^T Q Ci) = L D L^T with a fixed pattern and no pivoting; D > 0 is checked per candidate.
 #include <cstdio>
+#include <cstdlib>
 
 #include "tno_plan.hpp"
 
@@ -88,6 +89,195 @@ __global__ void k_factor(DevPlan P, double* __restrict__ ws, int64_t NC, int64_t
     }
   }
   status[c] = st;
+}
+
+// ---- level-scheduled factorisation and solves ----------------------------------------------------------------------
+// A thread per candidate leaves a large problem latency bound: at discretisation 40 a chunk of ~9k candidates is two
+// warps per SM walking 0.65 M dependent updates.  These kernels take the parallelism of the elimination tree as well:
+// one launch per level, a thread per (candidate, item of the level); a warp still holds 32 candidates of ONE item, so
+// every access to the batch-interleaved values stays coalesced and the index loads are warp-uniform.
+// Storage while they run: off-diagonals hold U = L D (unscaled), diagonals hold 1 / d.
+//   factor (left-looking):  U(i, j) = A(i, j) - sum_c U(i, c) U(j, c) / d_c ,  d_j likewise
+//   forward (pull):         z_i = (b_i - sum_c U(i, c) z_c) / d_i            (L y = b and y = D z in one sweep)
+//   backward:               x_j = z_j - (sum_i U(i, j) x_i) / d_j
+__global__ void __launch_bounds__(128) k_factor_level(DevPlan P, DevLevels L, double* __restrict__ ws, int64_t NC, int64_t ncand,
+                                                      int item0, int item1, int tile, int32_t* __restrict__ status) {
+  const int64_t c = (int64_t)blockIdx.y * blockDim.x + threadIdx.x;
+  if (c >= ncand) return;
+  const int sl = P.slot.s_l;
+  const int i0 = item0 + blockIdx.x * tile;
+  const int i1 = min(item1, i0 + tile);
+  for (int it = i0; it < i1; ++it) {
+    const int pe = L.items[it];
+    const int p = pe & 0x7fffffff;
+    const int d0 = L.dotptr[it], d1 = L.dotptr[it + 1];
+    double v = WS(sl + p);
+#pragma unroll 8
+    for (int t = d0; t < d1; ++t) {
+      const int a = L.dot[3 * t], b = L.dot[3 * t + 1], dg = L.dot[3 * t + 2];
+      v = fma(-(WS(sl + a) * WS(sl + dg)), WS(sl + b), v);
+    }
+    if (pe < 0) {
+      if (!(v > 0.0)) atomicOr(status + c, TNO_STATUS_NOT_PD);
+      v = 1.0 / v;
+    }
+    WS(sl + p) = v;
+  }
+}
+
+template <int RB>
+__global__ void __launch_bounds__(128) k_forward_level(DevPlan P, DevLevels L, double* __restrict__ ws, int64_t NC, int64_t ncand,
+                                                       int row0, int nrows, int col0, int ncols, int ngroups) {
+  const int64_t c = (int64_t)blockIdx.y * blockDim.x + threadIdx.x;
+  if (c >= ncand) return;
+  const int item = blockIdx.x / ngroups, grp = blockIdx.x - item * ngroups;
+  if (item >= nrows) return;
+  const int i = L.cols[row0 + item];
+  const int cb = col0 + grp * RB;
+  const int nr = min(RB, col0 + ncols - cb);
+  const int nrhs = P.rhs.nrhs;
+  const int sl = P.slot.s_l, sr = P.slot.s_r + cb;
+  double acc[RB];
+#pragma unroll
+  for (int r = 0; r < RB; ++r) acc[r] = (r < nr) ? WS(sr + i * nrhs + r) : 0.0;
+  const int t1 = L.rowptr[i + 1];
+#pragma unroll(RB > 4 ? 4 : 8)
+  for (int t = L.rowptr[i]; t < t1; ++t) {
+    const double u = WS(sl + L.rowpos[t]);
+    const int kc = L.rowcol[t];
+#pragma unroll
+    for (int r = 0; r < RB; ++r)
+      if (r < nr) acc[r] = fma(-u, WS(sr + kc * nrhs + r), acc[r]);
+  }
+  const double inv = WS(sl + P.colptr[i]);
+#pragma unroll
+  for (int r = 0; r < RB; ++r)
+    if (r < nr) WS(sr + i * nrhs + r) = acc[r] * inv;
+}
+
+template <int RB>
+__global__ void __launch_bounds__(128) k_backward_level(DevPlan P, DevLevels L, double* __restrict__ ws, int64_t NC, int64_t ncand,
+                                                        int row0, int nrows, int col0, int ncols, int ngroups) {
+  const int64_t c = (int64_t)blockIdx.y * blockDim.x + threadIdx.x;
+  if (c >= ncand) return;
+  const int item = blockIdx.x / ngroups, grp = blockIdx.x - item * ngroups;
+  if (item >= nrows) return;
+  const int j = L.cols[row0 + item];
+  const int p0 = P.colptr[j], p1 = P.colptr[j + 1];
+  if (p1 - p0 == 1) return;
+  const int cb = col0 + grp * RB;
+  const int nr = min(RB, col0 + ncols - cb);
+  const int nrhs = P.rhs.nrhs;
+  const int sl = P.slot.s_l, sr = P.slot.s_r + cb;
+  double acc[RB];
+#pragma unroll
+  for (int r = 0; r < RB; ++r) acc[r] = 0.0;
+#pragma unroll(RB > 4 ? 4 : 8)
+  for (int p = p0 + 1; p < p1; ++p) {
+    const double u = WS(sl + p);
+    const int i = P.rowidx[p];
+#pragma unroll
+    for (int r = 0; r < RB; ++r)
+      if (r < nr) acc[r] = fma(u, WS(sr + i * nrhs + r), acc[r]);
+  }
+  const double inv = WS(sl + p0);
+#pragma unroll
+  for (int r = 0; r < RB; ++r)
+    if (r < nr) WS(sr + j * nrhs + r) = fma(-inv, acc[r], WS(sr + j * nrhs + r));
+}
+
+// Narrow levels (the top of the tree: one or two long rows per level) leave the kernels above latency bound: few
+// threads, each walking a long dependent list.  The *_seg variants split the list of one item over SEG threads per
+// candidate (a block = 32 candidates x SEG segments) and reduce through shared memory in a fixed order.
+template <int SEG>
+__global__ void __launch_bounds__(32 * SEG) k_factor_level_seg(DevPlan P, DevLevels L, double* __restrict__ ws, int64_t NC,
+                                                               int64_t ncand, int item0, int32_t* __restrict__ status) {
+  __shared__ double red[SEG][32];
+  const int lane = threadIdx.x & 31, seg = threadIdx.x >> 5;
+  const int64_t c = (int64_t)blockIdx.y * 32 + lane;
+  const bool ok = c < ncand;
+  const int sl = P.slot.s_l;
+  const int it = item0 + blockIdx.x;
+  const int pe = L.items[it];
+  const int p = pe & 0x7fffffff;
+  const int d0 = L.dotptr[it], d1 = L.dotptr[it + 1];
+  double v = 0.0;
+  if (ok) {
+#pragma unroll 4
+    for (int t = d0 + seg; t < d1; t += SEG) {
+      const int a = L.dot[3 * t], b = L.dot[3 * t + 1], dg = L.dot[3 * t + 2];
+      v = fma(-(WS(sl + a) * WS(sl + dg)), WS(sl + b), v);
+    }
+  }
+  red[seg][lane] = v;
+  __syncthreads();
+  if (seg == 0 && ok) {
+    double tot = WS(sl + p);
+#pragma unroll
+    for (int g = 0; g < SEG; ++g) tot += red[g][lane];
+    if (pe < 0) {
+      if (!(tot > 0.0)) atomicOr(status + c, TNO_STATUS_NOT_PD);
+      tot = 1.0 / tot;
+    }
+    WS(sl + p) = tot;
+  }
+}
+
+template <int RB, int SEG, bool BACKWARD>
+__global__ void __launch_bounds__(32 * SEG) k_solve_level_seg(DevPlan P, DevLevels L, double* __restrict__ ws, int64_t NC,
+                                                              int64_t ncand, int row0, int nrows, int col0, int ncols, int ngroups) {
+  __shared__ double red[SEG][RB][32];
+  const int lane = threadIdx.x & 31, seg = threadIdx.x >> 5;
+  const int64_t c = (int64_t)blockIdx.y * 32 + lane;
+  const bool ok = c < ncand;
+  const int item = blockIdx.x / ngroups, grp = blockIdx.x - item * ngroups;
+  const int i = L.cols[row0 + item];
+  const int cb = col0 + grp * RB;
+  const int nr = min(RB, col0 + ncols - cb);
+  const int nrhs = P.rhs.nrhs;
+  const int sl = P.slot.s_l, sr = P.slot.s_r + cb;
+  const int pd = P.colptr[i];
+  double acc[RB];
+#pragma unroll
+  for (int r = 0; r < RB; ++r) acc[r] = 0.0;
+  if (ok) {
+    if (BACKWARD) {
+      const int p1 = P.colptr[i + 1];
+#pragma unroll 4
+      for (int p = pd + 1 + seg; p < p1; p += SEG) {
+        const double u = WS(sl + p);
+        const int ii = P.rowidx[p];
+#pragma unroll
+        for (int r = 0; r < RB; ++r)
+          if (r < nr) acc[r] = fma(u, WS(sr + ii * nrhs + r), acc[r]);
+      }
+    } else {
+      const int t1 = L.rowptr[i + 1];
+#pragma unroll 4
+      for (int t = L.rowptr[i] + seg; t < t1; t += SEG) {
+        const double u = WS(sl + L.rowpos[t]);
+        const int kc = L.rowcol[t];
+#pragma unroll
+        for (int r = 0; r < RB; ++r)
+          if (r < nr) acc[r] = fma(u, WS(sr + kc * nrhs + r), acc[r]);
+      }
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < RB; ++r) red[seg][r][lane] = acc[r];
+  __syncthreads();
+  if (seg == 0 && ok) {
+    const double inv = WS(sl + pd);
+#pragma unroll
+    for (int r = 0; r < RB; ++r) {
+      if (r >= nr) continue;
+      double tot = 0.0;
+#pragma unroll
+      for (int g = 0; g < SEG; ++g) tot += red[g][r][lane];
+      const double rhs = WS(sr + i * nrhs + r);
+      WS(sr + i * nrhs + r) = BACKWARD ? fma(-inv, tot, rhs) : (rhs - tot) * inv;
+    }
+  }
 }
 
 __device__ __forceinline__ double zfixed(const DevPlan& P, const double* ws, int64_t NC, int64_t c, int b) {
@@ -632,13 +822,61 @@ const char* const kKernelNames[KK_COUNT] = {"k_pack", "k_q", "k_assemble", "k_fa
                                             "k_solve(phase2)", "k_epilogue", "k_emit(g,grad,z,q)", "k_emit(J)", "k_copy_status",
                                             "k_onchip"};
 
+// Level lists of the level-scheduled kernels (built on first use; the plan keeps them).
+static int build_levels(Plan* PL) {
+  const Symbolic& S = PL->sym;
+  std::vector<int> items, dotptr(1, 0), dot;
+  PL->lv_item_ptr.assign(S.nlevels + 1, 0);
+  PL->lv_seg.clear();
+  for (int l = 0; l < S.nlevels; ++l) {
+    for (int q = S.level_ptr[l]; q < S.level_ptr[l + 1]; ++q) {
+      const int j = S.level_cols[q];
+      for (int p = S.colptr[j]; p < S.colptr[j + 1]; ++p) {
+        items.push_back(p == S.colptr[j] ? (int)(0x80000000u | (unsigned)p) : p);
+        for (int64_t t = S.dot_ptr[p]; t < S.dot_ptr[p + 1]; ++t) {
+          dot.push_back(S.dot_a[t]);
+          dot.push_back(S.dot_b[t]);
+          dot.push_back(S.colptr[S.dot_c[t]]);
+        }
+        dotptr.push_back((int)(dot.size() / 3));
+      }
+    }
+    PL->lv_item_ptr[l + 1] = (int)items.size();
+    // long pair lists on few items: split every list over the threads of a block (k_factor_level_seg)
+    const int nit = PL->lv_item_ptr[l + 1] - PL->lv_item_ptr[l];
+    const int64_t npairs = (int64_t)dotptr.back() - dotptr[PL->lv_item_ptr[l]];
+    PL->lv_seg.push_back(nit > 0 && npairs >= 16 * (int64_t)nit && nit < 4096);
+  }
+  if (dot.empty()) dot.push_back(0);
+  int rc;
+  if ((rc = upload_vec(PL, items, &PL->lv.items))) return rc;
+  if ((rc = upload_vec(PL, dotptr, &PL->lv.dotptr))) return rc;
+  if ((rc = upload_vec(PL, dot, &PL->lv.dot))) return rc;
+  if ((rc = upload_vec(PL, S.level_cols, &PL->lv.cols))) return rc;
+  if ((rc = upload_vec(PL, S.rowptr, &PL->lv.rowptr))) return rc;
+  std::vector<int> rowcol = S.rowcol, rowpos = S.rowpos;
+  if (rowcol.empty()) { rowcol.push_back(0); rowpos.push_back(0); }
+  if ((rc = upload_vec(PL, rowcol, &PL->lv.rowcol))) return rc;
+  if ((rc = upload_vec(PL, rowpos, &PL->lv.rowpos))) return rc;
+  PL->lv_ready = true;
+  return TNO_OK;
+}
+
 int run_interleaved(Plan* PL, const double* x_dev, int64_t N, int64_t ldx, const tno_batch_inputs* opt,
                     const tno_outputs* out, cudaStream_t stream) {
   const DevPlan& P = PL->dp;
+  const Symbolic& S = PL->sym;
   const int64_t NC = PL->chunk;
   double* ws = PL->scratch;
   int32_t* st = PL->status_scratch;
   const int TB = 128;
+  // level-scheduled factor / solves unless the developer knob asks for the thread-per-candidate originals
+  static const bool v1 = getenv("TNO_INTERLEAVED_V1") != nullptr;
+  const bool levelled = !v1;
+  if (levelled && !PL->lv_ready) {
+    const int rc = build_levels(PL);
+    if (rc) return rc;
+  }
 #define LAUNCH(kind, kernel, grid, block, ...)              \
   do {                                                      \
     PL->prof_begin(kind, stream);                           \
@@ -655,17 +893,64 @@ int run_interleaved(Plan* PL, const double* x_dev, int64_t N, int64_t ldx, const
     LAUNCH(KK_Q, k_q, grid1(nc, TB, (P.m + etile - 1) / etile), TB, P, ws, NC, nc, etile);
     const int ptile = 128;
     LAUNCH(KK_ASSEMBLE, k_assemble, grid1(nc, TB, (P.nnz_l + ptile - 1) / ptile), TB, P, ws, NC, nc, ptile);
-    LAUNCH(KK_FACTOR, k_factor, grid1(nc, TB), TB, P, ws, NC, nc, st);
+    const unsigned cblocks = (unsigned)((nc + TB - 1) / TB), cblocks32 = (unsigned)((nc + 31) / 32);
+    constexpr int SEG = 8;
+    if (levelled) {
+      TNO_CUDA_OK(cudaMemsetAsync(st, 0, (size_t)nc * 4, stream));
+      for (int l = 0; l < S.nlevels; ++l) {
+        const int i0 = PL->lv_item_ptr[l], i1 = PL->lv_item_ptr[l + 1];
+        // a few thousand blocks per launch are plenty; longer tiles amortise the block start-up on the wide leaf levels
+        const int tile = std::max(1, (int)(((int64_t)(i1 - i0) * cblocks) / 16384));
+        if (PL->lv_seg[l])
+          LAUNCH(KK_FACTOR, k_factor_level_seg<SEG>, dim3((unsigned)(i1 - i0), cblocks32, 1), 32 * SEG, P, PL->lv, ws, NC, nc, i0, st);
+        else
+          LAUNCH(KK_FACTOR, k_factor_level, dim3((unsigned)((i1 - i0 + tile - 1) / tile), cblocks, 1), TB, P, PL->lv, ws, NC, nc, i0, i1, tile, st);
+      }
+    } else {
+      LAUNCH(KK_FACTOR, k_factor, grid1(nc, TB), TB, P, ws, NC, nc, st);
+    }
     const int rtile = 32;
     const int gyr = (P.ni + rtile - 1) / rtile;
     LAUNCH(KK_RHS1, k_rhs1, grid1(nc, TB, gyr), TB, P, ws, NC, nc, rtile);
     constexpr int RB = 4;
-    LAUNCH(KK_SOLVE1, k_solve<RB>, grid1(nc, TB, (P.rhs.nrhs1 + RB - 1) / RB), TB, P, ws, NC, nc, 0, P.rhs.nrhs1);
+    auto solve_levelled = [&](int kind, int col0, int ncols) {
+      const int ngroups = (ncols + RB - 1) / RB;
+      const auto seg_fwd = k_solve_level_seg<RB, SEG, false>;
+      const auto seg_bwd = k_solve_level_seg<RB, SEG, true>;
+      for (int pass = 0; pass < 2; ++pass) {
+        // forward over ascending levels, backward over descending ones (the roots have no off-diagonals)
+        for (int q = 0; q < S.nlevels - pass; ++q) {
+          const int l = pass ? S.nlevels - 2 - q : q;
+          const int r0 = S.level_ptr[l], nr = S.level_ptr[l + 1] - r0;
+          const bool seg = (int64_t)nr * ngroups * cblocks < 4096;  // less than ~two waves of 128-thread blocks
+          if (seg) {
+            const dim3 g((unsigned)(nr * ngroups), cblocks32, 1);
+            if (pass)
+              LAUNCH(kind, seg_bwd, g, 32 * SEG, P, PL->lv, ws, NC, nc, r0, nr, col0, ncols, ngroups);
+            else
+              LAUNCH(kind, seg_fwd, g, 32 * SEG, P, PL->lv, ws, NC, nc, r0, nr, col0, ncols, ngroups);
+          } else {
+            const dim3 g((unsigned)(nr * ngroups), cblocks, 1);
+            if (pass)
+              LAUNCH(kind, k_backward_level<RB>, g, TB, P, PL->lv, ws, NC, nc, r0, nr, col0, ncols, ngroups);
+            else
+              LAUNCH(kind, k_forward_level<RB>, g, TB, P, PL->lv, ws, NC, nc, r0, nr, col0, ncols, ngroups);
+          }
+        }
+      }
+    };
+    if (levelled)
+      solve_levelled(KK_SOLVE1, 0, P.rhs.nrhs1);
+    else
+      LAUNCH(KK_SOLVE1, k_solve<RB>, grid1(nc, TB, (P.rhs.nrhs1 + RB - 1) / RB), TB, P, ws, NC, nc, 0, P.rhs.nrhs1);
     // the dz/dq_ind columns only feed the Jacobian and the bestfit gradient
     const bool need2 = P.rhs.nrhs2 > 0 && (out->J != nullptr || (P.objective >= TNO_OBJ_BESTFIT && P.objective != TNO_OBJ_FEASIBILITY && out->grad != nullptr));
     if (need2) {
       LAUNCH(KK_RHS2, k_rhs2, grid1(nc, TB, gyr), TB, P, ws, NC, nc, rtile);
-      LAUNCH(KK_SOLVE2, k_solve<RB>, grid1(nc, TB, (P.rhs.nrhs2 + RB - 1) / RB), TB, P, ws, NC, nc, P.rhs.nrhs1, P.rhs.nrhs2);
+      if (levelled)
+        solve_levelled(KK_SOLVE2, P.rhs.nrhs1, P.rhs.nrhs2);
+      else
+        LAUNCH(KK_SOLVE2, k_solve<RB>, grid1(nc, TB, (P.rhs.nrhs2 + RB - 1) / RB), TB, P, ws, NC, nc, P.rhs.nrhs1, P.rhs.nrhs2);
     }
     LAUNCH(KK_EPILOGUE, k_epilogue, grid1(nc, TB), TB, P, ws, NC, nc, out->f ? out->f + c0 : nullptr,
            out->gmin ? out->gmin + c0 : nullptr, st);

@@ -225,6 +225,18 @@ struct ProfRec {
   cudaEvent_t a, b;
 };
 
+// Level-scheduled variant of the interleaved family (tno_interleaved.cu): one launch per elimination-tree level,
+// a thread per (candidate, item of the level).  Item = entry of L for the factorisation, row / column for the solves.
+struct DevLevels {
+  const int* items;      // entry positions in level order (bit 31 set: diagonal entry)
+  const int* dotptr;     // nitems + 1 : pairs of every item
+  const int* dot;        // 3 per pair: position of U(i, c), position of U(j, c), position of the diagonal of column c
+  const int* cols;       // columns (= rows) in level order
+  const int* rowptr;     // CSR view of the strictly lower part of L
+  const int* rowcol;
+  const int* rowpos;
+};
+
 struct Plan {
   tno_plan_info info{};
   bool profiling = false;
@@ -277,6 +289,11 @@ struct Plan {
   size_t d_stage_bytes = 0;
   int64_t launches = 0;
   int sm_count = 148;
+  // level-scheduled interleaved kernels
+  bool lv_ready = false;
+  DevLevels lv{};
+  std::vector<int> lv_item_ptr;   // nlevels + 1 : items of each level
+  std::vector<char> lv_seg;       // per level: use the segmented factor kernel
 };
 
 // kernel family entry points (defined in the .cu files); all asynchronous on `stream`
