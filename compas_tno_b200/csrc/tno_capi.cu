@@ -446,6 +446,15 @@ int tno_plan_create(const tno_problem_desc* D, tno_plan** out_plan) {
     if (C.r_reac >= 0)
       for (int i = 0; i < 2 * nb; ++i)
         for (int j = 0; j < nvar; ++j) at(C.r_reac + i, j) = one(SL.s_rj + i * nvar + j, +1.f);
+    if (C.r_fun == 0 && m > 0) {
+      // the funicular rows are constants: they leave the table and are replicated by a streaming kernel
+      const size_t cnt = (size_t)2 * m * nvar;
+      std::vector<double> blockv(cnt);
+      for (size_t i = 0; i < cnt; ++i) blockv[i] = t[i].c;
+      if ((rc = upload(P, blockv, &P->jfun))) return rc;
+      P->jfun_count = (int64_t)cnt;
+      t.erase(t.begin(), t.begin() + cnt);
+    }
     if ((rc = upload_table(P, t, &P->t_J))) return rc;
   }
 

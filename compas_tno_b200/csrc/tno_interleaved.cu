@@ -954,16 +954,22 @@ int run_interleaved(Plan* PL, const double* x_dev, int64_t N, int64_t ldx, const
     }
     LAUNCH(KK_EPILOGUE, k_epilogue, grid1(nc, TB), TB, P, ws, NC, nc, out->f ? out->f + c0 : nullptr,
            out->gmin ? out->gmin + c0 : nullptr, st);
-    auto emit = [&](int kind, const EmitTable& T, double* dst) {
+    // stride = elements per candidate of the user-facing array, offset = first element the table describes
+    auto emit = [&](int kind, const EmitTable& T, double* dst, int64_t stride = -1, int64_t offset = 0) {
       if (!dst || T.count == 0) return;
+      if (stride < 0) stride = T.count;
       dim3 g((unsigned)((T.count + EMIT_TW - 1) / EMIT_TW), (unsigned)((nc + 31) / 32), 1);
-      LAUNCH(kind, k_emit, g, 256, T.dev, T.count, dst + c0 * T.count, T.count, ws, NC, nc);
+      LAUNCH(kind, k_emit, g, 256, T.dev, T.count, dst + c0 * stride + offset, stride, ws, NC, nc);
     };
     emit(KK_EMIT_SMALL, PL->t_g, out->g);
     emit(KK_EMIT_SMALL, PL->t_grad, out->grad);
     emit(KK_EMIT_SMALL, PL->t_z, out->z);
     emit(KK_EMIT_SMALL, PL->t_q, out->q);
-    emit(KK_EMIT_J, PL->t_J, out->J);
+    if (out->J) {
+      const int64_t jstride = (int64_t)P.con.ng * P.var.nvar;
+      if (PL->jfun) launch_fill_funicular(PL, PL->jfun, PL->jfun_count, out->J + c0 * jstride, nc, stream);
+      emit(KK_EMIT_J, PL->t_J, out->J, jstride, PL->jfun_count);
+    }
     if (out->status) LAUNCH(KK_STATUS, k_copy_status, grid1(nc, 256), 256, st, out->status + c0, nc);
   }
 #undef LAUNCH

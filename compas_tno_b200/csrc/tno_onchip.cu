@@ -1182,6 +1182,17 @@ int build_onchip(Plan* PL, const tno_problem_desc* D) {
   return rc;
 }
 
+void launch_fill_funicular(Plan* PL, const double* block, int64_t count, double* J, int64_t N, cudaStream_t stream) {
+  const int64_t chunks = count / 2;  // count = 2 m nvar is even
+  const int64_t cand_stride = (int64_t)PL->dp.con.ng * PL->dp.var.nvar;
+  dim3 g((unsigned)((chunks + 255) / 256), (unsigned)((N + FILL_CPB - 1) / FILL_CPB), 1);
+  PL->prof_begin(KK_EMIT_J, stream);
+  k_fill_funicular<<<g, 256, 0, stream>>>(reinterpret_cast<const double2*>(block), chunks, J, cand_stride,
+                                          (int64_t)PL->dp.con.r_fun * PL->dp.var.nvar, N);
+  PL->prof_end(stream);
+  PL->launches += 1;
+}
+
 static int build_onchip_impl(Plan* PL, const tno_problem_desc* D, const int THREADS) {
   const Symbolic& S = PL->sym;
   DevPlan& P = PL->dp;
@@ -1833,17 +1844,8 @@ int run_onchip(Plan* PL, const double* x_dev, int64_t N, int64_t ldx, const tno_
   const int threads = PL->onchip_threads;
   auto kern = threads == 512 ? k_onchip<512, 1> : (PL->onchip_ctas_per_sm >= 2 ? k_onchip<256, 2> : k_onchip<256, 1>);
   TNO_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  if (out->J && PL->dp.con.r_fun >= 0) {
-    const int64_t count = (int64_t)2 * PL->dp.m * PL->dp.var.nvar;  // even
-    const int64_t chunks = count / 2;
-    const int64_t cand_stride = (int64_t)PL->dp.con.ng * PL->dp.var.nvar;
-    dim3 g((unsigned)((chunks + 255) / 256), (unsigned)((N + FILL_CPB - 1) / FILL_CPB), 1);
-    PL->prof_begin(KK_EMIT_J, stream);
-    k_fill_funicular<<<g, 256, 0, stream>>>(reinterpret_cast<const double2*>(PL->oc.Jfun), chunks, out->J, cand_stride,
-                                            (int64_t)PL->dp.con.r_fun * PL->dp.var.nvar, N);
-    PL->prof_end(stream);
-    PL->launches += 1;
-  }
+  if (out->J && PL->dp.con.r_fun >= 0)
+    launch_fill_funicular(PL, PL->oc.Jfun, (int64_t)2 * PL->dp.m * PL->dp.var.nvar, out->J, N, stream);
   PL->prof_begin(KK_ONCHIP, stream);
   kern<<<grid, threads, smem, stream>>>(PL->dp, PL->oc, A);
   PL->prof_end(stream);

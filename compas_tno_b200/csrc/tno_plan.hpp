@@ -275,7 +275,9 @@ struct Plan {
   int kernel = TNO_KERNEL_INTERLEAVED;
   std::vector<void*> dev_allocs;       // everything to cudaFree at destroy
   // emit tables
-  EmitTable t_g, t_grad, t_z, t_q, t_J;
+  EmitTable t_g, t_grad, t_z, t_q, t_J;   // t_J covers the rows below the funicular block when jfun is set
+  const double* jfun = nullptr;           // 2m x nvar candidate-independent rows [B 0; -B 0] (+ d0 column) of J
+  int64_t jfun_count = 0;
   // scratch (interleaved family): nslots x chunk doubles
   double* scratch = nullptr;
   int32_t* status_scratch = nullptr;
@@ -303,6 +305,9 @@ int run_interleaved(Plan* P, const double* x_dev, int64_t N, int64_t ldx, const 
 int build_onchip(Plan* P, const tno_problem_desc* D);   // host schedule + upload; sets onchip_ok
 int run_onchip(Plan* P, const double* x_dev, int64_t N, int64_t ldx, const tno_batch_inputs* opt,
                const tno_outputs* out, cudaStream_t stream);
+
+// replicate the candidate-independent funicular rows of J for N candidates (streaming kernel, tno_onchip.cu)
+void launch_fill_funicular(Plan* P, const double* block, int64_t count, double* J, int64_t N, cudaStream_t stream);
 
 void set_error(const std::string& msg);
 int upload_bytes(Plan* P, const void* host, size_t bytes, const void** dev);
