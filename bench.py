@@ -87,8 +87,9 @@ def sweep_specs():
         return P, np.ascontiguousarray(X), obj, LIGHT, np.ascontiguousarray(pzs)
 
     def dome_lambdh():
-        P, xs = W.dome_lambdh_problem(20, 16, n_states=6)
-        return P, W.lambdh_candidates(P, xs, 8192, seed=20261019 + 5), "max_load", FULL, None
+        P, xs = W.dome_direction_problem(20, 16, n_states=6)
+        X, load_dir = W.direction_candidates(P, xs, 8192, seed=20261019 + 5)
+        return P, X, "max_load", FULL, None, load_dir
 
     return [
         {"name": "dome_16x20", "what": "config 2: dome, radial form, max thrust + reac_bounds, 4096 multi-start", "build": dome_multistart},
@@ -97,8 +98,8 @@ def sweep_specs():
         {"name": "crossvault_disc40_mc", "what": "config 4: cross vault disc 40, Monte-Carlo self-weight scale N(1, 0.05^2) clipped to "
                                                  "[0.8, 1.2]; 8192 candidates = one GPU's share of 65,536 over 8; objectives + feasibility only",
          "build": disc40_montecarlo, "reps": 2},
-        {"name": "dome_lambdh", "what": "config 5: dome, horizontal-load multiplier lambdh as a variable + reac_bounds, 8192 candidates with "
-                                        "batched Jacobians; one load direction per plan (per-candidate directions: one plan per direction)",
+        {"name": "dome_lambdh", "what": "config 5: dome, horizontal-load multiplier lambdh as a variable + reac_bounds, 8192 load directions "
+                                        "theta_j = 2 pi j / 8192 (d0(theta) = cos d0x + sin d0y per candidate), batched Jacobians",
          "build": dome_lambdh, "reps": 3},
     ]
 
@@ -417,20 +418,22 @@ def run_ours(args):
     if rank == 0 and world == 1 and not args.no_sweeps:
         sweeps = {}
         for spec in sweep_specs():
-            Pw, Xw_host, objw, namesw, pzs_host = spec["build"]()
+            built = spec["build"]()
+            Pw, Xw_host, objw, namesw, pzs_host = built[:5]
+            dirw = torch.from_numpy(built[5]).to(dev) if len(built) > 5 else None
             wbatch = len(Xw_host)
             planw = TnoPlan(Pw, objective=objw, device=local)
             Xw = torch.from_numpy(Xw_host).to(dev)
             pzsw = torch.from_numpy(pzs_host).to(dev) if pzs_host is not None else None
             outw = {k: torch.empty(planw._shape(k, wbatch), device=dev, dtype=torch.int32 if k == "status" else torch.float64) for k in namesw}
             for _ in range(2):
-                planw.evaluate_device(Xw, namesw, out=outw, pz_scale=pzsw)
+                planw.evaluate_device(Xw, namesw, out=outw, pz_scale=pzsw, load_dir=dirw)
             torch.cuda.synchronize()
             a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             reps = spec.get("reps", 5)
             a0.record()
             for _ in range(reps):
-                planw.evaluate_device(Xw, namesw, out=outw, pz_scale=pzsw)
+                planw.evaluate_device(Xw, namesw, out=outw, pz_scale=pzsw, load_dir=dirw)
             a1.record()
             torch.cuda.synchronize()
             msw = a0.elapsed_time(a1) / reps

@@ -37,7 +37,7 @@ class ProblemDesc(C.Structure):
         ("variables", C.c_uint32), ("constraints", C.c_uint32), ("objective", C.c_int32),
         ("envelope_kind", C.c_int32), ("env_params", C.c_double * 8), ("thk", C.c_double),
         ("device", C.c_int32), ("kernel", C.c_int32), ("ordering", C.c_int32), ("reserved", C.c_int32),
-        ("dXb", _dp), ("stiff", _dp),
+        ("dXb", _dp), ("stiff", _dp), ("d_b", _dp), ("px0_b", _dp), ("py0_b", _dp),
     ]
 
 
@@ -54,7 +54,7 @@ class PlanInfo(C.Structure):
 
 
 class BatchInputs(C.Structure):
-    _fields_ = [("pz_scale", C.c_void_p), ("reserved0", C.c_void_p), ("reserved1", C.c_void_p)]
+    _fields_ = [("pz_scale", C.c_void_p), ("load_dir", C.c_void_p), ("reserved1", C.c_void_p)]
 
 
 class Outputs(C.Structure):
@@ -90,7 +90,7 @@ def load():
     lib.tno_eval_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.POINTER(BatchInputs),
                                    C.POINTER(Outputs), C.c_void_p]
     lib.tno_eval_batch.restype = C.c_int
-    lib.tno_eval_batch_host.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.POINTER(Outputs)]
+    lib.tno_eval_batch_host.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.POINTER(BatchInputs), C.POINTER(Outputs)]
     lib.tno_eval_batch_host.restype = C.c_int
     lib.tno_plan_launch_count.argtypes = [C.c_void_p]
     lib.tno_plan_launch_count.restype = C.c_int64

@@ -134,6 +134,10 @@ int tno_plan_create(const tno_problem_desc* D, tno_plan** out_plan) {
   if ((D->constraints & TNO_CON_REAC_BOUNDS) && !D->b) return fail(TNO_EINVAL, "reac_bounds needs b");
   if ((D->variables & TNO_VAR_LAMBDH) && (!D->px0 || !D->py0)) return fail(TNO_EINVAL, "lambdh needs px0 / py0");
   if ((D->variables & TNO_VAR_LAMBDV) && (!D->pzv || !D->pz0)) return fail(TNO_EINVAL, "lambdv needs pzv / pz0");
+  if (D->d_b || D->px0_b || D->py0_b) {
+    if (!(D->d_b && D->px0_b && D->py0_b)) return fail(TNO_EINVAL, "second load basis needs d_b, px0_b and py0_b");
+    if (!(D->variables & TNO_VAR_LAMBDH)) return fail(TNO_EINVAL, "second load basis needs the lambdh variable");
+  }
   if (D->objective < TNO_OBJ_NONE || D->objective > TNO_OBJ_ECOMP_NONLINEAR) return fail(TNO_EINVAL, "bad objective");
   const bool ecomp = D->objective == TNO_OBJ_ECOMP_LINEAR || D->objective == TNO_OBJ_ECOMP_NONLINEAR;
   if (D->objective == TNO_OBJ_BESTFIT || D->objective == TNO_OBJ_LOADPATH || ecomp) {
@@ -296,6 +300,7 @@ int tno_plan_create(const tno_problem_desc* D, tno_plan** out_plan) {
   pos = 0;
   SL.s_x = pos; pos += V.nvar;
   SL.s_pzs = pos; pos += 1;
+  SL.s_dir = pos; pos += 2;
   SL.s_q = pos; pos += m;
   SL.s_l = pos; pos += nnz_l;
   SL.s_r = pos; pos += ni * R.nrhs;
@@ -341,6 +346,9 @@ int tno_plan_create(const tno_problem_desc* D, tno_plan** out_plan) {
   UP(pz0, vec(D->pz0, (size_t)n));
   UP(dXb, vec(D->dXb, (size_t)nb * 3));
   UP(stiff, vec(D->stiff, (size_t)m));
+  UP(d_b, vec(D->d_b, (size_t)m));
+  UP(px0_b, vec(D->px0_b, (size_t)n));
+  UP(py0_b, vec(D->py0_b, (size_t)n));
 #undef UP
 
   // ---- emit tables (user-facing row-major layouts as affine gathers of the scratch slots) --
@@ -597,7 +605,7 @@ int tno_eval_batch(tno_plan* plan, const double* x_dev, int64_t N, int64_t ldx, 
   return run_interleaved(P, x_dev, N, ldx, opt, out_dev, (cudaStream_t)cuda_stream);
 }
 
-int tno_eval_batch_host(tno_plan* plan, const double* x_host, int64_t N, int64_t ldx, const double* pz_scale_host,
+int tno_eval_batch_host(tno_plan* plan, const double* x_host, int64_t N, int64_t ldx, const tno_batch_inputs* in_host,
                         const tno_outputs* oh) {
   Plan* P = reinterpret_cast<Plan*>(plan);
   if (!P || !x_host || !oh) return fail(TNO_EINVAL, "null argument");
@@ -613,7 +621,10 @@ int tno_eval_batch_host(tno_plan* plan, const double* x_host, int64_t N, int64_t
     return o;
   };
   const size_t o_x = take(true, (size_t)N * ldx);
+  const double* pz_scale_host = in_host ? in_host->pz_scale : nullptr;
+  const double* load_dir_host = in_host ? in_host->load_dir : nullptr;
   const size_t o_pzs = take(pz_scale_host != nullptr, (size_t)N);
+  const size_t o_dir = take(load_dir_host != nullptr, (size_t)N * 2);
   const size_t o_f = take(oh->f != nullptr, (size_t)N);
   const size_t o_grad = take(oh->grad != nullptr, (size_t)N * nvar);
   const size_t o_g = take(oh->g != nullptr, (size_t)N * ng);
@@ -637,6 +648,10 @@ int tno_eval_batch_host(tno_plan* plan, const double* x_host, int64_t N, int64_t
   if (pz_scale_host) {
     TNO_CUDA_OK(cudaMemcpyAsync(base + o_pzs, pz_scale_host, (size_t)N * 8, cudaMemcpyHostToDevice, s));
     opt.pz_scale = base + o_pzs;
+  }
+  if (load_dir_host) {
+    TNO_CUDA_OK(cudaMemcpyAsync(base + o_dir, load_dir_host, (size_t)N * 16, cudaMemcpyHostToDevice, s));
+    opt.load_dir = base + o_dir;
   }
   tno_outputs od{};
   od.f = oh->f ? base + o_f : nullptr;

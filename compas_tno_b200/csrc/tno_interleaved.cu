@@ -23,13 +23,24 @@ namespace tno {
 
 #define WS(slot) ws[(int64_t)(slot) * NC + c]
 
+// Horizontal load basis of a candidate: (c, s) = its load direction (tno_batch_inputs.load_dir), (1, 0) without one;
+// the second basis is only dereferenced when the plan has it, and c = 1, s = 0 reproduces the single-basis values bit
+// for bit.
+#define DIR_C WS(P.slot.s_dir)
+#define DIR_S WS(P.slot.s_dir + 1)
+__device__ __forceinline__ double mix2(const double* __restrict__ a, const double* __restrict__ b, int i, double c, double s) {
+  return b ? fma(s, b[i], c * a[i]) : a[i];
+}
+
 __global__ void k_pack(DevPlan P, double* __restrict__ ws, int64_t NC, int64_t ncand, const double* __restrict__ x,
-                       int64_t ldx, const double* __restrict__ pz_scale) {
+                       int64_t ldx, const double* __restrict__ pz_scale, const double* __restrict__ load_dir) {
   const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= ncand) return;
   const int nvar = P.var.nvar;
   for (int j = 0; j < nvar; ++j) WS(P.slot.s_x + j) = x[c * ldx + j];
   WS(P.slot.s_pzs) = pz_scale ? pz_scale[c] : 1.0;
+  DIR_C = load_dir ? load_dir[2 * c] : 1.0;
+  DIR_S = load_dir ? load_dir[2 * c + 1] : 0.0;
 }
 
 // q_e = lambdh * d_e + sum_j B[e, j] q_ind[j]
@@ -40,8 +51,9 @@ __global__ void k_q(DevPlan P, double* __restrict__ ws, int64_t NC, int64_t ncan
   const int e1 = min(P.m, e0 + etile);
   const int k = P.k;
   const double lam = P.var.o_lambdh >= 0 ? WS(P.slot.s_x + P.var.o_lambdh) : 1.0;
+  const double dc = DIR_C, ds = DIR_S;
   for (int e = e0; e < e1; ++e) {
-    double acc = lam * P.d[e];
+    double acc = lam * mix2(P.d, P.d_b, e, dc, ds);
     const double* Brow = P.B + (int64_t)e * k;
     for (int j = 0; j < k; ++j) acc = fma(Brow[j], WS(P.slot.s_x + j), acc);
     WS(P.slot.s_q + e) = acc;
@@ -294,12 +306,13 @@ __global__ void k_rhs1(DevPlan P, double* __restrict__ ws, int64_t NC, int64_t n
   const double lamh = P.var.o_lambdh >= 0 ? WS(P.slot.s_x + P.var.o_lambdh) : 1.0;
   const double lamv = P.var.o_lambdv >= 0 ? WS(P.slot.s_x + P.var.o_lambdv) : 1.0;
   const double pzs = WS(P.slot.s_pzs);
+  const double dc = DIR_C, ds = DIR_S;
   for (int r = r0; r < r1; ++r) {
     const int v = P.row_vertex[r];
     double px, py, pz;
     if (P.var.o_lambdh >= 0) {
-      px = lamh * P.px0[v];
-      py = lamh * P.py0[v];
+      px = lamh * mix2(P.px0, P.px0_b, v, dc, ds);
+      py = lamh * mix2(P.py0, P.py0_b, v, dc, ds);
     } else {
       px = P.P[3 * v + 0];
       py = P.P[3 * v + 1];
@@ -390,6 +403,7 @@ __global__ void k_rhs2(DevPlan P, double* __restrict__ ws, int64_t NC, int64_t n
   const int r0 = blockIdx.y * rtile;
   const int r1 = min(P.ni, r0 + rtile);
   const int nrhs = P.rhs.nrhs, k = P.k;
+  const double dc = DIR_C, ds = DIR_S;
   for (int r = r0; r < r1; ++r) {
     const int v = P.row_vertex[r];
     const int base = P.slot.s_r + r * nrhs;
@@ -411,7 +425,7 @@ __global__ void k_rhs2(DevPlan P, double* __restrict__ ws, int64_t NC, int64_t n
         const double zo = zval(P, ws, NC, c, P.vadj_other[t]);
         const double sg = (double)P.vadj_sign[t];
         const double w = sg > 0 ? (zv - zo) : (zo - zv);
-        acc = fma(sg * w, P.d[P.vadj_edge[t]], acc);
+        acc = fma(sg * w, mix2(P.d, P.d_b, P.vadj_edge[t], dc, ds), acc);
       }
       WS(base + P.rhs.c_lambdh) = acc;
     }
@@ -454,6 +468,7 @@ __global__ void k_epilogue(DevPlan P, double* __restrict__ ws, int64_t NC, int64
   const double lamh = P.var.o_lambdh >= 0 ? WS(P.slot.s_x + P.var.o_lambdh) : 1.0;
   const double lamv = P.var.o_lambdv >= 0 ? WS(P.slot.s_x + P.var.o_lambdv) : 1.0;
   const double pzs = WS(P.slot.s_pzs);
+  const double dc = DIR_C, ds = DIR_S;
   double gmin = 1e300;
   bool bad = false;
 
@@ -499,8 +514,8 @@ __global__ void k_epilogue(DevPlan P, double* __restrict__ ws, int64_t NC, int64
       const double xb = P.X[3 * vb + 0], yb = P.X[3 * vb + 1], zb = zfixed(P, ws, NC, c, b);
       double px, py, pz;
       if (P.var.o_lambdh >= 0) {
-        px = lamh * P.px0[vb];
-        py = lamh * P.py0[vb];
+        px = lamh * mix2(P.px0, P.px0_b, vb, dc, ds);
+        py = lamh * mix2(P.py0, P.py0_b, vb, dc, ds);
       } else {
         px = P.P[3 * vb + 0];
         py = P.P[3 * vb + 1];
@@ -625,7 +640,7 @@ __global__ void k_epilogue(DevPlan P, double* __restrict__ ws, int64_t NC, int64
             const double u = sg > 0 ? (xb - xo) : (xo - xb);
             const double vv = sg > 0 ? (yb - yo) : (yo - yb);
             const double w = sg > 0 ? (zb - zo) : (zo - zb);
-            const double d0 = P.d[e];
+            const double d0 = mix2(P.d, P.d_b, e, dc, ds);
             dRx = fma(sg * u, d0, dRx);
             dRy = fma(sg * vv, d0, dRy);
             dRz = fma(sg * w, d0, dRz);
@@ -635,8 +650,8 @@ __global__ void k_epilogue(DevPlan P, double* __restrict__ ws, int64_t NC, int64
               dRz = fma(sg * qe, sg > 0 ? -dzo : dzo, dRz);
             }
           }
-          dRx -= P.px0[vb];
-          dRy -= P.py0[vb];
+          dRx -= mix2(P.px0, P.px0_b, vb, dc, ds);
+          dRy -= mix2(P.py0, P.py0_b, vb, dc, ds);
           WS(rowx + P.var.o_lambdh) = zb * sx * (-Rz * dRx + Rx * dRz) / rz2 / sz;
           WS(rowy + P.var.o_lambdh) = zb * sy * (-Rz * dRy + Ry * dRz) / rz2 / sz;
         }
@@ -779,6 +794,18 @@ __global__ void k_epilogue(DevPlan P, double* __restrict__ ws, int64_t NC, int64
   if (bad) status[c] |= TNO_STATUS_NONFINITE;
 }
 
+// Per-candidate load direction: rows e and m + e of the funicular block get +-(c d[e] + s d_b[e]) in the lambdh column.
+__global__ void __launch_bounds__(256) k_dir_column(DevPlan P, const double* __restrict__ load_dir, double* __restrict__ J,
+                                                    int64_t cand_stride) {
+  const int e = blockIdx.y * blockDim.x + threadIdx.x;
+  if (e >= P.m) return;
+  const int64_t cand = blockIdx.x;
+  const double v = fma(load_dir[2 * cand + 1], P.d_b[e], load_dir[2 * cand] * P.d[e]);
+  double* Jc = J + cand * cand_stride + (int64_t)P.con.r_fun * P.var.nvar + P.var.o_lambdh;
+  Jc[(int64_t)e * P.var.nvar] = v;
+  Jc[(int64_t)(P.m + e) * P.var.nvar] = -v;
+}
+
 // Table-driven transposing emitter: out[c][e] = sa * ws[a][c] + sb * ws[b][c] + const.
 // A CTA stages TW elements x 32 candidates in shared memory: reads are coalesced along the candidate
 // axis of the scratch, writes are coalesced along the element axis of the user-facing row-major output.
@@ -888,7 +915,12 @@ int run_interleaved(Plan* PL, const double* x_dev, int64_t N, int64_t ldx, const
     const int64_t nc = std::min(NC, N - c0);
     const double* xs = x_dev + c0 * ldx;
     const double* pzs = (opt && opt->pz_scale) ? opt->pz_scale + c0 : nullptr;
-    LAUNCH(KK_PACK, k_pack, grid1(nc, TB), TB, P, ws, NC, nc, xs, ldx, pzs);
+    const double* ldir = (opt && opt->load_dir) ? opt->load_dir + 2 * c0 : nullptr;
+    if (ldir && !P.d_b) {
+      set_error("load_dir needs a plan created with the second load basis (d_b, px0_b, py0_b)");
+      return TNO_EINVAL;
+    }
+    LAUNCH(KK_PACK, k_pack, grid1(nc, TB), TB, P, ws, NC, nc, xs, ldx, pzs, ldir);
     const int etile = 32;
     LAUNCH(KK_Q, k_q, grid1(nc, TB, (P.m + etile - 1) / etile), TB, P, ws, NC, nc, etile);
     const int ptile = 128;
@@ -968,6 +1000,8 @@ int run_interleaved(Plan* PL, const double* x_dev, int64_t N, int64_t ldx, const
     if (out->J) {
       const int64_t jstride = (int64_t)P.con.ng * P.var.nvar;
       if (PL->jfun) launch_fill_funicular(PL, PL->jfun, PL->jfun_count, out->J + c0 * jstride, nc, stream);
+      if (ldir && PL->jfun)  // the lambdh column of the funicular rows is +-d0 of the candidate's direction
+        LAUNCH(KK_EMIT_J, k_dir_column, dim3((unsigned)nc, (unsigned)((P.m + 255) / 256), 1), 256, P, ldir, out->J + c0 * jstride, jstride);
       emit(KK_EMIT_J, PL->t_J, out->J, jstride, PL->jfun_count);
     }
     if (out->status) LAUNCH(KK_STATUS, k_copy_status, grid1(nc, 256), 256, st, out->status + c0, nc);

@@ -31,6 +31,7 @@ struct OcArgs {
   const double* x;
   int64_t ldx;
   const double* pzs;
+  const double* dir;   // N x 2 load directions or null
   double* f;
   double* grad;
   double* g;
@@ -464,6 +465,9 @@ __global__ void __launch_bounds__(THREADS, MINB) k_onchip(const __grid_constant_
     const double lamh = P.var.o_lambdh >= 0 ? xs[P.var.o_lambdh] : 1.0;
     const double lamv = P.var.o_lambdv >= 0 ? xs[P.var.o_lambdv] : 1.0;
     const double pzs = A.pzs ? A.pzs[cand] : 1.0;
+    // horizontal load basis of the candidate: (c, s) = load direction; (1, 0) reproduces the single-basis values bit for bit
+    const double dirc = A.dir ? A.dir[2 * cand] : 1.0, dirs = A.dir ? A.dir[2 * cand + 1] : 0.0;
+    auto mix2 = [&](const double* a, const double* b, int i) -> double { return b ? fma(dirs, b[i], dirc * a[i]) : a[i]; };
     double gmin = 1e300;
     double fpart = 0.0;
     bool bad = false;
@@ -476,7 +480,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_onchip(const __grid_constant_
       // four edges per thread at once: 4 x unroll independent loads of B in flight
       double acc4[4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) acc4[i] = (e0 + i * THREADS < m) ? lamh * P.d[e0 + i * THREADS] : 0.0;
+      for (int i = 0; i < 4; ++i) acc4[i] = (e0 + i * THREADS < m) ? lamh * mix2(P.d, P.d_b, e0 + i * THREADS) : 0.0;
 #pragma unroll 4
       for (int j = 0; j < k; ++j) {
         const double xj = xs[j];
@@ -491,6 +495,11 @@ __global__ void __launch_bounds__(THREADS, MINB) k_onchip(const __grid_constant_
       if (e >= m) continue;
       const double acc = acc4[i];
       qs[e] = acc;
+      if (A.dir && Jout && P.con.r_fun >= 0) {  // the lambdh column of the funicular rows follows the candidate's direction
+        const double de = mix2(P.d, P.d_b, e);
+        Jout[(int64_t)(P.con.r_fun + e) * nvar + P.var.o_lambdh] = de;
+        Jout[(int64_t)(P.con.r_fun + m + e) * nvar + P.var.o_lambdh] = -de;
+      }
       if (want_ecomp_nl) {  // 'simplified' quadratic energy sum stiff q^2 and the weight of its gradient B^T (2 stiff q)
         const double se = __ldg(P.stiff + e);
         fpart = fma(se * acc, acc, fpart);
@@ -637,8 +646,8 @@ __global__ void __launch_bounds__(THREADS, MINB) k_onchip(const __grid_constant_
       const int v = rowv_s[r];
       double px, py, pz;
       if (P.var.o_lambdh >= 0) {
-        px = lamh * P.px0[v];
-        py = lamh * P.py0[v];
+        px = lamh * mix2(P.px0, P.px0_b, v);
+        py = lamh * mix2(P.py0, P.py0_b, v);
       } else {
         px = P.P[3 * v + 0];
         py = P.P[3 * v + 1];
@@ -823,7 +832,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_onchip(const __grid_constant_
           Ry = fma(sg * qe, vv, Ry);
           Rz = fma(sg * qe, w, Rz);
           if (P.var.o_lambdh >= 0) {
-            const double d0 = P.d[supedge_s[t]];
+            const double d0 = mix2(P.d, P.d_b, supedge_s[t]);
             ud0 = fma(sg * u, d0, ud0);
             vd0 = fma(sg * vv, d0, vd0);
           }
@@ -834,8 +843,8 @@ __global__ void __launch_bounds__(THREADS, MINB) k_onchip(const __grid_constant_
         }
         double px, py, pz;
         if (P.var.o_lambdh >= 0) {
-          px = lamh * P.px0[vb];
-          py = lamh * P.py0[vb];
+          px = lamh * mix2(P.px0, P.px0_b, vb);
+          py = lamh * mix2(P.py0, P.py0_b, vb);
         } else {
           px = P.P[3 * vb + 0];
           py = P.P[3 * vb + 1];
@@ -904,6 +913,8 @@ __global__ void __launch_bounds__(THREADS, MINB) k_onchip(const __grid_constant_
               const bool ok = cok && e < p1;
               rc[u] = ok ? __ldg(O.ec_rec + e) : 0xffffffffu;
               cc[u] = ok ? __ldg(O.Bc + (int64_t)e * O.bc_stride + cidx) : 0.0;
+              // lambdh column with a second load basis: d0 of the candidate's direction (the basis sits one column on)
+              if (ok && P.d_b && cidx == k) cc[u] = fma(dirs, __ldg(O.Bc + (int64_t)e * O.bc_stride + k + 1), dirc * cc[u]);
             }
           };
           fetch(0, rec, cf);
@@ -965,7 +976,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_onchip(const __grid_constant_
             const double qe = qsup[t];
             const double zo = zval(o);
             const double w = sg > 0 ? (zb - zo) : (zo - zb);
-            const double coef = isq ? P.B[(int64_t)e * k + col] : P.d[e];
+            const double coef = isq ? P.B[(int64_t)e * k + col] : mix2(P.d, P.d_b, e);
             dRz = fma(sg * w, coef, dRz);
             const int ro = vrow_s[o];
             if ((has_env || !isq) && ro >= 0) {
@@ -974,8 +985,8 @@ __global__ void __launch_bounds__(THREADS, MINB) k_onchip(const __grid_constant_
             }
           }
           if (!isq) {  // lambdh column: Cb^T U d0 - px0, Cb^T V d0 - py0 (formed in step 7 while x, y were live)
-            dRx = gxy[2 * nb * k + b] - P.px0[vb];
-            dRy = gxy[2 * nb * k + nb + b] - P.py0[vb];
+            dRx = gxy[2 * nb * k + b] - mix2(P.px0, P.px0_b, vb);
+            dRy = gxy[2 * nb * k + nb + b] - mix2(P.py0, P.py0_b, vb);
           }
           vx = zb * sx * (-Rz * dRx + Rx * dRz) / rz2 / sz;
           vy = zb * sy * (-Rz * dRy + Ry * dRz) / rz2 / sz;
@@ -1586,7 +1597,7 @@ static int build_onchip_impl(Plan* PL, const tno_problem_desc* D, const int THRE
   std::vector<uint32_t> ec_rec;
   std::vector<double> Bc;
   {
-    const int stride = k + (P.var.o_lambdh >= 0 ? 1 : 0);
+    const int stride = k + (P.var.o_lambdh >= 0 ? 1 : 0) + (D->d_b ? 1 : 0);
     O.bc_stride = stride;
     std::vector<int> color(m, -1);
     std::vector<std::vector<char>> used;  // used[c][row]
@@ -1623,6 +1634,7 @@ static int build_onchip_impl(Plan* PL, const tno_problem_desc* D, const int THRE
         ec_rec.push_back(head | (tail << 16));
         for (int j = 0; j < k; ++j) Bc.push_back(D->B[(size_t)e * k + j]);
         if (P.var.o_lambdh >= 0) Bc.push_back(D->d[e]);
+        if (D->d_b) Bc.push_back(D->d_b[e]);
       }
       ec_ptr.push_back((int)ec_rec.size());
     }
@@ -1822,6 +1834,11 @@ int run_onchip(Plan* PL, const double* x_dev, int64_t N, int64_t ldx, const tno_
   A.x = x_dev;
   A.ldx = ldx;
   A.pzs = (opt && opt->pz_scale) ? opt->pz_scale : nullptr;
+  A.dir = (opt && opt->load_dir) ? opt->load_dir : nullptr;
+  if (A.dir && !PL->dp.d_b) {
+    set_error("load_dir needs a plan created with the second load basis (d_b, px0_b, py0_b)");
+    return TNO_EINVAL;
+  }
   A.f = out->f;
   A.grad = out->grad;
   A.g = out->g;

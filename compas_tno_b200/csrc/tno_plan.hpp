@@ -39,6 +39,7 @@ struct ConLayout {
 struct SlotLayout {
   int s_x = 0;      // nvar
   int s_pzs = 0;    // 1
+  int s_dir = 0;    // 2 : (c, s) of the candidate's load direction, (1, 0) without one
   int s_q = 0;      // m
   int s_l = 0;      // nnz_l
   int s_r = 0;      // ni * nrhs, row-major by permuted row
@@ -105,6 +106,9 @@ struct DevPlan {
   const double* pz0;
   const double* dXb;        // nb x 3 (complementary-energy objectives)
   const double* stiff;      // m (Ecomp-nonlinear)
+  const double* d_b;        // second horizontal load basis (per-candidate load directions), null = absent
+  const double* px0_b;
+  const double* py0_b;
 };
 
 // ---- on-chip kernel family (tno_onchip.cu) -----------------------------------------------------------

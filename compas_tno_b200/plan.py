@@ -119,6 +119,11 @@ class TnoPlan:
         D.py0 = dptr(getattr(M, "py0", None), (n,)) if "lambdh" in variables else None
         D.pzv = dptr(getattr(M, "pzv", None), (n,)) if "lambdv" in variables else None
         D.pz0 = dptr(getattr(M, "pz0", None), (n,)) if "lambdv" in variables else None
+        # second horizontal load basis (per-candidate load directions): d0_b, px0_b, py0_b next to d0, px0, py0
+        if "lambdh" in variables and getattr(M, "d0_b", None) is not None:
+            D.d_b = dptr(M.d0_b, (m,))
+            D.px0_b = dptr(M.px0_b, (n,))
+            D.py0_b = dptr(M.py0_b, (n,))
         if objective in ("Ecomp-linear", "Ecomp-nonlinear"):
             D.dXb = dptr(getattr(M, "dXb", None), (nb, 3))
         if objective == "Ecomp-nonlinear":
@@ -206,8 +211,10 @@ class TnoPlan:
                 "z": (N, self.n), "q": (N, self.m), "gmin": (N,), "status": (N,)}[name]
 
     # ------------------------------------------------------------------------------------------
-    def evaluate_host(self, x, outputs: Iterable[str] = ALL_OUTPUTS, pz_scale=None) -> Dict[str, np.ndarray]:
-        """Host buffers in, host buffers out (tno_eval_batch_host); no torch involved."""
+    def evaluate_host(self, x, outputs: Iterable[str] = ALL_OUTPUTS, pz_scale=None, load_dir=None) -> Dict[str, np.ndarray]:
+        """Host buffers in, host buffers out (tno_eval_batch_host); no torch involved.
+        ``pz_scale`` (N,): vertical load multiplier per candidate; ``load_dir`` (N, 2): (cos, sin) of the horizontal
+        load direction per candidate (problems with ``lambdh`` and a second load basis ``d0_b, px0_b, py0_b``)."""
         x = _f64(x)
         if x.ndim == 1:
             x = x.reshape(1, -1)
@@ -219,12 +226,17 @@ class TnoPlan:
             arr = np.empty(self._shape(name, N), dtype=np.int32 if name == "status" else np.float64)
             res[name] = arr
             setattr(O, name, arr.ctypes.data)
+        inp = _lib.BatchInputs()
         pz = _f64(pz_scale, (N,)) if pz_scale is not None else None
-        _lib.check(self._lib.tno_eval_batch_host(self._handle, x.ctypes.data, N, ld,
-                                                 pz.ctypes.data if pz is not None else None, C.byref(O)))
+        ld2 = _f64(load_dir, (N, 2)) if load_dir is not None else None
+        if pz is not None:
+            inp.pz_scale = pz.ctypes.data
+        if ld2 is not None:
+            inp.load_dir = ld2.ctypes.data
+        _lib.check(self._lib.tno_eval_batch_host(self._handle, x.ctypes.data, N, ld, C.byref(inp), C.byref(O)))
         return res
 
-    def evaluate_device(self, x, outputs: Iterable[str] = ALL_OUTPUTS, pz_scale=None, out=None, stream=None):
+    def evaluate_device(self, x, outputs: Iterable[str] = ALL_OUTPUTS, pz_scale=None, out=None, stream=None, load_dir=None):
         """Device tensors in, device tensors out (tno_eval_batch); asynchronous on the current torch stream."""
         import torch
         if not x.is_cuda or x.dtype != torch.float64 or x.dim() != 2 or x.stride(1) != 1:
@@ -247,6 +259,10 @@ class TnoPlan:
         opt = _lib.BatchInputs()
         if pz_scale is not None:
             opt.pz_scale = pz_scale.data_ptr()
+        if load_dir is not None:
+            if tuple(load_dir.shape) != (N, 2) or load_dir.dtype != torch.float64 or not load_dir.is_contiguous() or not load_dir.is_cuda:
+                raise ValueError("load_dir must be a contiguous (N, 2) float64 CUDA tensor")
+            opt.load_dir = load_dir.data_ptr()
         st = torch.cuda.current_stream(x.device).cuda_stream if stream is None else stream
         _lib.check(self._lib.tno_eval_batch(self._handle, x.data_ptr(), N, x.stride(0), C.byref(opt), C.byref(O),
                                             C.c_void_p(st)))

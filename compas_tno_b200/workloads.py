@@ -165,6 +165,35 @@ def dome_lambdh_problem(n_hoops: int = 20, n_parallels: int = 16, thk: float = 0
     return Ph, np.concatenate([xq, x0[Ph.k:], [lambd]])
 
 
+def dome_direction_problem(n_hoops: int = 20, n_parallels: int = 16, thk: float = 0.5, radius: float = 5.0, rho: float = 20.0,
+                           lambd: float = 0.02, constraints=("funicular", "envelope", "reac_bounds"), n_states: int = 12):
+    """Dome for a sweep over horizontal load *directions* (BASELINE configuration 5):
+    two load bases, theta = 0 (px0 = |pz|, py0 = 0, d0) and theta = 90 degrees (px0_b = 0, py0_b = |pz|, d0_b), so that
+    a candidate with direction (c, s) sees d0(theta) = c d0 + s d0_b.  Returns (problem, x_star) with x_star for
+    theta = 0; ``direction_candidates`` builds the batch."""
+    Px, x0 = dome_lambdh_problem(n_hoops, n_parallels, thk, radius, rho, 0.0, lambd, constraints, n_states)
+    Py, _ = dome_lambdh_problem(n_hoops, n_parallels, thk, radius, rho, 0.5 * np.pi, lambd, constraints, n_states)
+    Py.px0[:] = 0.0  # cos(pi / 2) leaves 6e-17 |pz| behind
+    Px.py0[:] = 0.0
+    Px.d0_b, Px.px0_b, Px.py0_b = Py.d0.copy(), Py.px0.copy(), Py.py0.copy()
+    Px.lambdh_shift_b = Py.lambdh_shift
+    return Px, x0
+
+
+def direction_candidates(problem, x_star, N: int, seed: int = SEED, sigma: float = 0.05):
+    """(X, load_dir): N candidates with directions theta_j = 2 pi j / N; q_ind carries the shift of its direction so
+    that q = B y + lambdh (c d0 + s d0_b) stays a compression-only state."""
+    k = problem.k
+    theta = 2.0 * np.pi * np.arange(N) / N
+    load_dir = np.ascontiguousarray(np.column_stack([np.cos(theta), np.sin(theta)]))
+    x0 = np.asarray(x_star, dtype=np.float64).copy()
+    x0[:k] += x0[-1] * problem.lambdh_shift
+    X = sample_candidates(problem, x0, N, seed=seed, sigma=sigma, basis=problem.candidate_basis)
+    shift = load_dir[:, [0]] * problem.lambdh_shift[None, :] + load_dir[:, [1]] * problem.lambdh_shift_b[None, :]
+    X[:, :k] -= X[:, [-1]] * shift
+    return np.ascontiguousarray(X), load_dir
+
+
 def lambdh_candidates(problem, x_star, N: int, seed: int = SEED, sigma: float = 0.05):
     """sample_candidates for a lambdh problem: convex combinations of the compressive basis, lambdh perturbed by
     sigma, and the q_ind shift that goes with each candidate's lambdh."""

@@ -128,6 +128,10 @@ typedef struct tno_problem_desc {
   int32_t reserved;
   const double* dXb;    /* nb x 3 prescribed support displacements (Ecomp objectives only)   Problem.dXb   */
   const double* stiff;  /* m   0.5 l^2 / k per edge (Ecomp-nonlinear only)                   Problem.stiff */
+  /* second horizontal load basis for per-candidate load directions (tno_batch_inputs.load_dir); all three or none */
+  const double* d_b;    /* m   particular solution of the second basis (d is that of the first) */
+  const double* px0_b;  /* n */
+  const double* py0_b;  /* n */
 } tno_problem_desc;
 
 /* What the symbolic analysis found; all sizes a caller needs to allocate outputs. */
@@ -151,7 +155,9 @@ typedef struct tno_plan_info {
 /* Optional per-candidate inputs that are not part of x (device pointers, NULL = not used). */
 typedef struct tno_batch_inputs {
   const double* pz_scale; /* N   vertical load multiplier: P[:,2] *= pz_scale[j] (Monte-Carlo self-weight) */
-  const double* reserved0;
+  const double* load_dir; /* N x 2 (c, s): horizontal load direction of candidate j (needs the lambdh variable and the
+                             second load basis d_b / px0_b / py0_b of the problem):
+                             d0 = c d + s d_b,  px0 = c px0 + s px0_b,  py0 = c py0 + s py0_b */
   const double* reserved1;
 } tno_batch_inputs;
 
@@ -198,7 +204,7 @@ int tno_eval_batch(tno_plan* plan, const double* x_dev, int64_t n_candidates, in
  * stream, copies the requested outputs back and synchronises.  This is the call behind the
  * batch-1 drop-in callbacks and the end-to-end figure of bench.py. */
 int tno_eval_batch_host(tno_plan* plan, const double* x_host, int64_t n_candidates, int64_t ldx,
-                        const double* pz_scale_host, const tno_outputs* out_host);
+                        const tno_batch_inputs* inputs_host, const tno_outputs* out_host);
 
 /* Number of kernel launches issued by this plan so far (bench.py reports it as gpu_launches). */
 int64_t tno_plan_launch_count(const tno_plan* plan);

@@ -220,6 +220,48 @@ def test_dropin_bestfit_and_feasibility_callbacks(tno):
 
 
 @pytest.mark.parametrize("kernel", ["interleaved", "onchip"])
+def test_load_direction_sweep_matches_oracle_per_direction(tno, kernel):
+    """tno_batch_inputs.load_dir: candidate j sees d0 = c d0 + s d0_b, px0 = c px0 + s px0_b, py0 likewise
+    (configuration 5).  The oracle evaluates each candidate on its own per-direction Problem."""
+    from compas_tno_b200 import workloads as W
+    from compas_tno_b200.plan import TnoPlan
+    from oracle import callbacks_np as onp
+    P, xs = W.dome_direction_problem(10, 8, n_states=4)
+    X, load_dir = W.direction_candidates(P, xs, 37, seed=9)
+    plan = TnoPlan(P, objective="max_load", kernel=kernel)
+    got = plan.evaluate_host(X, load_dir=load_dir)
+    assert np.all(got["status"] == 0)
+    for j in (0, 5, 9, 18, 36):
+        c, s = load_dir[j]
+        M = onp.clone_problem(P)
+        M.d0 = c * P.d0 + s * P.d0_b
+        M.d = M.d0.copy()
+        M.px0 = c * P.px0 + s * P.px0_b
+        M.py0 = c * P.py0 + s * P.py0_b
+        ref = onp.evaluate(X[j], M, "max_load")
+        assert rel_err(got["q"][j], ref["q"]) < TOL_VAL
+        assert rel_err(got["z"][j], ref["z"]) < TOL_VAL
+        assert rel_err(got["g"][j], ref["g"]) < TOL_VAL
+        assert abs(got["f"][j] - ref["f"]) <= TOL_VAL * max(1.0, abs(ref["f"]))
+        assert rel_err(got["grad"][j], ref["grad"]) < TOL_JAC
+        assert rel_err(got["J"][j], ref["J"]) < TOL_JAC
+        m, n = P.m, P.n
+        for lo, hi in ((0, 2 * m), (2 * m, 2 * m + 2 * n), (2 * m + 2 * n, plan.ng)):
+            assert rel_err(got["J"][j][lo:hi], ref["J"][lo:hi]) < TOL_JAC
+    # without directions the same plan reproduces the single-basis results bit for bit
+    P1, x1 = W.dome_lambdh_problem(10, 8, theta=0.0, n_states=4)
+    P1.py0[:] = 0.0
+    X1 = W.lambdh_candidates(P1, x1, 9, seed=4)
+    a = plan.evaluate_host(X1)
+    b = TnoPlan(P1, objective="max_load", kernel=kernel).evaluate_host(X1)
+    for key in a:
+        assert np.array_equal(a[key], b[key]), key
+    # a plan without the second basis refuses directions
+    with pytest.raises(NotImplementedError):
+        TnoPlan(P1, objective="max_load", kernel=kernel).evaluate_host(X1, load_dir=np.tile([1.0, 0.0], (9, 1)))
+
+
+@pytest.mark.parametrize("kernel", ["interleaved", "onchip"])
 def test_pz_scale_matches_oracle_with_scaled_loads(tno, kernel):
     """Monte-Carlo self-weight input: pz_scale[j] multiplies the vertical loads of candidate j."""
     import copy

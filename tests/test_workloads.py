@@ -35,3 +35,17 @@ def test_dome_lambdh_candidates_are_compressive_and_in_equilibrium():
         assert _min_eig(P, q) > 0.0
         # E q = lambdh * ph : the horizontal loads scale with the multiplier
         assert np.abs(P.E @ q.reshape(-1, 1) - lam * P.ph).max() < 1e-8
+
+
+def test_direction_sweep_candidates_follow_their_direction():
+    P, xs = W.dome_direction_problem(8, 8, n_states=4)
+    X, load_dir = W.direction_candidates(P, xs, 8, seed=5)
+    assert np.allclose(np.hypot(load_dir[:, 0], load_dir[:, 1]), 1.0)
+    w = np.abs(P.P[P.free, 2:3])
+    for x, (c, s) in zip(X, load_dir):
+        lam = x[-1]
+        q = (P.B @ x[: P.k].reshape(-1, 1) + lam * (c * P.d0 + s * P.d0_b)).ravel()
+        assert q.max() <= 1e-9
+        assert _min_eig(P, q) > 0.0
+        ph = np.vstack([c * w, s * w])
+        assert np.abs(P.E @ q.reshape(-1, 1) - lam * ph).max() < 1e-8
