@@ -392,7 +392,9 @@ __device__ __forceinline__ void oc_chain_dense(const DevOnchip& O, const OcDense
   __syncthreads();
 }
 
-template <int THREADS, int MINB>
+// DIR: per-candidate horizontal load directions (tno_batch_inputs.load_dir); a separate instantiation so that the
+// common single-basis path carries none of its registers or branches.
+template <int THREADS, int MINB, bool DIR>
 __global__ void __launch_bounds__(THREADS, MINB) k_onchip(const __grid_constant__ DevPlan P, const __grid_constant__ DevOnchip O,
                                                             const __grid_constant__ OcArgs A) {
   extern __shared__ __align__(16) unsigned char smraw[];
@@ -466,8 +468,11 @@ __global__ void __launch_bounds__(THREADS, MINB) k_onchip(const __grid_constant_
     const double lamv = P.var.o_lambdv >= 0 ? xs[P.var.o_lambdv] : 1.0;
     const double pzs = A.pzs ? A.pzs[cand] : 1.0;
     // horizontal load basis of the candidate: (c, s) = load direction; (1, 0) reproduces the single-basis values bit for bit
-    const double dirc = A.dir ? A.dir[2 * cand] : 1.0, dirs = A.dir ? A.dir[2 * cand + 1] : 0.0;
-    auto mix2 = [&](const double* a, const double* b, int i) -> double { return b ? fma(dirs, b[i], dirc * a[i]) : a[i]; };
+    const double dirc = DIR ? A.dir[2 * cand] : 1.0, dirs = DIR ? A.dir[2 * cand + 1] : 0.0;
+    auto mix2 = [&](const double* a, const double* b, int i) -> double {
+      if constexpr (DIR) return fma(dirs, b[i], dirc * a[i]);
+      else return a[i];
+    };
     double gmin = 1e300;
     double fpart = 0.0;
     bool bad = false;
@@ -495,7 +500,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_onchip(const __grid_constant_
       if (e >= m) continue;
       const double acc = acc4[i];
       qs[e] = acc;
-      if (A.dir && Jout && P.con.r_fun >= 0) {  // the lambdh column of the funicular rows follows the candidate's direction
+      if (DIR && Jout && P.con.r_fun >= 0) {  // the lambdh column of the funicular rows follows the candidate's direction
         const double de = mix2(P.d, P.d_b, e);
         Jout[(int64_t)(P.con.r_fun + e) * nvar + P.var.o_lambdh] = de;
         Jout[(int64_t)(P.con.r_fun + m + e) * nvar + P.var.o_lambdh] = -de;
@@ -914,7 +919,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_onchip(const __grid_constant_
               rc[u] = ok ? __ldg(O.ec_rec + e) : 0xffffffffu;
               cc[u] = ok ? __ldg(O.Bc + (int64_t)e * O.bc_stride + cidx) : 0.0;
               // lambdh column with a second load basis: d0 of the candidate's direction (the basis sits one column on)
-              if (ok && P.d_b && cidx == k) cc[u] = fma(dirs, __ldg(O.Bc + (int64_t)e * O.bc_stride + k + 1), dirc * cc[u]);
+              if (DIR && ok && cidx == k) cc[u] = fma(dirs, __ldg(O.Bc + (int64_t)e * O.bc_stride + k + 1), dirc * cc[u]);
             }
           };
           fetch(0, rec, cf);
@@ -1859,7 +1864,8 @@ int run_onchip(Plan* PL, const double* x_dev, int64_t N, int64_t ldx, const tno_
   const int ctas = force_ctas ? std::max(1, atoi(force_ctas)) : PL->onchip_ctas_per_sm;
   const int grid = (int)std::min<int64_t>(N, (int64_t)PL->sm_count * ctas);
   const int threads = PL->onchip_threads;
-  auto kern = threads == 512 ? k_onchip<512, 1> : (PL->onchip_ctas_per_sm >= 2 ? k_onchip<256, 2> : k_onchip<256, 1>);
+  auto kern = A.dir ? (threads == 512 ? k_onchip<512, 1, true> : (PL->onchip_ctas_per_sm >= 2 ? k_onchip<256, 2, true> : k_onchip<256, 1, true>))
+                    : (threads == 512 ? k_onchip<512, 1, false> : (PL->onchip_ctas_per_sm >= 2 ? k_onchip<256, 2, false> : k_onchip<256, 1, false>));
   TNO_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   if (out->J && PL->dp.con.r_fun >= 0)
     launch_fill_funicular(PL, PL->oc.Jfun, (int64_t)2 * PL->dp.m * PL->dp.var.nvar, out->J, N, stream);
