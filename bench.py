@@ -437,6 +437,21 @@ def run_ours(args):
     e2e["objectives_only"] = {"value": world * N * esteps / dt2, "unit": UNIT, "h2d_bytes_per_step": int(xh2.numel() * 8),
                               "d2h_bytes_per_step": int(N * (8 + 8 + 4)), "note": "f, gmin, status to host; grad, g, J, z materialised in HBM"}
 
+    # feasibility sweeps (Monte-Carlo, multi-start screening) need neither J nor the gradient: the dz/dq_ind solve is skipped
+    bufs3 = {}
+    for _ in range(2):
+        plan.evaluate_batch(xh2, to_host=("f", "gmin", "status"), on_device=(), buffers=bufs3)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(esteps):
+        plan.evaluate_batch(xh2, to_host=("f", "gmin", "status"), on_device=(), buffers=bufs3)
+    barrier()
+    dt3 = time.perf_counter() - t0
+    e2e["screening_only"] = {"value": world * N * esteps / dt3, "unit": "candidates/s", "h2d_bytes_per_step": int(xh2.numel() * 8),
+                             "d2h_bytes_per_step": int(N * (8 + 8 + 4)),
+                             "note": "NOT the headline metric: f, gmin, status only; no J, no gradient, sensitivity solve skipped"}
+    del bufs2, bufs3
+
     # ---- CPU baseline (rank 0, N = 1 only): bounded sample of the same workload ----
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
