@@ -10,8 +10,8 @@ LIB_PATH = os.path.join(HERE, "libtno_b200.so")
 ABI_VERSION = 2
 
 # masks / enums (mirror include/tno_b200.h)
-VAR_Q, VAR_ZB, VAR_T, VAR_LAMBDH, VAR_LAMBDV = 1, 2, 4, 8, 16
-CON_FUNICULAR, CON_ENVELOPE, CON_REAC_BOUNDS = 1, 2, 4
+VAR_Q, VAR_ZB, VAR_T, VAR_LAMBDH, VAR_LAMBDV, VAR_XYB = 1, 2, 4, 8, 16, 32
+CON_FUNICULAR, CON_ENVELOPE, CON_REAC_BOUNDS, CON_ENVELOPEXY = 1, 2, 4, 8
 OBJ_NONE, OBJ_MIN, OBJ_MAX, OBJ_T, OBJ_NEG_LAST, OBJ_BESTFIT, OBJ_FEASIBILITY, OBJ_LOADPATH = 0, 1, 2, 3, 4, 5, 6, 7
 OBJ_ECOMP_LINEAR, OBJ_ECOMP_NONLINEAR = 8, 9
 ENV_FIXED, ENV_DOME, ENV_CROSSVAULT = 0, 1, 2
@@ -38,6 +38,7 @@ class ProblemDesc(C.Structure):
         ("envelope_kind", C.c_int32), ("env_params", C.c_double * 8), ("thk", C.c_double),
         ("device", C.c_int32), ("kernel", C.c_int32), ("ordering", C.c_int32), ("reserved", C.c_int32),
         ("dXb", _dp), ("stiff", _dp), ("d_b", _dp), ("px0_b", _dp), ("py0_b", _dp),
+        ("xlimits", _dp), ("ylimits", _dp),
     ]
 
 

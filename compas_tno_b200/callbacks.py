@@ -45,6 +45,12 @@ class _State:
             try:
                 problem.q = self.res["q"][0].reshape(-1, 1).copy()
                 problem.X[:, 2] = self.res["z"][0]
+                if "envelopexy" in self.plan.constraints:
+                    # x and y of the moved geometry come back inside g: rows x - xlim0 and y - ylim0
+                    g, m, n = self.res["g"][0], self.plan.m, self.plan.n
+                    r0 = 2 * m if "funicular" in self.plan.constraints else 0
+                    problem.X[:, 0] = g[r0: r0 + n] + np.asarray(problem.xlimits)[:, 0]
+                    problem.X[:, 1] = g[r0 + 2 * n: r0 + 3 * n] + np.asarray(problem.ylimits)[:, 0]
             except Exception:
                 pass
         return self.res

@@ -122,10 +122,21 @@ int tno_plan_create(const tno_problem_desc* D, tno_plan** out_plan) {
   if (!D->edges || !D->fixed || !D->B || !D->d || !D->P || !D->X || !D->qmin || !D->qmax)
     return fail(TNO_EINVAL, "missing mandatory array");
   if (!(D->variables & TNO_VAR_Q)) return fail(TNO_EINVAL, "variables must contain q");
-  if (D->variables & ~(TNO_VAR_Q | TNO_VAR_ZB | TNO_VAR_T | TNO_VAR_LAMBDH | TNO_VAR_LAMBDV))
-    return fail(TNO_EINVAL, "unsupported variable (supported: q, zb, t/n, lambdh, lambdv)");
-  if (D->constraints & ~(TNO_CON_FUNICULAR | TNO_CON_ENVELOPE | TNO_CON_REAC_BOUNDS))
-    return fail(TNO_EINVAL, "unsupported constraint (supported: funicular, envelope, reac_bounds)");
+  if (D->variables & ~(TNO_VAR_Q | TNO_VAR_ZB | TNO_VAR_T | TNO_VAR_LAMBDH | TNO_VAR_LAMBDV | TNO_VAR_XYB))
+    return fail(TNO_EINVAL, "unsupported variable (supported: q, xyb, zb, t/n, lambdh, lambdv)");
+  if (D->constraints & ~(TNO_CON_FUNICULAR | TNO_CON_ENVELOPE | TNO_CON_REAC_BOUNDS | TNO_CON_ENVELOPEXY))
+    return fail(TNO_EINVAL, "unsupported constraint (supported: funicular, envelopexy, envelope, reac_bounds)");
+  if ((D->constraints & TNO_CON_ENVELOPEXY) && (!D->xlimits || !D->ylimits)) return fail(TNO_EINVAL, "envelopexy needs xlimits / ylimits");
+  if ((D->variables & TNO_VAR_XYB) || (D->constraints & TNO_CON_ENVELOPEXY)) {
+    // the reference stacks the xyb columns against the envelopexy AND envelope row blocks (jacobian.py:269-273)
+    if ((D->variables & TNO_VAR_XYB) && (D->constraints & (TNO_CON_ENVELOPEXY | TNO_CON_ENVELOPE)) != (TNO_CON_ENVELOPEXY | TNO_CON_ENVELOPE))
+      return fail(TNO_EINVAL, "xyb variables need the envelopexy and envelope constraints");
+    if (D->constraints & TNO_CON_REAC_BOUNDS) return fail(TNO_EINVAL, "reac_bounds with xyb / envelopexy is not available");
+    if (D->variables & (TNO_VAR_LAMBDH | TNO_VAR_LAMBDV)) return fail(TNO_EINVAL, "load multipliers with xyb / envelopexy are not available");
+    if (D->objective > TNO_OBJ_NEG_LAST && D->objective != TNO_OBJ_FEASIBILITY)
+      return fail(TNO_EINVAL, "xyb / envelopexy support the objectives min, max, t, n, feasibility");
+    if (D->kernel == TNO_KERNEL_ONCHIP) return fail(TNO_EINVAL, "xyb / envelopexy run on the interleaved kernel family");
+  }
   if ((D->constraints & TNO_CON_ENVELOPE) && (!D->lb || !D->ub)) return fail(TNO_EINVAL, "envelope needs lb / ub");
   if ((D->variables & TNO_VAR_T) && D->envelope_kind != TNO_ENV_DOME && D->envelope_kind != TNO_ENV_CROSSVAULT)
     return fail(TNO_EINVAL, "thickness variable needs a parametric envelope");
@@ -272,6 +283,7 @@ int tno_plan_create(const tno_problem_desc* D, tno_plan** out_plan) {
   dp.nnz_l = nnz_l;
   VarLayout& V = dp.var;
   int pos = k;
+  if (D->variables & TNO_VAR_XYB) { V.o_xyb = pos; pos += 2 * nb; }
   if (D->variables & TNO_VAR_ZB) { V.o_zb = pos; pos += nb; }
   if (D->variables & TNO_VAR_T) { V.o_t = pos; pos += 1; }
   if (D->variables & TNO_VAR_LAMBDH) { V.o_lambdh = pos; pos += 1; }
@@ -280,12 +292,13 @@ int tno_plan_create(const tno_problem_desc* D, tno_plan** out_plan) {
   ConLayout& C = dp.con;
   pos = 0;
   if (D->constraints & TNO_CON_FUNICULAR) { C.r_fun = pos; pos += 2 * m; }
+  if (D->constraints & TNO_CON_ENVELOPEXY) { C.r_envxy = pos; pos += 4 * n; }
   if (D->constraints & TNO_CON_ENVELOPE) { C.r_env = pos; pos += 2 * n; }
   if (D->constraints & TNO_CON_REAC_BOUNDS) { C.r_reac = pos; pos += 2 * nb; }
   C.ng = pos;
   RhsLayout& R = dp.rhs;
   pos = 3;
-  if (V.o_zb >= 0) { R.c_zb = pos; pos += nb; }
+  if (V.o_zb >= 0 || V.o_xyb >= 0) { R.c_zb = pos; pos += nb; }   // A = A^-1 (-Ci^T Q Cb): dz/dzb = dx/dxb = dy/dyb
   if (V.o_lambdv >= 0) { R.c_lambdv = pos; pos += 1; }
   R.nrhs1 = pos;
   const bool need_dq = (D->constraints & (TNO_CON_ENVELOPE | TNO_CON_REAC_BOUNDS)) != 0 || D->objective == TNO_OBJ_BESTFIT ||
@@ -293,6 +306,11 @@ int tno_plan_create(const tno_problem_desc* D, tno_plan** out_plan) {
   if (need_dq) {
     R.c_q = pos; pos += k;
     if (V.o_lambdh >= 0) { R.c_lambdh = pos; pos += 1; }
+  }
+  const bool thrust = D->objective == TNO_OBJ_MIN || D->objective == TNO_OBJ_MAX;
+  if ((D->constraints & TNO_CON_ENVELOPEXY) || (V.o_xyb >= 0 && thrust)) {
+    R.c_qx = pos; pos += k;
+    R.c_qy = pos; pos += k;
   }
   R.nrhs = pos;
   R.nrhs2 = R.nrhs - R.nrhs1;
@@ -349,6 +367,8 @@ int tno_plan_create(const tno_problem_desc* D, tno_plan** out_plan) {
   UP(d_b, vec(D->d_b, (size_t)m));
   UP(px0_b, vec(D->px0_b, (size_t)n));
   UP(py0_b, vec(D->py0_b, (size_t)n));
+  UP(xlimits, vec(D->xlimits, (size_t)n * 2));
+  UP(ylimits, vec(D->ylimits, (size_t)n * 2));
 #undef UP
 
   // ---- emit tables (user-facing row-major layouts as affine gathers of the scratch slots) --
@@ -359,6 +379,12 @@ int tno_plan_create(const tno_problem_desc* D, tno_plan** out_plan) {
     if (V.o_zb >= 0) return one(SL.s_x + V.o_zb + b, sign);
     return cst(sign * D->X[3 * v + 2]);
   };
+  auto xydesc = [&](int v, int axis, float sign) -> EmitDesc2 {
+    if (vrow[v] >= 0) return one(SL.s_r + vrow[v] * R.nrhs + (axis == 0 ? R.cx : R.cy), sign);
+    const int b = -1 - vrow[v];
+    if (V.o_xyb >= 0) return one(SL.s_x + V.o_xyb + axis * nb + b, sign);
+    return cst(sign * D->X[3 * v + axis]);
+  };
   {
     std::vector<EmitDesc2> t((size_t)ng);
     if (C.r_fun >= 0)
@@ -366,6 +392,16 @@ int tno_plan_create(const tno_problem_desc* D, tno_plan** out_plan) {
         t[C.r_fun + e] = one(SL.s_q + e, +1.f, -D->qmin[e]);
         t[C.r_fun + m + e] = one(SL.s_q + e, -1.f, +D->qmax[e]);
       }
+    if (C.r_envxy >= 0)
+      for (int v = 0; v < n; ++v)
+        for (int axis = 0; axis < 2; ++axis) {
+          const double* lim = axis == 0 ? D->xlimits : D->ylimits;
+          EmitDesc2 lo = xydesc(v, axis, +1.f), hi = xydesc(v, axis, -1.f);
+          lo.c += -lim[2 * v + 0];
+          hi.c += +lim[2 * v + 1];
+          t[C.r_envxy + 2 * axis * n + v] = lo;
+          t[C.r_envxy + (2 * axis + 1) * n + v] = hi;
+        }
     if (C.r_env >= 0)
       for (int v = 0; v < n; ++v) {
         EmitDesc2 lo = zdesc(v, +1.f), hi = zdesc(v, -1.f);
@@ -387,8 +423,11 @@ int tno_plan_create(const tno_problem_desc* D, tno_plan** out_plan) {
   }
   {
     std::vector<EmitDesc2> t((size_t)nvar, cst(0.0));
-    if (D->objective == TNO_OBJ_MIN || D->objective == TNO_OBJ_MAX)
+    if (D->objective == TNO_OBJ_MIN || D->objective == TNO_OBJ_MAX) {
       for (int j = 0; j < k; ++j) t[j] = one(SL.s_grad + j, +1.f);
+      if (V.o_xyb >= 0)
+        for (int j = 0; j < 2 * nb; ++j) t[V.o_xyb + j] = one(SL.s_grad + V.o_xyb + j, +1.f);
+    }
     else if (D->objective == TNO_OBJ_BESTFIT || D->objective == TNO_OBJ_LOADPATH || ecomp)
       for (int j = 0; j < nvar; ++j) t[j] = one(SL.s_grad + j, +1.f);
     else if (D->objective == TNO_OBJ_T)
@@ -451,6 +490,29 @@ int tno_plan_create(const tno_problem_desc* D, tno_plan** out_plan) {
           at(r2, V.o_t) = one(SL.s_env + 2 * n + v, +1.f);  // +dub/dt
         }
       }
+    if (C.r_envxy >= 0)   // rows [dx; -dx; dy; -dy]: q columns from the Dx / Dy panels, xb (yb) columns = A (jacobian.py:173-186,269-273)
+      for (int v = 0; v < n; ++v)
+        for (int axis = 0; axis < 2; ++axis) {
+          const int r1 = C.r_envxy + 2 * axis * n + v, r2 = r1 + n;
+          const int ocol = V.o_xyb >= 0 ? V.o_xyb + axis * nb : -1;
+          if (vrow[v] >= 0) {
+            const int base = SL.s_r + vrow[v] * R.nrhs;
+            const int cq = axis == 0 ? R.c_qx : R.c_qy;
+            for (int j = 0; j < k; ++j) {
+              at(r1, j) = one(base + cq + j, +1.f);
+              at(r2, j) = one(base + cq + j, -1.f);
+            }
+            if (ocol >= 0)
+              for (int b = 0; b < nb; ++b) {
+                at(r1, ocol + b) = one(base + R.c_zb + b, +1.f);
+                at(r2, ocol + b) = one(base + R.c_zb + b, -1.f);
+              }
+          } else if (ocol >= 0) {
+            const int b = -1 - vrow[v];
+            at(r1, ocol + b) = cst(1.0);
+            at(r2, ocol + b) = cst(-1.0);
+          }
+        }
     if (C.r_reac >= 0)
       for (int i = 0; i < 2 * nb; ++i)
         for (int j = 0; j < nvar; ++j) at(C.r_reac + i, j) = one(SL.s_rj + i * nvar + j, +1.f);

@@ -295,6 +295,10 @@ __global__ void __launch_bounds__(32 * SEG) k_solve_level_seg(DevPlan P, DevLeve
 __device__ __forceinline__ double zfixed(const DevPlan& P, const double* ws, int64_t NC, int64_t c, int b) {
   return P.var.o_zb >= 0 ? WS(P.slot.s_x + P.var.o_zb + b) : P.X[3 * P.fixed[b] + 2];
 }
+// x (axis 0) or y (axis 1) of support b: a variable with xyb (x block first, then y: constraints.py:52-55)
+__device__ __forceinline__ double xyfixed(const DevPlan& P, const double* ws, int64_t NC, int64_t c, int b, int axis) {
+  return P.var.o_xyb >= 0 ? WS(P.slot.s_x + P.var.o_xyb + axis * P.nb + b) : P.X[3 * P.fixed[b] + axis];
+}
 
 // phase-1 right-hand sides of  -(Ci^T Q Ci) X = -(P_i - Ci^T Q Cb X_b)  and the zb / lambdv blocks
 __global__ void k_rhs1(DevPlan P, double* __restrict__ ws, int64_t NC, int64_t ncand, int rtile) {
@@ -329,8 +333,8 @@ __global__ void k_rhs1(DevPlan P, double* __restrict__ ws, int64_t NC, int64_t n
       if (ro >= 0) continue;
       const int b = -1 - ro;
       const double qe = WS(P.slot.s_q + P.vadj_edge[t]);
-      bx = fma(-qe, P.X[3 * o + 0], bx);
-      by = fma(-qe, P.X[3 * o + 1], by);
+      bx = fma(-qe, xyfixed(P, ws, NC, c, b, 0), bx);
+      by = fma(-qe, xyfixed(P, ws, NC, c, b, 1), by);
       bz = fma(-qe, zfixed(P, ws, NC, c, b), bz);
       if (P.rhs.c_zb >= 0) WS(base + P.rhs.c_zb + b) -= qe;
     }
@@ -393,7 +397,7 @@ __device__ __forceinline__ double zval(const DevPlan& P, const double* ws, int64
 }
 __device__ __forceinline__ double xval(const DevPlan& P, const double* ws, int64_t NC, int64_t c, int v, int axis) {
   const int r = P.vrow[v];
-  return r >= 0 ? WS(P.slot.s_r + r * P.rhs.nrhs + axis) : P.X[3 * v + axis];
+  return r >= 0 ? WS(P.slot.s_r + r * P.rhs.nrhs + axis) : xyfixed(P, ws, NC, c, -1 - r, axis);
 }
 
 // phase-2 right-hand sides:  Ci^T W B  (k columns) and  Ci^T W d0  (lambdh column), W = diag(C z)
@@ -428,6 +432,21 @@ __global__ void k_rhs2(DevPlan P, double* __restrict__ ws, int64_t NC, int64_t n
         acc = fma(sg * w, mix2(P.d, P.d_b, P.vadj_edge[t], dc, ds), acc);
       }
       WS(base + P.rhs.c_lambdh) = acc;
+    }
+    if (P.rhs.c_qx >= 0) {  // Ci^T U B and Ci^T V B, U = diag(C x), V = diag(C y)  (jacobian.py:173-186)
+      const double xv = WS(base + P.rhs.cx), yv = WS(base + P.rhs.cy);
+      for (int j = 0; j < k; ++j) {
+        double ax = 0.0, ay = 0.0;
+        for (int t = a0; t < a1; ++t) {
+          const int o = P.vadj_other[t];
+          const double Bej = P.B[(int64_t)P.vadj_edge[t] * k + j];
+          // C[e, v] (C x)_e = x_v - x_o whichever end v is
+          ax = fma(xv - xval(P, ws, NC, c, o, 0), Bej, ax);
+          ay = fma(yv - xval(P, ws, NC, c, o, 1), Bej, ay);
+        }
+        WS(base + P.rhs.c_qx + j) = ax;
+        WS(base + P.rhs.c_qy + j) = ay;
+      }
     }
   }
 }
@@ -500,6 +519,14 @@ __global__ void k_epilogue(DevPlan P, double* __restrict__ ws, int64_t NC, int64
     }
   }
 
+  if (P.con.r_envxy >= 0) {
+    for (int v = 0; v < n; ++v) {
+      const double x = xval(P, ws, NC, c, v, 0), y = xval(P, ws, NC, c, v, 1);
+      gmin = fmin(gmin, fmin(fmin(x - P.xlimits[2 * v], P.xlimits[2 * v + 1] - x), fmin(y - P.ylimits[2 * v], P.ylimits[2 * v + 1] - y)));
+      bad |= !isfinite(x) || !isfinite(y);
+    }
+  }
+
   const bool want_thrust = (P.objective == TNO_OBJ_MIN || P.objective == TNO_OBJ_MAX);
   const bool want_reac = (P.constraints & TNO_CON_REAC_BOUNDS) != 0;
   double f = 0.0;
@@ -511,7 +538,7 @@ __global__ void k_epilogue(DevPlan P, double* __restrict__ ws, int64_t NC, int64
     for (int b = 0; b < nb; ++b) {
       const int vb = P.fixed[b];
       const int a0 = P.vadj_ptr[vb], a1 = P.vadj_ptr[vb + 1];
-      const double xb = P.X[3 * vb + 0], yb = P.X[3 * vb + 1], zb = zfixed(P, ws, NC, c, b);
+      const double xb = xyfixed(P, ws, NC, c, b, 0), yb = xyfixed(P, ws, NC, c, b, 1), zb = zfixed(P, ws, NC, c, b);
       double px, py, pz;
       if (P.var.o_lambdh >= 0) {
         px = lamh * mix2(P.px0, P.px0_b, vb, dc, ds);
@@ -555,8 +582,29 @@ __global__ void k_epilogue(DevPlan P, double* __restrict__ ws, int64_t NC, int64
             const double Bej = P.B[(int64_t)P.vadj_edge[t] * k + j];
             gx = fma(sg * u, Bej, gx);
             gy = fma(sg * vv, Bej, gy);
+            if (P.rhs.c_qx >= 0) {  // + Cb^T Q C dx/dq_ind: the free neighbours move with q once the supports do (derivatives.py:303-306)
+              const int ro = P.vrow[o];
+              if (ro >= 0) {
+                const double qe = WS(P.slot.s_q + P.vadj_edge[t]);
+                gx = fma(-qe, WS(P.slot.s_r + ro * nrhs + P.rhs.c_qx + j), gx);
+                gy = fma(-qe, WS(P.slot.s_r + ro * nrhs + P.rhs.c_qy + j), gy);
+              }
+            }
           }
           WS(P.slot.s_grad + j) += cx * gx + cy * gy;
+        }
+        if (P.var.o_xyb >= 0) {
+          // xb / yb blocks: (Rx / R)^T Cb^T Q C A and (Ry / R)^T Cb^T Q C A, A = [A^-1 (-Ci^T Q Cb); I]  (derivatives.py:310-326)
+          for (int cb = 0; cb < nb; ++cb) {
+            double acc = 0.0;
+            for (int t = a0; t < a1; ++t) {
+              const int ro = P.vrow[P.vadj_other[t]];
+              const double Ao = ro >= 0 ? WS(P.slot.s_r + ro * nrhs + P.rhs.c_zb + cb) : ((-1 - ro) == cb ? 1.0 : 0.0);
+              acc = fma(WS(P.slot.s_q + P.vadj_edge[t]), (cb == b ? 1.0 : 0.0) - Ao, acc);
+            }
+            WS(P.slot.s_grad + P.var.o_xyb + cb) += cx * acc;
+            WS(P.slot.s_grad + P.var.o_xyb + nb + cb) += cy * acc;
+          }
         }
       }
       if (want_reac) {
@@ -741,7 +789,7 @@ __global__ void k_epilogue(DevPlan P, double* __restrict__ ws, int64_t NC, int64
     for (int b = 0; b < nb; ++b) {
       const int vb = P.fixed[b];
       const int a0 = P.vadj_ptr[vb], a1 = P.vadj_ptr[vb + 1];
-      const double xb = P.X[3 * vb + 0], yb = P.X[3 * vb + 1], zb = zfixed(P, ws, NC, c, b);
+      const double xb = xyfixed(P, ws, NC, c, b, 0), yb = xyfixed(P, ws, NC, c, b, 1), zb = zfixed(P, ws, NC, c, b);
       const double dx = P.dXb[3 * b + 0], dy = P.dXb[3 * b + 1], dz = P.dXb[3 * b + 2];
       double Rx = -P.P[3 * vb + 0], Ry = -P.P[3 * vb + 1], Rz = -pzs * P.P[3 * vb + 2];
       for (int t = a0; t < a1; ++t) {
@@ -976,7 +1024,8 @@ int run_interleaved(Plan* PL, const double* x_dev, int64_t N, int64_t ldx, const
     else
       LAUNCH(KK_SOLVE1, k_solve<RB>, grid1(nc, TB, (P.rhs.nrhs1 + RB - 1) / RB), TB, P, ws, NC, nc, 0, P.rhs.nrhs1);
     // the dz/dq_ind columns only feed the Jacobian and the bestfit gradient
-    const bool need2 = P.rhs.nrhs2 > 0 && (out->J != nullptr || (P.objective >= TNO_OBJ_BESTFIT && P.objective != TNO_OBJ_FEASIBILITY && out->grad != nullptr));
+    const bool need2 = P.rhs.nrhs2 > 0 && (out->J != nullptr || (P.objective >= TNO_OBJ_BESTFIT && P.objective != TNO_OBJ_FEASIBILITY && out->grad != nullptr) ||
+                                            (P.rhs.c_qx >= 0 && P.var.o_xyb >= 0 && out->grad != nullptr));
     if (need2) {
       LAUNCH(KK_RHS2, k_rhs2, grid1(nc, TB, gyr), TB, P, ws, NC, nc, rtile);
       if (levelled)

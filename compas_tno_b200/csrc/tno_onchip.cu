@@ -1216,6 +1216,7 @@ static int build_onchip_impl(Plan* PL, const tno_problem_desc* D, const int THRE
   PL->onchip_ok = false;
   const int ni = P.ni, m = P.m, nb = P.nb, k = P.k, nvar = P.var.nvar;
   const int nnz = P.nnz_l;
+  if (P.var.o_xyb >= 0 || P.con.r_envxy >= 0) { set_error("on-chip family not applicable: xyb / envelopexy run on the interleaved family"); return TNO_OK; }
   if (nnz >= 60000 || ni >= 32768 || S.nlevels < 1 || m >= 65535) { set_error("on-chip family not applicable: nnz >= 60000 || ni >= 32768 || S.nlevels < 1 || m >= 65535"); return TNO_OK; }
 
   // ---- panel columns.  phase 1: [z | z_lambdv | Az (nb) | x | y]   phase 2: [Dq (k) | z_lambdh] -------------

@@ -13,25 +13,27 @@ namespace tno {
 
 // Column layout of the right-hand-side panel R (ni rows x nrhs columns, permuted row order).
 //   phase 1 (independent of z):  [ x | y | z | Az_0..Az_{nb-1} (zb variable) | z_lambdv (lambdv variable) ]
-//   phase 2 (needs W = diag(C z)): [ Dq_0..Dq_{k-1} | z_lambdh (lambdh variable) ]
+//   phase 2 (needs W = diag(C z)): [ Dq_0..Dq_{k-1} | z_lambdh (lambdh variable) | Dx_0..Dx_{k-1} | Dy_0..Dy_{k-1} ]
+//   (Dx = dx/dq_ind, Dy = dy/dq_ind: envelopexy constraint or xyb variable with a thrust objective)
 struct RhsLayout {
   int cx = 0, cy = 1, cz = 2;
   int c_zb = -1;      // first Az column
   int c_lambdv = -1;
   int c_q = -1;       // first Dq column
   int c_lambdh = -1;
+  int c_qx = -1, c_qy = -1;
   int nrhs1 = 0, nrhs2 = 0, nrhs = 0;
 };
 
 // Offsets of x = [q_ind | zb | t | lambdh | lambdv]  (-1 = absent)
 struct VarLayout {
-  int o_q = 0, o_zb = -1, o_t = -1, o_lambdh = -1, o_lambdv = -1;
+  int o_q = 0, o_xyb = -1, o_zb = -1, o_t = -1, o_lambdh = -1, o_lambdv = -1;   // o_xyb: xb block, yb = o_xyb + nb
   int nvar = 0;
 };
 
 // Offsets of g / rows of J
 struct ConLayout {
-  int r_fun = -1, r_env = -1, r_reac = -1;
+  int r_fun = -1, r_envxy = -1, r_env = -1, r_reac = -1;
   int ng = 0;
 };
 
@@ -109,6 +111,8 @@ struct DevPlan {
   const double* d_b;        // second horizontal load basis (per-candidate load directions), null = absent
   const double* px0_b;
   const double* py0_b;
+  const double* xlimits;    // n x 2 (envelopexy)
+  const double* ylimits;
 };
 
 // ---- on-chip kernel family (tno_onchip.cu) -----------------------------------------------------------

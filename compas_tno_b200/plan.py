@@ -15,9 +15,10 @@ import numpy as np
 from . import _lib
 from .envelopes import abi_envelope
 
-_VAR_BITS = {"q": _lib.VAR_Q, "zb": _lib.VAR_ZB, "t": _lib.VAR_T, "n": _lib.VAR_T,
+_VAR_BITS = {"q": _lib.VAR_Q, "xyb": _lib.VAR_XYB, "zb": _lib.VAR_ZB, "t": _lib.VAR_T, "n": _lib.VAR_T,
              "lambdh": _lib.VAR_LAMBDH, "lambdv": _lib.VAR_LAMBDV}
-_CON_BITS = {"funicular": _lib.CON_FUNICULAR, "envelope": _lib.CON_ENVELOPE, "reac_bounds": _lib.CON_REAC_BOUNDS}
+_CON_BITS = {"funicular": _lib.CON_FUNICULAR, "envelopexy": _lib.CON_ENVELOPEXY, "envelope": _lib.CON_ENVELOPE,
+             "reac_bounds": _lib.CON_REAC_BOUNDS}
 _OBJ = {None: _lib.OBJ_NONE, "none": _lib.OBJ_NONE, "min": _lib.OBJ_MIN, "max": _lib.OBJ_MAX, "t": _lib.OBJ_T,
         "n": _lib.OBJ_NEG_LAST, "s": _lib.OBJ_NEG_LAST, "max_load": _lib.OBJ_NEG_LAST,
         "bestfit": _lib.OBJ_BESTFIT, "target": _lib.OBJ_BESTFIT, "feasibility": _lib.OBJ_FEASIBILITY,
@@ -119,6 +120,9 @@ class TnoPlan:
         D.py0 = dptr(getattr(M, "py0", None), (n,)) if "lambdh" in variables else None
         D.pzv = dptr(getattr(M, "pzv", None), (n,)) if "lambdv" in variables else None
         D.pz0 = dptr(getattr(M, "pz0", None), (n,)) if "lambdv" in variables else None
+        if "envelopexy" in constraints:
+            D.xlimits = dptr(getattr(M, "xlimits", None), (n, 2))
+            D.ylimits = dptr(getattr(M, "ylimits", None), (n, 2))
         # second horizontal load basis (per-candidate load directions): d0_b, px0_b, py0_b next to d0, px0, py0
         if "lambdh" in variables and getattr(M, "d0_b", None) is not None:
             D.d_b = dptr(M.d0_b, (m,))

@@ -46,17 +46,20 @@ extern "C" {
 #define TNO_ENOMEM (-4)
 
 /* variables present in x, in the reference's unpacking order (problems/constraints.py:47-88):
- *   x = [ q_ind (k) | zb (nb) | t (1) | lambdh (1) | lambdv (1) ]                                  */
+ *   x = [ q_ind (k) | xyb (2 nb: x of the supports, then y) | zb (nb) | t (1) | lambdh (1) | lambdv (1) ]   */
 #define TNO_VAR_Q 1u
 #define TNO_VAR_ZB 2u
 #define TNO_VAR_T 4u      /* 't' or 'n': thickness handed to the parametric envelope */
 #define TNO_VAR_LAMBDH 8u
 #define TNO_VAR_LAMBDV 16u
+#define TNO_VAR_XYB 32u   /* horizontal support positions (needs the envelopexy and envelope constraints, like the
+                             reference's Jacobian assembly problems/jacobian.py:269-273; interleaved kernel family) */
 
 /* constraint blocks, stacked in this order (problems/constraints.py:104-155) */
 #define TNO_CON_FUNICULAR 1u   /* q - qmin ; qmax - q                      2m rows */
 #define TNO_CON_ENVELOPE 2u    /* z - lb ; ub - z                          2n rows */
 #define TNO_CON_REAC_BOUNDS 4u /* |b| - (zb - s) |R_xy / R_z|              2nb rows */
+#define TNO_CON_ENVELOPEXY 8u  /* x - xlim0 ; xlim1 - x ; y - ylim0 ; ylim1 - y   4n rows, between funicular and envelope */
 
 /* objectives (problems/objectives.py:27-88) */
 #define TNO_OBJ_NONE 0
@@ -132,6 +135,8 @@ typedef struct tno_problem_desc {
   const double* d_b;    /* m   particular solution of the second basis (d is that of the first) */
   const double* px0_b;  /* n */
   const double* py0_b;  /* n */
+  const double* xlimits; /* n x 2 (envelopexy only)                      Problem.xlimits */
+  const double* ylimits; /* n x 2 (envelopexy only)                      Problem.ylimits */
 } tno_problem_desc;
 
 /* What the symbolic analysis found; all sizes a caller needs to allocate outputs. */

@@ -94,6 +94,10 @@ def run_case(ref, name, form, P, variables, constraints, objective, xs, thk, env
             fun[:m, c] = extra["d0"].ravel()
             fun[m:, c] = -extra["d0"].ravel()
         assert np.array_equal(J[: 2 * m], fun)
+        nxy = 4 * n if "envelopexy" in constraints else 0
+        if nxy:
+            out.setdefault("J_envxy", []).append(J[2 * m: 2 * m + nxy].copy())
+            J = np.vstack([J[: 2 * m], J[2 * m + nxy:]])
         env = J[2 * m: 2 * m + n]
         neg = J[2 * m + n: 2 * m + 2 * n].copy()
         if "t" in variables:
@@ -169,6 +173,15 @@ def main():
     stiff = np.random.default_rng(SEED + 77).uniform(0.01, 0.05, size=(P.m, 1))
     run_case(ref, "cross14_q_zb_ecomp_nonlinear", form, P, ["q", "zb"], ["funicular", "envelope"], "Ecomp-nonlinear", xs[:3], 0.5,
              extra={"dXb": dXb, "stiff": stiff})
+    # moving supports: x = [q_ind | xb | yb | zb], x / y limits of +-0.25 m around the form diagram
+    xyb0 = form["xyz"][P.fixed, :2].flatten("F")
+    rxy = np.random.default_rng(SEED + 78)
+    xs_xyb = np.array([np.concatenate([x[: P.k], xyb0 + (0.0 if j == 0 else 1.0) * rxy.uniform(-0.08, 0.08, size=xyb0.shape), x[P.k:]])
+                       for j, x in enumerate(xs[:3])])
+    lim = {"xlimits": np.column_stack([form["xyz"][:, 0] - 0.25, form["xyz"][:, 0] + 0.25]),
+           "ylimits": np.column_stack([form["xyz"][:, 1] - 0.25, form["xyz"][:, 1] + 0.25])}
+    run_case(ref, "cross14_q_xyb_zb_min", form, P, ["q", "xyb", "zb"], ["funicular", "envelopexy", "envelope"], "min", xs_xyb, 0.5,
+             extra=lim)
     run_case(ref, "cross14_q_zb_feasibility", form, P, ["q", "zb"], ["funicular", "envelope"], "feasibility", xs[:2], 0.5)
 
     # ---- B: cross vault, thickness variable -------------------------------------------------

@@ -20,7 +20,7 @@ CASES = [
     "dome_q_zb_lambdv",
     "freeform_q_zb_min",
     "cross14_q_zb_bestfit", "cross14_q_zb_feasibility", "cross14_q_zb_loadpath", "dome_q_zb_loadpath",
-    "cross14_q_zb_ecomp_nonlinear", "dome_q_zb_ecomp_linear",
+    "cross14_q_zb_ecomp_nonlinear", "dome_q_zb_ecomp_linear", "cross14_q_xyb_zb_min",
     "dome_q_zb_bestfit",
 ]
 
@@ -81,7 +81,8 @@ def load_case(name, envelope_factory=None):
         if "t" in P.variables:
             c = var_offset(P.variables, k, nb, "t")
             neg[:, c] = z["J_dub"][j]
-        J.append(np.vstack([fun, env, neg, z["J_reac"][j]]))
+        mid = [z["J_envxy"][j]] if "J_envxy" in z.files else []
+        J.append(np.vstack([fun] + mid + [env, neg, z["J_reac"][j]]))
     expected = dict(g=z["g"], J=np.array(J), f=np.asarray(z["f"]).reshape(len(z["x"])), grad=z["grad"], X=z["X"], q=z["q"], mineig=z["mineig"])
     return P, objective, xs, expected
 

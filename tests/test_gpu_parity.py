@@ -30,8 +30,9 @@ def test_golden_parity_host_abi(tno, name, kernel):
     try:
         plan = TnoPlan(P, objective=objective, kernel=kernel)
     except NotImplementedError:
-        assert kernel == "onchip" and name == "freeform_q_zb_min"   # k = 360: panel does not fit in shared memory
-        pytest.skip("on-chip family does not fit this problem; the interleaved family covers it")
+        # k = 360: panel does not fit in shared memory; moving supports (xyb): interleaved family only
+        assert kernel == "onchip" and name in ("freeform_q_zb_min", "cross14_q_xyb_zb_min")
+        pytest.skip("on-chip family does not cover this problem; the interleaved family does")
     assert plan.info["kernel"] == {"interleaved": 1, "onchip": 2}[kernel]
     assert (plan.nvar, plan.ng) == (xs.shape[1], exp["g"].shape[1])
     got = plan.evaluate_host(xs)
@@ -186,6 +187,36 @@ def test_output_subsets_skip_the_sensitivity_solve(tno, name, kernel):
     ref = onp.evaluate_batch(X[:4], P, objective)
     assert rel_err(full["f"][:4], ref["f"]) < 1e-10
     assert rel_err(full["grad"][:4], ref["grad"]) < 1e-8
+
+
+def test_moving_supports_xyb_envelopexy(tno):
+    """xyb variables + envelopexy constraints: auto picks the interleaved family, the
+    drop-in callbacks leave the moved geometry on the problem like the reference's, output subsets agree."""
+    import compas_tno_b200 as tb
+    from compas_tno_b200.plan import TnoPlan
+    from oracle import callbacks_np as onp
+    P, objective, xs, exp = load_case("cross14_q_xyb_zb_min")
+    plan = TnoPlan(P, objective=objective)
+    assert plan.info["kernel"] == 1 and plan.nvar == P.k + 3 * P.nb and plan.ng == 2 * P.m + 6 * P.n
+    rng = np.random.default_rng(21)
+    X = np.repeat(xs[1][None, :], 40, axis=0)
+    X[:, : P.k] *= 1.0 + 0.02 * rng.uniform(-1, 1, size=(40, 1))
+    X[:, P.k: P.k + 2 * P.nb] += rng.uniform(-0.1, 0.1, size=(40, 2 * P.nb))
+    full = plan.evaluate_host(X)
+    light = plan.evaluate_host(X, outputs=("f", "g", "z", "gmin", "status"))
+    for key in light:
+        assert np.array_equal(light[key], full[key]), key
+    ref = onp.evaluate_batch(X[:3], P, objective)
+    for key, tol in (("z", TOL_VAL), ("g", TOL_VAL), ("f", TOL_VAL), ("grad", TOL_JAC), ("J", TOL_JAC)):
+        assert rel_err(full[key][:3], ref[key]) < tol, key
+    assert np.allclose(full["gmin"][:3], ref["g"].min(axis=1), rtol=1e-9, atol=1e-9)
+    tb.accelerate(P, "min")
+    g = P.fconstr(xs[2], P)
+    assert rel_err(g, exp["g"][2]) < TOL_VAL
+    assert np.max(np.abs(P.X - exp["X"][2])) < 1e-9
+    assert rel_err(P.fgrad(xs[2], P), exp["grad"][2]) < TOL_JAC
+    with pytest.raises(NotImplementedError):
+        TnoPlan(P, objective="min", kernel="onchip")
 
 
 def test_dropin_bestfit_and_feasibility_callbacks(tno):
