@@ -371,7 +371,9 @@ def run_ours(args):
     roofline = None
     if prof:
         jfun_bytes = 8 * 2 * plan.m * plan.nvar if "funicular" in plan.constraints else 0
-        if info["kernel"] == 2:
+        info = plan.info                       # after the timed calls: last_kernel = the family that actually ran
+        family = info.get("last_kernel") or info["kernel"]
+        if family == 2:
             kbytes = {"k_onchip": B_alg - jfun_bytes, "k_emit(J)": jfun_bytes}
         else:
             kbytes = {"k_emit(J)": 8 * plan.ng * plan.nvar}
@@ -491,7 +493,7 @@ def run_ours(args):
             msw = a0.elapsed_time(a1) / reps
             sweeps[spec["name"]] = {
                 "what": spec["what"], "candidates": wbatch, "outputs": list(namesw), "wall_ms_per_sweep": msw,
-                "evals_per_s": wbatch / (msw * 1e-3), "kernel_family": {1: "interleaved", 2: "onchip"}.get(planw.info["kernel"]),
+                "evals_per_s": wbatch / (msw * 1e-3), "kernel_family": {1: "interleaved", 2: "onchip"}.get(planw.info.get("last_kernel") or planw.info["kernel"]),
                 "nvar": planw.nvar, "ng": planw.ng, "bytes_per_eval": planw.bytes_per_eval,
                 "status_nonzero": int((outw["status"] != 0).sum().item()),
                 "feasible": int((outw["gmin"] >= -1e-9).sum().item()) if "gmin" in outw else None}
@@ -536,7 +538,7 @@ def run_ours(args):
             "config": {"workload": args.workload, "candidates_per_gpu_per_step": N, "objective": objective,
                        "variables": plan.variables, "constraints": plan.constraints, "n": plan.n, "m": plan.m, "k": plan.k,
                        "nvar": plan.nvar, "ng": plan.ng, "nnz_l": info["nnz_l"], "etree_height": info["etree_height"],
-                       "kernel_family": {1: "interleaved", 2: "onchip"}.get(info["kernel"], str(info["kernel"])),
+                       "kernel_family": {1: "interleaved", 2: "onchip"}.get(info.get("last_kernel") or info["kernel"], str(info["kernel"])),
                        "l2_policy": "outputs per step (%.2f GB) exceed the 126 MB L2; inputs re-read each step" % (N * B_alg / 1e9),
                        "parallelism": "candidates sharded, plan replicated, all_gather(f, status)" if world > 1 else "single GPU"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "sweeps": sweeps,

@@ -48,6 +48,7 @@ class PlanInfo(C.Structure):
         ("nvar", C.c_int32), ("ng", C.c_int32), ("nrhs", C.c_int32), ("nnz_a", C.c_int32), ("nnz_l", C.c_int32),
         ("etree_height", C.c_int32), ("max_colcount", C.c_int32), ("kernel", C.c_int32), ("chunk", C.c_int32),
         ("scratch_bytes", C.c_int64), ("factor_flops", C.c_int64), ("solve_flops", C.c_int64), ("smem_bytes", C.c_int64),
+        ("last_kernel", C.c_int32), ("onchip_ctas_per_sm", C.c_int32),
     ]
 
     def as_dict(self):

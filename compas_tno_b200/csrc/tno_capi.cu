@@ -542,7 +542,9 @@ int tno_plan_create(const tno_problem_desc* D, tno_plan** out_plan) {
     if ((rc = build_onchip(P, D))) return rc;
     if (P->onchip_ok) {
       P->kernel = TNO_KERNEL_ONCHIP;
+      P->auto_family = D->kernel == TNO_KERNEL_AUTO;
       I.smem_bytes = (int64_t)P->oc.smem_bytes;
+      I.onchip_ctas_per_sm = P->onchip_ctas_per_sm;
     } else if (D->kernel == TNO_KERNEL_ONCHIP) {
       return fail(TNO_EINVAL, std::string("problem does not fit the on-chip kernel family: ") + tno_last_error());
     }
@@ -661,7 +663,16 @@ int tno_eval_batch(tno_plan* plan, const double* x_dev, int64_t N, int64_t ldx, 
   if (N < 0 || ldx < P->dp.var.nvar) return fail(TNO_EINVAL, "bad N / ldx");
   if (N == 0) return TNO_OK;
   TNO_CUDA_OK(cudaSetDevice(P->device));
-  if (P->kernel == TNO_KERNEL_ONCHIP) return run_onchip(P, x_dev, N, ldx, opt, out_dev, (cudaStream_t)cuda_stream);
+  bool onchip = P->kernel == TNO_KERNEL_ONCHIP;
+  if (onchip && P->auto_family && P->onchip_ctas_per_sm == 1) {
+    // one resident candidate per SM: beyond ~8k candidates the level-scheduled interleaved family is faster
+    // (dome 16x20, B200: 12.4 vs 11.4 ms at 8192, 24.6 vs 19.1 ms at 16384; 6.3 vs 8.0 ms at 4096)
+    static const char* env = getenv("TNO_AUTO_SWITCH_N");
+    const int64_t thr = env ? atoll(env) : 8192;
+    if (N >= thr) onchip = false;
+  }
+  P->info.last_kernel = onchip ? TNO_KERNEL_ONCHIP : TNO_KERNEL_INTERLEAVED;
+  if (onchip) return run_onchip(P, x_dev, N, ldx, opt, out_dev, (cudaStream_t)cuda_stream);
   int rc = ensure_scratch(P, N);
   if (rc) return rc;
   return run_interleaved(P, x_dev, N, ldx, opt, out_dev, (cudaStream_t)cuda_stream);

@@ -281,6 +281,7 @@ struct Plan {
   std::vector<float> h_vadj_sign;
   int device = 0;
   int kernel = TNO_KERNEL_INTERLEAVED;
+  bool auto_family = false;            // created with TNO_KERNEL_AUTO: large batches may go to the other family
   std::vector<void*> dev_allocs;       // everything to cudaFree at destroy
   // emit tables
   EmitTable t_g, t_grad, t_z, t_q, t_J;   // t_J covers the rows below the funicular block when jfun is set

@@ -189,6 +189,30 @@ def test_output_subsets_skip_the_sensitivity_solve(tno, name, kernel):
     assert rel_err(full["grad"][:4], ref["grad"]) < 1e-8
 
 
+def test_auto_plan_hands_large_batches_to_the_interleaved_family(tno):
+    """A plan created with kernel='auto' whose on-chip layout fits one CTA per SM only runs batches of >= 8192
+    candidates on the level-scheduled interleaved family (faster there); both families agree to rounding."""
+    from compas_tno_b200 import workloads as W
+    from compas_tno_b200.plan import TnoPlan
+    P, xs = W.dome_problem(20, 16, constraints=("funicular", "envelope", "reac_bounds"), n_states=4)
+    plan = TnoPlan(P, objective="max")
+    info = plan.info
+    if not (info["kernel"] == 2 and info["onchip_ctas_per_sm"] == 1):
+        pytest.skip("this device fits more than one CTA per SM for the dome: no switch")
+    X = W.sample_candidates(P, xs, 8192, seed=13, basis=P.candidate_basis)
+    small = plan.evaluate_host(X[:100], outputs=("f", "z", "gmin", "status"))
+    assert plan.info["last_kernel"] == 2
+    big = plan.evaluate_host(X, outputs=("f", "z", "gmin", "status"))
+    assert plan.info["last_kernel"] == 1
+    assert np.all(big["status"] == 0)
+    assert rel_err(big["f"][:100], small["f"]) < TOL_VAL
+    assert rel_err(big["z"][:100], small["z"]) < TOL_VAL
+    assert np.allclose(big["gmin"][:100], small["gmin"], rtol=1e-9, atol=1e-9)
+    fixed = TnoPlan(P, objective="max", kernel="onchip")
+    fixed.evaluate_host(X, outputs=("f", "status"))
+    assert fixed.info["last_kernel"] == 2          # an explicit family is never overridden
+
+
 def test_moving_supports_xyb_envelopexy(tno):
     """xyb variables + envelopexy constraints: auto picks the interleaved family, the
     drop-in callbacks leave the moved geometry on the problem like the reference's, output subsets agree."""
