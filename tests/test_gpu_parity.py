@@ -103,6 +103,47 @@ def test_random_batch_against_oracle(tno, kernel):
     assert rel_err(got2["z"], lin) < 1e-11
 
 
+def test_full_size_batch_properties_and_family_cross_check(tno):
+    """BASELINE's headline size (disc-20 cross vault, 16 384 candidates) on the device: the two kernel families are
+    independent implementations (different factorisation order, different solve schedule), so their agreement at full size
+    is a parity statement that does not need the CPU oracle; plus the size-independent properties of g and J."""
+    import torch
+    from compas_tno_b200 import workloads as W
+    from compas_tno_b200.plan import TnoPlan
+    P, xs = W.crossvault_problem(20, n_states=6)
+    N = 16384
+    X = torch.from_numpy(W.sample_candidates(P, xs, N, seed=20261019, basis=P.candidate_basis)).cuda()
+    m, n, k = P.m, P.n, P.k
+    res = {}
+    for kernel in ("onchip", "interleaved"):
+        plan = TnoPlan(P, objective="min", kernel=kernel)
+        r = plan.evaluate_device(X, ("f", "grad", "g", "z", "gmin", "status"))
+        Jsub = plan.evaluate_device(X[:1024], ("J",))["J"]
+        torch.cuda.synchronize()
+        assert int((r["status"] != 0).sum()) == 0
+        g = r["g"]
+        span_q = torch.from_numpy((P.qmax - P.qmin).ravel() * np.ones(m)).cuda()
+        span_z = torch.from_numpy((P.ub - P.lb).ravel()).cuda()
+        assert torch.allclose(g[:, :m] + g[:, m:2 * m], span_q.expand(N, m), rtol=0, atol=1e-9)
+        assert torch.allclose(g[:, 2 * m:2 * m + n] + g[:, 2 * m + n:], span_z.expand(N, n), rtol=0, atol=1e-9)
+        assert torch.equal(r["gmin"], g.min(dim=1).values)
+        B = torch.from_numpy(np.ascontiguousarray(P.B)).cuda()
+        assert torch.equal(Jsub[:, :m, :k], B.expand(1024, m, k))
+        assert torch.equal(Jsub[:, m:2 * m], -Jsub[:, :m])
+        assert torch.equal(Jsub[:, 2 * m + n:2 * m + 2 * n], -Jsub[:, 2 * m:2 * m + n])
+        res[kernel] = {key: val.cpu().numpy() for key, val in r.items()}
+        res[kernel]["J"] = Jsub[:, 2 * m:2 * m + n].cpu().numpy()
+        plan.close()
+        del r, Jsub, g
+        torch.cuda.empty_cache()
+    a, b = res["onchip"], res["interleaved"]
+    assert rel_err(a["z"], b["z"]) < TOL_VAL
+    assert rel_err(a["g"], b["g"]) < TOL_VAL
+    assert rel_err(a["f"], b["f"]) < TOL_VAL
+    assert rel_err(a["grad"], b["grad"]) < TOL_JAC
+    assert rel_err(a["J"], b["J"]) < TOL_JAC
+
+
 def test_indefinite_candidate_is_flagged_not_fatal(tno):
     from compas_tno_b200.plan import TnoPlan
     P, objective, xs, _ = load_case("cross6_q_zb_min")
