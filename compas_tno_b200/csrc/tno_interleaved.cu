@@ -866,14 +866,26 @@ __global__ void __launch_bounds__(256) k_emit(const EmitDesc2* __restrict__ tabl
   const int64_t cand0 = (int64_t)blockIdx.y * 32;
   const int ne = (int)min((int64_t)EMIT_TW, count - e0);
   const int64_t c = cand0 + lane;
-  for (int e = warp; e < ne; e += 8) {
-    const EmitDesc2 d = table[e0 + e];
-    double v = d.c;
-    if (c < ncand) {
-      if (d.slot_a >= 0) v = fma((double)d.sign_a, ws[(int64_t)d.slot_a * NC + c], v);
-      if (d.slot_b >= 0) v = fma((double)d.sign_b, ws[(int64_t)d.slot_b * NC + c], v);
+  // four elements per pass: descriptors first, then all gathers, so that the loads of a pass overlap
+  const bool cok = c < ncand;
+  for (int eb = warp; eb < ne; eb += 32) {
+    EmitDesc2 d[4];
+    double va[4], vb[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int e = eb + 8 * u;
+      d[u] = e < ne ? table[e0 + e] : EmitDesc2{-1, -1, 0.f, 0.f, 0.0};
     }
-    tile[e][lane] = v;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      va[u] = (cok && d[u].slot_a >= 0) ? ws[(int64_t)d[u].slot_a * NC + c] : 0.0;
+      vb[u] = (cok && d[u].slot_b >= 0) ? ws[(int64_t)d[u].slot_b * NC + c] : 0.0;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int e = eb + 8 * u;
+      if (e < ne) tile[e][lane] = fma((double)d[u].sign_b, vb[u], fma((double)d[u].sign_a, va[u], d[u].c));
+    }
   }
   __syncthreads();
   for (int cc = warp; cc < 32; cc += 8) {
