@@ -325,7 +325,8 @@ int tno_plan_create(const tno_problem_desc* D, tno_plan** out_plan) {
   SL.s_env = pos; pos += (V.o_t >= 0) ? 4 * n : 0;
   SL.s_grad = pos; pos += V.nvar;
   SL.s_rg = pos; pos += 2 * nb;
-  SL.s_rj = pos; pos += 2 * nb * V.nvar;
+  SL.s_rj = pos; pos += (D->constraints & TNO_CON_REAC_BOUNDS) ? 2 * nb * V.nvar : 0;
+  SL.s_cxy = pos; pos += 2 * nb;
   SL.nslots = pos;
 
   // ---- uploads ----------------------------------------------------------------------------

@@ -401,19 +401,20 @@ __device__ __forceinline__ double xval(const DevPlan& P, const double* ws, int64
 }
 
 // phase-2 right-hand sides:  Ci^T W B  (k columns) and  Ci^T W d0  (lambdh column), W = diag(C z)
-__global__ void k_rhs2(DevPlan P, double* __restrict__ ws, int64_t NC, int64_t ncand, int rtile) {
+__global__ void k_rhs2(DevPlan P, double* __restrict__ ws, int64_t NC, int64_t ncand, int rtile, int jtile) {
   const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= ncand) return;
   const int r0 = blockIdx.y * rtile;
   const int r1 = min(P.ni, r0 + rtile);
   const int nrhs = P.rhs.nrhs, k = P.k;
+  const int j0 = blockIdx.z * jtile, j1 = min(k, j0 + jtile);   // column tile: problems with hundreds of independents
   const double dc = DIR_C, ds = DIR_S;
   for (int r = r0; r < r1; ++r) {
     const int v = P.row_vertex[r];
     const int base = P.slot.s_r + r * nrhs;
     const double zv = WS(base + P.rhs.cz);
     const int a0 = P.vadj_ptr[v], a1 = P.vadj_ptr[v + 1];
-    for (int j = 0; j < k; ++j) {
+    for (int j = j0; j < j1; ++j) {
       double acc = 0.0;
       for (int t = a0; t < a1; ++t) {
         const double zo = zval(P, ws, NC, c, P.vadj_other[t]);
@@ -423,7 +424,7 @@ __global__ void k_rhs2(DevPlan P, double* __restrict__ ws, int64_t NC, int64_t n
       }
       WS(base + P.rhs.c_q + j) = acc;
     }
-    if (P.rhs.c_lambdh >= 0) {
+    if (P.rhs.c_lambdh >= 0 && blockIdx.z == 0) {
       double acc = 0.0;
       for (int t = a0; t < a1; ++t) {
         const double zo = zval(P, ws, NC, c, P.vadj_other[t]);
@@ -435,7 +436,7 @@ __global__ void k_rhs2(DevPlan P, double* __restrict__ ws, int64_t NC, int64_t n
     }
     if (P.rhs.c_qx >= 0) {  // Ci^T U B and Ci^T V B, U = diag(C x), V = diag(C y)  (jacobian.py:173-186)
       const double xv = WS(base + P.rhs.cx), yv = WS(base + P.rhs.cy);
-      for (int j = 0; j < k; ++j) {
+      for (int j = j0; j < j1; ++j) {
         double ax = 0.0, ay = 0.0;
         for (int t = a0; t < a1; ++t) {
           const int o = P.vadj_other[t];
@@ -570,29 +571,9 @@ __global__ void k_epilogue(DevPlan P, double* __restrict__ ws, int64_t NC, int64
         const double Rn = sqrt(Rx * Rx + Ry * Ry);
         f += Rn;
         const double cx = osign * Rx / Rn, cy = osign * Ry / Rn;
-        // grad_j += cx * (Cb^T U B)[b, j] + cy * (Cb^T V B)[b, j]
-        for (int j = 0; j < k; ++j) {
-          double gx = 0.0, gy = 0.0;
-          for (int t = a0; t < a1; ++t) {
-            const int o = P.vadj_other[t];
-            const double sg = (double)P.vadj_sign[t];
-            const double xo = xval(P, ws, NC, c, o, 0), yo = xval(P, ws, NC, c, o, 1);
-            const double u = sg > 0 ? (xb - xo) : (xo - xb);
-            const double vv = sg > 0 ? (yb - yo) : (yo - yb);
-            const double Bej = P.B[(int64_t)P.vadj_edge[t] * k + j];
-            gx = fma(sg * u, Bej, gx);
-            gy = fma(sg * vv, Bej, gy);
-            if (P.rhs.c_qx >= 0) {  // + Cb^T Q C dx/dq_ind: the free neighbours move with q once the supports do (derivatives.py:303-306)
-              const int ro = P.vrow[o];
-              if (ro >= 0) {
-                const double qe = WS(P.slot.s_q + P.vadj_edge[t]);
-                gx = fma(-qe, WS(P.slot.s_r + ro * nrhs + P.rhs.c_qx + j), gx);
-                gy = fma(-qe, WS(P.slot.s_r + ro * nrhs + P.rhs.c_qy + j), gy);
-              }
-            }
-          }
-          WS(P.slot.s_grad + j) += cx * gx + cy * gy;
-        }
+        // the q block of the gradient is formed by k_thrust_grad (a thread per candidate and column tile)
+        WS(P.slot.s_cxy + b) = cx;
+        WS(P.slot.s_cxy + nb + b) = cy;
         if (P.var.o_xyb >= 0) {
           // xb / yb blocks: (Rx / R)^T Cb^T Q C A and (Ry / R)^T Cb^T Q C A, A = [A^-1 (-Ci^T Q Cb); I]  (derivatives.py:310-326)
           for (int cb = 0; cb < nb; ++cb) {
@@ -842,6 +823,45 @@ __global__ void k_epilogue(DevPlan P, double* __restrict__ ws, int64_t NC, int64
   if (bad) status[c] |= TNO_STATUS_NONFINITE;
 }
 
+// q block of the thrust gradient (derivatives.py:303-309):
+//   grad_j = sum_b  cx_b (Cb^T U B + Cb^T Q C dx/dq_ind)[b, j] + cy_b (Cb^T V B + Cb^T Q C dy/dq_ind)[b, j]
+// with cx_b = +-Rx_b / |R_h,b|, cy_b likewise (left in the scratch by k_epilogue).  One thread per candidate and tile of
+// columns, so that problems with hundreds of independents do not serialise k x nb x degree terms in one thread.
+__global__ void k_thrust_grad(DevPlan P, double* __restrict__ ws, int64_t NC, int64_t ncand, int jtile) {
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= ncand) return;
+  const int k = P.k, nb = P.nb, nrhs = P.rhs.nrhs;
+  const int j0 = blockIdx.y * jtile, j1 = min(k, j0 + jtile);
+  for (int j = j0; j < j1; ++j) {
+    double acc = 0.0;
+    for (int b = 0; b < nb; ++b) {
+      const int vb = P.fixed[b];
+      const double xb = xyfixed(P, ws, NC, c, b, 0), yb = xyfixed(P, ws, NC, c, b, 1);
+      double gx = 0.0, gy = 0.0;
+      for (int t = P.vadj_ptr[vb]; t < P.vadj_ptr[vb + 1]; ++t) {
+        const int o = P.vadj_other[t];
+        const double sg = (double)P.vadj_sign[t];
+        const double xo = xval(P, ws, NC, c, o, 0), yo = xval(P, ws, NC, c, o, 1);
+        const double u = sg > 0 ? (xb - xo) : (xo - xb);
+        const double vv = sg > 0 ? (yb - yo) : (yo - yb);
+        const double Bej = P.B[(int64_t)P.vadj_edge[t] * k + j];
+        gx = fma(sg * u, Bej, gx);
+        gy = fma(sg * vv, Bej, gy);
+        if (P.rhs.c_qx >= 0) {  // + Cb^T Q C dx/dq_ind: the free neighbours move with q once the supports do
+          const int ro = P.vrow[o];
+          if (ro >= 0) {
+            const double qe = WS(P.slot.s_q + P.vadj_edge[t]);
+            gx = fma(-qe, WS(P.slot.s_r + ro * nrhs + P.rhs.c_qx + j), gx);
+            gy = fma(-qe, WS(P.slot.s_r + ro * nrhs + P.rhs.c_qy + j), gy);
+          }
+        }
+      }
+      acc += WS(P.slot.s_cxy + b) * gx + WS(P.slot.s_cxy + nb + b) * gy;
+    }
+    WS(P.slot.s_grad + j) = acc;
+  }
+}
+
 // Per-candidate load direction: rows e and m + e of the funicular block get +-(c d[e] + s d_b[e]) in the lambdh column.
 __global__ void __launch_bounds__(256) k_dir_column(DevPlan P, const double* __restrict__ load_dir, double* __restrict__ J,
                                                     int64_t cand_stride) {
@@ -981,7 +1001,7 @@ int run_interleaved(Plan* PL, const double* x_dev, int64_t N, int64_t ldx, const
       return TNO_EINVAL;
     }
     LAUNCH(KK_PACK, k_pack, grid1(nc, TB), TB, P, ws, NC, nc, xs, ldx, pzs, ldir);
-    const int etile = 32;
+    const int etile = P.k > 64 ? 4 : 32;   // many independents: shorter edge tiles keep the machine busy
     LAUNCH(KK_Q, k_q, grid1(nc, TB, (P.m + etile - 1) / etile), TB, P, ws, NC, nc, etile);
     const int ptile = 128;
     LAUNCH(KK_ASSEMBLE, k_assemble, grid1(nc, TB, (P.nnz_l + ptile - 1) / ptile), TB, P, ws, NC, nc, ptile);
@@ -1001,7 +1021,7 @@ int run_interleaved(Plan* PL, const double* x_dev, int64_t N, int64_t ldx, const
     } else {
       LAUNCH(KK_FACTOR, k_factor, grid1(nc, TB), TB, P, ws, NC, nc, st);
     }
-    const int rtile = 32;
+    const int rtile = P.k > 64 ? 8 : 32;
     const int gyr = (P.ni + rtile - 1) / rtile;
     LAUNCH(KK_RHS1, k_rhs1, grid1(nc, TB, gyr), TB, P, ws, NC, nc, rtile);
     constexpr int RB = 4;
@@ -1039,7 +1059,8 @@ int run_interleaved(Plan* PL, const double* x_dev, int64_t N, int64_t ldx, const
     const bool need2 = P.rhs.nrhs2 > 0 && (out->J != nullptr || (P.objective >= TNO_OBJ_BESTFIT && P.objective != TNO_OBJ_FEASIBILITY && out->grad != nullptr) ||
                                             (P.rhs.c_qx >= 0 && P.var.o_xyb >= 0 && out->grad != nullptr));
     if (need2) {
-      LAUNCH(KK_RHS2, k_rhs2, grid1(nc, TB, gyr), TB, P, ws, NC, nc, rtile);
+      const int jtile = 32;
+      LAUNCH(KK_RHS2, k_rhs2, dim3((unsigned)((nc + TB - 1) / TB), (unsigned)gyr, (unsigned)((P.k + jtile - 1) / jtile)), TB, P, ws, NC, nc, rtile, jtile);
       if (levelled)
         solve_levelled(KK_SOLVE2, P.rhs.nrhs1, P.rhs.nrhs2);
       else
@@ -1047,6 +1068,10 @@ int run_interleaved(Plan* PL, const double* x_dev, int64_t N, int64_t ldx, const
     }
     LAUNCH(KK_EPILOGUE, k_epilogue, grid1(nc, TB), TB, P, ws, NC, nc, out->f ? out->f + c0 : nullptr,
            out->gmin ? out->gmin + c0 : nullptr, st);
+    if (out->grad && (P.objective == TNO_OBJ_MIN || P.objective == TNO_OBJ_MAX)) {
+      const int jtile = 16;
+      LAUNCH(KK_EPILOGUE, k_thrust_grad, grid1(nc, TB, (P.k + jtile - 1) / jtile), TB, P, ws, NC, nc, jtile);
+    }
     // stride = elements per candidate of the user-facing array, offset = first element the table describes
     auto emit = [&](int kind, const EmitTable& T, double* dst, int64_t stride = -1, int64_t offset = 0) {
       if (!dst || T.count == 0) return;

@@ -48,7 +48,8 @@ struct SlotLayout {
   int s_env = 0;    // 4 * n : ub, lb, dub/dt, dlb/dt  (thickness variable only)
   int s_grad = 0;   // nvar
   int s_rg = 0;     // 2 nb   reac_bounds constraint values
-  int s_rj = 0;     // 2 nb * nvar   reac_bounds Jacobian rows
+  int s_rj = 0;     // 2 nb * nvar   reac_bounds Jacobian rows (reac_bounds only)
+  int s_cxy = 0;    // 2 nb : +-Rx / |R_h|, +-Ry / |R_h| of the supports (thrust objectives), read by k_thrust_grad
   int nslots = 0;
 };
 
