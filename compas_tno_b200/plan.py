@@ -273,11 +273,14 @@ class TnoPlan:
         return res
 
     def evaluate_batch(self, x_host, to_host: Sequence[str] = ("f", "gmin", "status"),
-                       on_device: Sequence[str] = ("grad", "g", "J", "z"), pz_scale=None, buffers=None):
+                       on_device: Sequence[str] = ("grad", "g", "J", "z"), pz_scale=None, buffers=None, load_dir=None,
+                       pipeline: int = 4):
         """End-to-end call: pinned host x -> device, evaluate, ``to_host`` outputs -> pinned host.
 
         Outputs named in ``on_device`` are materialised in HBM (for an on-device consumer) and returned as
         CUDA tensors; ``to_host`` ones come back as pinned CPU tensors.  Synchronises before returning.
+        Large batches are evaluated in ``pipeline`` slices so that the device-to-host copy of one slice (on a second
+        stream) overlaps the evaluation of the next; results are identical to the unsliced call.
         """
         import torch
         dev = torch.device("cuda", self.device)
@@ -291,23 +294,53 @@ class TnoPlan:
             xd = torch.empty(xh.shape, dtype=torch.float64, device=dev)
             buffers["x_dev"] = xd
         xd.copy_(xh, non_blocking=True)
-        pzd = None
-        if pz_scale is not None:
-            pzh = pz_scale if isinstance(pz_scale, torch.Tensor) else torch.from_numpy(_f64(pz_scale))
-            pzd = pzh.to(dev, non_blocking=True)
+
+        def to_dev(a):
+            if a is None:
+                return None
+            t = a if isinstance(a, torch.Tensor) else torch.from_numpy(_f64(a))
+            return t.to(dev, non_blocking=True)
+
+        pzd, ldd = to_dev(pz_scale), to_dev(load_dir)
         names = tuple(dict.fromkeys(tuple(to_host) + tuple(on_device)))
-        res = self.evaluate_device(xd, names, pz_scale=pzd, out=buffers.get("out"))
-        buffers["out"] = res
-        ret = {}
-        for name in names:
-            if name in to_host:
-                h = buffers.get("h_" + name)
-                if h is None or h.shape != res[name].shape:
-                    h = torch.empty(res[name].shape, dtype=res[name].dtype, pin_memory=True)
-                    buffers["h_" + name] = h
-                h.copy_(res[name], non_blocking=True)
-                ret[name] = h
-            else:
-                ret[name] = res[name]
-        torch.cuda.current_stream(dev).synchronize()
+        out = buffers.get("out")
+        if out is None or any(k not in out or tuple(out[k].shape) != self._shape(k, N) for k in names):
+            out = {k: torch.empty(self._shape(k, N), device=dev, dtype=torch.int32 if k == "status" else torch.float64)
+                   for k in names}
+            buffers["out"] = out
+        host = {}
+        for name in to_host:
+            h = buffers.get("h_" + name)
+            if h is None or h.shape != out[name].shape:
+                h = torch.empty(out[name].shape, dtype=out[name].dtype, pin_memory=True)
+                buffers["h_" + name] = h
+            host[name] = h
+        d2h_bytes = sum(host[k].numel() * host[k].element_size() for k in host)
+        nslices = pipeline if (pipeline > 1 and N >= 256 * pipeline and d2h_bytes >= (64 << 20)) else 1
+        main = torch.cuda.current_stream(dev)
+        if nslices == 1:
+            self.evaluate_device(xd, names, pz_scale=pzd, out=out, load_dir=ldd)
+            for name in to_host:
+                host[name].copy_(out[name], non_blocking=True)
+        else:
+            copy_stream = buffers.get("copy_stream")
+            if copy_stream is None:
+                copy_stream = torch.cuda.Stream(device=dev)
+                buffers["copy_stream"] = copy_stream
+            copy_stream.wait_stream(main)          # earlier users of the host / device buffers on either stream
+            step = -(-N // nslices)
+            for i0 in range(0, N, step):
+                i1 = min(N, i0 + step)
+                self.evaluate_device(xd[i0:i1], names, out={k: out[k][i0:i1] for k in names},
+                                     pz_scale=None if pzd is None else pzd[i0:i1],
+                                     load_dir=None if ldd is None else ldd[i0:i1])
+                done = torch.cuda.Event()
+                done.record(main)
+                copy_stream.wait_event(done)
+                with torch.cuda.stream(copy_stream):
+                    for name in to_host:
+                        host[name][i0:i1].copy_(out[name][i0:i1], non_blocking=True)
+            main.wait_stream(copy_stream)
+        main.synchronize()
+        ret = {name: (host[name] if name in host else out[name]) for name in names}
         return ret

@@ -144,6 +144,29 @@ def test_full_size_batch_properties_and_family_cross_check(tno):
     assert rel_err(a["J"], b["J"]) < TOL_JAC
 
 
+def test_evaluate_batch_pipelined_slices_equal_the_single_call(tno):
+    """evaluate_batch overlaps the device-to-host copy of one slice with the evaluation of the next: same bits."""
+    import torch
+    from compas_tno_b200 import workloads as W
+    from compas_tno_b200.plan import TnoPlan
+    P, xs = W.crossvault_problem(20, n_states=4)
+    N = 1100
+    X = W.sample_candidates(P, xs, N, seed=5, basis=P.candidate_basis)
+    plan = TnoPlan(P, objective="min")
+    names = ("f", "grad", "g", "J", "z", "gmin", "status")
+    xh = torch.from_numpy(X).pin_memory()
+    bufs = {}
+    piped = plan.evaluate_batch(xh, to_host=names, on_device=(), buffers=bufs)
+    assert "copy_stream" in bufs                      # the sliced path ran
+    again = {k: v.clone() for k, v in plan.evaluate_batch(xh, to_host=names, on_device=(), buffers=bufs).items()}
+    single = plan.evaluate_batch(xh, to_host=names, on_device=(), pipeline=1)
+    for k in names:
+        assert torch.equal(piped[k], single[k]), k
+        assert torch.equal(again[k], single[k]), k
+    mixed = plan.evaluate_batch(xh, to_host=("f", "J"), on_device=("g",))
+    assert mixed["g"].is_cuda and not mixed["J"].is_cuda and torch.equal(mixed["J"], single["J"])
+
+
 def test_indefinite_candidate_is_flagged_not_fatal(tno):
     from compas_tno_b200.plan import TnoPlan
     P, objective, xs, _ = load_case("cross6_q_zb_min")
