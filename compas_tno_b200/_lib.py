@@ -21,7 +21,7 @@ STATUS_OK, STATUS_NOT_PD, STATUS_NONFINITE = 0, 1, 2
 EXPORTS = [
     "tno_abi_version", "tno_last_error", "tno_plan_create", "tno_plan_destroy", "tno_plan_query",
     "tno_plan_symbolic", "tno_eval_batch", "tno_eval_batch_host", "tno_plan_launch_count",
-    "tno_plan_profile", "tno_plan_profile_read", "tno_symbolic_analyse",
+    "tno_plan_profile", "tno_plan_profile_read", "tno_symbolic_analyse", "tno_fetch_jacobian_host",
 ]
 
 _dp = C.POINTER(C.c_double)
@@ -94,6 +94,8 @@ def load():
     lib.tno_eval_batch.restype = C.c_int
     lib.tno_eval_batch_host.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.POINTER(BatchInputs), C.POINTER(Outputs)]
     lib.tno_eval_batch_host.restype = C.c_int
+    lib.tno_fetch_jacobian_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
+    lib.tno_fetch_jacobian_host.restype = C.c_int
     lib.tno_plan_launch_count.argtypes = [C.c_void_p]
     lib.tno_plan_launch_count.restype = C.c_int64
     lib.tno_plan_profile.argtypes = [C.c_void_p, C.c_int]

@@ -7,6 +7,11 @@
 #include <map>
 #include <new>
 #include <string>
+#include <thread>
+#include <vector>
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
 
 #include "tno_plan.hpp"
 
@@ -57,6 +62,20 @@ int upload_table(Plan* P, const std::vector<EmitDesc2>& t, EmitTable* T) {
 EmitDesc2 cst(double c) { return EmitDesc2{-1, -1, 0.f, 0.f, c}; }
 EmitDesc2 one(int slot, float sign, double c = 0.0) { return EmitDesc2{slot, -1, sign, 0.f, c}; }
 EmitDesc2 two(int a, float sa, int b, float sb) { return EmitDesc2{a, b, sa, sb, 0.0}; }
+
+// dst <- src, count doubles, with non-temporal stores where the ISA has them: the destination (a user's Jacobian
+// buffer, hundreds of MB) is written once and not read here, so it should not be pulled through the caches first.
+void copy_streaming(double* dst, const double* src, size_t count) {
+#if defined(__SSE2__)
+  size_t i = 0;
+  if ((reinterpret_cast<uintptr_t>(dst) & 15u) && count) { dst[0] = src[0]; i = 1; }
+  for (; i + 2 <= count; i += 2)
+    _mm_stream_pd(dst + i, _mm_loadu_pd(src + i));
+  if (i < count) dst[i] = src[i];
+#else
+  std::memcpy(dst, src, count * sizeof(double));
+#endif
+}
 
 int fail(int code, const std::string& msg) {
   set_error(msg);
@@ -524,6 +543,7 @@ int tno_plan_create(const tno_problem_desc* D, tno_plan** out_plan) {
       for (size_t i = 0; i < cnt; ++i) blockv[i] = t[i].c;
       if ((rc = upload(P, blockv, &P->jfun))) return rc;
       P->jfun_count = (int64_t)cnt;
+      P->h_jfun = blockv;
       t.erase(t.begin(), t.begin() + cnt);
     }
     if ((rc = upload_table(P, t, &P->t_J))) return rc;
@@ -743,13 +763,57 @@ int tno_eval_batch_host(tno_plan* plan, const double* x_host, int64_t N, int64_t
   BACK(f, N, 8);
   BACK(grad, N * nvar, 8);
   BACK(g, N * ng, 8);
-  BACK(J, N * ng * nvar, 8);
+  if (oh->J) {
+    // constant funicular rows are written by host threads, the rest crosses PCIe (not with per-candidate directions:
+    // the lambdh column of those rows then differs per candidate)
+    if (load_dir_host) {
+      TNO_CUDA_OK(cudaMemcpyAsync(oh->J, od.J, (size_t)N * ng * nvar * 8, cudaMemcpyDeviceToHost, s));
+    } else {
+      rc = tno_fetch_jacobian_host(plan, od.J, oh->J, N, (void*)s);
+      if (rc) return rc;
+    }
+  }
   BACK(z, N * n, 8);
   BACK(q, N * m, 8);
   BACK(gmin, N, 8);
   BACK(status, N, 4);
 #undef BACK
   TNO_CUDA_OK(cudaStreamSynchronize(s));
+  return TNO_OK;
+}
+
+int tno_fetch_jacobian_host(tno_plan* plan, const double* J_dev, double* J_host, int64_t N, void* cuda_stream) {
+  Plan* P = reinterpret_cast<Plan*>(plan);
+  if (!P || !J_dev || !J_host || N < 0) return fail(TNO_EINVAL, "null argument");
+  if (N == 0) return TNO_OK;
+  TNO_CUDA_OK(cudaSetDevice(P->device));
+  cudaStream_t s = (cudaStream_t)cuda_stream;
+  const size_t per = (size_t)P->dp.con.ng * P->dp.var.nvar;           // doubles per candidate
+  const size_t cst = P->h_jfun.size();                                 // leading constant doubles per candidate
+  if (cst == 0 || cst >= per) {
+    TNO_CUDA_OK(cudaMemcpyAsync(J_host, J_dev, (size_t)N * per * 8, cudaMemcpyDeviceToHost, s));
+    return TNO_OK;
+  }
+  TNO_CUDA_OK(cudaMemcpy2DAsync(J_host + cst, per * 8, J_dev + cst, per * 8, (per - cst) * 8, (size_t)N, cudaMemcpyDeviceToHost, s));
+  // constant rows: plain memcpy from the plan's host copy, candidates split over a few threads
+  const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+  const int64_t nthreads = std::max<int64_t>(1, std::min<int64_t>({(int64_t)hw, (int64_t)16, N / 64 + 1}));
+  const double* src = P->h_jfun.data();
+  auto work = [=](int64_t a, int64_t b) {
+    for (int64_t c = a; c < b; ++c) copy_streaming(J_host + (size_t)c * per, src, cst);
+#if defined(__SSE2__)
+    _mm_sfence();
+#endif
+  };
+  if (nthreads == 1) {
+    work(0, N);
+  } else {
+    std::vector<std::thread> pool;
+    const int64_t step = (N + nthreads - 1) / nthreads;
+    for (int64_t a = step; a < N; a += step) pool.emplace_back(work, a, std::min(N, a + step));
+    work(0, std::min(N, step));
+    for (auto& t : pool) t.join();
+  }
   return TNO_OK;
 }
 

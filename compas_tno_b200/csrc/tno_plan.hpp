@@ -288,6 +288,7 @@ struct Plan {
   EmitTable t_g, t_grad, t_z, t_q, t_J;   // t_J covers the rows below the funicular block when jfun is set
   const double* jfun = nullptr;           // 2m x nvar candidate-independent rows [B 0; -B 0] (+ d0 column) of J
   int64_t jfun_count = 0;
+  std::vector<double> h_jfun;             // host copy of the same block (tno_fetch_jacobian_host)
   // scratch (interleaved family): nslots x chunk doubles
   double* scratch = nullptr;
   int32_t* status_scratch = nullptr;

@@ -318,10 +318,21 @@ class TnoPlan:
         d2h_bytes = sum(host[k].numel() * host[k].element_size() for k in host)
         nslices = pipeline if (pipeline > 1 and N >= 256 * pipeline and d2h_bytes >= (64 << 20)) else 1
         main = torch.cuda.current_stream(dev)
+
+        def fetch(name, i0, i1, stream):
+            """device -> pinned host for one output slice; J goes through tno_fetch_jacobian_host (constant rows filled by
+            host threads instead of crossing PCIe) unless its funicular rows vary with a per-candidate load direction"""
+            if name == "J" and ldd is None and i1 > i0:
+                _lib.check(self._lib.tno_fetch_jacobian_host(self._handle, out["J"][i0:i1].data_ptr(), host["J"][i0:i1].data_ptr(),
+                                                      i1 - i0, C.c_void_p(stream.cuda_stream)))
+            else:
+                with torch.cuda.stream(stream):
+                    host[name][i0:i1].copy_(out[name][i0:i1], non_blocking=True)
+
         if nslices == 1:
             self.evaluate_device(xd, names, pz_scale=pzd, out=out, load_dir=ldd)
             for name in to_host:
-                host[name].copy_(out[name], non_blocking=True)
+                fetch(name, 0, N, main)
         else:
             copy_stream = buffers.get("copy_stream")
             if copy_stream is None:
@@ -337,9 +348,8 @@ class TnoPlan:
                 done = torch.cuda.Event()
                 done.record(main)
                 copy_stream.wait_event(done)
-                with torch.cuda.stream(copy_stream):
-                    for name in to_host:
-                        host[name][i0:i1].copy_(out[name][i0:i1], non_blocking=True)
+                for name in sorted(to_host, key=lambda k: k == "J"):   # small outputs first, J (with its host fill) last
+                    fetch(name, i0, i1, copy_stream)
             main.wait_stream(copy_stream)
         main.synchronize()
         ret = {name: (host[name] if name in host else out[name]) for name in names}

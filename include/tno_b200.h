@@ -225,6 +225,13 @@ int64_t tno_plan_launch_count(const tno_plan* plan);
 int tno_plan_profile(tno_plan* plan, int enable);
 int tno_plan_profile_read(tno_plan* plan, int32_t max_kinds, char* names, double* total_ms, int64_t* launches);
 
+/* Bring the dense Jacobians of n_candidates evaluations from device memory (J_dev, layout of tno_outputs.J) to host
+ * memory (J_host, same layout; pinned memory makes the copy asynchronous).  The candidate-independent funicular rows
+ * [B 0; -B 0] (+ d0 column) do not cross PCIe: host threads write them from the plan's copy while the DMA engine moves
+ * the other rows on `cuda_stream`.  Returns when the host threads are done; the caller synchronises the stream.
+ * With per-candidate load directions (tno_batch_inputs.load_dir) the funicular rows are not constant: use a plain copy. */
+int tno_fetch_jacobian_host(tno_plan* plan, const double* J_dev, double* J_host, int64_t n_candidates, void* cuda_stream);
+
 #ifdef __cplusplus
 }
 #endif
