@@ -340,8 +340,14 @@ def run_ours(args):
     for _ in range(args.warmup):
         step()
     barrier()
+    # The per-kernel CUDA events of the library sit between the launches.  With two launches per step (on-chip family) they
+    # cost nothing and the timed region is profiled directly; the level-scheduled interleaved family issues ~10^3 launches
+    # per step, where the events themselves take ~10 % -- there the timed region runs unprofiled and the kernel
+    # durations come from a second pass of the same K steps.
+    profiled_inline = (plan.info.get("last_kernel") or plan.info["kernel"]) == 2
     launches0 = plan.launch_count
-    plan.profile(True)
+    if profiled_inline:
+        plan.profile(True)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     sampler.mark_begin()
@@ -353,9 +359,19 @@ def run_ours(args):
     sampler.mark_end()
     ms = e0.elapsed_time(e1)
     clocks = sampler.stop() if rank == 0 else None
+    launches = plan.launch_count - launches0
+    profiled_ms = ms
+    if not profiled_inline:
+        plan.profile(True)
+        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        p0.record()
+        for _ in range(args.steps):
+            step()
+        p1.record()
+        barrier()
+        profiled_ms = p0.elapsed_time(p1)
     prof = plan.profile_read()
     plan.profile(False)
-    launches = plan.launch_count - launches0
     if world > 1:
         t = torch.tensor([ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -378,6 +394,7 @@ def run_ours(args):
         else:
             kbytes = {"k_emit(J)": 8 * plan.ng * plan.nvar}
         total_kernel_ms = sum(v[0] for v in prof.values())
+        profile_pass = "timed region" if profiled_inline else "second pass of the same %d steps (%.3f ms/step with events)" % (args.steps, profiled_ms / args.steps)
         name, (kms, kcount) = max(prof.items(), key=lambda kv: kv[1][0])
         bytes_per_eval = kbytes.get(name, B_alg)
         evals_per_launch = N * args.steps / kcount
@@ -399,6 +416,7 @@ def run_ours(args):
         roofline = {"bound": "hbm", "kernel": name, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                     "traffic": traffic, "peak_source": peak_src, "kernel_share_of_step": kms / total_kernel_ms,
                     "bytes_per_eval": bytes_per_eval, "evals_per_launch": evals_per_launch,
+                    "kernel_durations_from": profile_pass,
                     "whole_step": {"bytes_per_eval": B_alg, "achieved": value / world * B_alg / 1e9,
                                    "frac": value / world * B_alg / 1e9 / peak},
                     "kernels": per_kernel}
