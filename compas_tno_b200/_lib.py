@@ -56,7 +56,7 @@ class PlanInfo(C.Structure):
 
 
 class BatchInputs(C.Structure):
-    _fields_ = [("pz_scale", C.c_void_p), ("load_dir", C.c_void_p), ("reserved1", C.c_void_p)]
+    _fields_ = [("pz_scale", C.c_void_p), ("load_dir", C.c_void_p), ("bounds", C.c_void_p)]
 
 
 class Outputs(C.Structure):

@@ -719,6 +719,8 @@ int tno_eval_batch_host(tno_plan* plan, const double* x_host, int64_t N, int64_t
   const double* load_dir_host = in_host ? in_host->load_dir : nullptr;
   const size_t o_pzs = take(pz_scale_host != nullptr, (size_t)N);
   const size_t o_dir = take(load_dir_host != nullptr, (size_t)N * 2);
+  const double* bounds_host = in_host ? in_host->bounds : nullptr;
+  const size_t o_bnd = take(bounds_host != nullptr, (size_t)N * 2 * n);
   const size_t o_f = take(oh->f != nullptr, (size_t)N);
   const size_t o_grad = take(oh->grad != nullptr, (size_t)N * nvar);
   const size_t o_g = take(oh->g != nullptr, (size_t)N * ng);
@@ -746,6 +748,10 @@ int tno_eval_batch_host(tno_plan* plan, const double* x_host, int64_t N, int64_t
   if (load_dir_host) {
     TNO_CUDA_OK(cudaMemcpyAsync(base + o_dir, load_dir_host, (size_t)N * 16, cudaMemcpyHostToDevice, s));
     opt.load_dir = base + o_dir;
+  }
+  if (bounds_host) {
+    TNO_CUDA_OK(cudaMemcpyAsync(base + o_bnd, bounds_host, (size_t)N * 2 * n * 8, cudaMemcpyHostToDevice, s));
+    opt.bounds = base + o_bnd;
   }
   tno_outputs od{};
   od.f = oh->f ? base + o_f : nullptr;

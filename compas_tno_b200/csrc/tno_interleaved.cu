@@ -480,7 +480,7 @@ __device__ __forceinline__ void envelope_eval(const DevPlan& P, double x, double
 
 // reactions, objective, gradient, reac_bounds rows, envelope update, feasibility margin, status
 __global__ void k_epilogue(DevPlan P, double* __restrict__ ws, int64_t NC, int64_t ncand, double* __restrict__ f_out,
-                           double* __restrict__ gmin_out, int32_t* __restrict__ status) {
+                           double* __restrict__ gmin_out, int32_t* __restrict__ status, const double* __restrict__ bounds) {
   const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= ncand) return;
   const int n = P.n, m = P.m, nb = P.nb, k = P.k, nvar = P.var.nvar, nrhs = P.rhs.nrhs;
@@ -513,8 +513,8 @@ __global__ void k_epilogue(DevPlan P, double* __restrict__ ws, int64_t NC, int64
   if (P.constraints & TNO_CON_ENVELOPE) {
     for (int v = 0; v < n; ++v) {
       const double z = zval(P, ws, NC, c, v);
-      const double ub = has_t ? WS(P.slot.s_env + v) : P.ub[v];
-      const double lb = has_t ? WS(P.slot.s_env + n + v) : P.lb[v];
+      const double ub = has_t ? WS(P.slot.s_env + v) : (bounds ? bounds[c * 2 * n + v] : P.ub[v]);
+      const double lb = has_t ? WS(P.slot.s_env + n + v) : (bounds ? bounds[c * 2 * n + n + v] : P.lb[v]);
       gmin = fmin(gmin, fmin(z - lb, ub - z));
       bad |= !isfinite(z);
     }
@@ -862,6 +862,21 @@ __global__ void k_thrust_grad(DevPlan P, double* __restrict__ ws, int64_t NC, in
   }
 }
 
+// Per-candidate envelope: g[r_env + v] = z_v - lb_v, g[r_env + n + v] = ub_v - z_v with the candidate's own bounds.
+__global__ void __launch_bounds__(256) k_bounds_rows(DevPlan P, const double* __restrict__ ws, int64_t NC, const double* __restrict__ bounds,
+                                                     double* __restrict__ g) {
+  const int v = blockIdx.y * blockDim.x + threadIdx.x;
+  if (v >= P.n) return;
+  const int64_t c = blockIdx.x;
+  const int r = P.vrow[v];
+  const double z = r >= 0 ? WS(P.slot.s_r + r * P.rhs.nrhs + P.rhs.cz)
+                          : (P.var.o_zb >= 0 ? WS(P.slot.s_x + P.var.o_zb + (-1 - r)) : P.X[3 * v + 2]);
+  const double* b = bounds + c * 2 * P.n;
+  double* gc = g + c * P.con.ng + P.con.r_env;
+  gc[v] = z - b[P.n + v];
+  gc[P.n + v] = b[v] - z;
+}
+
 // Per-candidate load direction: rows e and m + e of the funicular block get +-(c d[e] + s d_b[e]) in the lambdh column.
 __global__ void __launch_bounds__(256) k_dir_column(DevPlan P, const double* __restrict__ load_dir, double* __restrict__ J,
                                                     int64_t cand_stride) {
@@ -995,6 +1010,11 @@ int run_interleaved(Plan* PL, const double* x_dev, int64_t N, int64_t ldx, const
     const int64_t nc = std::min(NC, N - c0);
     const double* xs = x_dev + c0 * ldx;
     const double* pzs = (opt && opt->pz_scale) ? opt->pz_scale + c0 : nullptr;
+    const double* bnd = (opt && opt->bounds) ? opt->bounds + 2 * c0 * P.n : nullptr;
+    if (bnd && (P.var.o_t >= 0 || P.con.r_env < 0)) {
+      set_error("per-candidate bounds need the envelope constraint and no thickness variable");
+      return TNO_EINVAL;
+    }
     const double* ldir = (opt && opt->load_dir) ? opt->load_dir + 2 * c0 : nullptr;
     if (ldir && !P.d_b) {
       set_error("load_dir needs a plan created with the second load basis (d_b, px0_b, py0_b)");
@@ -1067,7 +1087,7 @@ int run_interleaved(Plan* PL, const double* x_dev, int64_t N, int64_t ldx, const
         LAUNCH(KK_SOLVE2, k_solve<RB>, grid1(nc, TB, (P.rhs.nrhs2 + RB - 1) / RB), TB, P, ws, NC, nc, P.rhs.nrhs1, P.rhs.nrhs2);
     }
     LAUNCH(KK_EPILOGUE, k_epilogue, grid1(nc, TB), TB, P, ws, NC, nc, out->f ? out->f + c0 : nullptr,
-           out->gmin ? out->gmin + c0 : nullptr, st);
+           out->gmin ? out->gmin + c0 : nullptr, st, bnd);
     if (out->grad && (P.objective == TNO_OBJ_MIN || P.objective == TNO_OBJ_MAX)) {
       const int jtile = 16;
       LAUNCH(KK_EPILOGUE, k_thrust_grad, grid1(nc, TB, (P.k + jtile - 1) / jtile), TB, P, ws, NC, nc, jtile);
@@ -1080,6 +1100,8 @@ int run_interleaved(Plan* PL, const double* x_dev, int64_t N, int64_t ldx, const
       LAUNCH(kind, k_emit, g, 256, T.dev, T.count, dst + c0 * stride + offset, stride, ws, NC, nc);
     };
     emit(KK_EMIT_SMALL, PL->t_g, out->g);
+    if (bnd && out->g)  // the table carries the plan's bounds: the envelope rows are rewritten with the candidate's own
+      LAUNCH(KK_EMIT_SMALL, k_bounds_rows, dim3((unsigned)nc, (unsigned)((P.n + 255) / 256), 1), 256, P, ws, NC, bnd, out->g + c0 * P.con.ng);
     emit(KK_EMIT_SMALL, PL->t_grad, out->grad);
     emit(KK_EMIT_SMALL, PL->t_z, out->z);
     emit(KK_EMIT_SMALL, PL->t_q, out->q);

@@ -32,6 +32,7 @@ struct OcArgs {
   int64_t ldx;
   const double* pzs;
   const double* dir;   // N x 2 load directions or null
+  const double* bounds;  // N x 2n per-candidate [ub | lb] or null
   double* f;
   double* grad;
   double* g;
@@ -468,9 +469,10 @@ __global__ void __launch_bounds__(THREADS, MINB) k_onchip(const __grid_constant_
     const double lamv = P.var.o_lambdv >= 0 ? xs[P.var.o_lambdv] : 1.0;
     const double pzs = A.pzs ? A.pzs[cand] : 1.0;
     // horizontal load basis of the candidate: (c, s) = load direction; (1, 0) reproduces the single-basis values bit for bit
-    const double dirc = DIR ? A.dir[2 * cand] : 1.0, dirs = DIR ? A.dir[2 * cand + 1] : 0.0;
+    const bool has_dir = DIR && A.dir != nullptr;
+    const double dirc = has_dir ? A.dir[2 * cand] : 1.0, dirs = has_dir ? A.dir[2 * cand + 1] : 0.0;
     auto mix2 = [&](const double* a, const double* b, int i) -> double {
-      if constexpr (DIR) return fma(dirs, b[i], dirc * a[i]);
+      if constexpr (DIR) return has_dir ? fma(dirs, b[i], dirc * a[i]) : a[i];
       else return a[i];
     };
     double gmin = 1e300;
@@ -500,7 +502,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_onchip(const __grid_constant_
       if (e >= m) continue;
       const double acc = acc4[i];
       qs[e] = acc;
-      if (DIR && Jout && P.con.r_fun >= 0) {  // the lambdh column of the funicular rows follows the candidate's direction
+      if (has_dir && Jout && P.con.r_fun >= 0) {  // the lambdh column of the funicular rows follows the candidate's direction
         const double de = mix2(P.d, P.d_b, e);
         Jout[(int64_t)(P.con.r_fun + e) * nvar + P.var.o_lambdh] = de;
         Jout[(int64_t)(P.con.r_fun + m + e) * nvar + P.var.o_lambdh] = -de;
@@ -722,6 +724,10 @@ __global__ void __launch_bounds__(THREADS, MINB) k_onchip(const __grid_constant_
         } else {
           ub = P.ub[v];
           lb = P.lb[v];
+          if (DIR && A.bounds) {   // per-candidate envelope (same instantiation as the load directions: off the common path)
+            ub = A.bounds[cand * 2 * n + v];
+            lb = A.bounds[cand * 2 * n + n + v];
+          }
         }
         const double g0 = z - lb, g1 = ub - z;
         if (gout) {
@@ -919,7 +925,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_onchip(const __grid_constant_
               rc[u] = ok ? __ldg(O.ec_rec + e) : 0xffffffffu;
               cc[u] = ok ? __ldg(O.Bc + (int64_t)e * O.bc_stride + cidx) : 0.0;
               // lambdh column with a second load basis: d0 of the candidate's direction (the basis sits one column on)
-              if (DIR && ok && cidx == k) cc[u] = fma(dirs, __ldg(O.Bc + (int64_t)e * O.bc_stride + k + 1), dirc * cc[u]);
+              if (has_dir && ok && cidx == k) cc[u] = fma(dirs, __ldg(O.Bc + (int64_t)e * O.bc_stride + k + 1), dirc * cc[u]);
             }
           };
           fetch(0, rec, cf);
@@ -1841,6 +1847,11 @@ int run_onchip(Plan* PL, const double* x_dev, int64_t N, int64_t ldx, const tno_
   A.ldx = ldx;
   A.pzs = (opt && opt->pz_scale) ? opt->pz_scale : nullptr;
   A.dir = (opt && opt->load_dir) ? opt->load_dir : nullptr;
+  A.bounds = (opt && opt->bounds) ? opt->bounds : nullptr;
+  if (A.bounds && (PL->dp.var.o_t >= 0 || PL->dp.con.r_env < 0)) {
+    set_error("per-candidate bounds need the envelope constraint and no thickness variable");
+    return TNO_EINVAL;
+  }
   if (A.dir && !PL->dp.d_b) {
     set_error("load_dir needs a plan created with the second load basis (d_b, px0_b, py0_b)");
     return TNO_EINVAL;
@@ -1865,7 +1876,7 @@ int run_onchip(Plan* PL, const double* x_dev, int64_t N, int64_t ldx, const tno_
   const int ctas = force_ctas ? std::max(1, atoi(force_ctas)) : PL->onchip_ctas_per_sm;
   const int grid = (int)std::min<int64_t>(N, (int64_t)PL->sm_count * ctas);
   const int threads = PL->onchip_threads;
-  auto kern = A.dir ? (threads == 512 ? k_onchip<512, 1, true> : (PL->onchip_ctas_per_sm >= 2 ? k_onchip<256, 2, true> : k_onchip<256, 1, true>))
+  auto kern = (A.dir || A.bounds) ? (threads == 512 ? k_onchip<512, 1, true> : (PL->onchip_ctas_per_sm >= 2 ? k_onchip<256, 2, true> : k_onchip<256, 1, true>))
                     : (threads == 512 ? k_onchip<512, 1, false> : (PL->onchip_ctas_per_sm >= 2 ? k_onchip<256, 2, false> : k_onchip<256, 1, false>));
   TNO_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   if (out->J && PL->dp.con.r_fun >= 0)

@@ -215,10 +215,11 @@ class TnoPlan:
                 "z": (N, self.n), "q": (N, self.m), "gmin": (N,), "status": (N,)}[name]
 
     # ------------------------------------------------------------------------------------------
-    def evaluate_host(self, x, outputs: Iterable[str] = ALL_OUTPUTS, pz_scale=None, load_dir=None) -> Dict[str, np.ndarray]:
+    def evaluate_host(self, x, outputs: Iterable[str] = ALL_OUTPUTS, pz_scale=None, load_dir=None, bounds=None) -> Dict[str, np.ndarray]:
         """Host buffers in, host buffers out (tno_eval_batch_host); no torch involved.
         ``pz_scale`` (N,): vertical load multiplier per candidate; ``load_dir`` (N, 2): (cos, sin) of the horizontal
-        load direction per candidate (problems with ``lambdh`` and a second load basis ``d0_b, px0_b, py0_b``)."""
+        load direction per candidate (problems with ``lambdh`` and a second load basis ``d0_b, px0_b, py0_b``);
+        ``bounds`` (N, 2n) = [ub | lb] per candidate replacing the problem's envelope in g (no thickness variable)."""
         x = _f64(x)
         if x.ndim == 1:
             x = x.reshape(1, -1)
@@ -237,10 +238,14 @@ class TnoPlan:
             inp.pz_scale = pz.ctypes.data
         if ld2 is not None:
             inp.load_dir = ld2.ctypes.data
+        bd = _f64(bounds, (N, 2 * self.n)) if bounds is not None else None
+        if bd is not None:
+            inp.bounds = bd.ctypes.data
         _lib.check(self._lib.tno_eval_batch_host(self._handle, x.ctypes.data, N, ld, C.byref(inp), C.byref(O)))
         return res
 
-    def evaluate_device(self, x, outputs: Iterable[str] = ALL_OUTPUTS, pz_scale=None, out=None, stream=None, load_dir=None):
+    def evaluate_device(self, x, outputs: Iterable[str] = ALL_OUTPUTS, pz_scale=None, out=None, stream=None, load_dir=None,
+                        bounds=None):
         """Device tensors in, device tensors out (tno_eval_batch); asynchronous on the current torch stream."""
         import torch
         if not x.is_cuda or x.dtype != torch.float64 or x.dim() != 2 or x.stride(1) != 1:
@@ -267,6 +272,10 @@ class TnoPlan:
             if tuple(load_dir.shape) != (N, 2) or load_dir.dtype != torch.float64 or not load_dir.is_contiguous() or not load_dir.is_cuda:
                 raise ValueError("load_dir must be a contiguous (N, 2) float64 CUDA tensor")
             opt.load_dir = load_dir.data_ptr()
+        if bounds is not None:
+            if tuple(bounds.shape) != (N, 2 * self.n) or bounds.dtype != torch.float64 or not bounds.is_contiguous() or not bounds.is_cuda:
+                raise ValueError("bounds must be a contiguous (N, 2n) float64 CUDA tensor [ub | lb]")
+            opt.bounds = bounds.data_ptr()
         st = torch.cuda.current_stream(x.device).cuda_stream if stream is None else stream
         _lib.check(self._lib.tno_eval_batch(self._handle, x.data_ptr(), N, x.stride(0), C.byref(opt), C.byref(O),
                                             C.c_void_p(st)))
@@ -274,7 +283,7 @@ class TnoPlan:
 
     def evaluate_batch(self, x_host, to_host: Sequence[str] = ("f", "gmin", "status"),
                        on_device: Sequence[str] = ("grad", "g", "J", "z"), pz_scale=None, buffers=None, load_dir=None,
-                       pipeline: int = 4):
+                       pipeline: int = 4, bounds=None):
         """End-to-end call: pinned host x -> device, evaluate, ``to_host`` outputs -> pinned host.
 
         Outputs named in ``on_device`` are materialised in HBM (for an on-device consumer) and returned as
@@ -301,7 +310,7 @@ class TnoPlan:
             t = a if isinstance(a, torch.Tensor) else torch.from_numpy(_f64(a))
             return t.to(dev, non_blocking=True)
 
-        pzd, ldd = to_dev(pz_scale), to_dev(load_dir)
+        pzd, ldd, bdd = to_dev(pz_scale), to_dev(load_dir), to_dev(bounds)
         names = tuple(dict.fromkeys(tuple(to_host) + tuple(on_device)))
         out = buffers.get("out")
         if out is None or any(k not in out or tuple(out[k].shape) != self._shape(k, N) for k in names):
@@ -330,7 +339,7 @@ class TnoPlan:
                     host[name][i0:i1].copy_(out[name][i0:i1], non_blocking=True)
 
         if nslices == 1:
-            self.evaluate_device(xd, names, pz_scale=pzd, out=out, load_dir=ldd)
+            self.evaluate_device(xd, names, pz_scale=pzd, out=out, load_dir=ldd, bounds=bdd)
             for name in to_host:
                 fetch(name, 0, N, main)
         else:
@@ -344,7 +353,8 @@ class TnoPlan:
                 i1 = min(N, i0 + step)
                 self.evaluate_device(xd[i0:i1], names, out={k: out[k][i0:i1] for k in names},
                                      pz_scale=None if pzd is None else pzd[i0:i1],
-                                     load_dir=None if ldd is None else ldd[i0:i1])
+                                     load_dir=None if ldd is None else ldd[i0:i1],
+                                     bounds=None if bdd is None else bdd[i0:i1])
                 done = torch.cuda.Event()
                 done.record(main)
                 copy_stream.wait_event(done)

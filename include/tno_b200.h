@@ -167,7 +167,8 @@ typedef struct tno_batch_inputs {
   const double* load_dir; /* N x 2 (c, s): horizontal load direction of candidate j (needs the lambdh variable and the
                              second load basis d_b / px0_b / py0_b of the problem):
                              d0 = c d + s d_b,  px0 = c px0 + s px0_b,  py0 = c py0 + s py0_b */
-  const double* reserved1;
+  const double* bounds;   /* N x 2n: per candidate [ub (n) | lb (n)] replacing Problem.ub / Problem.lb in the envelope rows
+                             of g (Monte-Carlo geometry perturbations of the intrados / extrados; not with the t variable) */
 } tno_batch_inputs;
 
 /* Output buffers (device pointers for tno_eval_batch, host pointers for tno_eval_batch_host).

@@ -381,6 +381,36 @@ def test_load_direction_sweep_matches_oracle_per_direction(tno, kernel):
 
 
 @pytest.mark.parametrize("kernel", ["interleaved", "onchip"])
+def test_per_candidate_bounds_match_oracle_with_perturbed_envelope(tno, kernel):
+    """tno_batch_inputs.bounds: candidate j is checked against its own intrados / extrados (Monte-Carlo geometry
+    perturbation of the envelope, SURVEY.md section 8b / configuration 4); J, z, f do not change."""
+    from compas_tno_b200.plan import TnoPlan
+    from oracle import callbacks_np as onp
+    P, objective, xs, exp = load_case("cross14_q_zb_min")
+    plan = TnoPlan(P, objective=objective, kernel=kernel)
+    rng = np.random.default_rng(31)
+    N, n = 45, P.n
+    X = xs[0] * (1.0 + 0.02 * rng.uniform(-1, 1, size=(N, xs.shape[1])))
+    ub = P.ub.ravel()[None, :] + rng.uniform(-0.05, 0.05, size=(N, n))
+    lb = P.lb.ravel()[None, :] + rng.uniform(-0.05, 0.05, size=(N, n))
+    bounds = np.ascontiguousarray(np.hstack([ub, lb]))
+    base = plan.evaluate_host(X)
+    got = plan.evaluate_host(X, bounds=bounds)
+    for key in ("f", "grad", "J", "z", "q", "status"):
+        assert np.array_equal(got[key], base[key]), key
+    m = P.m
+    assert np.array_equal(got["g"][:, : 2 * m], base["g"][:, : 2 * m])
+    for j in (0, 7, 44):
+        M = onp.clone_problem(P)
+        M.ub, M.lb = ub[j].reshape(-1, 1), lb[j].reshape(-1, 1)
+        ref = onp.evaluate(X[j], M, objective)
+        assert rel_err(got["g"][j], ref["g"]) < TOL_VAL
+        assert abs(got["gmin"][j] - ref["g"].min()) < 1e-9
+    light = plan.evaluate_host(X, outputs=("gmin", "status"), bounds=bounds)
+    assert np.array_equal(light["gmin"], got["gmin"])
+
+
+@pytest.mark.parametrize("kernel", ["interleaved", "onchip"])
 def test_pz_scale_matches_oracle_with_scaled_loads(tno, kernel):
     """Monte-Carlo self-weight input: pz_scale[j] multiplies the vertical loads of candidate j."""
     import copy
