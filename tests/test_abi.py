@@ -62,3 +62,36 @@ def test_product_package_never_imports_oracle():
             if fn.endswith((".py", ".cu", ".cpp", ".hpp", ".h")):
                 text = open(os.path.join(dirpath, fn)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle", text, flags=re.M), fn
+
+
+def test_unsupported_combinations_are_rejected_before_any_device_work():
+    """Argument validation mirrors the reference's NotImplementedError for combinations its callbacks do not cover; it
+    runs before the device is touched, so it is testable on a machine without a GPU."""
+    import copy
+    import numpy as np
+    from golden_io import load_case
+    from compas_tno_b200.plan import TnoPlan
+    P, objective, xs, _ = load_case("cross14_q_zb_min")
+
+    def variant(**kw):
+        Q = copy.copy(P)
+        for key, val in kw.items():
+            setattr(Q, key, val)
+        return Q
+
+    lim = np.column_stack([P.X[:, 0] - 1.0, P.X[:, 0] + 1.0])
+    cases = [
+        (variant(variables=["q", "zb", "t"]), "bestfit"),                                   # gradient_bestfit knows q and zb only
+        (variant(variables=["q", "zb", "t"]), "loadpath"),
+        (variant(variables=["q", "zb"]), "Ecomp-linear"),                                   # no dXb on the problem
+        (variant(variables=["q", "xyb", "zb"], constraints=["funicular", "envelope"]), "min"),          # xyb needs envelopexy too
+        (variant(variables=["q", "xyb", "zb"], constraints=["funicular", "envelopexy", "envelope"]), "min"),  # no xlimits
+        (variant(variables=["q", "xyb", "zb"], constraints=["funicular", "envelopexy", "envelope"], xlimits=lim, ylimits=lim), "bestfit"),
+        (variant(variables=["q", "zb", "tub"]), "min"),                                     # not accelerated at all
+        (variant(constraints=["funicular", "envelope", "displ_map"]), "min"),
+        (variant(features=["sym"]), "min"),
+        (P, "Ecomp-complete"),
+    ]
+    for prob, obj in cases:
+        with pytest.raises(NotImplementedError):
+            TnoPlan(prob, objective=obj)
