@@ -167,6 +167,24 @@ def test_evaluate_batch_pipelined_slices_equal_the_single_call(tno):
     assert mixed["g"].is_cuda and not mixed["J"].is_cuda and torch.equal(mixed["J"], single["J"])
 
 
+@pytest.mark.parametrize("kernel", ["interleaved", "onchip"])
+def test_strided_candidate_matrix_ldx(tno, kernel):
+    """x may be a view with a row stride larger than nvar (tno_eval_batch's ldx)."""
+    import torch
+    from compas_tno_b200.plan import TnoPlan
+    P, objective, xs, exp = load_case("cross14_q_zb_min")
+    plan = TnoPlan(P, objective=objective, kernel=kernel)
+    wide = torch.full((len(xs), plan.nvar + 5), float("nan"), dtype=torch.float64, device="cuda")
+    wide[:, : plan.nvar] = torch.from_numpy(xs).cuda()
+    view = wide[:, : plan.nvar]
+    assert view.stride(0) == plan.nvar + 5
+    got = plan.evaluate_device(view, ("f", "g", "J", "status"))
+    ref = plan.evaluate_device(torch.from_numpy(xs).cuda(), ("f", "g", "J", "status"))
+    for key in got:
+        assert torch.equal(got[key], ref[key]), key
+    assert rel_err(got["J"].cpu().numpy(), exp["J"]) < TOL_JAC
+
+
 def test_indefinite_candidate_is_flagged_not_fatal(tno):
     from compas_tno_b200.plan import TnoPlan
     P, objective, xs, _ = load_case("cross6_q_zb_min")
