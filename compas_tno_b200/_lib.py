@@ -15,7 +15,7 @@ CON_FUNICULAR, CON_ENVELOPE, CON_REAC_BOUNDS, CON_ENVELOPEXY = 1, 2, 4, 8
 OBJ_NONE, OBJ_MIN, OBJ_MAX, OBJ_T, OBJ_NEG_LAST, OBJ_BESTFIT, OBJ_FEASIBILITY, OBJ_LOADPATH = 0, 1, 2, 3, 4, 5, 6, 7
 OBJ_ECOMP_LINEAR, OBJ_ECOMP_NONLINEAR = 8, 9
 ENV_FIXED, ENV_DOME, ENV_CROSSVAULT = 0, 1, 2
-KERNEL_AUTO, KERNEL_INTERLEAVED, KERNEL_ONCHIP = 0, 1, 2
+KERNEL_AUTO, KERNEL_INTERLEAVED, KERNEL_ONCHIP, KERNEL_INTERLEAVED_TPC = 0, 1, 2, 3
 STATUS_OK, STATUS_NOT_PD, STATUS_NONFINITE = 0, 1, 2
 
 EXPORTS = [

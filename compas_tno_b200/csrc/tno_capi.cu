@@ -559,7 +559,8 @@ int tno_plan_create(const tno_problem_desc* D, tno_plan** out_plan) {
   I.solve_flops = (int64_t)4 * nnz_l * R.nrhs;
   P->kernel = TNO_KERNEL_INTERLEAVED;
   I.smem_bytes = 0;
-  if (D->kernel != TNO_KERNEL_INTERLEAVED) {
+  P->thread_per_candidate = D->kernel == TNO_KERNEL_INTERLEAVED_TPC;
+  if (D->kernel != TNO_KERNEL_INTERLEAVED && D->kernel != TNO_KERNEL_INTERLEAVED_TPC) {
     if ((rc = build_onchip(P, D))) return rc;
     if (P->onchip_ok) {
       P->kernel = TNO_KERNEL_ONCHIP;

@@ -992,9 +992,10 @@ int run_interleaved(Plan* PL, const double* x_dev, int64_t N, int64_t ldx, const
   double* ws = PL->scratch;
   int32_t* st = PL->status_scratch;
   const int TB = 128;
-  // level-scheduled factor / solves unless the developer knob asks for the thread-per-candidate originals
+  // level-scheduled factor / solves unless the plan (TNO_KERNEL_INTERLEAVED_TPC) or the developer knob asks for the
+  // thread-per-candidate originals
   static const bool v1 = getenv("TNO_INTERLEAVED_V1") != nullptr;
-  const bool levelled = !v1;
+  const bool levelled = !(v1 || PL->thread_per_candidate);
   if (levelled && !PL->lv_ready) {
     const int rc = build_levels(PL);
     if (rc) return rc;

@@ -283,6 +283,7 @@ struct Plan {
   int device = 0;
   int kernel = TNO_KERNEL_INTERLEAVED;
   bool auto_family = false;            // created with TNO_KERNEL_AUTO: large batches may go to the other family
+  bool thread_per_candidate = false;   // TNO_KERNEL_INTERLEAVED_TPC: the unscheduled factor / solve kernels
   std::vector<void*> dev_allocs;       // everything to cudaFree at destroy
   // emit tables
   EmitTable t_g, t_grad, t_z, t_q, t_J;   // t_J covers the rows below the funicular block when jfun is set

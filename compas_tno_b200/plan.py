@@ -24,7 +24,8 @@ _OBJ = {None: _lib.OBJ_NONE, "none": _lib.OBJ_NONE, "min": _lib.OBJ_MIN, "max": 
         "bestfit": _lib.OBJ_BESTFIT, "target": _lib.OBJ_BESTFIT, "feasibility": _lib.OBJ_FEASIBILITY,
         "loadpath": _lib.OBJ_LOADPATH, "Ecomp-linear": _lib.OBJ_ECOMP_LINEAR,
         "Ecomp-nonlinear": _lib.OBJ_ECOMP_NONLINEAR}
-_KERNELS = {"auto": _lib.KERNEL_AUTO, "interleaved": _lib.KERNEL_INTERLEAVED, "onchip": _lib.KERNEL_ONCHIP}
+_KERNELS = {"auto": _lib.KERNEL_AUTO, "interleaved": _lib.KERNEL_INTERLEAVED, "onchip": _lib.KERNEL_ONCHIP,
+            "interleaved_tpc": _lib.KERNEL_INTERLEAVED_TPC}
 _ORDERINGS = {"auto": 0, "natural": 1, "mindeg": 2, "nested": 3}
 
 ALL_OUTPUTS = ("f", "grad", "g", "J", "z", "q", "gmin", "status")

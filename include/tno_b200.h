@@ -85,8 +85,10 @@ extern "C" {
 
 /* kernel families (tno_problem_desc.kernel) */
 #define TNO_KERNEL_AUTO 0
-#define TNO_KERNEL_INTERLEAVED 1 /* thread per candidate, batch-interleaved scratch in HBM; any size */
+#define TNO_KERNEL_INTERLEAVED 1 /* batch-interleaved scratch in HBM, level-scheduled factor and solves; any size */
 #define TNO_KERNEL_ONCHIP 2      /* factor + right-hand sides resident in shared memory; size limited */
+#define TNO_KERNEL_INTERLEAVED_TPC 3 /* interleaved family with its original thread-per-candidate factor / solve kernels
+                                        (kept as an independent cross-check; slow on large problems) */
 
 /* per-candidate status bits */
 #define TNO_STATUS_OK 0

@@ -185,6 +185,22 @@ def test_strided_candidate_matrix_ldx(tno, kernel):
     assert rel_err(got["J"].cpu().numpy(), exp["J"]) < TOL_JAC
 
 
+@pytest.mark.parametrize("name", ["cross14_q_zb_min", "dome_q_zb_lambdh_reac", "cross14_q_xyb_zb_min", "dome_q_zb_t"])
+def test_thread_per_candidate_originals_still_agree(tno, name):
+    """kernel='interleaved_tpc' keeps the unscheduled right-looking factor and column-oriented solve of the first
+    version of the family: a third independent implementation of the numeric kernel."""
+    from compas_tno_b200.plan import TnoPlan
+    P, objective, xs, exp = load_case(name)
+    plan = TnoPlan(P, objective=objective, kernel="interleaved_tpc")
+    assert plan.info["kernel"] == 1
+    got = plan.evaluate_host(xs)
+    assert np.all(got["status"] == 0)
+    assert rel_err(got["z"], exp["X"][:, :, 2]) < TOL_VAL
+    assert rel_err(got["g"], exp["g"]) < TOL_VAL
+    assert rel_err(got["f"], exp["f"]) < TOL_VAL
+    assert rel_err(got["J"], exp["J"]) < TOL_JAC
+
+
 def test_indefinite_candidate_is_flagged_not_fatal(tno):
     from compas_tno_b200.plan import TnoPlan
     P, objective, xs, _ = load_case("cross6_q_zb_min")
