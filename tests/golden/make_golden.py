@@ -135,11 +135,11 @@ def run_case(ref, name, form, P, variables, constraints, objective, xs, thk, env
 
 def variables_offset(variables, P, name):
     pos = P.k
-    for v in ("zb", "t", "lambdh", "lambdv"):
+    for v in ("xyb", "zb", "t", "lambdh", "lambdv"):
         if v == name:
             return pos
         if v in variables:
-            pos += P.nb if v == "zb" else 1
+            pos += 2 * P.nb if v == "xyb" else (P.nb if v == "zb" else 1)
     raise KeyError(name)
 
 
@@ -189,6 +189,11 @@ def main():
     tail = lambda j, rng: np.array([0.5 if j == 0 else rng.uniform(0.3, 0.5)])  # noqa: E731
     xs = sample_points(rng, P, form, 3, tail)
     run_case(ref, "cross14_q_zb_t", form, P, ["q", "zb", "t"], ["funicular", "envelope"], "t", xs, 0.5, envelope=env)
+    # moving supports and a variable thickness together: the parametric envelope is evaluated at the moved x, y
+    xs_xt = np.array([np.concatenate([x[: P.k], xyb0 + (0.0 if j == 0 else 1.0) * rxy.uniform(-0.08, 0.08, size=xyb0.shape), x[P.k:]])
+                      for j, x in enumerate(xs)])
+    run_case(ref, "cross14_q_xyb_zb_t", form, P, ["q", "xyb", "zb", "t"], ["funicular", "envelopexy", "envelope"], "t", xs_xt, 0.5,
+             envelope=env, extra=lim)
 
     # ---- C: fan fixture ---------------------------------------------------------------------
     form = fixtures.load_form("fan_form.json")

@@ -20,18 +20,18 @@ CASES = [
     "dome_q_zb_lambdv",
     "freeform_q_zb_min",
     "cross14_q_zb_bestfit", "cross14_q_zb_feasibility", "cross14_q_zb_loadpath", "dome_q_zb_loadpath",
-    "cross14_q_zb_ecomp_nonlinear", "dome_q_zb_ecomp_linear", "cross14_q_xyb_zb_min",
+    "cross14_q_zb_ecomp_nonlinear", "dome_q_zb_ecomp_linear", "cross14_q_xyb_zb_min", "cross14_q_xyb_zb_t",
     "dome_q_zb_bestfit",
 ]
 
 
 def var_offset(variables, k, nb, name):
     pos = k
-    for v in ("zb", "t", "lambdh", "lambdv"):
+    for v in ("xyb", "zb", "t", "lambdh", "lambdv"):
         if v == name:
             return pos
         if v in variables:
-            pos += nb if v == "zb" else 1
+            pos += 2 * nb if v == "xyb" else (nb if v == "zb" else 1)
     raise KeyError(name)
 
 
