@@ -150,7 +150,6 @@ int tno_plan_create(const tno_problem_desc* D, tno_plan** out_plan) {
     // the reference stacks the xyb columns against the envelopexy AND envelope row blocks (jacobian.py:269-273)
     if ((D->variables & TNO_VAR_XYB) && (D->constraints & (TNO_CON_ENVELOPEXY | TNO_CON_ENVELOPE)) != (TNO_CON_ENVELOPEXY | TNO_CON_ENVELOPE))
       return fail(TNO_EINVAL, "xyb variables need the envelopexy and envelope constraints");
-    if (D->constraints & TNO_CON_REAC_BOUNDS) return fail(TNO_EINVAL, "reac_bounds with xyb / envelopexy is not available");
     if (D->variables & (TNO_VAR_LAMBDH | TNO_VAR_LAMBDV)) return fail(TNO_EINVAL, "load multipliers with xyb / envelopexy are not available");
     if (D->objective > TNO_OBJ_NEG_LAST && D->objective != TNO_OBJ_FEASIBILITY)
       return fail(TNO_EINVAL, "xyb / envelopexy support the objectives min, max, t, n, feasibility");

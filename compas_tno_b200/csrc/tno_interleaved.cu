@@ -628,6 +628,10 @@ __global__ void k_epilogue(DevPlan P, double* __restrict__ ws, int64_t NC, int64
               // (C dz)_e with dz_b = 0:  head - tail
               dRz = fma(sg * qe, sg > 0 ? -dzo : dzo, dRz);
             }
+            if (P.rhs.c_qx >= 0 && ro >= 0) {  // + Cb^T Q C dx/dq_ind, dy/dq_ind (formed with 'envelopexy', jacobian.py:206-207)
+              dRx = fma(-qe, WS(P.slot.s_r + ro * nrhs + P.rhs.c_qx + j), dRx);
+              dRy = fma(-qe, WS(P.slot.s_r + ro * nrhs + P.rhs.c_qy + j), dRy);
+            }
           }
           WS(rowx + j) = zb * sx * (-Rz * dRx + Rx * dRz) / rz2 / sz;
           WS(rowy + j) = zb * sy * (-Rz * dRy + Ry * dRz) / rz2 / sz;

@@ -211,6 +211,14 @@ def main():
     run_case(ref, "dome_q_zb_reac_min", form, P, ["q", "zb"], ["funicular", "envelope", "reac_bounds"], "min",
              xs, thk, extra={"b": form["b"]})
 
+    xyb0d = form["xyz"][P.fixed, :2].flatten("F")
+    rxyd = np.random.default_rng(SEED + 79)
+    xs_d = np.array([np.concatenate([x[: P.k], xyb0d + (0.0 if j == 0 else 1.0) * rxyd.uniform(-0.05, 0.05, size=xyb0d.shape), x[P.k:]])
+                     for j, x in enumerate(xs[:2])])
+    limd = {"xlimits": np.column_stack([form["xyz"][:, 0] - 0.3, form["xyz"][:, 0] + 0.3]),
+            "ylimits": np.column_stack([form["xyz"][:, 1] - 0.3, form["xyz"][:, 1] + 0.3]), "b": form["b"]}
+    run_case(ref, "dome_q_xyb_zb_reac_min", form, P, ["q", "xyb", "zb"], ["funicular", "envelopexy", "envelope", "reac_bounds"], "min",
+             xs_d, thk, extra=limd)
     run_case(ref, "dome_q_zb_loadpath", form, P, ["q", "zb"], ["funicular", "envelope"], "loadpath", xs[:2], thk)
     out = form["xyz"][P.fixed, :2] - np.array([5.0, 5.0])
     dXb = np.column_stack([out / np.linalg.norm(out, axis=1, keepdims=True), np.linspace(-0.4, 0.2, P.nb)])

@@ -20,7 +20,7 @@ CASES = [
     "dome_q_zb_lambdv",
     "freeform_q_zb_min",
     "cross14_q_zb_bestfit", "cross14_q_zb_feasibility", "cross14_q_zb_loadpath", "dome_q_zb_loadpath",
-    "cross14_q_zb_ecomp_nonlinear", "dome_q_zb_ecomp_linear", "cross14_q_xyb_zb_min", "cross14_q_xyb_zb_t",
+    "cross14_q_zb_ecomp_nonlinear", "dome_q_zb_ecomp_linear", "cross14_q_xyb_zb_min", "cross14_q_xyb_zb_t", "dome_q_xyb_zb_reac_min",
     "dome_q_zb_bestfit",
 ]
 
