@@ -33,7 +33,7 @@ def build(force=False, verbose=False):
         return LIB
     srcs = [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
     cmd = [
-        _nvcc(), "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
+        _nvcc(), "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "--threads", "4",
         "-Xcompiler", "-fPIC,-O3", "-shared", "-Xptxas", "-v" if verbose else "-O3",
         "-o", LIB,
     ] + srcs
