@@ -417,6 +417,10 @@ def run_ours(args):
                     "traffic": traffic, "peak_source": peak_src, "kernel_share_of_step": kms / total_kernel_ms,
                     "bytes_per_eval": bytes_per_eval, "evals_per_launch": evals_per_launch,
                     "kernel_durations_from": profile_pass,
+                    # secondary bound (north_star: "fraction of the HBM or FP64 roofline"): algorithmic flops of SURVEY 8d
+                    "fp64": (lambda fl: {"flops_per_eval": fl, "achieved_tflops": value / world * fl / 1e12, "peak_tflops": 40.0,
+                                         "peak_source": "nominal B200 FP64 (not measured)", "frac": value / world * fl / 1e12 / 40.0})(
+                        int(info["factor_flops"] + info["solve_flops"] + 6 * plan.m * plan.k + 8 * plan.m)),
                     "whole_step": {"bytes_per_eval": B_alg, "achieved": value / world * B_alg / 1e9,
                                    "frac": value / world * B_alg / 1e9 / peak},
                     "kernels": per_kernel}
