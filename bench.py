@@ -302,6 +302,8 @@ def run_ours(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    # host threads of the Jacobian fetch: the ranks of one box share its cores
+    os.environ.setdefault("TNO_HOST_THREADS", str(max(2, min(16, (os.cpu_count() or 16) // world))))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback); use --impl reference for the CPU arm")
     torch.cuda.set_device(local)

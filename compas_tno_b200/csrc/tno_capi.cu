@@ -802,8 +802,11 @@ int tno_fetch_jacobian_host(tno_plan* plan, const double* J_dev, double* J_host,
   }
   TNO_CUDA_OK(cudaMemcpy2DAsync(J_host + cst, per * 8, J_dev + cst, per * 8, (per - cst) * 8, (size_t)N, cudaMemcpyDeviceToHost, s));
   // constant rows: plain memcpy from the plan's host copy, candidates split over a few threads
+  // up to 16 threads, or TNO_HOST_THREADS (one process per GPU on a shared host: cores / ranks)
+  static const char* env_threads = getenv("TNO_HOST_THREADS");
   const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
-  const int64_t nthreads = std::max<int64_t>(1, std::min<int64_t>({(int64_t)hw, (int64_t)16, N / 64 + 1}));
+  const int64_t cap = env_threads ? std::max(1, atoi(env_threads)) : 16;
+  const int64_t nthreads = std::max<int64_t>(1, std::min<int64_t>({(int64_t)hw, cap, N / 64 + 1}));
   const double* src = P->h_jfun.data();
   auto work = [=](int64_t a, int64_t b) {
     for (int64_t c = a; c < b; ++c) copy_streaming(J_host + (size_t)c * per, src, cst);
