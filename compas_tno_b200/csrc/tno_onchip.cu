@@ -1876,8 +1876,9 @@ int run_onchip(Plan* PL, const double* x_dev, int64_t N, int64_t ldx, const tno_
   const int ctas = force_ctas ? std::max(1, atoi(force_ctas)) : PL->onchip_ctas_per_sm;
   const int grid = (int)std::min<int64_t>(N, (int64_t)PL->sm_count * ctas);
   const int threads = PL->onchip_threads;
-  auto kern = (A.dir || A.bounds) ? (threads == 512 ? k_onchip<512, 1, true> : (PL->onchip_ctas_per_sm >= 2 ? k_onchip<256, 2, true> : k_onchip<256, 1, true>))
-                    : (threads == 512 ? k_onchip<512, 1, false> : (PL->onchip_ctas_per_sm >= 2 ? k_onchip<256, 2, false> : k_onchip<256, 1, false>));
+  // <256, 2>: two CTAs per SM (the common case; also serves the rare 256-thread single-CTA fallback), <512, 1> otherwise
+  auto kern = (A.dir || A.bounds) ? (threads == 512 ? k_onchip<512, 1, true> : k_onchip<256, 2, true>)
+                                  : (threads == 512 ? k_onchip<512, 1, false> : k_onchip<256, 2, false>);
   TNO_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   if (out->J && PL->dp.con.r_fun >= 0)
     launch_fill_funicular(PL, PL->oc.Jfun, (int64_t)2 * PL->dp.m * PL->dp.var.nvar, out->J, N, stream);
