@@ -29,20 +29,35 @@ def needs_build():
 
 
 def build(force=False, verbose=False):
+    """Compile every translation unit (in parallel, one nvcc process each) and link the shared library."""
     if not force and not needs_build():
         return LIB
-    srcs = [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
-    cmd = [
-        _nvcc(), "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "--threads", "4",
-        "-Xcompiler", "-fPIC,-O3", "-shared", "-Xptxas", "-v" if verbose else "-O3",
-        "-o", LIB,
-    ] + srcs
-    r = subprocess.run(cmd, capture_output=True, text=True)
+    from concurrent.futures import ThreadPoolExecutor
+    objdir = os.path.join(HERE, "..", "build", "obj")
+    os.makedirs(objdir, exist_ok=True)
+    srcs = [s for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
+    flags = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-Xcompiler", "-fPIC,-O3"]
+    if verbose:
+        flags += ["-Xptxas", "-v"]
+
+    def compile_one(src):
+        obj = os.path.join(objdir, os.path.splitext(src)[0] + ".o")
+        r = subprocess.run([_nvcc()] + flags + ["-c", os.path.join(CSRC, src), "-o", obj], capture_output=True, text=True)
+        return src, obj, r
+
+    with ThreadPoolExecutor(max_workers=len(srcs)) as pool:
+        results = list(pool.map(compile_one, srcs))
+    for src, _, r in results:
+        if r.returncode != 0:
+            sys.stderr.write(r.stdout + r.stderr)
+            raise RuntimeError("nvcc failed on %s" % src)
+        if verbose:
+            sys.stderr.write(r.stderr)
+    r = subprocess.run([_nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + [o for _, o, _ in results],
+                       capture_output=True, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)
-        raise RuntimeError("nvcc failed")
-    if verbose:
-        sys.stderr.write(r.stderr)
+        raise RuntimeError("nvcc link failed")
     return LIB
 
 
