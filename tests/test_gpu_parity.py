@@ -201,6 +201,44 @@ def test_thread_per_candidate_originals_still_agree(tno, name):
     assert rel_err(got["J"], exp["J"]) < TOL_JAC
 
 
+@pytest.mark.parametrize("spec", [("cross", 6, "min"), ("cross", 9, "max"), ("cross", 13, "bestfit"), ("cross", 17, "loadpath"),
+                                  ("cross", 24, "min"), ("dome", (6, 8), "max"), ("dome", (11, 12), "min"), ("dome", (14, 10), "bestfit"),
+                                  ("cross_t", 12, "t"), ("dome_reac", (9, 10), "max")])
+def test_families_agree_on_generated_problems(tno, spec):
+    """Form diagrams of other sizes than the fixtures (different elimination trees, chain partitions, panel widths):
+    the on-chip family, the level-scheduled interleaved family and its thread-per-candidate original must agree on
+    every output, including the flags of candidates that are not compression-only."""
+    from compas_tno_b200 import workloads as W
+    from compas_tno_b200.plan import TnoPlan
+    kind, size, objective = spec
+    if kind == "cross":
+        P, xs = W.crossvault_problem(size, n_states=4)
+    elif kind == "cross_t":
+        P, xs = W.crossvault_problem(size, variables=("q", "zb", "t"), n_states=4)
+    elif kind == "dome":
+        P, xs = W.dome_problem(size[0], size[1], n_states=4)
+    else:
+        P, xs = W.dome_problem(size[0], size[1], constraints=("funicular", "envelope", "reac_bounds"), n_states=4)
+    N = 96
+    X = W.sample_candidates(P, xs, N, seed=sum(str(spec).encode()) % 1000, basis=P.candidate_basis)
+    X[5, : P.k] *= -1.0                       # tension: flagged, not fatal
+    X[17, 0] += 0.5 * abs(X[17, : P.k]).max()  # one independent edge pushed towards tension
+    res = {}
+    for kernel in ("onchip", "interleaved", "interleaved_tpc"):
+        plan = TnoPlan(P, objective=objective, kernel=kernel)
+        res[kernel] = plan.evaluate_host(X)
+        plan.close()
+    a = res["onchip"]
+    ok = a["status"] == 0
+    assert ok.sum() >= N - 2 and (a["status"][5] & 1)
+    for other in ("interleaved", "interleaved_tpc"):
+        b = res[other]
+        assert np.array_equal(a["status"] & 1, b["status"] & 1), other
+        for key, tol in (("q", TOL_VAL), ("z", TOL_VAL), ("g", TOL_VAL), ("f", TOL_VAL), ("grad", TOL_JAC), ("J", TOL_JAC)):
+            assert rel_err(a[key][ok], b[key][ok]) < tol, (other, key)
+        assert np.allclose(a["gmin"][ok], b["gmin"][ok], rtol=1e-9, atol=1e-9)
+
+
 def test_indefinite_candidate_is_flagged_not_fatal(tno):
     from compas_tno_b200.plan import TnoPlan
     P, objective, xs, _ = load_case("cross6_q_zb_min")
