@@ -401,6 +401,7 @@ __device__ __forceinline__ double xval(const DevPlan& P, const double* ws, int64
 }
 
 // phase-2 right-hand sides:  Ci^T W B  (k columns) and  Ci^T W d0  (lambdh column), W = diag(C z)
+constexpr int RHS2_JT = 32;   // columns per thread of k_rhs2 (= the launch's jtile)
 __global__ void k_rhs2(DevPlan P, double* __restrict__ ws, int64_t NC, int64_t ncand, int rtile, int jtile) {
   const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= ncand) return;
@@ -414,15 +415,25 @@ __global__ void k_rhs2(DevPlan P, double* __restrict__ ws, int64_t NC, int64_t n
     const int base = P.slot.s_r + r * nrhs;
     const double zv = WS(base + P.rhs.cz);
     const int a0 = P.vadj_ptr[v], a1 = P.vadj_ptr[v + 1];
-    for (int j = j0; j < j1; ++j) {
-      double acc = 0.0;
+    // edges outside, the (at most RHS2_JT) columns of the tile in registers: the end-point heights and the row of B of
+    // an edge are read once per edge instead of once per (edge, column)
+    {
+      double acc[RHS2_JT];
+#pragma unroll
+      for (int jj = 0; jj < RHS2_JT; ++jj) acc[jj] = 0.0;
       for (int t = a0; t < a1; ++t) {
         const double zo = zval(P, ws, NC, c, P.vadj_other[t]);
         const double sg = (double)P.vadj_sign[t];
         const double w = sg > 0 ? (zv - zo) : (zo - zv);  // (C z)_e
-        acc = fma(sg * w, P.B[(int64_t)P.vadj_edge[t] * k + j], acc);
+        const double sw = sg * w;
+        const double* Brow = P.B + (int64_t)P.vadj_edge[t] * k + j0;
+#pragma unroll
+        for (int jj = 0; jj < RHS2_JT; ++jj)
+          if (j0 + jj < j1) acc[jj] = fma(sw, Brow[jj], acc[jj]);
       }
-      WS(base + P.rhs.c_q + j) = acc;
+#pragma unroll
+      for (int jj = 0; jj < RHS2_JT; ++jj)
+        if (j0 + jj < j1) WS(base + P.rhs.c_q + j0 + jj) = acc[jj];
     }
     if (P.rhs.c_lambdh >= 0 && blockIdx.z == 0) {
       double acc = 0.0;
@@ -436,17 +447,24 @@ __global__ void k_rhs2(DevPlan P, double* __restrict__ ws, int64_t NC, int64_t n
     }
     if (P.rhs.c_qx >= 0) {  // Ci^T U B and Ci^T V B, U = diag(C x), V = diag(C y)  (jacobian.py:173-186)
       const double xv = WS(base + P.rhs.cx), yv = WS(base + P.rhs.cy);
-      for (int j = j0; j < j1; ++j) {
-        double ax = 0.0, ay = 0.0;
+#pragma unroll 1
+      for (int axis = 0; axis < 2; ++axis) {
+        const double cv = axis == 0 ? xv : yv;
+        double acc[RHS2_JT];
+#pragma unroll
+        for (int jj = 0; jj < RHS2_JT; ++jj) acc[jj] = 0.0;
         for (int t = a0; t < a1; ++t) {
-          const int o = P.vadj_other[t];
-          const double Bej = P.B[(int64_t)P.vadj_edge[t] * k + j];
           // C[e, v] (C x)_e = x_v - x_o whichever end v is
-          ax = fma(xv - xval(P, ws, NC, c, o, 0), Bej, ax);
-          ay = fma(yv - xval(P, ws, NC, c, o, 1), Bej, ay);
+          const double du = cv - xval(P, ws, NC, c, P.vadj_other[t], axis);
+          const double* Brow = P.B + (int64_t)P.vadj_edge[t] * k + j0;
+#pragma unroll
+          for (int jj = 0; jj < RHS2_JT; ++jj)
+            if (j0 + jj < j1) acc[jj] = fma(du, Brow[jj], acc[jj]);
         }
-        WS(base + P.rhs.c_qx + j) = ax;
-        WS(base + P.rhs.c_qy + j) = ay;
+        const int cq = axis == 0 ? P.rhs.c_qx : P.rhs.c_qy;
+#pragma unroll
+        for (int jj = 0; jj < RHS2_JT; ++jj)
+          if (j0 + jj < j1) WS(base + cq + j0 + jj) = acc[jj];
       }
     }
   }
@@ -1084,7 +1102,7 @@ int run_interleaved(Plan* PL, const double* x_dev, int64_t N, int64_t ldx, const
     const bool need2 = P.rhs.nrhs2 > 0 && (out->J != nullptr || (P.objective >= TNO_OBJ_BESTFIT && P.objective != TNO_OBJ_FEASIBILITY && out->grad != nullptr) ||
                                             (P.rhs.c_qx >= 0 && P.var.o_xyb >= 0 && out->grad != nullptr));
     if (need2) {
-      const int jtile = 32;
+      const int jtile = RHS2_JT;
       LAUNCH(KK_RHS2, k_rhs2, dim3((unsigned)((nc + TB - 1) / TB), (unsigned)gyr, (unsigned)((P.k + jtile - 1) / jtile)), TB, P, ws, NC, nc, rtile, jtile);
       if (levelled)
         solve_levelled(KK_SOLVE2, P.rhs.nrhs1, P.rhs.nrhs2);
