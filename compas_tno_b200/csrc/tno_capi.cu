@@ -686,10 +686,10 @@ int tno_eval_batch(tno_plan* plan, const double* x_dev, int64_t N, int64_t ldx, 
   TNO_CUDA_OK(cudaSetDevice(P->device));
   bool onchip = P->kernel == TNO_KERNEL_ONCHIP;
   if (onchip && P->auto_family && P->onchip_ctas_per_sm == 1) {
-    // one resident candidate per SM: beyond ~8k candidates the level-scheduled interleaved family is faster
-    // (dome 16x20, B200: 12.4 vs 11.4 ms at 8192, 24.6 vs 19.1 ms at 16384; 6.3 vs 8.0 ms at 4096)
+    // one resident candidate per SM: beyond ~6k candidates the level-scheduled interleaved family is faster
+    // (dome 16x20, B200: 12.4 vs 10.5 ms at 8192, 24.5 vs 17.8 ms at 16384; 6.2 vs 7.2 ms at 4096)
     static const char* env = getenv("TNO_AUTO_SWITCH_N");
-    const int64_t thr = env ? atoll(env) : 8192;
+    const int64_t thr = env ? atoll(env) : 6144;
     if (N >= thr) onchip = false;
   }
   P->info.last_kernel = onchip ? TNO_KERNEL_ONCHIP : TNO_KERNEL_INTERLEAVED;

@@ -159,7 +159,7 @@ typedef struct tno_plan_info {
   int64_t smem_bytes;      /* dynamic shared memory per CTA of the main kernel */
   int32_t last_kernel;     /* TNO_KERNEL_* the most recent tno_eval_batch ran (0 before the first call).  A plan created
                               with TNO_KERNEL_AUTO whose on-chip layout leaves room for one CTA per SM only hands batches
-                              of >= 8192 candidates to the interleaved family, which is faster there */
+                              of >= 6144 candidates to the interleaved family, which is faster there */
   int32_t onchip_ctas_per_sm;
 } tno_plan_info;
 

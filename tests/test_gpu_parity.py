@@ -326,7 +326,7 @@ def test_output_subsets_skip_the_sensitivity_solve(tno, name, kernel):
 
 
 def test_auto_plan_hands_large_batches_to_the_interleaved_family(tno):
-    """A plan created with kernel='auto' whose on-chip layout fits one CTA per SM only runs batches of >= 8192
+    """A plan created with kernel='auto' whose on-chip layout fits one CTA per SM only runs batches of >= 6144
     candidates on the level-scheduled interleaved family (faster there); both families agree to rounding."""
     from compas_tno_b200 import workloads as W
     from compas_tno_b200.plan import TnoPlan
