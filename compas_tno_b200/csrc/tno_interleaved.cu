@@ -849,39 +849,42 @@ __global__ void k_epilogue(DevPlan P, double* __restrict__ ws, int64_t NC, int64
 //   grad_j = sum_b  cx_b (Cb^T U B + Cb^T Q C dx/dq_ind)[b, j] + cy_b (Cb^T V B + Cb^T Q C dy/dq_ind)[b, j]
 // with cx_b = +-Rx_b / |R_h,b|, cy_b likewise (left in the scratch by k_epilogue).  One thread per candidate and tile of
 // columns, so that problems with hundreds of independents do not serialise k x nb x degree terms in one thread.
+constexpr int TG_JT = 16;   // columns per thread of k_thrust_grad (= the launch's jtile)
 __global__ void k_thrust_grad(DevPlan P, double* __restrict__ ws, int64_t NC, int64_t ncand, int jtile) {
   const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= ncand) return;
   const int k = P.k, nb = P.nb, nrhs = P.rhs.nrhs;
   const int j0 = blockIdx.y * jtile, j1 = min(k, j0 + jtile);
-  for (int j = j0; j < j1; ++j) {
-    double acc = 0.0;
-    for (int b = 0; b < nb; ++b) {
-      const int vb = P.fixed[b];
-      const double xb = xyfixed(P, ws, NC, c, b, 0), yb = xyfixed(P, ws, NC, c, b, 1);
-      double gx = 0.0, gy = 0.0;
-      for (int t = P.vadj_ptr[vb]; t < P.vadj_ptr[vb + 1]; ++t) {
-        const int o = P.vadj_other[t];
-        const double sg = (double)P.vadj_sign[t];
-        const double xo = xval(P, ws, NC, c, o, 0), yo = xval(P, ws, NC, c, o, 1);
-        const double u = sg > 0 ? (xb - xo) : (xo - xb);
-        const double vv = sg > 0 ? (yb - yo) : (yo - yb);
-        const double Bej = P.B[(int64_t)P.vadj_edge[t] * k + j];
-        gx = fma(sg * u, Bej, gx);
-        gy = fma(sg * vv, Bej, gy);
-        if (P.rhs.c_qx >= 0) {  // + Cb^T Q C dx/dq_ind: the free neighbours move with q once the supports do
-          const int ro = P.vrow[o];
-          if (ro >= 0) {
-            const double qe = WS(P.slot.s_q + P.vadj_edge[t]);
-            gx = fma(-qe, WS(P.slot.s_r + ro * nrhs + P.rhs.c_qx + j), gx);
-            gy = fma(-qe, WS(P.slot.s_r + ro * nrhs + P.rhs.c_qy + j), gy);
-          }
-        }
+  // edge terms outside, the columns of the tile in registers: the geometry of a support edge is read once
+  double acc[TG_JT];
+#pragma unroll
+  for (int jj = 0; jj < TG_JT; ++jj) acc[jj] = 0.0;
+  for (int b = 0; b < nb; ++b) {
+    const int vb = P.fixed[b];
+    const double xb = xyfixed(P, ws, NC, c, b, 0), yb = xyfixed(P, ws, NC, c, b, 1);
+    const double cx = WS(P.slot.s_cxy + b), cy = WS(P.slot.s_cxy + nb + b);
+    for (int t = P.vadj_ptr[vb]; t < P.vadj_ptr[vb + 1]; ++t) {
+      const int o = P.vadj_other[t];
+      const int e = P.vadj_edge[t];
+      // C[e, vb] (C x)_e = x_b - x_o whichever end the support is
+      const double coef = cx * (xb - xval(P, ws, NC, c, o, 0)) + cy * (yb - xval(P, ws, NC, c, o, 1));
+      const double* Brow = P.B + (int64_t)e * k + j0;
+#pragma unroll
+      for (int jj = 0; jj < TG_JT; ++jj)
+        if (j0 + jj < j1) acc[jj] = fma(coef, Brow[jj], acc[jj]);
+      const int ro = P.vrow[o];
+      if (P.rhs.c_qx >= 0 && ro >= 0) {  // + Cb^T Q C dx/dq_ind: the free neighbours move with q once the supports do
+        const double qe = WS(P.slot.s_q + e);
+        const int bx = P.slot.s_r + ro * nrhs + P.rhs.c_qx + j0, by = P.slot.s_r + ro * nrhs + P.rhs.c_qy + j0;
+#pragma unroll
+        for (int jj = 0; jj < TG_JT; ++jj)
+          if (j0 + jj < j1) acc[jj] = fma(-qe, cx * WS(bx + jj) + cy * WS(by + jj), acc[jj]);
       }
-      acc += WS(P.slot.s_cxy + b) * gx + WS(P.slot.s_cxy + nb + b) * gy;
     }
-    WS(P.slot.s_grad + j) = acc;
   }
+#pragma unroll
+  for (int jj = 0; jj < TG_JT; ++jj)
+    if (j0 + jj < j1) WS(P.slot.s_grad + j0 + jj) = acc[jj];
 }
 
 // Per-candidate envelope: g[r_env + v] = z_v - lb_v, g[r_env + n + v] = ub_v - z_v with the candidate's own bounds.
@@ -1112,7 +1115,7 @@ int run_interleaved(Plan* PL, const double* x_dev, int64_t N, int64_t ldx, const
     LAUNCH(KK_EPILOGUE, k_epilogue, grid1(nc, TB), TB, P, ws, NC, nc, out->f ? out->f + c0 : nullptr,
            out->gmin ? out->gmin + c0 : nullptr, st, bnd);
     if (out->grad && (P.objective == TNO_OBJ_MIN || P.objective == TNO_OBJ_MAX)) {
-      const int jtile = 16;
+      const int jtile = TG_JT;
       LAUNCH(KK_EPILOGUE, k_thrust_grad, grid1(nc, TB, (P.k + jtile - 1) / jtile), TB, P, ws, NC, nc, jtile);
     }
     // stride = elements per candidate of the user-facing array, offset = first element the table describes
