@@ -1,5 +1,5 @@
 """Fill-reducing ordering (minimum degree vs geometric nested dissection) against step time, interleaved family."""
-import os, sys, numpy as np, torch
+import os, sys, torch
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
 from bench import build_workload, candidates
 from compas_tno_b200.plan import TnoPlan

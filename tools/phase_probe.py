@@ -1,4 +1,4 @@
-import sys, os, numpy as np, torch
+import sys, os, torch
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), '..'))
 from bench import build_workload, candidates
 from compas_tno_b200.plan import TnoPlan
