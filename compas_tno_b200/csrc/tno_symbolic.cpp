@@ -29,7 +29,9 @@ Adj build_adjacency(int n, const std::vector<std::pair<int, int>>& edges) {
 
 // Exact minimum (external) degree on the explicit elimination graph.  The graphs here have a few
 // thousand vertices of degree <= 8, so the quadratic selection loop is irrelevant next to one pinv.
-std::vector<int> order_mindeg(const Adj& adj0, const std::vector<int>& subset) {
+// tie_break 0: first vertex of minimum degree; 1: among those, the one whose elimination creates the least fill
+// (minimum deficiency).  fill_out (optional) receives nnz(L) of the ordering, diagonal included.
+std::vector<int> order_mindeg(const Adj& adj0, const std::vector<int>& subset, int tie_break = 0, int64_t* fill_out = nullptr) {
   const int n = (int)adj0.size();
   std::vector<char> in(n, 0), done(n, 0);
   for (int v : subset) in[v] = 1;
@@ -40,6 +42,16 @@ std::vector<int> order_mindeg(const Adj& adj0, const std::vector<int>& subset) {
   std::vector<int> order;
   order.reserve(subset.size());
   std::vector<int> merged;
+  int64_t nnz = 0;
+  auto deficiency = [&](int v) {
+    // pairs of neighbours of v that are not adjacent yet
+    const std::vector<int>& nb = adj[v];
+    int64_t miss = 0;
+    for (size_t a = 0; a < nb.size(); ++a)
+      for (size_t b = a + 1; b < nb.size(); ++b)
+        if (!std::binary_search(adj[nb[a]].begin(), adj[nb[a]].end(), nb[b])) ++miss;
+    return miss;
+  };
   for (size_t step = 0; step < subset.size(); ++step) {
     int best = -1;
     size_t bestdeg = (size_t)-1;
@@ -50,9 +62,22 @@ std::vector<int> order_mindeg(const Adj& adj0, const std::vector<int>& subset) {
         best = v;
       }
     }
+    if (tie_break == 1 && bestdeg > 1) {
+      int64_t bestmiss = -1;
+      for (int v : subset) {
+        if (done[v] || adj[v].size() != bestdeg) continue;
+        const int64_t miss = deficiency(v);
+        if (bestmiss < 0 || miss < bestmiss) {
+          bestmiss = miss;
+          best = v;
+          if (miss == 0) break;
+        }
+      }
+    }
     const int v = best;
     done[v] = 1;
     order.push_back(v);
+    nnz += 1 + (int64_t)adj[v].size();
     const std::vector<int> nb = adj[v];
     for (int u : nb) {
       merged.clear();
@@ -62,6 +87,7 @@ std::vector<int> order_mindeg(const Adj& adj0, const std::vector<int>& subset) {
     }
     adj[v].clear();
   }
+  if (fill_out) *fill_out = nnz;
   return order;
 }
 
@@ -184,7 +210,11 @@ void analyse(int ni, const std::vector<std::pair<int, int>>& edges, int ordering
   } else if (ordering == ORD_NESTED && coords != nullptr) {
     order_nested(adj, coords, all, 12, &order);
   } else {
-    order = order_mindeg(adj, all);
+    // minimum degree with two tie-breaking rules: keep the ordering with the smaller factor
+    int64_t f0 = 0, f1 = 0;
+    std::vector<int> o0 = order_mindeg(adj, all, 0, &f0);
+    std::vector<int> o1 = order_mindeg(adj, all, 1, &f1);
+    order = (f1 < f0) ? o1 : o0;
   }
 
   auto permuted_adj = [&](const std::vector<int>& ord) {
