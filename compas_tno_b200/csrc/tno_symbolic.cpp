@@ -30,7 +30,8 @@ Adj build_adjacency(int n, const std::vector<std::pair<int, int>>& edges) {
 // Exact minimum (external) degree on the explicit elimination graph.  The graphs here have a few
 // thousand vertices of degree <= 8, so the quadratic selection loop is irrelevant next to one pinv.
 // tie_break 0: first vertex of minimum degree; 1: among those, the one whose elimination creates the least fill
-// (minimum deficiency).  fill_out (optional) receives nnz(L) of the ordering, diagonal included.
+// (minimum deficiency); 2: minimum deficiency among the vertices within two of the minimum degree (degree breaks ties).
+// fill_out (optional) receives nnz(L) of the ordering, diagonal included.
 std::vector<int> order_mindeg(const Adj& adj0, const std::vector<int>& subset, int tie_break = 0, int64_t* fill_out = nullptr) {
   const int n = (int)adj0.size();
   std::vector<char> in(n, 0), done(n, 0);
@@ -62,15 +63,18 @@ std::vector<int> order_mindeg(const Adj& adj0, const std::vector<int>& subset, i
         best = v;
       }
     }
-    if (tie_break == 1 && bestdeg > 1) {
+    if (tie_break >= 1 && bestdeg > 1) {
+      const size_t slack = tie_break == 2 ? 2 : 0;
       int64_t bestmiss = -1;
+      size_t missdeg = 0;
       for (int v : subset) {
-        if (done[v] || adj[v].size() != bestdeg) continue;
+        if (done[v] || adj[v].size() > bestdeg + slack) continue;
         const int64_t miss = deficiency(v);
-        if (bestmiss < 0 || miss < bestmiss) {
+        if (bestmiss < 0 || miss < bestmiss || (miss == bestmiss && adj[v].size() < missdeg)) {
           bestmiss = miss;
+          missdeg = adj[v].size();
           best = v;
-          if (miss == 0) break;
+          if (miss == 0 && missdeg == bestdeg) break;
         }
       }
     }
@@ -210,11 +214,17 @@ void analyse(int ni, const std::vector<std::pair<int, int>>& edges, int ordering
   } else if (ordering == ORD_NESTED && coords != nullptr) {
     order_nested(adj, coords, all, 12, &order);
   } else {
-    // minimum degree with two tie-breaking rules: keep the ordering with the smaller factor
-    int64_t f0 = 0, f1 = 0;
-    std::vector<int> o0 = order_mindeg(adj, all, 0, &f0);
-    std::vector<int> o1 = order_mindeg(adj, all, 1, &f1);
-    order = (f1 < f0) ? o1 : o0;
+    // minimum degree with three tie-breaking / look-aside rules: keep the ordering with the smallest factor
+    int64_t fbest = 0;
+    order = order_mindeg(adj, all, 0, &fbest);
+    for (int rule = 1; rule <= 2; ++rule) {
+      int64_t f = 0;
+      std::vector<int> o = order_mindeg(adj, all, rule, &f);
+      if (f < fbest) {
+        fbest = f;
+        order.swap(o);
+      }
+    }
   }
 
   auto permuted_adj = [&](const std::vector<int>& ord) {
