@@ -1,4 +1,4 @@
-"""Small run of every objective / variable combination through both kernel families, for compute-sanitizer."""
+"""Small run of every objective / variable combination through both kernel families (a quick end-to-end probe; also the command to put under compute-sanitizer where that tool is available)."""
 import os, sys, numpy as np
 ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
