@@ -9,7 +9,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libtno_b200.so")
-SOURCES = ["tno_capi.cu", "tno_interleaved.cu", "tno_onchip.cu", "tno_symbolic.cpp"]
+SOURCES = ["tno_capi.cu", "tno_interleaved.cu", "tno_onchip.cu", "tno_util.cu", "tno_symbolic.cpp"]
 HEADERS = ["tno_plan.hpp", "tno_symbolic.hpp", os.path.join("..", "..", "include", "tno_b200.h")]
 
 
@@ -20,18 +20,52 @@ def _nvcc():
     return exe
 
 
+STAMP = os.path.join(HERE, "libtno_b200.srchash")
+
+
+def source_hash():
+    """sha1 over the sources and headers the library is built from (content, not mtime: the tree is copied to the GPU
+    box, which does not keep time stamps in order)."""
+    import hashlib
+    h = hashlib.sha1()
+    for name in SOURCES + HEADERS:
+        path = os.path.join(CSRC, name)
+        if os.path.exists(path):
+            h.update(name.encode())
+            with open(path, "rb") as fh:
+                h.update(fh.read())
+    return h.hexdigest()
+
+
 def needs_build():
     if not os.path.exists(LIB):
         return True
-    t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, s) for s in SOURCES + HEADERS]
-    return any(os.path.exists(d) and os.path.getmtime(d) > t for d in deps)
+    try:
+        with open(STAMP) as fh:
+            return fh.read().strip() != source_hash()
+    except OSError:
+        return True
 
 
 def build(force=False, verbose=False):
     """Compile every translation unit (in parallel, one nvcc process each) and link the shared library."""
     if not force and not needs_build():
         return LIB
+    import fcntl
+    from concurrent.futures import ThreadPoolExecutor
+    # one build at a time: the ranks of a torchrun job and the workers of pytest-xdist share this directory
+    lock = open(os.path.join(HERE, ".build.lock"), "w")
+    fcntl.flock(lock, fcntl.LOCK_EX)
+    try:
+        if not force and not needs_build():
+            return LIB
+        return _build_locked(verbose)
+    finally:
+        fcntl.flock(lock, fcntl.LOCK_UN)
+        lock.close()
+
+
+def _build_locked(verbose):
     from concurrent.futures import ThreadPoolExecutor
     objdir = os.path.join(HERE, "..", "build", "obj")
     os.makedirs(objdir, exist_ok=True)
@@ -53,11 +87,15 @@ def build(force=False, verbose=False):
             raise RuntimeError("nvcc failed on %s" % src)
         if verbose:
             sys.stderr.write(r.stderr)
-    r = subprocess.run([_nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + [o for _, o, _ in results],
+    tmp = LIB + ".tmp.%d" % os.getpid()
+    r = subprocess.run([_nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", tmp] + [o for _, o, _ in results],
                        capture_output=True, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)
         raise RuntimeError("nvcc link failed")
+    os.replace(tmp, LIB)                 # atomic: a process that is loading the old library keeps its mapping
+    with open(STAMP, "w") as fh:
+        fh.write(source_hash())
     return LIB
 
 

@@ -21,7 +21,7 @@ STATUS_OK, STATUS_NOT_PD, STATUS_NONFINITE = 0, 1, 2
 EXPORTS = [
     "tno_abi_version", "tno_last_error", "tno_plan_create", "tno_plan_destroy", "tno_plan_query",
     "tno_plan_symbolic", "tno_eval_batch", "tno_eval_batch_host", "tno_plan_launch_count",
-    "tno_plan_profile", "tno_plan_profile_read", "tno_symbolic_analyse", "tno_fetch_jacobian_host",
+    "tno_plan_profile", "tno_plan_profile_read", "tno_symbolic_analyse", "tno_fetch_jacobian_host", "tno_device_peak",
 ]
 
 _dp = C.POINTER(C.c_double)
@@ -68,13 +68,17 @@ _lib = None
 
 
 def load():
-    """Load libtno_b200.so (building it first if the sources are newer).  No fallback."""
+    """Load libtno_b200.so, building it first when it is missing or when the sources changed since it was built
+    (content hash recorded beside the library, see _build.needs_build; TNO_REBUILD=1 forces a build,
+    TNO_NO_AUTOBUILD=1 loads whatever is there).  No fallback."""
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH) or os.environ.get("TNO_REBUILD") == "1":
-        from ._build import build
+    from ._build import build, needs_build
+    if os.environ.get("TNO_REBUILD") == "1":
         build(force=True)
+    elif not os.path.exists(LIB_PATH) or (os.environ.get("TNO_NO_AUTOBUILD") != "1" and needs_build()):
+        build(force=False)
     if not os.path.exists(LIB_PATH):
         raise RuntimeError("compas_tno_b200: CUDA library %s is missing and could not be built; "
                            "there is no CPU fallback" % LIB_PATH)
@@ -105,6 +109,8 @@ def load():
     lib.tno_symbolic_analyse.argtypes = [C.c_int32, C.c_int32, _ip, C.c_int32, C.c_int32, _ip, _ip, _ip, C.c_int32, _ip, _ip,
                                          C.c_int32, _ip]
     lib.tno_symbolic_analyse.restype = C.c_int
+    lib.tno_device_peak.argtypes = [C.c_int32, C.c_int32, _dp]
+    lib.tno_device_peak.restype = C.c_int
     if lib.tno_abi_version() != ABI_VERSION:
         raise RuntimeError("libtno_b200.so ABI %d != binding ABI %d" % (lib.tno_abi_version(), ABI_VERSION))
     _lib = lib
@@ -118,9 +124,18 @@ class TnoError(RuntimeError):
 def check(rc):
     if rc != 0:
         msg = load().tno_last_error().decode("utf-8", "replace")
-        if rc == -1:
-            raise NotImplementedError("tno_b200: " + msg)  # mirrors the reference's NotImplementedError
+        if rc == -5:   # TNO_EUNSUPPORTED: the reference raises NotImplementedError for its unsupported combinations
+            raise NotImplementedError("tno_b200: " + msg)
+        if rc == -1:   # TNO_EINVAL: a plain argument error
+            raise ValueError("tno_b200: " + msg)
         raise TnoError("tno_b200 error %d: %s" % (rc, msg))
+
+
+def device_peak(what="fp64_fma", device=0):
+    """TFLOP/s of the FP64 FMA pipe ("fp64_fma") or the FP64 tensor-core instruction ("fp64_mma"), measured in place."""
+    v = C.c_double(0.0)
+    check(load().tno_device_peak(int(device), {"fp64_fma": 0, "fp64_mma": 1}[what], C.byref(v)))
+    return float(v.value)
 
 
 def symbolic_analyse(n_free, edges, ordering=0, chain_width=4):

@@ -88,6 +88,8 @@ int ensure_scratch(Plan* P, int64_t N) {
   const int64_t budget = (int64_t)6 << 30;
   int64_t cmax = std::max<int64_t>(128, (budget / per_cand) / 128 * 128);
   cmax = std::min<int64_t>(cmax, 65536);
+  if (const char* cap = getenv("TNO_CHUNK_MAX"))   // test knob: small chunks make a modest batch cross chunk boundaries
+    cmax = std::max<int64_t>(128, std::min<int64_t>(cmax, atoll(cap) / 128 * 128));
   int64_t want = std::min<int64_t>(cmax, (N + 127) / 128 * 128);
   if (P->scratch && P->chunk >= want) return TNO_OK;
   if (P->scratch) {
@@ -142,24 +144,24 @@ int tno_plan_create(const tno_problem_desc* D, tno_plan** out_plan) {
     return fail(TNO_EINVAL, "missing mandatory array");
   if (!(D->variables & TNO_VAR_Q)) return fail(TNO_EINVAL, "variables must contain q");
   if (D->variables & ~(TNO_VAR_Q | TNO_VAR_ZB | TNO_VAR_T | TNO_VAR_LAMBDH | TNO_VAR_LAMBDV | TNO_VAR_XYB))
-    return fail(TNO_EINVAL, "unsupported variable (supported: q, xyb, zb, t/n, lambdh, lambdv)");
+    return fail(TNO_EUNSUPPORTED, "unsupported variable (supported: q, xyb, zb, t/n, lambdh, lambdv)");
   if (D->constraints & ~(TNO_CON_FUNICULAR | TNO_CON_ENVELOPE | TNO_CON_REAC_BOUNDS | TNO_CON_ENVELOPEXY))
-    return fail(TNO_EINVAL, "unsupported constraint (supported: funicular, envelopexy, envelope, reac_bounds)");
+    return fail(TNO_EUNSUPPORTED, "unsupported constraint (supported: funicular, envelopexy, envelope, reac_bounds)");
   if ((D->constraints & TNO_CON_ENVELOPEXY) && (!D->xlimits || !D->ylimits)) return fail(TNO_EINVAL, "envelopexy needs xlimits / ylimits");
   if ((D->variables & TNO_VAR_XYB) || (D->constraints & TNO_CON_ENVELOPEXY)) {
     // the reference stacks the xyb columns against the envelopexy AND envelope row blocks (jacobian.py:269-273)
     if ((D->variables & TNO_VAR_XYB) && (D->constraints & (TNO_CON_ENVELOPEXY | TNO_CON_ENVELOPE)) != (TNO_CON_ENVELOPEXY | TNO_CON_ENVELOPE))
-      return fail(TNO_EINVAL, "xyb variables need the envelopexy and envelope constraints");
-    if (D->variables & (TNO_VAR_LAMBDH | TNO_VAR_LAMBDV)) return fail(TNO_EINVAL, "load multipliers with xyb / envelopexy are not available");
+      return fail(TNO_EUNSUPPORTED, "xyb variables need the envelopexy and envelope constraints");
+    if (D->variables & (TNO_VAR_LAMBDH | TNO_VAR_LAMBDV)) return fail(TNO_EUNSUPPORTED, "load multipliers with xyb / envelopexy are not available");
     if (D->objective > TNO_OBJ_NEG_LAST && D->objective != TNO_OBJ_FEASIBILITY)
-      return fail(TNO_EINVAL, "xyb / envelopexy support the objectives min, max, t, n, feasibility");
-    if (D->kernel == TNO_KERNEL_ONCHIP) return fail(TNO_EINVAL, "xyb / envelopexy run on the interleaved kernel family");
+      return fail(TNO_EUNSUPPORTED, "xyb / envelopexy support the objectives min, max, t, n, feasibility");
+    if (D->kernel == TNO_KERNEL_ONCHIP) return fail(TNO_EUNSUPPORTED, "xyb / envelopexy run on the interleaved kernel family");
   }
   if ((D->constraints & TNO_CON_ENVELOPE) && (!D->lb || !D->ub)) return fail(TNO_EINVAL, "envelope needs lb / ub");
   if ((D->variables & TNO_VAR_T) && D->envelope_kind != TNO_ENV_DOME && D->envelope_kind != TNO_ENV_CROSSVAULT)
     return fail(TNO_EINVAL, "thickness variable needs a parametric envelope");
   if ((D->variables & TNO_VAR_T) && (D->constraints & TNO_CON_REAC_BOUNDS))
-    return fail(TNO_EINVAL, "reac_bounds with variable thickness is not available (broken on the reference branch too)");
+    return fail(TNO_EUNSUPPORTED, "reac_bounds with variable thickness is not available (broken on the reference branch too)");
   if ((D->constraints & TNO_CON_REAC_BOUNDS) && !D->b) return fail(TNO_EINVAL, "reac_bounds needs b");
   if ((D->variables & TNO_VAR_LAMBDH) && (!D->px0 || !D->py0)) return fail(TNO_EINVAL, "lambdh needs px0 / py0");
   if ((D->variables & TNO_VAR_LAMBDV) && (!D->pzv || !D->pz0)) return fail(TNO_EINVAL, "lambdv needs pzv / pz0");
@@ -173,7 +175,7 @@ int tno_plan_create(const tno_problem_desc* D, tno_plan** out_plan) {
     // gradient_bestfit / gradient_loadpath / gradient_complementary_energy (derivatives.py:355-413, 640-718, 503-620):
     // of the variables this library supports they only know the q and zb blocks
     if (D->variables & ~(TNO_VAR_Q | TNO_VAR_ZB))
-      return fail(TNO_EINVAL, "bestfit / loadpath / Ecomp objectives support the variables q and zb only");
+      return fail(TNO_EUNSUPPORTED, "bestfit / loadpath / Ecomp objectives support the variables q and zb only");
     if (D->objective == TNO_OBJ_BESTFIT && !D->s) return fail(TNO_EINVAL, "bestfit objective needs the target surface s");
     if (ecomp && !D->dXb) return fail(TNO_EINVAL, "Ecomp objectives need the support displacements dXb");
     if (D->objective == TNO_OBJ_ECOMP_NONLINEAR && !D->stiff) return fail(TNO_EINVAL, "Ecomp-nonlinear needs stiff");
@@ -567,7 +569,7 @@ int tno_plan_create(const tno_problem_desc* D, tno_plan** out_plan) {
       I.smem_bytes = (int64_t)P->oc.smem_bytes;
       I.onchip_ctas_per_sm = P->onchip_ctas_per_sm;
     } else if (D->kernel == TNO_KERNEL_ONCHIP) {
-      return fail(TNO_EINVAL, std::string("problem does not fit the on-chip kernel family: ") + tno_last_error());
+      return fail(TNO_EUNSUPPORTED, std::string("problem does not fit the on-chip kernel family: ") + tno_last_error());
     }
   }
   I.kernel = P->kernel;
@@ -683,6 +685,8 @@ int tno_eval_batch(tno_plan* plan, const double* x_dev, int64_t N, int64_t ldx, 
   if (!P || !x_dev || !out_dev) return fail(TNO_EINVAL, "null argument");
   if (N < 0 || ldx < P->dp.var.nvar) return fail(TNO_EINVAL, "bad N / ldx");
   if (N == 0) return TNO_OK;
+  // the Jacobian is written with 16-byte stores; ng is even, so every candidate's block is aligned when the base is
+  if (out_dev->J && (reinterpret_cast<uintptr_t>(out_dev->J) & 15u)) return fail(TNO_EINVAL, "out->J must be 16-byte aligned");
   TNO_CUDA_OK(cudaSetDevice(P->device));
   bool onchip = P->kernel == TNO_KERNEL_ONCHIP;
   if (onchip && P->auto_family && P->onchip_ctas_per_sm == 1) {

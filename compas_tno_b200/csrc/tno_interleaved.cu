@@ -341,7 +341,7 @@ __global__ void k_rhs1(DevPlan P, double* __restrict__ ws, int64_t NC, int64_t n
     WS(base + P.rhs.cx) = bx;
     WS(base + P.rhs.cy) = by;
     WS(base + P.rhs.cz) = bz;
-    if (P.rhs.c_lambdv >= 0) WS(base + P.rhs.c_lambdv) = -P.pzv[v];
+    if (P.rhs.c_lambdv >= 0) WS(base + P.rhs.c_lambdv) = -P.pzv[v] * pzs;   // d(pz)/d(lambdv) = pz_scale * pzv
   }
 }
 
@@ -718,7 +718,7 @@ __global__ void k_epilogue(DevPlan P, double* __restrict__ ws, int64_t NC, int64
               dRz = fma(sg * qe, sg > 0 ? -dzo : dzo, dRz);
             }
           }
-          dRz -= P.pzv[vb];
+          dRz -= P.pzv[vb] * pzs;
           WS(rowx + P.var.o_lambdv) = sz * zb * fabs(Rx) / rz2 * dRz;
           WS(rowy + P.var.o_lambdv) = sz * zb * fabs(Ry) / rz2 * dRz;
         }
@@ -873,7 +873,10 @@ __global__ void k_thrust_grad(DevPlan P, double* __restrict__ ws, int64_t NC, in
       for (int jj = 0; jj < TG_JT; ++jj)
         if (j0 + jj < j1) acc[jj] = fma(coef, Brow[jj], acc[jj]);
       const int ro = P.vrow[o];
-      if (P.rhs.c_qx >= 0 && ro >= 0) {  // + Cb^T Q C dx/dq_ind: the free neighbours move with q once the supports do
+      // + Cb^T Q C dx/dq_ind: the free neighbours move with q once the supports do.  Only with the xyb variable: on a
+      // fixed plan the reference keeps dx/dq_ind = 0 in this gradient (derivatives.py:257-301), and the Dx / Dy panels of an
+      // envelopexy-only problem are not solved unless J is requested.
+      if (P.rhs.c_qx >= 0 && P.var.o_xyb >= 0 && ro >= 0) {
         const double qe = WS(P.slot.s_q + e);
         const int bx = P.slot.s_r + ro * nrhs + P.rhs.c_qx + j0, by = P.slot.s_r + ro * nrhs + P.rhs.c_qy + j0;
 #pragma unroll
@@ -1039,12 +1042,12 @@ int run_interleaved(Plan* PL, const double* x_dev, int64_t N, int64_t ldx, const
     const double* bnd = (opt && opt->bounds) ? opt->bounds + 2 * c0 * P.n : nullptr;
     if (bnd && (P.var.o_t >= 0 || P.con.r_env < 0)) {
       set_error("per-candidate bounds need the envelope constraint and no thickness variable");
-      return TNO_EINVAL;
+      return TNO_EUNSUPPORTED;
     }
     const double* ldir = (opt && opt->load_dir) ? opt->load_dir + 2 * c0 : nullptr;
     if (ldir && !P.d_b) {
       set_error("load_dir needs a plan created with the second load basis (d_b, px0_b, py0_b)");
-      return TNO_EINVAL;
+      return TNO_EUNSUPPORTED;
     }
     LAUNCH(KK_PACK, k_pack, grid1(nc, TB), TB, P, ws, NC, nc, xs, ldx, pzs, ldir);
     const int etile = P.k > 64 ? 4 : 32;   // many independents: shorter edge tiles keep the machine busy

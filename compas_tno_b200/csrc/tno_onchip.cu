@@ -678,7 +678,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_onchip(const __grid_constant_
       row[O.c_x] = bx;
       row[O.c_y] = by;
       row[O.c_z] = bz;
-      if (O.c_lambdv >= 0) row[O.c_lambdv] = -P.pzv[v];
+      if (O.c_lambdv >= 0) row[O.c_lambdv] = -P.pzv[v] * pzs;   // d(pz)/d(lambdv) = pz_scale * pzv
     }
     __syncthreads();
 
@@ -1027,7 +1027,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_onchip(const __grid_constant_
               dRz = fma(sg * qsup[t], sg > 0 ? -dzo : dzo, dRz);
             }
           }
-          dRz -= P.pzv[vb];
+          dRz -= P.pzv[vb] * pzs;
           vx = sz * zb * fabs(Rx) / rz2 * dRz;
           vy = sz * zb * fabs(Ry) / rz2 * dRz;
         }
@@ -1190,6 +1190,12 @@ int build_onchip(Plan* PL, const tno_problem_desc* D) {
   const size_t mark = PL->dev_allocs.size();
   int rc = build_onchip_impl(PL, D, 256);
   if (rc != TNO_OK || !PL->onchip_ok) return rc;
+  if (getenv("TNO_ONCHIP_512X2") && PL->onchip_ctas_per_sm >= 2) {   // experiment: 512-thread CTAs, two per SM (64 registers)
+    for (size_t i = mark; i < PL->dev_allocs.size(); ++i) cudaFree(PL->dev_allocs[i]);
+    PL->dev_allocs.resize(mark);
+    rc = build_onchip_impl(PL, D, 512);
+    return rc;
+  }
   if (PL->onchip_ctas_per_sm == 1 && !getenv("TNO_ONCHIP_256")) {
     for (size_t i = mark; i < PL->dev_allocs.size(); ++i) cudaFree(PL->dev_allocs[i]);
     PL->dev_allocs.resize(mark);
@@ -1207,12 +1213,16 @@ int build_onchip(Plan* PL, const tno_problem_desc* D) {
 void launch_fill_funicular(Plan* PL, const double* block, int64_t count, double* J, int64_t N, cudaStream_t stream) {
   const int64_t chunks = count / 2;  // count = 2 m nvar is even
   const int64_t cand_stride = (int64_t)PL->dp.con.ng * PL->dp.var.nvar;
-  dim3 g((unsigned)((chunks + 255) / 256), (unsigned)((N + FILL_CPB - 1) / FILL_CPB), 1);
+  const int64_t per_launch = (int64_t)65535 * FILL_CPB;   // grid.y limit: about one million candidates per launch
   PL->prof_begin(KK_EMIT_J, stream);
-  k_fill_funicular<<<g, 256, 0, stream>>>(reinterpret_cast<const double2*>(block), chunks, J, cand_stride,
-                                          (int64_t)PL->dp.con.r_fun * PL->dp.var.nvar, N);
+  for (int64_t c0 = 0; c0 < N; c0 += per_launch) {
+    const int64_t nc = std::min(per_launch, N - c0);
+    dim3 g((unsigned)((chunks + 255) / 256), (unsigned)((nc + FILL_CPB - 1) / FILL_CPB), 1);
+    k_fill_funicular<<<g, 256, 0, stream>>>(reinterpret_cast<const double2*>(block), chunks, J + c0 * cand_stride, cand_stride,
+                                            (int64_t)PL->dp.con.r_fun * PL->dp.var.nvar, nc);
+    PL->launches += 1;
+  }
   PL->prof_end(stream);
-  PL->launches += 1;
 }
 
 static int build_onchip_impl(Plan* PL, const tno_problem_desc* D, const int THREADS) {
@@ -1780,7 +1790,8 @@ static int build_onchip_impl(Plan* PL, const tno_problem_desc* D, const int THRE
   if (O.smem_bytes > max_optin) { set_error("on-chip family not applicable: O.smem_bytes > max_optin"); return TNO_OK; }
   PL->onchip_threads = THREADS;
   PL->onchip_ctas_per_sm = std::max(1, std::min(8, smem_sm / (O.smem_bytes + 1024)));
-  if (THREADS == 512) PL->onchip_ctas_per_sm = 1;
+  if (THREADS == 512 && !getenv("TNO_ONCHIP_512X2")) PL->onchip_ctas_per_sm = 1;
+  if (THREADS == 512 && getenv("TNO_ONCHIP_512X2")) PL->onchip_ctas_per_sm = std::min(PL->onchip_ctas_per_sm, 2);
 
   std::vector<double> Bt((size_t)k * m);
   for (int e = 0; e < m; ++e)
@@ -1850,11 +1861,11 @@ int run_onchip(Plan* PL, const double* x_dev, int64_t N, int64_t ldx, const tno_
   A.bounds = (opt && opt->bounds) ? opt->bounds : nullptr;
   if (A.bounds && (PL->dp.var.o_t >= 0 || PL->dp.con.r_env < 0)) {
     set_error("per-candidate bounds need the envelope constraint and no thickness variable");
-    return TNO_EINVAL;
+    return TNO_EUNSUPPORTED;
   }
   if (A.dir && !PL->dp.d_b) {
     set_error("load_dir needs a plan created with the second load basis (d_b, px0_b, py0_b)");
-    return TNO_EINVAL;
+    return TNO_EUNSUPPORTED;
   }
   A.f = out->f;
   A.grad = out->grad;
@@ -1878,7 +1889,7 @@ int run_onchip(Plan* PL, const double* x_dev, int64_t N, int64_t ldx, const tno_
   const int threads = PL->onchip_threads;
   // <256, 2>: two CTAs per SM (the common case; also serves the rare 256-thread single-CTA fallback), <512, 1> otherwise
   auto kern = (A.dir || A.bounds) ? (threads == 512 ? k_onchip<512, 1, true> : k_onchip<256, 2, true>)
-                                  : (threads == 512 ? k_onchip<512, 1, false> : k_onchip<256, 2, false>);
+                                  : (threads == 512 ? (ctas >= 2 ? k_onchip<512, 2, false> : k_onchip<512, 1, false>) : k_onchip<256, 2, false>);
   TNO_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   if (out->J && PL->dp.con.r_fun >= 0)
     launch_fill_funicular(PL, PL->oc.Jfun, (int64_t)2 * PL->dp.m * PL->dp.var.nvar, out->J, N, stream);

@@ -40,10 +40,12 @@ extern "C" {
 
 /* error codes */
 #define TNO_OK 0
-#define TNO_EINVAL (-1)    /* bad argument / unsupported combination (reference raises NotImplementedError) */
+#define TNO_EINVAL (-1)    /* bad argument (null pointer, sizes, alignment, malformed arrays) */
 #define TNO_ENODEVICE (-2) /* no usable CUDA device */
 #define TNO_ECUDA (-3)     /* CUDA runtime error */
 #define TNO_ENOMEM (-4)
+#define TNO_EUNSUPPORTED (-5) /* valid arguments, but a combination this library (like the reference: NotImplementedError)
+                                 does not provide */
 
 /* variables present in x, in the reference's unpacking order (problems/constraints.py:47-88):
  *   x = [ q_ind (k) | xyb (2 nb: x of the supports, then y) | zb (nb) | t (1) | lambdh (1) | lambdv (1) ]   */
@@ -179,7 +181,7 @@ typedef struct tno_outputs {
   double* f;       /* N                       objective */
   double* grad;    /* N x nvar                gradient of the objective */
   double* g;       /* N x ng                  constraints, g >= 0 feasible */
-  double* J;       /* N x ng x nvar           dense Jacobian of g, row-major per candidate */
+  double* J;       /* N x ng x nvar           dense Jacobian of g, row-major per candidate; 16-byte aligned base */
   double* z;       /* N x n                   node heights (all vertices, supports included) */
   double* q;       /* N x m                   force densities */
   double* gmin;    /* N                       min_r g[r]  (feasibility margin) */
@@ -234,6 +236,14 @@ int tno_plan_profile_read(tno_plan* plan, int32_t max_kinds, char* names, double
  * the other rows on `cuda_stream`.  Returns when the host threads are done; the caller synchronises the stream.
  * With per-candidate load directions (tno_batch_inputs.load_dir) the funicular rows are not constant: use a plain copy. */
 int tno_fetch_jacobian_host(tno_plan* plan, const double* J_dev, double* J_host, int64_t n_candidates, void* cuda_stream);
+
+/* Device peaks measured in place with register-resident kernels (a few milliseconds each), the denominators of the
+ * secondary FP64 roofline bench.py reports (north_star: "fraction of the HBM or FP64 roofline", "FP64 tensor-pipe
+ * utilisation").  what = TNO_PEAK_FP64_FMA: DFMA throughput;  TNO_PEAK_FP64_MMA: mma.sync m8n8k4 f64 (FP64 tensor core)
+ * throughput.  *value receives TFLOP/s. */
+#define TNO_PEAK_FP64_FMA 0
+#define TNO_PEAK_FP64_MMA 1
+int tno_device_peak(int32_t device, int32_t what, double* value);
 
 #ifdef __cplusplus
 }

@@ -95,3 +95,53 @@ def rel_err(a, b):
     if scale == 0.0:
         scale = 1.0
     return float(np.max(np.abs(a - b)) / scale) if b.size else 0.0
+
+
+def row_blocks(P):
+    """Row ranges of g / J by constraint block, in the reference's stacking order (problems/constraints.py:104-155):
+    funicular (2m), envelopexy (4n), envelope (2n), reac_bounds (2nb).  The funicular and envelope blocks are further
+    split into their two halves (q - qmin | qmax - q, z - lb | ub - z): the halves have very different magnitudes."""
+    m, n, nb = P.m, P.n, P.nb
+    out, pos = [], 0
+    for name in ("funicular", "envelopexy", "envelope", "reac_bounds"):
+        if name not in P.constraints:
+            continue
+        if name == "funicular":
+            out += [("funicular:q-qmin", pos, pos + m), ("funicular:qmax-q", pos + m, pos + 2 * m)]
+            pos += 2 * m
+        elif name == "envelopexy":
+            out += [("envelopexy:x", pos, pos + 2 * n), ("envelopexy:y", pos + 2 * n, pos + 4 * n)]
+            pos += 4 * n
+        elif name == "envelope":
+            out += [("envelope:z-lb", pos, pos + n), ("envelope:ub-z", pos + n, pos + 2 * n)]
+            pos += 2 * n
+        else:
+            out += [("reac_bounds", pos, pos + 2 * nb)]
+            pos += 2 * nb
+    return out
+
+
+def elem_err(a, b, floor_frac=1e-3):
+    """Element-wise relative error with an absolute floor:  max_i |a_i - b_i| / max(|b_i|, floor_frac * max|b|).
+    A small entry cannot hide behind the largest one of its block (the norm-wise rel_err lets it)."""
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    if not b.size:
+        return 0.0
+    scale = np.max(np.abs(b))
+    if scale == 0.0:
+        return float(np.max(np.abs(a - b)))
+    return float(np.max(np.abs(a - b) / np.maximum(np.abs(b), floor_frac * scale)))
+
+
+def assert_blockwise(got_g, ref_g, got_J, ref_J, P, tol_val, tol_jac, what=""):
+    """g and J against the reference block by block: norm-wise and element-wise (absolute floor = 1e-3 of the block's
+    largest entry).  g / J have the candidate axis first or not at all."""
+    for name, lo, hi in row_blocks(P):
+        gg, rg = np.asarray(got_g)[..., lo:hi], np.asarray(ref_g)[..., lo:hi]
+        assert rel_err(gg, rg) < tol_val, (what, "g", name, rel_err(gg, rg))
+        assert elem_err(gg, rg) < tol_val * 10, (what, "g elementwise", name, elem_err(gg, rg))
+        if got_J is not None:
+            gj, rj = np.asarray(got_J)[..., lo:hi, :], np.asarray(ref_J)[..., lo:hi, :]
+            assert rel_err(gj, rj) < tol_jac, (what, "J", name, rel_err(gj, rj))
+            assert elem_err(gj, rj) < tol_jac * 10, (what, "J elementwise", name, elem_err(gj, rj))

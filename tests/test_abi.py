@@ -80,18 +80,22 @@ def test_unsupported_combinations_are_rejected_before_any_device_work():
         return Q
 
     lim = np.column_stack([P.X[:, 0] - 1.0, P.X[:, 0] + 1.0])
+    from compas_tno_b200.envelopes import CrossVaultEnvelope
+    env = CrossVaultEnvelope((0.0, 10.0), (0.0, 10.0), 0.5)
+    U, A = NotImplementedError, ValueError       # unsupported combination (TNO_EUNSUPPORTED) / plain argument error (TNO_EINVAL)
     cases = [
-        (variant(variables=["q", "zb", "t"]), "bestfit"),                                   # gradient_bestfit knows q and zb only
-        (variant(variables=["q", "zb", "t"]), "loadpath"),
-        (variant(variables=["q", "zb"]), "Ecomp-linear"),                                   # no dXb on the problem
-        (variant(variables=["q", "xyb", "zb"], constraints=["funicular", "envelope"]), "min"),          # xyb needs envelopexy too
-        (variant(variables=["q", "xyb", "zb"], constraints=["funicular", "envelopexy", "envelope"]), "min"),  # no xlimits
-        (variant(variables=["q", "xyb", "zb"], constraints=["funicular", "envelopexy", "envelope"], xlimits=lim, ylimits=lim), "bestfit"),
-        (variant(variables=["q", "zb", "tub"]), "min"),                                     # not accelerated at all
-        (variant(constraints=["funicular", "envelope", "displ_map"]), "min"),
-        (variant(features=["sym"]), "min"),
-        (P, "Ecomp-complete"),
+        (variant(variables=["q", "zb", "t"], envelope=env), "bestfit", U),                  # gradient_bestfit knows q and zb only
+        (variant(variables=["q", "zb", "t"], envelope=env), "loadpath", U),
+        (variant(variables=["q", "zb", "t"]), "t", A),                                      # no parametric envelope on the problem
+        (variant(variables=["q", "zb"]), "Ecomp-linear", A),                                # no dXb on the problem
+        (variant(variables=["q", "xyb", "zb"], constraints=["funicular", "envelope"]), "min", U),          # xyb needs envelopexy too
+        (variant(variables=["q", "xyb", "zb"], constraints=["funicular", "envelopexy", "envelope"]), "min", A),  # no xlimits
+        (variant(variables=["q", "xyb", "zb"], constraints=["funicular", "envelopexy", "envelope"], xlimits=lim, ylimits=lim), "bestfit", U),
+        (variant(variables=["q", "zb", "tub"]), "min", U),                                  # not accelerated at all
+        (variant(constraints=["funicular", "envelope", "displ_map"]), "min", U),
+        (variant(features=["sym"]), "min", U),
+        (P, "Ecomp-complete", U),
     ]
-    for prob, obj in cases:
-        with pytest.raises(NotImplementedError):
+    for prob, obj, exc in cases:
+        with pytest.raises(exc):
             TnoPlan(prob, objective=obj)

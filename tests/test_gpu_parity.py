@@ -6,7 +6,7 @@ gradients 1e-8 relative (relative = max |a - b| / max |b|, see golden_io.rel_err
 import numpy as np
 import pytest
 
-from golden_io import CASES, load_case, rel_err
+from golden_io import CASES, assert_blockwise, load_case, rel_err
 
 pytestmark = pytest.mark.gpu
 
@@ -51,6 +51,9 @@ def test_golden_parity_host_abi(tno, name, kernel):
     for lo, hi in ((0, 2 * m), (2 * m, 2 * m + 2 * n), (2 * m + 2 * n, plan.ng)):
         if hi > lo:
             assert rel_err(got["J"][:, lo:hi], exp["J"][:, lo:hi]) < TOL_JAC
+    # every constraint block of g and J on its own scale, norm-wise and element-wise (funicular rows are ~1e4, reaction
+    # rows ~0.1: one vector-wide norm would let a 1e-7 error in g_reac pass)
+    assert_blockwise(got["g"], exp["g"], got["J"], exp["J"], P, TOL_VAL, TOL_JAC, name)
     assert np.allclose(got["gmin"], exp["g"].min(axis=1), rtol=1e-9, atol=1e-9)
     plan.close()
 
