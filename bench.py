@@ -88,57 +88,209 @@ def slsqp_config1(device):
             "note": "wall time includes scipy's own QP work per iteration, identical in both arms"}
 
 
+def _block_rng(seed, lo, hi, block=4096):
+    """Per-candidate random streams that do not depend on how the sweep is sharded: candidate j always draws from the
+    generator of its 4096-block, so rank slices [lo, hi) of any world size see the same candidates."""
+    for b in range(lo // block, (hi - 1) // block + 1):
+        a0, a1 = max(lo, b * block), min(hi, (b + 1) * block)
+        yield a0 - lo, a1 - lo, a0 - b * block, a1 - b * block, np.random.default_rng([seed, b]), block
+
+
+def _ladder(center, lo, hi, seed, sigma_lo, sigma_hi):
+    """Rows [lo, hi) of the sharding-independent candidate ladder around ``center`` (see workloads.sample_around)."""
+    xc = np.asarray(center, dtype=np.float64).ravel()
+    X = np.empty((hi - lo, len(xc)))
+    for o0, o1, b0, b1, rng, block in _block_rng(seed, lo, hi):
+        sig = np.exp(rng.uniform(np.log(sigma_lo), np.log(sigma_hi), size=(block, 1)))
+        xi = rng.uniform(-1, 1, size=(block, len(xc)))
+        X[o0:o1] = xc[None, :] * (1.0 + sig[b0:b1] * xi[b0:b1])
+    return np.ascontiguousarray(X)
+
+
 def sweep_specs():
-    """The BASELINE configurations 2-5 as single-GPU sweeps (per-GPU share where the configuration names 8 GPUs)."""
-    import numpy as np
+    """The BASELINE configurations 2-5 (+ a full-output discretisation-40 sweep) as sweeps sharded over the ranks.
+    ``total(world)`` is the number of candidates of the whole sweep; ``build(device)`` returns the problem, its plan and
+    ``make(lo, hi)`` -> (X, extras) for the candidates [lo, hi) of the sweep, identical for every sharding.  Candidates are
+    scattered around a strictly feasible state (workloads.max_margin_state) so that part of every sweep is feasible and
+    the best-feasible reduction has something to find."""
     from compas_tno_b200 import workloads as W
+    from compas_tno_b200.plan import TnoPlan
     FULL = ("f", "grad", "g", "J", "z", "gmin", "status")
     LIGHT = ("f", "gmin", "status")
+    cache = {}
 
-    def dome_multistart():
+    def disc40(device):
+        if "disc40" not in cache:
+            P, xs, obj = build_workload("crossvault_disc40", n_states=6)
+            plan = TnoPlan(P, objective=obj, device=device)
+            xc, margin = W.max_margin_state(plan, xs, rows=W.margin_rows(P, plan))
+            cache["disc40"] = (P, plan, obj, xc, margin)
+        return cache["disc40"]
+
+    def dome_multistart(device):
         P, xs, obj = build_workload("dome_16x20", n_states=6)
-        return P, candidates(P, xs, 4096, seed=20261019 + 2), obj, FULL, None
+        plan = TnoPlan(P, objective=obj, device=device)
+        xc, margin = W.max_margin_state(plan, xs, rows=W.margin_rows(P, plan))
+        return dict(P=P, plan=plan, names=FULL, margin=margin,
+                    make=lambda lo, hi: (_ladder(xc, lo, hi, 20261019 + 2, 1e-4, 0.1), {}))
 
-    def fan_thickness():
+    def fan_thickness(device):
         # fan form diagram of the reference fixture (tests/golden/fan_q_zb_max.npz carries its arrays) under the
         # closed-form cross-vault envelope the fixture's lb / ub follow; the pavilion-vault envelope of the
         # configuration is not pinned by any fixture (SURVEY.md section 8c), so the cross vault stands in for it
+        import copy
         from compas_tno_b200.envelopes import CrossVaultEnvelope
         from compas_tno_b200.problems import FixedProblem
-        z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "tests", "golden", "fan_q_zb_max.npz"))
+        z = np.load(os.path.join(ROOT, "tests", "golden", "fan_q_zb_max.npz"))
         P = FixedProblem.from_arrays(z["xyz"], z["edges"], z["fixed"], z["loads"], z["lb"], z["ub"], z["target"], z["q_form"],
                                      ind=z["ind"])
         P.B, P.d = z["B"].copy(), z["d"].reshape(-1, 1).copy()
-        P.variables, P.constraints, P.features = ["q", "zb", "t"], ["funicular", "envelope"], ["fixed"]
+        P.variables, P.constraints, P.features = ["q", "zb"], ["funicular", "envelope"], ["fixed"]
         P.thk, P.envelope = 0.5, CrossVaultEnvelope((0.0, 10.0), (0.0, 10.0), 0.5)
-        x0 = z["x"][0]
-        X = np.repeat(np.concatenate([x0, [0.5]])[None, :], 256, axis=0)
-        X[:, -1] = 0.50 - np.arange(256) * (0.45 / 255.0)
-        return P, np.ascontiguousarray(X), "t", FULL, None
+        p0 = TnoPlan(P, objective="max", device=device)           # the design: widest margin at thickness 0.50
+        xc, margin = W.max_margin_state(p0, z["x"][0], rows=W.margin_rows(P, p0))
+        p0.close()
+        Pt = copy.copy(P)
+        Pt.variables = ["q", "zb", "t"]
+        plan = TnoPlan(Pt, objective="t", device=device)
 
-    def disc40_montecarlo():
-        P, xs, obj = build_workload("crossvault_disc40", n_states=6)
-        N = 8192
-        X = np.repeat(np.asarray(xs, dtype=np.float64)[None, :], N, axis=0)
-        pzs = np.clip(np.random.default_rng(20261019 + 4).normal(1.0, 0.05, size=N), 0.8, 1.2)
-        return P, np.ascontiguousarray(X), obj, LIGHT, np.ascontiguousarray(pzs)
+        def make(lo, hi):
+            X = np.repeat(np.concatenate([xc, [0.5]])[None, :], hi - lo, axis=0)
+            X[:, -1] = 0.50 - np.arange(lo, hi) * (0.45 / 255.0)
+            return np.ascontiguousarray(X), {}
+        return dict(P=Pt, plan=plan, names=FULL, margin=margin, make=make)
 
-    def dome_lambdh():
+    def disc40_montecarlo(device):
+        P, plan, obj, xc, margin = disc40(device)
+        n = P.n
+        ub0, lb0 = P.ub.ravel(), P.lb.ravel()
+
+        def make(lo, hi):
+            X = _ladder(xc, lo, hi, 20261019 + 4, 1e-5, 1e-2)
+            pzs = np.empty(hi - lo)
+            bounds = np.empty((hi - lo, 2 * n))
+            for o0, o1, b0, b1, rng, block in _block_rng(20261019 + 40, lo, hi):
+                pz = np.clip(rng.normal(1.0, 0.05, size=block), 0.8, 1.2)
+                du = rng.normal(0.0, 0.02, size=(block, 2 * n))        # intrados / extrados heights perturbed by 2 cm (1 sigma)
+                pzs[o0:o1] = pz[b0:b1]
+                bounds[o0:o1, :n] = ub0[None, :] + du[b0:b1, :n]
+                bounds[o0:o1, n:] = lb0[None, :] + du[b0:b1, n:]
+            return X, {"pz_scale": np.ascontiguousarray(pzs), "bounds": np.ascontiguousarray(bounds)}
+        return dict(P=P, plan=plan, names=LIGHT, margin=margin, make=make, keep_plan=True)
+
+    def disc40_full(device):
+        P, plan, obj, xc, margin = disc40(device)
+        return dict(P=P, plan=plan, names=FULL, margin=margin, keep_plan=True,
+                    make=lambda lo, hi: (_ladder(xc, lo, hi, 20261019 + 41, 1e-4, 0.1), {}))
+
+    def dome_lambdh(device):
+        P0, x0, _ = build_workload("dome_16x20", n_states=6)
+        p0 = TnoPlan(P0, objective="max", device=device)           # vertically loaded dome: the state the load is added to
+        xc, margin = W.max_margin_state(p0, x0, rows=W.margin_rows(P0, p0))
+        p0.close()
         P, xs = W.dome_direction_problem(20, 16, n_states=6)
-        X, load_dir = W.direction_candidates(P, xs, 8192, seed=20261019 + 5)
-        return P, X, "max_load", FULL, None, load_dir
+        plan = TnoPlan(P, objective="max_load", device=device)
+        k = P.k
+        NT = 8192
+
+        def make(lo, hi):
+            theta = 2.0 * np.pi * np.arange(lo, hi) / NT
+            load_dir = np.ascontiguousarray(np.column_stack([np.cos(theta), np.sin(theta)]))
+            X = np.empty((hi - lo, plan.nvar))
+            for o0, o1, b0, b1, rng, block in _block_rng(20261019 + 5, lo, hi):
+                lam = np.exp(rng.uniform(np.log(1e-4), np.log(0.05), size=block))[b0:b1]    # load multiplier ladder
+                shift = load_dir[o0:o1, [0]] * P.lambdh_shift[None, :] + load_dir[o0:o1, [1]] * P.lambdh_shift_b[None, :]
+                X[o0:o1, :k] = xc[None, :k] - lam[:, None] * shift      # q = B y* + lambdh (d0(theta) - B B^+ d0(theta))
+                X[o0:o1, k:-1] = xc[None, k:]
+                X[o0:o1, -1] = lam
+            return np.ascontiguousarray(X), {"load_dir": load_dir}
+        return dict(P=P, plan=plan, names=FULL, margin=margin, make=make)
 
     return [
-        {"name": "dome_16x20", "what": "config 2: dome, radial form, max thrust + reac_bounds, 4096 multi-start", "build": dome_multistart},
-        {"name": "fan_thickness", "what": "config 3: fan form diagram (reference fixture), thickness sweep 0.50 -> 0.05 m in 256 steps, "
-                                          "objective t; cross-vault closed-form envelope (pavilion envelope unpinned)", "build": fan_thickness},
-        {"name": "crossvault_disc40_mc", "what": "config 4: cross vault disc 40, Monte-Carlo self-weight scale N(1, 0.05^2) clipped to "
-                                                 "[0.8, 1.2]; 8192 candidates = one GPU's share of 65,536 over 8; objectives + feasibility only",
-         "build": disc40_montecarlo, "reps": 2},
-        {"name": "dome_lambdh", "what": "config 5: dome, horizontal-load multiplier lambdh as a variable + reac_bounds, 8192 load directions "
-                                        "theta_j = 2 pi j / 8192 (d0(theta) = cos d0x + sin d0y per candidate), batched Jacobians",
-         "build": dome_lambdh, "reps": 3},
+        {"name": "dome_16x20", "config": 2, "scaling": "strong", "total": lambda world: 4096, "build": dome_multistart,
+         "what": "config 2: dome, radial form, max thrust + reac_bounds, 4096 multi-start candidates scattered (relative sigma 1e-4 .. 0.1) "
+                 "around the widest-margin state"},
+        {"name": "fan_thickness", "config": 3, "scaling": "strong", "total": lambda world: 256, "build": fan_thickness,
+         "what": "config 3: fan form diagram (reference fixture), thickness sweep 0.50 -> 0.05 m in 256 steps at the widest-margin "
+                 "state of thickness 0.50, objective t; cross-vault closed-form envelope (pavilion envelope unpinned)"},
+        {"name": "crossvault_disc40_mc", "config": 4, "scaling": "weak", "total": lambda world: 8192 * world, "build": disc40_montecarlo,
+         "reps": 3,
+         "what": "config 4: cross vault disc 40, Monte-Carlo: self-weight scale N(1, 0.05^2) clipped to [0.8, 1.2] (pz_scale) AND "
+                 "intrados / extrados heights perturbed N(0, 2 cm) per vertex (bounds), distinct x per candidate; 8192 candidates "
+                 "per GPU = 65,536 on 8 GPUs; objectives + feasibility only"},
+        {"name": "crossvault_disc40_full", "config": 4, "scaling": "weak", "total": lambda world: 4096 * world, "build": disc40_full,
+         "reps": 3,
+         "what": "cross vault disc 40, every output incl. the dense 10082 x 29 Jacobian, 4096 candidates per GPU"},
+        {"name": "dome_lambdh", "config": 5, "scaling": "strong", "total": lambda world: 8192, "build": dome_lambdh, "reps": 3,
+         "what": "config 5: dome, horizontal-load multiplier lambdh as a variable + reac_bounds, 8192 load directions "
+                 "theta_j = 2 pi j / 8192 (d0(theta) = cos d0x + sin d0y per candidate), multiplier ladder 1e-4 .. 0.05, batched Jacobians"},
     ]
+
+
+def run_sweeps(dev, local, world, rank, barrier):
+    """Every sweep of sweep_specs(), sharded over the ranks through distributed.ShardedSweep: each rank evaluates its
+    contiguous slice on its own plan replica; ONE packed all_gather of (f, gmin, status) per sweep is the only exchange,
+    every rank then knows the best feasible candidate.  Timed with CUDA events between barriers, max over ranks."""
+    import torch
+    import torch.distributed as dist
+    from compas_tno_b200.distributed import ShardedSweep, best_of_packed
+    sweeps = {}
+    plans = []
+    for spec in sweep_specs():
+        built = spec["build"](local)
+        plan, namesw = built["plan"], built["names"]
+        NT = int(spec["total"](world))
+        sw = ShardedSweep(plan, NT)
+        Xh, extras_h = built["make"](sw.lo, sw.hi)
+        nloc = sw.hi - sw.lo
+        Xw = torch.from_numpy(Xh).to(dev)
+        extras = {key: torch.from_numpy(val).to(dev) for key, val in extras_h.items()}
+        outw = {key: torch.empty(plan._shape(key, nloc), device=dev, dtype=torch.int32 if key == "status" else torch.float64)
+                for key in namesw}
+        gbuf = None
+
+        def one():
+            nonlocal gbuf
+            res = sw.evaluate(Xw, namesw, out=outw, **extras)
+            gbuf = sw.gather_packed(res, out=gbuf if world > 1 else None)
+            return gbuf
+
+        for _ in range(2):
+            one()
+        barrier()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = spec.get("reps", 5)
+        a0.record()
+        for _ in range(reps):
+            packed = one()
+        a1.record()
+        barrier()
+        msw = a0.elapsed_time(a1) / reps
+        if world > 1:
+            t = torch.tensor([msw], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            msw = float(t.item())
+        best_f, best_i, nfeas = best_of_packed(packed, tol=1e-9)
+        bad = int((packed[:, 2] != 0).sum().item())
+        sweeps[spec["name"]] = {
+            "what": spec["what"], "baseline_config": spec["config"], "candidates": NT, "candidates_per_gpu": nloc, "n_gpus": world,
+            "scaling": spec["scaling"], "outputs": list(namesw), "per_candidate_inputs": sorted(extras),
+            "wall_ms_per_sweep": msw, "evals_per_s": NT / (msw * 1e-3),
+            "kernel_family": {1: "interleaved", 2: "onchip"}.get(plan.info.get("last_kernel") or plan.info["kernel"]),
+            "nvar": plan.nvar, "ng": plan.ng, "bytes_per_eval": plan.bytes_per_eval,
+            "hbm_frac_whole_step": (NT / world) / (msw * 1e-3) * plan.bytes_per_eval / 1e9 / measured_peak()[0] if "J" in namesw else None,
+            "status_nonzero": bad, "feasible": nfeas, "centre_margin": built["margin"],
+            "best_feasible": {"f": best_f if nfeas else None, "index": best_i},
+            "exchange": "one all_gather of (f, gmin, status), 24 B per candidate" if world > 1 else "none (single GPU)"}
+        del outw, Xw, extras
+        if built.get("keep_plan"):
+            plans.append(plan)
+        else:
+            plan.close()
+        torch.cuda.empty_cache()
+    for pl in set(plans):
+        pl.close()
+    return sweeps
 
 
 class ClockSampler:
@@ -308,6 +460,8 @@ def run_ours(args):
         raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback); use --impl reference for the CPU arm")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    from compas_tno_b200.distributed import bind_to_gpu_numa
+    numa = bind_to_gpu_numa(local) if world > 1 else None   # pinned buffers and fill threads on the GPU's own NUMA node
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -320,16 +474,15 @@ def run_ours(args):
     x_dev = torch.from_numpy(X).to(dev)
     names = ("f", "grad", "g", "J", "z", "gmin", "status")
     out = {k: torch.empty(plan._shape(k, N), device=dev, dtype=torch.int32 if k == "status" else torch.float64) for k in names}
-    gather_f = torch.empty(world * N, device=dev, dtype=torch.float64) if world > 1 else None
-    gather_s = torch.empty(world * N, device=dev, dtype=torch.int32) if world > 1 else None
-    best_f = torch.empty((), device=dev, dtype=torch.float64)
+    from compas_tno_b200.distributed import best_of_packed, gather_packed
+    gather_buf = torch.empty((world * N, 3), device=dev, dtype=torch.float64) if world > 1 else None
+    packed_all = None
 
     def step():
+        nonlocal packed_all
         plan.evaluate_device(x_dev, names, out=out)
-        if world > 1:   # the path's only exchange: objectives + feasibility flags
-            dist.all_gather_into_tensor(gather_f, out["f"])
-            dist.all_gather_into_tensor(gather_s, out["status"])
-            dist.all_reduce(best_f.copy_(out["f"].min()), op=dist.ReduceOp.MIN)
+        if world > 1:   # the path's only exchange: ONE all_gather of (f, gmin, status), 24 B / candidate
+            packed_all = gather_packed(out["f"], out["gmin"], out["status"], world * N, out=gather_buf)
 
     def barrier():
         if world > 1:
@@ -391,16 +544,26 @@ def run_ours(args):
         jfun_bytes = 8 * 2 * plan.m * plan.nvar if "funicular" in plan.constraints else 0
         info = plan.info                       # after the timed calls: last_kernel = the family that actually ran
         family = info.get("last_kernel") or info["kernel"]
-        if family == 2:
-            kbytes = {"k_onchip": B_alg - jfun_bytes, "k_emit(J)": jfun_bytes}
-        else:
-            kbytes = {"k_emit(J)": 8 * plan.ng * plan.nvar}
         total_kernel_ms = sum(v[0] for v in prof.values())
         profile_pass = "timed region" if profiled_inline else "second pass of the same %d steps (%.3f ms/step with events)" % (args.steps, profiled_ms / args.steps)
-        name, (kms, kcount) = max(prof.items(), key=lambda kv: kv[1][0])
-        bytes_per_eval = kbytes.get(name, B_alg)
-        evals_per_launch = N * args.steps / kcount
-        achieved = bytes_per_eval * evals_per_launch / (kms / kcount * 1e-3) / 1e9
+        if family == 2:
+            # on-chip family: two kernels, each moves its own share of the algorithmic bytes exactly once
+            kbytes = {"k_onchip": B_alg - jfun_bytes, "k_emit(J)": jfun_bytes}
+            name, (kms, kcount) = max(prof.items(), key=lambda kv: kv[1][0])
+            bytes_per_eval = kbytes.get(name, 0)
+            evals_per_launch = N * args.steps / kcount
+            achieved = bytes_per_eval * evals_per_launch / (kms / kcount * 1e-3) / 1e9
+            roof_kernel, share = name, kms / total_kernel_ms
+        else:
+            # interleaved family: ~10^3 launches per step keep their state in HBM scratch and only the emitters write
+            # outputs, so no single kernel owns the algorithmic bytes.  The roofline figure is the WHOLE STEP on B_alg
+            # (the dominant kernel is named for information, without a byte claim of its own).
+            kbytes = {"k_emit(J)": 8 * plan.ng * plan.nvar}
+            name, (kms, kcount) = max(prof.items(), key=lambda kv: kv[1][0])
+            bytes_per_eval = B_alg
+            evals_per_launch = N
+            achieved = value / world * B_alg / 1e9
+            roof_kernel, share = "whole step (all launches; dominant by time: %s)" % name, 1.0
         per_kernel = {}
         for kname, (ms_k, cnt_k) in sorted(prof.items(), key=lambda kv: -kv[1][0]):
             ent = {"ms_per_step": ms_k / args.steps, "launches_per_step": cnt_k / args.steps}
@@ -408,20 +571,32 @@ def run_ours(args):
                 ent["bytes_per_eval"] = kbytes[kname]
                 ent["GB/s"] = kbytes[kname] * N * args.steps / (ms_k * 1e-3) / 1e9
             per_kernel[kname] = ent
-        traffic = None   # DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture
+        traffic = None   # DRAM bytes per launch (per step for the interleaved family) from the committed ncu --set full captures
+        for tfile in ("r2_traffic.json", "r1_traffic.json"):
+            try:
+                tj = json.load(open(os.path.join(ROOT, "profiles", tfile)))
+                ent = tj.get(args.workload, tj if args.workload == "crossvault_disc20" else {})
+                key = name if family == 2 else "whole_step"
+                if key in ent:
+                    traffic = ent[key]["dram_bytes_per_candidate"] * evals_per_launch
+                    break
+            except Exception:
+                continue
+        fp64_peak, fp64_src = 40.0, "nominal B200 FP64 (measurement failed)"
         try:
-            tj = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
-            if args.workload == "crossvault_disc20" and name in tj:
-                traffic = tj[name]["dram_bytes_per_candidate"] * evals_per_launch
+            from compas_tno_b200 import _lib as _tl
+            fp64_peak = _tl.device_peak("fp64_fma", local)
+            fp64_src = "measured in place: tno_device_peak (DFMA chains, %.1f TFLOP/s; FP64 tensor-core mma.sync m8n8k4: %.1f TFLOP/s)" % (
+                fp64_peak, _tl.device_peak("fp64_mma", local))
         except Exception:
-            traffic = None
-        roofline = {"bound": "hbm", "kernel": name, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "traffic": traffic, "peak_source": peak_src, "kernel_share_of_step": kms / total_kernel_ms,
+            pass
+        roofline = {"bound": "hbm", "kernel": roof_kernel, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                    "traffic": traffic, "peak_source": peak_src, "kernel_share_of_step": share,
                     "bytes_per_eval": bytes_per_eval, "evals_per_launch": evals_per_launch,
                     "kernel_durations_from": profile_pass,
                     # secondary bound (north_star: "fraction of the HBM or FP64 roofline"): algorithmic flops of SURVEY 8d
-                    "fp64": (lambda fl: {"flops_per_eval": fl, "achieved_tflops": value / world * fl / 1e12, "peak_tflops": 40.0,
-                                         "peak_source": "nominal B200 FP64 (not measured)", "frac": value / world * fl / 1e12 / 40.0})(
+                    "fp64": (lambda fl: {"flops_per_eval": fl, "achieved_tflops": value / world * fl / 1e12, "peak_tflops": fp64_peak,
+                                         "peak_source": fp64_src, "frac": value / world * fl / 1e12 / fp64_peak})(
                         int(info["factor_flops"] + info["solve_flops"] + 6 * plan.m * plan.k + 8 * plan.m)),
                     "whole_step": {"bytes_per_eval": B_alg, "achieved": value / world * B_alg / 1e9,
                                    "frac": value / world * B_alg / 1e9 / peak},
@@ -447,8 +622,13 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dt = float(t.item())
     d2h = sum(res[k].numel() * res[k].element_size() for k in host_names)
+    host_filled = Ne * 8 * 2 * plan.m * plan.nvar if "funicular" in plan.constraints else 0
     e2e = {"value": world * Ne * esteps / dt, "unit": UNIT, "h2d_bytes_per_step": int(xh.numel() * 8), "d2h_bytes_per_step": int(d2h),
-           "candidates_per_step": Ne, "note": "every output incl. the dense J copied to pinned host memory (PCIe-bound)"}
+           "d2h_bytes_over_pcie_per_step": int(d2h - host_filled), "host_filled_bytes_per_step": int(host_filled),
+           "candidates_per_step": Ne, "numa": numa,
+           "note": "every output incl. the dense J delivered to pinned host memory; d2h_bytes_per_step = delivered bytes, of which the "
+                   "candidate-independent funicular rows of J (host_filled_bytes_per_step) are written by host threads from the plan's "
+                   "copy and only d2h_bytes_over_pcie_per_step cross PCIe"}
     # the sweep use-case: only objectives + feasibility cross PCIe, g / J / z stay in HBM for an on-device consumer
     bufs2 = {}
     xh2 = torch.from_numpy(X).pin_memory()
@@ -491,39 +671,10 @@ def run_ours(args):
                "sample": "%d candidates of %s through oracle/callbacks_np.py (reference call order: constr_wrapper, "
                          "sensitivities_wrapper, objective, gradient), one process per core" % (ns, args.workload)}
 
-    # ---- sweep wall-times of the other BASELINE configurations (N = 1 only; each a few launches) ----
+    # ---- sweep wall-times of the other BASELINE configurations, sharded over the ranks (every world size) ----
     sweeps = None
-    if rank == 0 and world == 1 and not args.no_sweeps:
-        sweeps = {}
-        for spec in sweep_specs():
-            built = spec["build"]()
-            Pw, Xw_host, objw, namesw, pzs_host = built[:5]
-            dirw = torch.from_numpy(built[5]).to(dev) if len(built) > 5 else None
-            wbatch = len(Xw_host)
-            planw = TnoPlan(Pw, objective=objw, device=local)
-            Xw = torch.from_numpy(Xw_host).to(dev)
-            pzsw = torch.from_numpy(pzs_host).to(dev) if pzs_host is not None else None
-            outw = {k: torch.empty(planw._shape(k, wbatch), device=dev, dtype=torch.int32 if k == "status" else torch.float64) for k in namesw}
-            for _ in range(2):
-                planw.evaluate_device(Xw, namesw, out=outw, pz_scale=pzsw, load_dir=dirw)
-            torch.cuda.synchronize()
-            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            reps = spec.get("reps", 5)
-            a0.record()
-            for _ in range(reps):
-                planw.evaluate_device(Xw, namesw, out=outw, pz_scale=pzsw, load_dir=dirw)
-            a1.record()
-            torch.cuda.synchronize()
-            msw = a0.elapsed_time(a1) / reps
-            sweeps[spec["name"]] = {
-                "what": spec["what"], "candidates": wbatch, "outputs": list(namesw), "wall_ms_per_sweep": msw,
-                "evals_per_s": wbatch / (msw * 1e-3), "kernel_family": {1: "interleaved", 2: "onchip"}.get(planw.info.get("last_kernel") or planw.info["kernel"]),
-                "nvar": planw.nvar, "ng": planw.ng, "bytes_per_eval": planw.bytes_per_eval,
-                "status_nonzero": int((outw["status"] != 0).sum().item()),
-                "feasible": int((outw["gmin"] >= -1e-9).sum().item()) if "gmin" in outw else None}
-            planw.close()
-            del outw, Xw
-            torch.cuda.empty_cache()
+    if not args.no_sweeps:
+        sweeps = run_sweeps(dev, local, world, rank, barrier)
 
     # ---- batch-size dependence (N in {1, 256, 4096, 65536}), device-resident, all outputs ----
     batch_sizes = None
@@ -566,6 +717,8 @@ def run_ours(args):
                        "l2_policy": "outputs per step (%.2f GB) exceed the 126 MB L2; inputs re-read each step" % (N * B_alg / 1e9),
                        "parallelism": "candidates sharded, plan replicated, all_gather(f, status)" if world > 1 else "single GPU"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "sweeps": sweeps,
+            "best_feasible_of_last_step": (lambda b: {"f": b[0] if b[2] else None, "index": b[1], "feasible": b[2]})(
+                best_of_packed(packed_all if packed_all is not None else gather_packed(out["f"], out["gmin"], out["status"], N), tol=1e-9)),
             "batch_sizes": batch_sizes, "slsqp_config1": slsqp,
             "status_nonzero": status_bad,
         }

@@ -13,7 +13,7 @@ from typing import Optional, Tuple
 import torch
 import torch.distributed as dist
 
-__all__ = ["shard_bounds", "gather_objectives", "argmin_feasible", "count_feasible", "ShardedSweep"]
+__all__ = ["bind_to_gpu_numa", "shard_bounds", "gather_objectives", "gather_packed", "best_of_packed", "argmin_feasible", "count_feasible", "ShardedSweep"]
 
 
 def shard_bounds(n_candidates: int, world_size: int, rank: int) -> Tuple[int, int]:
@@ -21,6 +21,34 @@ def shard_bounds(n_candidates: int, world_size: int, rank: int) -> Tuple[int, in
     if not (0 <= rank < world_size):
         raise ValueError("rank out of range")
     return (rank * n_candidates) // world_size, ((rank + 1) * n_candidates) // world_size
+
+
+def bind_to_gpu_numa(device_index: int):
+    """Pin this process (and the threads it creates later: the host fill threads of tno_fetch_jacobian_host) to the CPUs
+    of the NUMA node the GPU hangs off, so that pinned host buffers allocated afterwards are first-touched on that node
+    and the ranks of one box do not all write into one socket's memory.  Linux sysfs only; returns a small dict saying
+    what was done (``bound`` False when the topology is not exposed, e.g. numa_node = -1 inside a container)."""
+    import os
+    info = {"bound": False}
+    try:
+        props = torch.cuda.get_device_properties(device_index)
+        bus = "%04x:%02x:%02x.0" % (getattr(props, "pci_domain_id", 0), props.pci_bus_id, props.pci_device_id)
+        base = "/sys/bus/pci/devices/" + bus
+        node = int(open(base + "/numa_node").read().strip())
+        info.update(pci=bus, numa_node=node)
+        if node < 0:
+            return info
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = cpus & set(os.sched_getaffinity(0))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            info.update(bound=True, cpus=len(allowed))
+    except Exception as exc:   # topology not exposed: stay unbound, say why
+        info["error"] = "%s: %s" % (type(exc).__name__, exc)
+    return info
 
 
 def _world(group):
@@ -54,6 +82,48 @@ def gather_objectives(f_local: torch.Tensor, flags_local: torch.Tensor, n_candid
     f_all = torch.cat([f_all[r * pad: r * pad + sizes[r]] for r in range(world)])
     s_all = torch.cat([s_all[r * pad: r * pad + sizes[r]] for r in range(world)])
     return f_all, s_all
+
+
+def gather_packed(f_local: torch.Tensor, gmin_local: torch.Tensor, status_local: torch.Tensor, n_candidates: int, group=None,
+                  out: Optional[torch.Tensor] = None):
+    """ONE collective per sweep: the three per-candidate results the sweep exchanges (objective, feasibility margin,
+    status word: 24 bytes per candidate) are packed into one (n_local, 3) float64 block and all-gathered.  Every rank
+    then holds the whole sweep's (f, gmin, status) in candidate order and can take the best feasible candidate locally,
+    with no further reduction.  Shards may differ by one element (shard_bounds); they are padded to the longest one
+    (f = +inf, status = -1 in the padding) and trimmed afterwards.  Returns the (n_candidates, 3) float64 tensor."""
+    world, rank = _world(group)
+    packed = torch.stack([f_local, gmin_local, status_local.to(f_local.dtype)], dim=1)
+    if world == 1:
+        return packed
+    sizes = [shard_bounds(n_candidates, world, r)[1] - shard_bounds(n_candidates, world, r)[0] for r in range(world)]
+    pad = max(sizes)
+    if packed.shape[0] != pad:
+        fill = torch.tensor([float("inf"), float("-inf"), -1.0], dtype=packed.dtype, device=packed.device)
+        packed = torch.cat([packed, fill.expand(pad - packed.shape[0], 3)], dim=0)
+    if out is None or tuple(out.shape) != (world * pad, 3):
+        out = torch.empty((world * pad, 3), dtype=packed.dtype, device=packed.device)
+    dist.all_gather_into_tensor(out, packed.contiguous(), group=group)
+    if all(sz == pad for sz in sizes):
+        return out
+    return torch.cat([out[r * pad: r * pad + sizes[r]] for r in range(world)], dim=0)
+
+
+def best_of_packed(packed: torch.Tensor, tol: float = 1e-8):
+    """(f_best, global index, number feasible) from the gathered (N, 3) block of gather_packed; (inf, -1, 0) when nothing
+    is feasible.  Lowest index wins ties, like argmin_feasible.  One host read of three numbers."""
+    f, gmin, status = packed[:, 0], packed[:, 1], packed[:, 2]
+    ok = (gmin >= -tol) & (status == 0) & torch.isfinite(f)
+    fm = torch.where(ok, f, torch.full_like(f, float("inf")))
+    if fm.numel() == 0:
+        return float("inf"), -1, 0
+    idx = torch.argmin(fm)          # first minimal element
+    res = torch.stack([fm[idx], idx.to(fm.dtype), ok.sum().to(fm.dtype)]).cpu()
+    best, i, cnt = float(res[0]), int(res[1]), int(res[2])
+    if not (best < float("inf")):
+        return float("inf"), -1, 0
+    # torch.argmin does not promise the first of equal minima on every backend: settle ties explicitly
+    first = int(torch.nonzero(fm == fm[idx], as_tuple=False)[0, 0])
+    return best, min(i, first), cnt
 
 
 def argmin_feasible(f_local: torch.Tensor, gmin_local: torch.Tensor, status_local: torch.Tensor, offset: int,
@@ -109,3 +179,7 @@ class ShardedSweep:
 
     def best(self, res, tol: float = 1e-8):
         return argmin_feasible(res["f"], res["gmin"], res["status"], self.lo, tol, self.group)
+
+    def gather_packed(self, res, out=None):
+        """One all_gather of (f, gmin, status) for the whole sweep; see gather_packed."""
+        return gather_packed(res["f"], res["gmin"], res["status"], self.n_candidates, self.group, out)

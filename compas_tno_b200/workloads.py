@@ -239,10 +239,15 @@ def _finish(P, zb, mid, variables, thk, n_states):
     return P, x_star
 
 
-def env_bound_react(env, xy, fixed, thk):
+def env_bound_react(env, xy, fixed, thk, floor: float = 0.1):
+    """Reaction bounds b = (t / 2) x unit radial (the closed form the dome fixture follows), with
+    every component kept at least ``floor`` x t / 2 in magnitude: a support on a coordinate axis would otherwise get a zero
+    bound, whose constraint row  |b| - rise |R_xy / R_z|  admits no asymmetric state at all -- a synthetic sweep over
+    perturbed candidates would then be infeasible by construction.  (Synthetic stand-in; the fixtures keep their own b.)"""
     d = xy[fixed] - np.array([env.xc, env.yc])
     r = np.linalg.norm(d, axis=1, keepdims=True)
-    return 0.5 * thk * d / r
+    b = 0.5 * thk * d / r
+    return np.where(np.abs(b) < floor * 0.5 * thk, np.where(b < 0, -1.0, 1.0) * floor * 0.5 * thk, b)
 
 
 def sample_candidates(problem, x_star, N: int, seed: int = SEED, sigma: float = 0.05, basis=None):
@@ -266,4 +271,102 @@ def sample_candidates(problem, x_star, N: int, seed: int = SEED, sigma: float = 
         X[:, k:k + nb] = np.where(ok[None, :], zb, X[:, k:k + nb])
     if X.shape[1] > k + nb:
         X[:, k + nb:] *= 1.0 + sigma * rng.uniform(-1, 1, size=(N, X.shape[1] - k - nb))
+    return np.ascontiguousarray(X)
+
+
+def margin_rows(problem, plan, q_frac: float = 0.1):
+    """Coefficient of the margin s in every row of g (0 = the row must merely hold):  envelope rows 1 (metres), the
+    reac_bounds rows with a non-zero bound 1, and the  qmax - q  rows of the edges whose force density can move with the
+    variables  q_frac x median|q|  per metre of margin -- so that a state with margin s keeps those edges in compression
+    by that much and stays compression-only under small perturbations.  Edges that are structurally force-free (zero row
+    of B and zero d: n^2 of them on the cross form) cannot carry slack and get 0."""
+    m, ng = plan.m, plan.ng
+    coef = np.zeros(ng)
+    nfun = 2 * m if "funicular" in plan.constraints else 0
+    coef[nfun:] = 1.0
+    if "reac_bounds" in plan.constraints:
+        b = np.abs(np.asarray(problem.b, dtype=np.float64))
+        coef[ng - 2 * plan.nb:] = (np.concatenate([b[:, 0], b[:, 1]]) > 1e-9).astype(np.float64)
+    if nfun:
+        B = np.asarray(problem.B, dtype=np.float64)
+        q0 = np.abs(np.asarray(problem.q, dtype=np.float64).ravel())
+        movable = (np.abs(B).max(axis=1) > 1e-12) & (q0 > 1e-9 * max(q0.max(), 1e-300))
+        coef[m:2 * m] = np.where(movable, q_frac * float(np.median(q0[movable])) if movable.any() else 0.0, 0.0)
+    return coef
+
+
+def max_margin_state(plan, x0, iters: int = 60, verbose: bool = False, rows=None, step: float = 0.1):
+    """A strictly feasible variable vector for sweeps that should contain feasible candidates (multi-start, Monte-Carlo,
+    thickness sweeps): maximise the smallest weighted constraint margin,
+
+        max s   s.t.   g_r(x) - coef_r s >= 0  for every row r      (coef = ``rows``, see margin_rows; 0 = plain g_r >= 0)
+
+    by sequential linear programming with a trust region: each iteration evaluates g and the dense J of the current
+    point on the GPU (``plan.evaluate_host``, the same callables the reference hands to its solvers, solvers/scipy.py:172),
+    solves  max s  s.t.  g + J dx - s coef >= 0, |dx_i| <= delta scale_i  with HiGHS, and accepts the step when the
+    true margin grows (else the region shrinks).  The linear programme is always feasible, so an infeasible start is fine.
+    One-time host set-up of a workload, not part of the timed path.  Returns (x, s): s > 0 means every constraint holds,
+    the weighted ones with that margin."""
+    from scipy.optimize import linprog
+    from scipy.sparse import csr_matrix, hstack
+    x = np.asarray(x0, dtype=np.float64).ravel().copy()
+    nvar = plan.nvar
+    if rows is None:
+        rows = np.zeros(plan.ng)
+        rows[(2 * plan.m if "funicular" in plan.constraints else 0):] = 1.0
+    coef = np.asarray(rows, dtype=np.float64)
+    wrows = coef > 0
+    other = ~wrows
+    scale = np.where(np.abs(x) > 1e-3, np.abs(x), 1.0)
+
+    def ev(xv):
+        r = plan.evaluate_host(xv.reshape(1, -1), ("g", "J", "status"))
+        g = r["g"][0]
+        ok = r["status"][0] == 0 and bool(np.all(np.isfinite(g)))
+        merit = -np.inf
+        if ok:
+            viol = float(g[other].min()) if other.any() else 0.0
+            mrg = float((g[wrows] / coef[wrows]).min())
+            merit = mrg if viol >= -1e-9 else min(mrg, 0.0) + 1e3 * viol
+        return g, r["J"][0], merit
+
+    g, J, merit = ev(x)
+    delta = step
+    col_s = csr_matrix(coef.reshape(-1, 1))
+    for it in range(iters):
+        if not np.isfinite(merit):
+            break
+        # -(J dx) + s coef <= g
+        A = hstack([csr_matrix(-J), col_s], format="csr")
+        c = np.concatenate([np.zeros(nvar), [-1.0]])
+        bnds = [(-delta * sc, delta * sc) for sc in scale] + [(None, None)]
+        res = linprog(c, A_ub=A, b_ub=g, bounds=bnds, method="highs")
+        if res.status != 0:
+            break
+        xn = x + res.x[:nvar]
+        gn, Jn, mn = ev(xn)
+        if verbose:
+            print("  max_margin it %d delta %.3g: merit %.6g -> %.6g (LP predicts %.6g)" % (it, delta, merit, mn, res.x[nvar]))
+        if mn > merit + 1e-12:
+            gain = mn - merit
+            x, g, J, merit = xn, gn, Jn, mn
+            delta = min(delta * 1.5, 0.5)
+            if gain < 1e-7 * max(1.0, abs(merit)):
+                break
+        else:
+            delta *= 0.4
+            if delta < 1e-6:
+                break
+    return x, float(merit)
+
+
+def sample_around(problem, x_center, N: int, seed: int = SEED, sigma_lo: float = 1e-4, sigma_hi: float = 0.1):
+    """Candidates scattered around a (feasible) centre with a ladder of relative perturbation sizes, log-uniform in
+    [sigma_lo, sigma_hi]: the tight ones stay feasible, the wide ones leave the envelope, so a sweep over them has a
+    feasible FRACTION (and a best feasible candidate that is not the centre itself).  Every variable is perturbed
+    independently: x_j = x_c * (1 + sigma_j * xi_j), xi ~ U(-1, 1)."""
+    rng = np.random.default_rng(seed)
+    xc = np.asarray(x_center, dtype=np.float64).ravel()
+    sig = np.exp(rng.uniform(np.log(sigma_lo), np.log(sigma_hi), size=(N, 1)))
+    X = xc[None, :] * (1.0 + sig * rng.uniform(-1, 1, size=(N, len(xc))))
     return np.ascontiguousarray(X)

@@ -53,6 +53,14 @@ def _worker(rank, world, port, N, out_dir):
     exp = np.where(ok, f, np.inf)
     assert idx == int(np.argmin(exp)) and best == float(exp.min())
     assert count_feasible(res["gmin"], res["status"], tol=0.0) == int(ok.sum())
+    # the packed single-collective form gives the same answer on every rank
+    from compas_tno_b200.distributed import best_of_packed
+    packed = sweep.gather_packed(res)
+    assert tuple(packed.shape) == (N, 3)
+    assert np.array_equal(packed[:, 0].numpy(), f) and np.array_equal(packed[:, 1].numpy(), gmin)
+    assert np.array_equal(packed[:, 2].numpy().astype(np.int32), status)
+    assert best_of_packed(packed, tol=0.0) == (float(exp.min()), int(np.argmin(exp)), int(ok.sum()))
+    assert best_of_packed(torch.stack([packed[:, 0], packed[:, 1] - 100.0, packed[:, 2]], dim=1), tol=0.0) == (float("inf"), -1, 0)
     # nothing feasible
     none = argmin_feasible(res["f"], res["gmin"] - 100.0, res["status"], lo, tol=0.0)
     assert none == (float("inf"), -1)
