@@ -107,6 +107,18 @@ def _ladder(center, lo, hi, seed, sigma_lo, sigma_hi):
     return np.ascontiguousarray(X)
 
 
+def _bcast(arr, device):
+    """Rank 0's copy of a small host array on every rank (set-up only): the centre of a candidate ladder comes out of a
+    linear-programming loop whose last bits may differ between processes; the sweep must not depend on the sharding."""
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return arr
+    t = torch.from_numpy(np.ascontiguousarray(arr, dtype=np.float64)).to(torch.device("cuda", device))
+    dist.broadcast(t, src=0)
+    return t.cpu().numpy()
+
+
 def sweep_specs():
     """The BASELINE configurations 2-5 (+ a full-output discretisation-40 sweep) as sweeps sharded over the ranks.
     ``total(world)`` is the number of candidates of the whole sweep; ``build(device)`` returns the problem, its plan and
@@ -124,6 +136,7 @@ def sweep_specs():
             P, xs, obj = build_workload("crossvault_disc40", n_states=6)
             plan = TnoPlan(P, objective=obj, device=device)
             xc, margin = W.max_margin_state(plan, xs, rows=W.margin_rows(P, plan))
+            xc = _bcast(xc, device)
             cache["disc40"] = (P, plan, obj, xc, margin)
         return cache["disc40"]
 
@@ -131,6 +144,7 @@ def sweep_specs():
         P, xs, obj = build_workload("dome_16x20", n_states=6)
         plan = TnoPlan(P, objective=obj, device=device)
         xc, margin = W.max_margin_state(plan, xs, rows=W.margin_rows(P, plan))
+        xc = _bcast(xc, device)
         return dict(P=P, plan=plan, names=FULL, margin=margin,
                     make=lambda lo, hi: (_ladder(xc, lo, hi, 20261019 + 2, 1e-4, 0.1), {}))
 
@@ -149,6 +163,7 @@ def sweep_specs():
         P.thk, P.envelope = 0.5, CrossVaultEnvelope((0.0, 10.0), (0.0, 10.0), 0.5)
         p0 = TnoPlan(P, objective="max", device=device)           # the design: widest margin at thickness 0.50
         xc, margin = W.max_margin_state(p0, z["x"][0], rows=W.margin_rows(P, p0))
+        xc = _bcast(xc, device)
         p0.close()
         Pt = copy.copy(P)
         Pt.variables = ["q", "zb", "t"]
@@ -187,6 +202,7 @@ def sweep_specs():
         P0, x0, _ = build_workload("dome_16x20", n_states=6)
         p0 = TnoPlan(P0, objective="max", device=device)           # vertically loaded dome: the state the load is added to
         xc, margin = W.max_margin_state(p0, x0, rows=W.margin_rows(P0, p0))
+        xc = _bcast(xc, device)
         p0.close()
         P, xs = W.dome_direction_problem(20, 16, n_states=6)
         plan = TnoPlan(P, objective="max_load", device=device)
@@ -622,10 +638,16 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dt = float(t.item())
     d2h = sum(res[k].numel() * res[k].element_size() for k in host_names)
-    host_filled = Ne * 8 * 2 * plan.m * plan.nvar if "funicular" in plan.constraints else 0
+    # host-filled share of the constant funicular rows: the split tno_fetch_jacobian_host computes from its thread count
+    _thr = max(1, min(int(os.environ.get("TNO_HOST_THREADS", "16")), os.cpu_count() or 1, Ne // 64 + 1))
+    _cst, _per = 2 * plan.m * plan.nvar if "funicular" in plan.constraints else 0, plan.ng * plan.nvar
+    _phi = float(os.environ.get("TNO_HOST_FILL_FRACTION", min(1.0, _per / (_cst * (1.0 + 52.0 / (4.5 * _thr)))) if _cst else 0.0))
+    _rows = min(2 * plan.m, int(_phi * 2 * plan.m + 0.5)) if _cst else 0
+    _rows -= (_rows * plan.nvar) & 1
+    host_filled = Ne * 8 * _rows * plan.nvar
     e2e = {"value": world * Ne * esteps / dt, "unit": UNIT, "h2d_bytes_per_step": int(xh.numel() * 8), "d2h_bytes_per_step": int(d2h),
            "d2h_bytes_over_pcie_per_step": int(d2h - host_filled), "host_filled_bytes_per_step": int(host_filled),
-           "candidates_per_step": Ne, "numa": numa,
+           "candidates_per_step": Ne, "numa": numa, "host_fill_threads": _thr, "host_fill_fraction_of_constant_rows": _phi,
            "note": "every output incl. the dense J delivered to pinned host memory; d2h_bytes_per_step = delivered bytes, of which the "
                    "candidate-independent funicular rows of J (host_filled_bytes_per_step) are written by host threads from the plan's "
                    "copy and only d2h_bytes_over_pcie_per_step cross PCIe"}

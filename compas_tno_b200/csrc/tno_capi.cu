@@ -804,16 +804,29 @@ int tno_fetch_jacobian_host(tno_plan* plan, const double* J_dev, double* J_host,
     TNO_CUDA_OK(cudaMemcpyAsync(J_host, J_dev, (size_t)N * per * 8, cudaMemcpyDeviceToHost, s));
     return TNO_OK;
   }
-  TNO_CUDA_OK(cudaMemcpy2DAsync(J_host + cst, per * 8, J_dev + cst, per * 8, (per - cst) * 8, (size_t)N, cudaMemcpyDeviceToHost, s));
-  // constant rows: plain memcpy from the plan's host copy, candidates split over a few threads
-  // up to 16 threads, or TNO_HOST_THREADS (one process per GPU on a shared host: cores / ranks)
+  // up to 16 host threads, or TNO_HOST_THREADS (one process per GPU on a shared host: cores / ranks)
   static const char* env_threads = getenv("TNO_HOST_THREADS");
   const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
   const int64_t cap = env_threads ? std::max(1, atoi(env_threads)) : 16;
   const int64_t nthreads = std::max<int64_t>(1, std::min<int64_t>({(int64_t)hw, cap, N / 64 + 1}));
+  // Split of the constant rows between the host threads and the DMA engine.  The device copy of J holds them too
+  // (k_fill_funicular), so any suffix of the constant block can ride along with the candidate-dependent rows.  With
+  // D = PCIe rate and H = host fill rate (~4.5 GB/s per streaming thread), both finish together when the host takes
+  //   phi = (v + c) / (c (1 + D / H))     of the c constant bytes (v = candidate-dependent bytes per candidate).
+  // Few threads per rank (8 ranks sharing one host) => small phi, the DMA engines of the 8 GPUs carry the load.
+  static const char* env_phi = getenv("TNO_HOST_FILL_FRACTION");
+  double phi = env_phi ? atof(env_phi) : ((double)per / ((double)cst * (1.0 + 52.0 / (4.5 * (double)nthreads))));
+  phi = std::min(1.0, std::max(0.0, phi));
+  const size_t row = (size_t)P->dp.var.nvar;
+  size_t rows_h = std::min(cst / row, (size_t)(phi * (double)(cst / row) + 0.5));   // whole rows of J
+  if ((rows_h * row) & 1) rows_h -= 1;                                              // the DMA part starts 16-byte aligned
+  const size_t cst_h = rows_h * row;
+  TNO_CUDA_OK(cudaMemcpy2DAsync(J_host + cst_h, per * 8, J_dev + cst_h, per * 8, (per - cst_h) * 8, (size_t)N, cudaMemcpyDeviceToHost, s));
+  const size_t cst_fill = cst_h;
+  if (cst_fill == 0) return TNO_OK;
   const double* src = P->h_jfun.data();
   auto work = [=](int64_t a, int64_t b) {
-    for (int64_t c = a; c < b; ++c) copy_streaming(J_host + (size_t)c * per, src, cst);
+    for (int64_t c = a; c < b; ++c) copy_streaming(J_host + (size_t)c * per, src, cst_fill);
 #if defined(__SSE2__)
     _mm_sfence();
 #endif
