@@ -425,7 +425,6 @@ __global__ void __launch_bounds__(THREADS, MINB) k_onchip(const __grid_constant_
   const OcDense* dense = reinterpret_cast<const OcDense*>(smraw + O.o_idx_bytes + O.idx_dense);
   const short* vrow_s = reinterpret_cast<const short*>(smraw + O.o_idx_bytes + O.idx_vrow);
   const short* rowv_s = reinterpret_cast<const short*>(smraw + O.o_idx_bytes + O.idx_rowv);
-  const int* ecptr_s = reinterpret_cast<const int*>(smraw + O.o_idx_bytes + O.idx_ecptr);
   const int* colsrc_s = reinterpret_cast<const int*>(smraw + O.o_idx_bytes + O.idx_colsrc);
   const int* supptr_s = reinterpret_cast<const int*>(smraw + O.o_idx_bytes + O.idx_supptr);
   const int* supother_s = reinterpret_cast<const int*>(smraw + O.o_idx_bytes + O.idx_supother);
@@ -899,57 +898,42 @@ __global__ void __launch_bounds__(THREADS, MINB) k_onchip(const __grid_constant_
     // ---- 8. phase-2 right-hand sides: Ci^T W B | Ci^T W d0 ------------------------------------------
     if (need2) {
       const int nc2 = O.ncols2;
-      const int g2 = O.rhs2_shift;  // 2^g2 lanes walk the columns of one row
-      const int r_ = tid & ((1 << g2) - 1);
-      // Edge-wise accumulation: B is read exactly once per candidate (coalesced rows in colour order) and every edge
-      // updates the panel rows of its two end points.  Edges of one colour share no free vertex, so the updates of a
-      // colour never collide; one barrier per colour.
-      for (int it = tid; it < ni * (W >> 1); it += THREADS) reinterpret_cast<double2*>(R)[it] = make_double2(0.0, 0.0);
-      __syncthreads();
-      // every colour holds at most 8 edges per thread slot (the plan splits larger colours): the records and
-      // coefficients of the NEXT colour are loaded into registers while the current colour is accumulated, so the
-      // L2 round trip is off the critical path
+      // Row-wise ("pull") accumulation: row r of Ci^T W [B | d0] is  sum over the edges e at vertex r of
+      // (z_r - z_other(e)) [B | d0][e, :]  whichever way the edge points (C[e, r] (C z)_e = z_r - z_other).  G lanes
+      // cover the column pairs of a row, rows are independent: no colouring, no read-modify-write, ONE barrier.  The
+      // coefficient rows are stored in row-adjacency order (Br: one 16-byte-aligned record per (row, edge) pair), so a
+      // row's loads are contiguous, independent of one another and issued back to back.
       {
-        const int ept = THREADS >> g2;  // edges per pass
-        for (int cb = 0; cb < nc2; cb += 1 << g2) {   // uniform trip count: every thread reaches every barrier
-          const int cidx = cb + r_;
-          const bool cok = cidx < nc2;
-          uint32_t rec[8], recn[8];
-          double cf[8], cfn[8];
-          auto fetch = [&](int color, uint32_t (&rc)[8], double (&cc)[8]) {
-            const int p0 = ecptr_s[color], p1 = ecptr_s[color + 1];
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-              const int e = p0 + (tid >> g2) + u * ept;
-              const bool ok = cok && e < p1;
-              rc[u] = ok ? __ldg(O.ec_rec + e) : 0xffffffffu;
-              cc[u] = ok ? __ldg(O.Bc + (int64_t)e * O.bc_stride + cidx) : 0.0;
-              // lambdh column with a second load basis: d0 of the candidate's direction (the basis sits one column on)
-              if (has_dir && ok && cidx == k) cc[u] = fma(dirs, __ldg(O.Bc + (int64_t)e * O.bc_stride + k + 1), dirc * cc[u]);
-            }
-          };
-          fetch(0, rec, cf);
-          for (int color = 0; color < O.ncolors; ++color) {
-            if (color + 1 < O.ncolors) fetch(color + 1, recn, cfn);
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-              if (rec[u] != 0xffffffffu) {
-                const int hv = (int)(rec[u] & 0xffffu), tv = (int)(rec[u] >> 16);
-                const double zh = zs[(hv & 0x8000) ? ni + (hv & 0x7fff) : hv];
-                const double zt = zs[(tv & 0x8000) ? ni + (tv & 0x7fff) : tv];
-                const double wc = (zh - zt) * cf[u];  // (C z)_e B[e, j]
-                if (!(hv & 0x8000)) R[hv * W + O.c_q + cidx] += wc;   // C[e, head] = +1
-                if (!(tv & 0x8000)) R[tv * W + O.c_q + cidx] -= wc;   // C[e, tail] = -1
+        const int gs = O.gshift[1];
+        const int c = 2 * (tid & ((1 << gs) - 1));
+        const bool cok = c < W;
+        for (int r = tid >> gs; r < ni; r += THREADS >> gs) {
+          const int t0 = __ldg(O.radj_ptr + r), t1 = __ldg(O.radj_ptr + r + 1);
+          const double zr = zs[r];
+          double ax = 0.0, ay = 0.0;
+          if (cok) {
+#pragma unroll 4
+            for (int t = t0; t < t1; ++t) {
+              const unsigned o = __ldg(O.radj + t) & 0xffffu;
+              const double dz = zr - zs[(o & 0x8000u) ? ni + (o & 0x7fffu) : o];
+              double2 cf = __ldg(reinterpret_cast<const double2*>(O.Br + (int64_t)t * O.br_stride + c));
+              if constexpr (DIR) {
+                // lambdh column with a second load basis: d0 of the candidate's direction (the basis sits one column on)
+                if (has_dir && (c == k || c + 1 == k)) {
+                  const double d0b = __ldg(O.Br + (int64_t)t * O.br_stride + k + 1);
+                  if (c == k) cf.x = fma(dirs, d0b, dirc * cf.x);
+                  else cf.y = fma(dirs, d0b, dirc * cf.y);
+                }
               }
+              ax = fma(dz, cf.x, ax);
+              ay = fma(dz, cf.y, ay);
             }
-            __syncthreads();
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-              rec[u] = recn[u];
-              cf[u] = cfn[u];
-            }
+            if (c >= nc2) ax = 0.0;        // padding columns (and the slot of the second load basis) stay zero
+            if (c + 1 >= nc2) ay = 0.0;
+            *reinterpret_cast<double2*>(R + r * W + c) = make_double2(ax, ay);
           }
         }
+        __syncthreads();
       }
       if (A.phase_clocks && blockIdx.x == 0 && tid == 0 && cand == (int64_t)(A.N > 4 * gridDim.x ? 4 * gridDim.x : 0)) A.phase_clocks[9] = clock64();
       // ---- 9. solve phase 2 ----
@@ -1614,55 +1598,21 @@ static int build_onchip_impl(Plan* PL, const tno_problem_desc* D, const int THRE
     }
   }
 
-  // ---- edge colouring for the phase-2 right-hand sides ----
-  std::vector<int> ec_ptr;
-  std::vector<uint32_t> ec_rec;
-  std::vector<double> Bc;
+  // ---- coefficient rows of the phase-2 right-hand sides in row-adjacency order ----
+  // Br[t] = [B[e, 0..k-1] | d0[e] (lambdh) | d0_b[e] (second load basis)] of the edge e of adjacency record t, zero padded
+  // to br_stride (even, >= the panel width): the kernel reads it with 16-byte loads, two columns per lane.
+  std::vector<double> Br;
   {
-    const int stride = k + (P.var.o_lambdh >= 0 ? 1 : 0) + (D->d_b ? 1 : 0);
-    O.bc_stride = stride;
-    std::vector<int> color(m, -1);
-    std::vector<std::vector<char>> used;  // used[c][row]
-    int ncol = 0;
-    for (int e = 0; e < m; ++e) {
-      const int ru = PL->h_vrow[D->edges[2 * e]], rv = PL->h_vrow[D->edges[2 * e + 1]];
-      if (ru < 0 && rv < 0) continue;  // support-to-support edge: no free row to update
-      int c = 0;
-      for (;; ++c) {
-        if (c == ncol) {
-          used.push_back(std::vector<char>(ni, 0));
-          ++ncol;
-        }
-        if ((ru < 0 || !used[c][ru]) && (rv < 0 || !used[c][rv])) break;
-      }
-      color[e] = c;
-      if (ru >= 0) used[c][ru] = 1;
-      if (rv >= 0) used[c][rv] = 1;
+    const int cols = k + (P.var.o_lambdh >= 0 ? 1 : 0) + (D->d_b ? 1 : 0);
+    O.br_stride = std::max(O.W, (cols + 1) / 2 * 2);
+    Br.assign(std::max<size_t>(radj.size(), 1) * O.br_stride, 0.0);
+    for (size_t t = 0; t < radj.size(); ++t) {
+      const int e = (int)(radj[t] >> 16);
+      double* dst = Br.data() + t * O.br_stride;
+      for (int j = 0; j < k; ++j) dst[j] = D->B[(size_t)e * k + j];
+      if (P.var.o_lambdh >= 0) dst[k] = D->d[e];
+      if (D->d_b) dst[k + 1] = D->d_b[e];
     }
-    const int max_per_color = 8 * (THREADS >> O.rhs2_shift);
-    ec_ptr.assign(1, 0);
-    for (int c = 0; c < ncol; ++c) {
-      int in_piece = 0;
-      for (int e = 0; e < m; ++e) {
-        if (color[e] != c) continue;
-        if (in_piece == max_per_color) {  // a subset of a colour is conflict free too
-          ec_ptr.push_back((int)ec_rec.size());
-          in_piece = 0;
-        }
-        ++in_piece;
-        const int ru = PL->h_vrow[D->edges[2 * e]], rv = PL->h_vrow[D->edges[2 * e + 1]];
-        const uint32_t tail = ru >= 0 ? (uint32_t)ru : (0x8000u | (uint32_t)(-1 - ru));   // C[e, u] = -1
-        const uint32_t head = rv >= 0 ? (uint32_t)rv : (0x8000u | (uint32_t)(-1 - rv));   // C[e, v] = +1
-        ec_rec.push_back(head | (tail << 16));
-        for (int j = 0; j < k; ++j) Bc.push_back(D->B[(size_t)e * k + j]);
-        if (P.var.o_lambdh >= 0) Bc.push_back(D->d[e]);
-        if (D->d_b) Bc.push_back(D->d_b[e]);
-      }
-      ec_ptr.push_back((int)ec_rec.size());
-    }
-    O.ncolors = (int)ec_ptr.size() - 1;
-    if (ec_rec.empty()) ec_rec.push_back(0);
-    if (Bc.empty()) Bc.push_back(0.0);
   }
 
   std::vector<int> colsrc(nvar, -1);
@@ -1722,7 +1672,6 @@ static int build_onchip_impl(Plan* PL, const tno_problem_desc* D, const int THRE
     std::vector<short> vrow16(PL->h_vrow.begin(), PL->h_vrow.end()), rowv16(row_vertex.begin(), row_vertex.end());
     put_table(&O.idx_vrow, vrow16.data(), vrow16.size() * 2);
     put_table(&O.idx_rowv, rowv16.data(), rowv16.size() * 2);
-    put_table(&O.idx_ecptr, ec_ptr.data(), ec_ptr.size() * 4);
     put_table(&O.idx_colsrc, colsrc.data(), colsrc.size() * 4);
     put_table(&O.idx_supptr, sup_ptr.data(), sup_ptr.size() * 4);
     put_table(&O.idx_supother, sup_other.data(), std::max<size_t>(sup_other.size(), 1) * 4);
@@ -1834,9 +1783,7 @@ static int build_onchip_impl(Plan* PL, const tno_problem_desc* D, const int THRE
   UPO(radj_ptr, radj_ptr);
   UPO(radj, radj);
   UPO(radj_pad, radj_pad);
-  UPO(ec_ptr, ec_ptr);
-  UPO(ec_rec, ec_rec);
-  UPO(Bc, Bc);
+  UPO(Br, Br);
   UPO(ct_ptr, ct_ptr);
   UPO(ct_col, ct_col);
   UPO(ct_ent, ct_ent);

@@ -199,12 +199,9 @@ struct DevOnchip {
   const int* radj_ptr;   // ni + 1
   const uint32_t* radj;  // other end (row, or 0x8000 | support index) | edge << 16
   const uint32_t* radj_pad;  // ni x adj_deg, padded with self references (zero contribution)
-  // phase-2 right-hand sides by edges: edges coloured so that edges of one colour share no free vertex
-  int ncolors;
-  const int* ec_ptr;         // ncolors + 1
-  const uint32_t* ec_rec;    // head | tail << 16 (row, or 0x8000 | support index), colour order
-  const double* Bc;          // coefficient rows in colour order: k columns of B (+ 1 column d0 when lambdh is a variable)
-  int bc_stride;
+  // phase-2 right-hand sides, row-wise: coefficient rows [B | d0 | d0_b] in row-adjacency order (one record per radj entry)
+  const double* Br;
+  int br_stride;             // doubles per record (even, >= W)
   // column-wise view of the chain rows' outside entries (backward solve): for every outside column ("target")
   // reached by the chains of one chain level, the entries (value position | row << 16) of the chain rows in it
   const unsigned short* ct_ptr;
@@ -214,7 +211,7 @@ struct DevOnchip {
   int idx_ct_row;
   // small lookup tables copied into the shared-memory index region (byte offsets): no L2 round trip in front of
   // the accesses that depend on them
-  int idx_vrow, idx_rowv, idx_ecptr, idx_colsrc, idx_supptr, idx_supother, idx_supedge, idx_supsign, idx_fixed;
+  int idx_vrow, idx_rowv, idx_colsrc, idx_supptr, idx_supother, idx_supedge, idx_supsign, idx_fixed;
   int ct_in_smem;        // 1: the three arrays live in the shared-memory index region at idx_ct_*
   int idx_ct_ptr, idx_ct_col, idx_ct_ent;
   const double* Jfun;    // 2m x nvar

@@ -2,6 +2,7 @@
 #include "tno_symbolic.hpp"
 
 #include <algorithm>
+#include <cstdlib>
 #include <cmath>
 #include <functional>
 #include <numeric>
@@ -325,6 +326,51 @@ void analyse(int ni, const std::vector<std::pair<int, int>>& edges, int ordering
           chain_first.push_back(j);
           chain_len.push_back(1);
           clev.push_back(cl);
+        }
+      }
+      // ---- merge short chains into their parent chain --------------------------------------------------
+      // Every chain level costs the kernels a fixed number of dependent, barrier-separated steps per sweep however
+      // short its chains are.  A chain of at most `merge_len` rows is therefore absorbed by the chain above it: the
+      // merged block is the dense triangle over a small SUBTREE of the elimination tree instead of a path (independent
+      // branches inside it are structural zeros, which the dense factorisation and the explicit inverse keep zero).
+      {
+        static const char* env = getenv("TNO_CHAIN_MERGE");
+        const int merge_len = env ? atoi(env) : 8;
+        const int nch0 = (int)chain_first.size();
+        std::vector<int> clast(nch0, -1), cpar(nch0, -1), rep(nch0), glen(chain_len);
+        for (int j = wide_rows; j < ni; ++j) clast[chain_of[j]] = j;
+        for (int c = 0; c < nch0; ++c) cpar[c] = parent[clast[c]] >= 0 ? chain_of[parent[clast[c]]] : -1;
+        std::iota(rep.begin(), rep.end(), 0);
+        std::vector<int> byl(nch0);
+        std::iota(byl.begin(), byl.end(), 0);
+        std::stable_sort(byl.begin(), byl.end(), [&](int a, int b) { return clev[a] > clev[b]; });   // parents first
+        for (int c : byl) {
+          if (cpar[c] < 0 || merge_len <= 0) continue;
+          const int g = rep[cpar[c]];
+          if (chain_len[c] <= merge_len && glen[g] + chain_len[c] <= 48) {
+            rep[c] = g;
+            glen[g] += chain_len[c];
+          }
+        }
+        bool merged = false;
+        for (int c = 0; c < nch0; ++c) merged |= rep[c] != c;
+        if (merged) {
+          std::vector<int> newid(nch0, -1);
+          int nn = 0;
+          for (int c = 0; c < nch0; ++c)
+            if (rep[c] == c) newid[c] = nn++;
+          for (int j = wide_rows; j < ni; ++j) chain_of[j] = newid[rep[chain_of[j]]];
+          chain_first.assign(nn, -1);
+          chain_len.assign(nn, 0);
+          for (int j = wide_rows; j < ni; ++j) {
+            if (chain_first[chain_of[j]] < 0) chain_first[chain_of[j]] = j;
+            chain_len[chain_of[j]]++;
+          }
+          // chain levels of the merged chain tree (children have smaller node indices than their parents)
+          clev.assign(nn, 0);
+          for (int j = wide_rows; j < ni; ++j)
+            if (parent[j] >= 0 && chain_of[parent[j]] != chain_of[j])
+              clev[chain_of[parent[j]]] = std::max(clev[chain_of[parent[j]]], clev[chain_of[j]] + 1);
         }
       }
       const int nch = (int)chain_first.size();

@@ -71,7 +71,9 @@ def test_level_order_and_chain_partition(n_div):
     for c in range(len(cp) - 1):
         chain_of[cp[c]:cp[c + 1]] = c
         for r in range(cp[c], cp[c + 1] - 1):
-            assert parent[r] == r + 1                                   # a chain is a tree path
+            # a chain is a tree path, or (short chains merged into their parent chain) a small subtree: every row but
+            # the last has its parent inside the same block, further on
+            assert cp[c] <= r < parent[r] < cp[c + 1]
     # rows of a chain only reach outside columns below the chain or earlier columns of the same chain
     for j in range(n):
         for i in S["rowidx"][S["colptr"][j] + 1:S["colptr"][j + 1]]:
