@@ -55,6 +55,27 @@ __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
 }
 
+// Reciprocal of a positive double without the IEEE division's slow path: hardware seed (about 20 bits) and two Newton
+// steps on the FP64 pipe; the result is within an ulp or two of 1 / d.
+__device__ __forceinline__ double oc_rcp(double d) {
+  double x;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(d));
+  double e = fma(-d, x, 1.0);
+  x = fma(x, e, x);
+  e = fma(-d, x, 1.0);
+  x = fma(x, e, x);
+  return x;
+}
+
+// Barrier of one candidate group.  A CTA holds G groups of NT threads, one candidate each, which share the index region
+// but nothing else: every group synchronises on its own named barrier (id = group + 1); a single-group CTA keeps
+// __syncthreads().
+template <int NT>
+__device__ __forceinline__ void oc_sync(int bar) {
+  if (bar == 0) __syncthreads();
+  else asm volatile("bar.sync %0, %1;" ::"r"(bar), "n"(NT) : "memory");
+}
+
 __device__ __forceinline__ void oc_envelope(const DevPlan& P, double x, double y, double t, double* ub, double* lb,
                                             double* dub, double* dlb) {
   const double dx = x - P.env[0], dy = y - P.env[1];
@@ -166,7 +187,7 @@ constexpr int OC_ZPASS = 4;
 template <int NT, bool TRANSPOSED>
 __device__ __forceinline__ void oc_chain_apply(const OcRange& L, const OcChain* __restrict__ chains,
                                                const unsigned char* __restrict__ rowchain, int wide_rows, int gshift, int tl, int c0,
-                                               int ncols, int W, const double* __restrict__ V, double* __restrict__ R) {
+                                               int ncols, int W, const double* __restrict__ V, double* __restrict__ R, int bar) {
   const int rows = L.row1 - L.row0;
   const int r = tl & ((1 << gshift) - 1);
   const bool colok = 2 * r < ncols;
@@ -207,7 +228,7 @@ __device__ __forceinline__ void oc_chain_apply(const OcRange& L, const OcChain* 
         res[ps] = acc;
       }
     }
-    __syncthreads();
+    oc_sync<NT>(bar);
 #pragma unroll
     for (int ps = 0; ps < OC_ZPASS; ++ps) {
       const int it = lo + ps * (NT >> gshift) + (tl >> gshift);
@@ -224,7 +245,7 @@ __device__ __forceinline__ void oc_solve(const DevOnchip& O, int phase, const Oc
                                          const unsigned short* __restrict__ rowcol16, const double* __restrict__ V,
                                          double* __restrict__ R, int ni, int c0, int ncols, int tid,
                                          const unsigned short* ct_ptr, const unsigned short* ct_col, const unsigned short* ct_ent,
-                                         const unsigned char* ct_row, long long* tc = nullptr) {
+                                         const unsigned char* ct_row, int bar, long long* tc = nullptr) {
   const int W = O.W;
   const int gshift = O.gshift[phase];
   long long tq = tc ? clock64() : 0;
@@ -239,16 +260,16 @@ __device__ __forceinline__ void oc_solve(const DevOnchip& O, int phase, const Oc
   for (int lev = 1; lev < O.nwide; ++lev) {
     const OcRange L = wide[lev];
     oc_pull_rows<THREADS>(L.row0, L.row1, L.pull_s[phase], gshift, tid, c0, ncols, W, rowptr16, rowcol16, V, R);
-    __syncthreads();
+    oc_sync<THREADS>(bar);
   }
   lap(0);
   for (int cl = 0; cl < O.nclev; ++cl) {
     const OcRange L = clev[cl];
     oc_pull_rows<THREADS>(L.row0, L.row1, L.pull_s[phase], gshift, tid, c0, ncols, W, rowptr16, rowcol16, V, R);
-    __syncthreads();
+    oc_sync<THREADS>(bar);
     lap(1);
-    oc_chain_apply<THREADS, false>(L, chains, rowchain, O.wide_rows, gshift, tid, c0, ncols, W, V, R);
-    __syncthreads();
+    oc_chain_apply<THREADS, false>(L, chains, rowchain, O.wide_rows, gshift, tid, c0, ncols, W, V, R, bar);
+    oc_sync<THREADS>(bar);
     lap(2);
   }
   // ---- diagonal: y_i / d_i ----
@@ -265,13 +286,13 @@ __device__ __forceinline__ void oc_solve(const DevOnchip& O, int phase, const Oc
       }
     }
   }
-  __syncthreads();
+  oc_sync<THREADS>(bar);
   lap(3);
   // ---- backward ----
   for (int cl = O.nclev - 1; cl >= 0; --cl) {
     const OcRange L = clev[cl];
-    oc_chain_apply<THREADS, true>(L, chains, rowchain, O.wide_rows, gshift, tid, c0, ncols, W, V, R);
-    __syncthreads();
+    oc_chain_apply<THREADS, true>(L, chains, rowchain, O.wide_rows, gshift, tid, c0, ncols, W, V, R, bar);
+    oc_sync<THREADS>(bar);
     lap(4);
     // the rows of one chain share their descendants, so their updates are gathered per outside column ("target")
     // instead of pushed per row: x_j -= sum_{i in chain} L_ij x_i.  Targets of one chain level are disjoint.
@@ -297,13 +318,13 @@ __device__ __forceinline__ void oc_solve(const DevOnchip& O, int phase, const Oc
         }
       }
     }
-    __syncthreads();
+    oc_sync<THREADS>(bar);
     lap(5);
   }
   for (int lev = O.nwide - 1; lev >= 1; --lev) {
     const OcRange L = wide[lev];
     oc_push_rows<THREADS>(L.row0, L.row1, L.push_s[phase], gshift, tid, c0, ncols, W, rowptr16, rowcol16, V, R);
-    __syncthreads();
+    oc_sync<THREADS>(bar);
   }
   lap(6);
 }
@@ -316,7 +337,7 @@ __device__ __forceinline__ void oc_solve(const DevOnchip& O, int phase, const Oc
 //       (columns are independent, no barriers), then the blocks are copied back over L.
 template <int THREADS>
 __device__ __forceinline__ void oc_chain_dense(const DevOnchip& O, const OcDense& DN, double* __restrict__ V,
-                                               double* __restrict__ tmpz, int* s_flags, int tid, long long* t_b) {
+                                               double* __restrict__ tmpz, int* s_flags, int tid, int bar, long long* t_b) {
   const long long tb0 = t_b ? clock64() : 0;
   const int zbase = O.nlo + (O.nv - O.nlo - O.nz);  // first dense position (= nlo + ni)
   // ---- (B) ----
@@ -340,7 +361,7 @@ __device__ __forceinline__ void oc_chain_dense(const DevOnchip& O, const OcDense
       double sv = fma(-uij * inv, ukj, V[sp]);
       if (kk == ii && j == ii - 1) {  // diagonal just became final
         if (!(sv > 0.0)) atomicOr(s_flags, TNO_STATUS_NOT_PD);
-        sv = 1.0 / sv;
+        sv = oc_rcp(sv);
       }
       V[sp] = sv;
     }
@@ -351,10 +372,10 @@ __device__ __forceinline__ void oc_chain_dense(const DevOnchip& O, const OcDense
       const int sp = (int)(d.y & 0xffffu);
       const double v = V[sp];
       if (!(v > 0.0)) atomicOr(s_flags, TNO_STATUS_NOT_PD);
-      V[sp] = 1.0 / v;
+      V[sp] = oc_rcp(v);
     }
   }
-  __syncthreads();
+  oc_sync<THREADS>(bar);
   for (int j = 0; j + 1 < (int)DN.tmax; ++j) {
     if (in_regs) {
       // elements are sorted by descending k: once a thread's first element is inactive, all of them are
@@ -365,14 +386,14 @@ __device__ __forceinline__ void oc_chain_dense(const DevOnchip& O, const OcDense
     } else {
       for (uint32_t e = DN.de0 + tid; e < DN.de1; e += THREADS) step_elem(__ldg(O.de + e), j);
     }
-    __syncthreads();
+    oc_sync<THREADS>(bar);
   }
   for (uint32_t e = DN.de0 + tid; e < DN.de1; e += THREADS) {
     const uint4 d = __ldg(O.de + e);
     const int kk = (int)(d.z & 0xffu), ii = (int)((d.z >> 8) & 0xffu);
     if (kk < ii) V[(int)(d.y & 0xffffu)] *= V[(int)(d.y >> 16) + kk];  // l_ik = u_ik / d_k
   }
-  __syncthreads();
+  oc_sync<THREADS>(bar);
   if (t_b) *t_b += clock64() - tb0;
   // ---- (C) ----
   for (uint32_t cidx = DN.dc0 + tid; cidx < DN.dc1; cidx += THREADS) {
@@ -388,18 +409,24 @@ __device__ __forceinline__ void oc_chain_dense(const DevOnchip& O, const OcDense
       Zt[rb + c] = -a;
     }
   }
-  __syncthreads();
+  oc_sync<THREADS>(bar);
   for (uint32_t p = DN.zlo + tid; p < DN.zhi; p += THREADS) V[p] = tmpz[p - zbase];
-  __syncthreads();
+  oc_sync<THREADS>(bar);
 }
 
 // DIR: per-candidate horizontal load directions (tno_batch_inputs.load_dir); a separate instantiation so that the
 // common single-basis path carries none of its registers or branches.
-template <int THREADS, int MINB, bool DIR>
-__global__ void __launch_bounds__(THREADS, MINB) k_onchip(const __grid_constant__ DevPlan P, const __grid_constant__ DevOnchip O,
-                                                            const __grid_constant__ OcArgs A) {
+// G: candidate groups per CTA.  Every group of THREADS threads works on its own candidate with its own value array and
+// panel (o_idx_bytes bytes each) and its own named barrier; the index region behind them is shared by all groups, which is
+// what lets a third candidate fit on an SM.
+template <int THREADS, int MINB, int G, bool DIR>
+__global__ void __launch_bounds__(THREADS * G, MINB) k_onchip(const __grid_constant__ DevPlan P, const __grid_constant__ DevOnchip O,
+                                                                const __grid_constant__ OcArgs A) {
   extern __shared__ __align__(16) unsigned char smraw[];
-  double* sm = reinterpret_cast<double*>(smraw);
+  const int grp = G > 1 ? (int)threadIdx.x / THREADS : 0;
+  const int bar = G > 1 ? grp + 1 : 0;
+  double* sm = reinterpret_cast<double*>(smraw + (size_t)grp * O.o_idx_bytes);
+  const unsigned char* idxb = smraw + (size_t)G * O.o_idx_bytes;
   double* xs = sm + O.o_x;
   double* V = sm + O.o_v;
   double* R = sm + O.o_r;
@@ -414,31 +441,32 @@ __global__ void __launch_bounds__(THREADS, MINB) k_onchip(const __grid_constant_
   double* lpe = sm + O.o_lpe;      // loadpath objective: sign(q_e) l_e^2 per edge (m)
   double* lpa = sm + O.o_lpa;      //                     |q_e| w_e per edge (m), then the direct gradient term (k)
   double* lpw = sm + O.o_lpw;      //                     omega = 2 C^T (|q| o w) per free row, then per support (ni + nb)
-  const unsigned short* rowptr16 = reinterpret_cast<const unsigned short*>(smraw + O.o_idx_bytes + O.idx_rowptr);
-  const unsigned short* rowcol16 = reinterpret_cast<const unsigned short*>(smraw + O.o_idx_bytes + O.idx_rowcol);
-  const OcRange* wide = reinterpret_cast<const OcRange*>(smraw + O.o_idx_bytes + O.idx_wide);
-  const OcRange* clev = reinterpret_cast<const OcRange*>(smraw + O.o_idx_bytes + O.idx_clev);
-  const OcChain* chains = reinterpret_cast<const OcChain*>(smraw + O.o_idx_bytes + O.idx_chains);
-  const unsigned char* rowchain = smraw + O.o_idx_bytes + O.idx_rowchain;
-  const OcChunk* chunks = reinterpret_cast<const OcChunk*>(smraw + O.o_idx_bytes + O.idx_chunks);
-  const OcOp* ops = reinterpret_cast<const OcOp*>(smraw + O.o_idx_bytes + O.idx_ops);
-  const OcDense* dense = reinterpret_cast<const OcDense*>(smraw + O.o_idx_bytes + O.idx_dense);
-  const short* vrow_s = reinterpret_cast<const short*>(smraw + O.o_idx_bytes + O.idx_vrow);
-  const short* rowv_s = reinterpret_cast<const short*>(smraw + O.o_idx_bytes + O.idx_rowv);
-  const int* colsrc_s = reinterpret_cast<const int*>(smraw + O.o_idx_bytes + O.idx_colsrc);
-  const int* supptr_s = reinterpret_cast<const int*>(smraw + O.o_idx_bytes + O.idx_supptr);
-  const int* supother_s = reinterpret_cast<const int*>(smraw + O.o_idx_bytes + O.idx_supother);
-  const int* supedge_s = reinterpret_cast<const int*>(smraw + O.o_idx_bytes + O.idx_supedge);
-  const float* supsign_s = reinterpret_cast<const float*>(smraw + O.o_idx_bytes + O.idx_supsign);
-  const int* fixed_s = reinterpret_cast<const int*>(smraw + O.o_idx_bytes + O.idx_fixed);
+  const unsigned short* rowptr16 = reinterpret_cast<const unsigned short*>(idxb + O.idx_rowptr);
+  const unsigned short* rowcol16 = reinterpret_cast<const unsigned short*>(idxb + O.idx_rowcol);
+  const OcRange* wide = reinterpret_cast<const OcRange*>(idxb + O.idx_wide);
+  const OcRange* clev = reinterpret_cast<const OcRange*>(idxb + O.idx_clev);
+  const OcChain* chains = reinterpret_cast<const OcChain*>(idxb + O.idx_chains);
+  const unsigned char* rowchain = idxb + O.idx_rowchain;
+  const OcChunk* chunks = reinterpret_cast<const OcChunk*>(idxb + O.idx_chunks);
+  const OcOp* ops = reinterpret_cast<const OcOp*>(idxb + O.idx_ops);
+  const OcDense* dense = reinterpret_cast<const OcDense*>(idxb + O.idx_dense);
+  const short* vrow_s = reinterpret_cast<const short*>(idxb + O.idx_vrow);
+  const short* rowv_s = reinterpret_cast<const short*>(idxb + O.idx_rowv);
+  const int* colsrc_s = reinterpret_cast<const int*>(idxb + O.idx_colsrc);
+  const int* supptr_s = reinterpret_cast<const int*>(idxb + O.idx_supptr);
+  const int* supother_s = reinterpret_cast<const int*>(idxb + O.idx_supother);
+  const int* supedge_s = reinterpret_cast<const int*>(idxb + O.idx_supedge);
+  const float* supsign_s = reinterpret_cast<const float*>(idxb + O.idx_supsign);
+  const int* fixed_s = reinterpret_cast<const int*>(idxb + O.idx_fixed);
   double* zs = sm + O.o_zs;        // z of the free rows (after phase 1) followed by zb of the supports
-  const unsigned short* ct_ptr = O.ct_in_smem ? reinterpret_cast<const unsigned short*>(smraw + O.o_idx_bytes + O.idx_ct_ptr) : O.ct_ptr;
-  const unsigned short* ct_col = O.ct_in_smem ? reinterpret_cast<const unsigned short*>(smraw + O.o_idx_bytes + O.idx_ct_col) : O.ct_col;
-  const unsigned short* ct_ent = O.ct_in_smem ? reinterpret_cast<const unsigned short*>(smraw + O.o_idx_bytes + O.idx_ct_ent) : O.ct_ent;
-  const unsigned char* ct_row = O.ct_in_smem ? smraw + O.o_idx_bytes + O.idx_ct_row : O.ct_row;
-  __shared__ int s_flags;
+  const unsigned short* ct_ptr = O.ct_in_smem ? reinterpret_cast<const unsigned short*>(idxb + O.idx_ct_ptr) : O.ct_ptr;
+  const unsigned short* ct_col = O.ct_in_smem ? reinterpret_cast<const unsigned short*>(idxb + O.idx_ct_col) : O.ct_col;
+  const unsigned short* ct_ent = O.ct_in_smem ? reinterpret_cast<const unsigned short*>(idxb + O.idx_ct_ent) : O.ct_ent;
+  const unsigned char* ct_row = O.ct_in_smem ? idxb + O.idx_ct_row : O.ct_row;
+  __shared__ int s_flags_all[4];
+  int& s_flags = s_flags_all[grp];
 
-  const int tid = threadIdx.x;
+  const int tid = G > 1 ? (int)threadIdx.x - grp * THREADS : (int)threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5;
   const int n = P.n, m = P.m, ni = P.ni, nb = P.nb, k = P.k, nvar = P.var.nvar, ng = P.con.ng, W = O.W;
   const int nlo = O.nlo;
@@ -454,16 +482,18 @@ __global__ void __launch_bounds__(THREADS, MINB) k_onchip(const __grid_constant_
   const bool need2 = O.ncols2 > 0 && (A.J != nullptr || ((want_wsum || want_ecomp) && A.grad != nullptr));
 
   // index region: loaded once per CTA, reused by every candidate
-  for (int i = tid; i < O.idx_bytes / 16; i += THREADS)
-    reinterpret_cast<uint4*>(smraw + O.o_idx_bytes)[i] = reinterpret_cast<const uint4*>(O.idx_init)[i];
+  for (int i = threadIdx.x; i < O.idx_bytes / 16; i += THREADS * G)
+    reinterpret_cast<uint4*>(smraw + (size_t)G * O.o_idx_bytes)[i] = reinterpret_cast<const uint4*>(O.idx_init)[i];
   __syncthreads();
 
-  for (int64_t cand = blockIdx.x; cand < A.N; cand += gridDim.x) {
-    if (A.phase_clocks && blockIdx.x == 0 && tid == 0 && cand == (int64_t)(A.N > 4 * gridDim.x ? 4 * gridDim.x : 0)) A.phase_clocks[0] = clock64();
+  const int64_t clk_cand = A.N > 4 * (int64_t)gridDim.x * G ? 4 * (int64_t)gridDim.x * G : 0;   // CTA 0, group 0, its 5th candidate
+  for (int64_t cand = (int64_t)blockIdx.x * G + grp; cand < A.N; cand += (int64_t)gridDim.x * G) {
+    const bool clk_here = A.phase_clocks && tid == 0 && cand == clk_cand;
+    if (clk_here) A.phase_clocks[0] = clock64();
     // ---- 0. variables ------------------------------------------------------------------------------
     if (tid < nvar) xs[tid] = A.x[cand * A.ldx + tid];
     if (tid == 0) s_flags = 0;
-    __syncthreads();
+    oc_sync<THREADS>(bar);
     const double lamh = P.var.o_lambdh >= 0 ? xs[P.var.o_lambdh] : 1.0;
     const double lamv = P.var.o_lambdv >= 0 ? xs[P.var.o_lambdv] : 1.0;
     const double pzs = A.pzs ? A.pzs[cand] : 1.0;
@@ -480,7 +510,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_onchip(const __grid_constant_
     double* gout = A.g ? A.g + cand * ng : nullptr;
     double* Jout = A.J ? A.J + cand * (int64_t)ng * nvar : nullptr;
 
-    if (A.phase_clocks && blockIdx.x == 0 && tid == 0 && cand == (int64_t)(A.N > 4 * gridDim.x ? 4 * gridDim.x : 0)) A.phase_clocks[1] = clock64();
+    if (clk_here) A.phase_clocks[1] = clock64();
     // ---- 1. q = B q_ind + lambdh d ; funicular rows of g -------------------------------------------
     for (int e0 = tid; e0 < m; e0 += 4 * THREADS) {
       // four edges per thread at once: 4 x unroll independent loads of B in flight
@@ -523,9 +553,9 @@ __global__ void __launch_bounds__(THREADS, MINB) k_onchip(const __grid_constant_
       bad |= !isfinite(acc);
       }
     }
-    __syncthreads();
+    oc_sync<THREADS>(bar);
 
-    if (A.phase_clocks && blockIdx.x == 0 && tid == 0 && cand == (int64_t)(A.N > 4 * gridDim.x ? 4 * gridDim.x : 0)) A.phase_clocks[2] = clock64();
+    if (clk_here) A.phase_clocks[2] = clock64();
     // ---- 2. assemble -(Ci^T Q Ci) into the pattern of L; keep q of the support edges ----------------
     if (O.simple_asm) {
       // off-diagonal positions: one edge or fill; diagonals: minus the sum over the incident edges
@@ -553,9 +583,9 @@ __global__ void __launch_bounds__(THREADS, MINB) k_onchip(const __grid_constant_
     }
     if (tid == 0) V[O.pos_m1] = -1.0;
     for (int t = tid; t < O.nsup; t += THREADS) qsup[t] = qs[supedge_s[t]];
-    __syncthreads();  // q consumed: the panel region is free for the factor stream
+    oc_sync<THREADS>(bar);  // q consumed: the panel region is free for the factor stream
 
-    if (A.phase_clocks && blockIdx.x == 0 && tid == 0 && cand == (int64_t)(A.N > 4 * gridDim.x ? 4 * gridDim.x : 0)) A.phase_clocks[3] = clock64();
+    if (clk_here) A.phase_clocks[3] = clock64();
     // ---- 3. numeric L D L^T: a short program of staged pull chunks (wide levels, chain S-steps, rectangular
     //         chain rows) and dense chain ops.  Off-diagonal CSR entries stay unscaled (U = L D) until step 4.
     {
@@ -573,22 +603,22 @@ __global__ void __launch_bounds__(THREADS, MINB) k_onchip(const __grid_constant_
       };
       issue(0);
       issue(1);
-      const bool clk = A.phase_clocks && blockIdx.x == 0 && tid == 0 && cand == (int64_t)(A.N > 4 * gridDim.x ? 4 * gridDim.x : 0);
+      const bool clk = clk_here;
       long long t_dense = 0, t_wait = 0, t_ldl = 0, t_last = clk ? clock64() : 0;
       for (int op = 0; op < O.nops; ++op) {
         const OcOp OP = ops[op];
         if (OP.type == OC_OP_DENSE) {
-          __syncthreads();
+          oc_sync<THREADS>(bar);
           const long long t0 = clk ? clock64() : 0;
-          oc_chain_dense<THREADS>(O, dense[OP.a], V, R + O.o_tmpz_doubles, &s_flags, tid, clk ? &t_ldl : nullptr);
-          __syncthreads();
+          oc_chain_dense<THREADS>(O, dense[OP.a], V, R + O.o_tmpz_doubles, &s_flags, tid, bar, clk ? &t_ldl : nullptr);
+          oc_sync<THREADS>(bar);
           if (clk) t_dense += clock64() - t0;
           continue;
         }
         const int c = OP.a;
         const long long tw0 = clk ? clock64() : 0;
         cp_async_wait<1>();
-        __syncthreads();
+        oc_sync<THREADS>(bar);
         if (clk) t_wait += clock64() - tw0;
         issue(c + 2);
         const OcChunk K = chunks[c];
@@ -621,33 +651,33 @@ __global__ void __launch_bounds__(THREADS, MINB) k_onchip(const __grid_constant_
               tmpbuf[it] = v;
             } else if (pf >> 31) {
               if (!(v > 0.0)) atomicOr(&s_flags, TNO_STATUS_NOT_PD);
-              V[pos] = 1.0 / v;
+              V[pos] = oc_rcp(v);
             } else {
               V[pos] = v;
             }
           }
         }
         if (K.kind == 1) {  // rectangular chain rows read each other's S values: write back after everyone has read
-          __syncthreads();
+          oc_sync<THREADS>(bar);
           for (int it = tid; it < K.nitems; it += THREADS) V[(int)(rec[it].x & 0xffffu)] = tmpbuf[it];
         }
       }
       cp_async_wait<0>();
-      __syncthreads();
+      oc_sync<THREADS>(bar);
       if (clk) {
         A.phase_clocks[14] = t_dense;
         A.phase_clocks[15] = t_ldl;
       }
     }
-    if (A.phase_clocks && blockIdx.x == 0 && tid == 0 && cand == (int64_t)(A.N > 4 * gridDim.x ? 4 * gridDim.x : 0)) A.phase_clocks[4] = clock64();
+    if (clk_here) A.phase_clocks[4] = clock64();
     // ---- 4. L_ij = U_ij / d_j for the CSR entries (the dense chain blocks are already final) ---------
     for (int p = tid; p < nlo; p += THREADS) V[p] *= V[nlo + (int)rowcol16[p]];
 
-    if (A.phase_clocks && blockIdx.x == 0 && tid == 0 && cand == (int64_t)(A.N > 4 * gridDim.x ? 4 * gridDim.x : 0)) A.phase_clocks[5] = clock64();
+    if (clk_here) A.phase_clocks[5] = clock64();
     // ---- 5. phase-1 right-hand sides: z | z_lambdv | Az | x | y -------------------------------------
     // (the scale pass above only touches V; the panel is cleared with coalesced 16-byte stores first)
     for (int it = tid; it < ni * (W >> 1); it += THREADS) reinterpret_cast<double2*>(R)[it] = make_double2(0.0, 0.0);
-    __syncthreads();
+    oc_sync<THREADS>(bar);
     for (int r = tid; r < ni; r += THREADS) {
       const int v = rowv_s[r];
       double px, py, pz;
@@ -679,13 +709,13 @@ __global__ void __launch_bounds__(THREADS, MINB) k_onchip(const __grid_constant_
       row[O.c_z] = bz;
       if (O.c_lambdv >= 0) row[O.c_lambdv] = -P.pzv[v] * pzs;   // d(pz)/d(lambdv) = pz_scale * pzv
     }
-    __syncthreads();
+    oc_sync<THREADS>(bar);
 
-    if (A.phase_clocks && blockIdx.x == 0 && tid == 0 && cand == (int64_t)(A.N > 4 * gridDim.x ? 4 * gridDim.x : 0)) A.phase_clocks[6] = clock64();
+    if (clk_here) A.phase_clocks[6] = clock64();
     // ---- 6. solve phase 1 ---------------------------------------------------------------------------
-    oc_solve<THREADS>(O, 0, wide, clev, chains, rowchain, rowptr16, rowcol16, V, R, ni, 0, O.ncols1, tid, ct_ptr, ct_col, ct_ent, ct_row);
+    oc_solve<THREADS>(O, 0, wide, clev, chains, rowchain, rowptr16, rowcol16, V, R, ni, 0, O.ncols1, tid, ct_ptr, ct_col, ct_ent, ct_row, bar);
 
-    if (A.phase_clocks && blockIdx.x == 0 && tid == 0 && cand == (int64_t)(A.N > 4 * gridDim.x ? 4 * gridDim.x : 0)) A.phase_clocks[7] = clock64();
+    if (clk_here) A.phase_clocks[7] = clock64();
     // ---- 7. everything that needs the transient columns (x, y, Az) or only z ------------------------
     auto zfix = [&](int b) -> double { return P.var.o_zb >= 0 ? xs[P.var.o_zb + b] : P.X[3 * fixed_s[b] + 2]; };
     // persistent phase-1 results leave the panel: phase 2 reuses all of its columns
@@ -694,7 +724,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_onchip(const __grid_constant_
       if (O.npers > 1) pers[r] = R[r * W + O.c_lambdv];
     }
     if (tid < nb) zs[ni + tid] = zfix(tid);
-    __syncthreads();
+    oc_sync<THREADS>(bar);
     auto zval = [&](int v) -> double {  // branch-free: free rows first, supports behind them
       const int r = vrow_s[v];
       return zs[r >= 0 ? r : ni - 1 - r];
@@ -752,7 +782,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_onchip(const __grid_constant_
         lpe[e] = qe > 0.0 ? l2 : (qe < 0.0 ? -l2 : 0.0);
         lpa[e] = fabs(qe) * w;
       }
-      __syncthreads();
+      oc_sync<THREADS>(bar);
       for (int v = tid; v < n; v += THREADS) {
         double om = 0.0;
         for (int t = __ldg(P.vadj_ptr + v); t < __ldg(P.vadj_ptr + v + 1); ++t)
@@ -760,7 +790,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_onchip(const __grid_constant_
         const int r = vrow_s[v];
         lpw[r >= 0 ? r : ni - 1 - r] = 2.0 * om;
       }
-      __syncthreads();
+      oc_sync<THREADS>(bar);
     }
     if ((want_loadpath || want_ecomp_nl) && A.grad) {
       {
@@ -774,13 +804,13 @@ __global__ void __launch_bounds__(THREADS, MINB) k_onchip(const __grid_constant_
             for (int e = warp * 2 + rsub; e < m; e += 2 * NW) acc = fma(lpe[e], __ldg(P.B + (int64_t)e * k + cb + csub), acc);
           acc += __shfl_xor_sync(0xffffffffu, acc, 16);
           if (lane < 16) bf[warp * 16 + lane] = acc;
-          __syncthreads();
+          oc_sync<THREADS>(bar);
           if (tid < 16 && cb + tid < k) {
             double sum = 0.0;
             for (int w = 0; w < NW; ++w) sum += bf[w * 16 + tid];
             lpa[cb + tid] = sum;
           }
-          __syncthreads();
+          oc_sync<THREADS>(bar);
         }
       }
     }
@@ -802,7 +832,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_onchip(const __grid_constant_
         }
         acc += __shfl_xor_sync(0xffffffffu, acc, 16);
         if (lane < 16) bf[warp * 16 + lane] = acc;
-        __syncthreads();
+        oc_sync<THREADS>(bar);
         if (tid < 16 && cb + tid < ncols) {
           double sum = 0.0;
           for (int w = 0; w < NW; ++w) sum += bf[w * 16 + tid];
@@ -810,7 +840,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_onchip(const __grid_constant_
           if (addend) sum += addend[cb + tid];
           dst[cb + tid] = sum;
         }
-        __syncthreads();
+        oc_sync<THREADS>(bar);
       }
     };
     if (want_wsum && A.grad && P.var.o_zb >= 0) wcolsum(O.c_az, nb, A.grad + cand * nvar + P.var.o_zb, nullptr, true);
@@ -892,9 +922,18 @@ __global__ void __launch_bounds__(THREADS, MINB) k_onchip(const __grid_constant_
         }
       }
     }
-    __syncthreads();
+    oc_sync<THREADS>(bar);
 
-    if (A.phase_clocks && blockIdx.x == 0 && tid == 0 && cand == (int64_t)(A.N > 4 * gridDim.x ? 4 * gridDim.x : 0)) A.phase_clocks[8] = clock64();
+    if (clk_here) A.phase_clocks[8] = clock64();
+    // ---- 8-11 run once per PASS over the phase-2 panel columns: when the panel is narrower than the dz/dq_ind block
+    //      (W < ncols2, chosen by the host when that lets another candidate fit on the SM), the columns are solved
+    //      pw2 at a time and every pass writes its own columns of J and of the gradient.
+    const int npass = need2 ? O.npass2 : 1;
+    double fval = 0.0;
+    for (int pass = 0; pass < npass; ++pass) {
+    const int cb = pass * O.pw2;                                    // first phase-2 column of this pass
+    const int ncp = need2 ? min(O.pw2, O.ncols2 - cb) : 0;          // columns of this pass
+    const bool last_pass = pass == npass - 1;
     // ---- 8. phase-2 right-hand sides: Ci^T W B | Ci^T W d0 ------------------------------------------
     if (need2) {
       const int nc2 = O.ncols2;
@@ -906,6 +945,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_onchip(const __grid_constant_
       {
         const int gs = O.gshift[1];
         const int c = 2 * (tid & ((1 << gs) - 1));
+        const int gc = cb + c;                // phase-2 column of the lane's first panel column
         const bool cok = c < W;
         for (int r = tid >> gs; r < ni; r += THREADS >> gs) {
           const int t0 = __ldg(O.radj_ptr + r), t1 = __ldg(O.radj_ptr + r + 1);
@@ -916,43 +956,49 @@ __global__ void __launch_bounds__(THREADS, MINB) k_onchip(const __grid_constant_
             for (int t = t0; t < t1; ++t) {
               const unsigned o = __ldg(O.radj + t) & 0xffffu;
               const double dz = zr - zs[(o & 0x8000u) ? ni + (o & 0x7fffu) : o];
-              double2 cf = __ldg(reinterpret_cast<const double2*>(O.Br + (int64_t)t * O.br_stride + c));
+              double2 cf = __ldg(reinterpret_cast<const double2*>(O.Br + (int64_t)t * O.br_stride + gc));
               if constexpr (DIR) {
                 // lambdh column with a second load basis: d0 of the candidate's direction (the basis sits one column on)
-                if (has_dir && (c == k || c + 1 == k)) {
+                if (has_dir && (gc == k || gc + 1 == k)) {
                   const double d0b = __ldg(O.Br + (int64_t)t * O.br_stride + k + 1);
-                  if (c == k) cf.x = fma(dirs, d0b, dirc * cf.x);
+                  if (gc == k) cf.x = fma(dirs, d0b, dirc * cf.x);
                   else cf.y = fma(dirs, d0b, dirc * cf.y);
                 }
               }
               ax = fma(dz, cf.x, ax);
               ay = fma(dz, cf.y, ay);
             }
-            if (c >= nc2) ax = 0.0;        // padding columns (and the slot of the second load basis) stay zero
-            if (c + 1 >= nc2) ay = 0.0;
+            if (gc >= nc2) ax = 0.0;        // padding columns (and the slot of the second load basis) stay zero
+            if (gc + 1 >= nc2) ay = 0.0;
             *reinterpret_cast<double2*>(R + r * W + c) = make_double2(ax, ay);
           }
         }
-        __syncthreads();
+        oc_sync<THREADS>(bar);
       }
-      if (A.phase_clocks && blockIdx.x == 0 && tid == 0 && cand == (int64_t)(A.N > 4 * gridDim.x ? 4 * gridDim.x : 0)) A.phase_clocks[9] = clock64();
+      if (clk_here && pass == 0) A.phase_clocks[9] = clock64();
       // ---- 9. solve phase 2 ----
       {
-        const bool clk2 = A.phase_clocks && blockIdx.x == 0 && tid == 0 && cand == (int64_t)(A.N > 4 * gridDim.x ? 4 * gridDim.x : 0);
-        long long tcs[7] = {0, 0, 0, 0, 0, 0, 0};
-        oc_solve<THREADS>(O, 1, wide, clev, chains, rowchain, rowptr16, rowcol16, V, R, ni, O.c_q, nc2, tid, ct_ptr, ct_col, ct_ent, ct_row,
-                          clk2 ? tcs : nullptr);
+        const bool clk2 = clk_here && pass == 0;
+        long long tcs[7];
+        if (clk2)
+          for (int q = 0; q < 7; ++q) tcs[q] = 0;
+        oc_solve<THREADS>(O, 1, wide, clev, chains, rowchain, rowptr16, rowcol16, V, R, ni, 0, ncp, tid, ct_ptr, ct_col, ct_ent, ct_row,
+                          bar, clk2 ? tcs : nullptr);
         if (clk2)
           for (int q = 0; q < 7; ++q) A.phase_clocks[16 + q] = tcs[q];
       }
     }
 
-    if (A.phase_clocks && blockIdx.x == 0 && tid == 0 && cand == (int64_t)(A.N > 4 * gridDim.x ? 4 * gridDim.x : 0)) A.phase_clocks[10] = clock64();
+    if (clk_here && pass == 0) A.phase_clocks[10] = clock64();
     // ---- 10. reac_bounds rows, objective, gradient ---------------------------------------------------
     if (want_reac) {
       const bool has_env = (P.constraints & TNO_CON_ENVELOPE) != 0;
       for (int it = tid; it < nb * nvar; it += THREADS) {  // one item per (support b, Jacobian column)
         const int b = it / nvar, col = it - b * nvar;
+        const bool ispanel = col < k || col == P.var.o_lambdh;
+        const int gcol = col < k ? col : k;                 // phase-2 column of a q_ind / lambdh variable
+        // a panel column belongs to the pass that solves it, everything else to the first pass
+        if (need2 && ispanel ? (gcol < cb || gcol >= cb + ncp) : pass != 0) continue;
         const int vb = fixed_s[b];
         const double Rx = react[3 * b], Ry = react[3 * b + 1], Rz = react[3 * b + 2];
         const double sx = Rx < 0 ? -1.0 : 1.0, sy = Ry < 0 ? -1.0 : 1.0, sz = Rz < 0 ? -1.0 : 1.0;
@@ -960,9 +1006,9 @@ __global__ void __launch_bounds__(THREADS, MINB) k_onchip(const __grid_constant_
         const double zb = zfix(b);
         double vx = 0.0, vy = 0.0;
         const int t0 = supptr_s[b], t1 = supptr_s[b + 1];
-        if (col < k || col == P.var.o_lambdh) {
+        if (ispanel) {
           const bool isq = col < k;
-          const int pcol = isq ? (O.c_q + col) : O.c_lambdh;
+          const int pcol = gcol - cb;
           double dRx = isq ? gxy[b * k + col] : 0.0, dRy = isq ? gxy[nb * k + b * k + col] : 0.0, dRz = 0.0;
           for (int t = t0; t < t1; ++t) {
             const int o = supother_s[t];
@@ -974,7 +1020,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_onchip(const __grid_constant_
             const double coef = isq ? P.B[(int64_t)e * k + col] : mix2(P.d, P.d_b, e);
             dRz = fma(sg * w, coef, dRz);
             const int ro = vrow_s[o];
-            if ((has_env || !isq) && ro >= 0) {
+            if (need2 && (has_env || !isq) && ro >= 0) {
               const double dzo = R[ro * W + pcol];
               dRz = fma(sg * qe, sg > 0 ? -dzo : dzo, dRz);
             }
@@ -987,17 +1033,17 @@ __global__ void __launch_bounds__(THREADS, MINB) k_onchip(const __grid_constant_
           vy = zb * sy * (-Rz * dRy + Ry * dRz) / rz2 / sz;
         } else if (P.var.o_zb >= 0 && col >= P.var.o_zb && col < P.var.o_zb + nb) {
           // dRz/dzb = Cb^T Q C A ; the reference adds COLUMN b of it to row b (jacobian.py:222)
-          const int cb = col - P.var.o_zb;
+          const int cbz = col - P.var.o_zb;
           double acc = 0.0;
-          for (int t = supptr_s[cb]; t < supptr_s[cb + 1]; ++t) {
+          for (int t = supptr_s[cbz]; t < supptr_s[cbz + 1]; ++t) {
             const double sg = (double)supsign_s[t];
             const double Ao = azsup[t * nb + b];
-            const double Ac = (cb == b) ? 1.0 : 0.0;
+            const double Ac = (cbz == b) ? 1.0 : 0.0;
             acc = fma(sg * qsup[t], sg > 0 ? (Ac - Ao) : (Ao - Ac), acc);
           }
           vx = sz * zb * fabs(Rx) / rz2 * acc;
           vy = sz * zb * fabs(Ry) / rz2 * acc;
-          if (cb == b) {
+          if (cbz == b) {
             vx += -fabs(Rx / Rz);
             vy += -fabs(Ry / Rz);
           }
@@ -1032,28 +1078,30 @@ __global__ void __launch_bounds__(THREADS, MINB) k_onchip(const __grid_constant_
         }
       }
     }
-    double fval = 0.0;
     if (want_thrust) {
-      const double osign = (P.objective == TNO_OBJ_MAX) ? -1.0 : 1.0;
-      if (tid < nvar && A.grad) {
-        double gsum = 0.0;
-        if (tid < k)
-          for (int b = 0; b < nb; ++b) {
-            const double Rx = react[3 * b], Ry = react[3 * b + 1];
-            const double Rn = sqrt(Rx * Rx + Ry * Ry);
-            gsum += (osign * Rx / Rn) * gxy[b * k + tid] + (osign * Ry / Rn) * gxy[nb * k + b * k + tid];
-          }
-        A.grad[cand * nvar + tid] = gsum;
-      }
-      if (tid == 0) {
-        for (int b = 0; b < nb; ++b) fval += sqrt(react[3 * b] * react[3 * b] + react[3 * b + 1] * react[3 * b + 1]);
-        fval *= osign;
+      if (pass == 0) {
+        const double osign = (P.objective == TNO_OBJ_MAX) ? -1.0 : 1.0;
+        if (tid < nvar && A.grad) {
+          double gsum = 0.0;
+          if (tid < k)
+            for (int b = 0; b < nb; ++b) {
+              const double Rx = react[3 * b], Ry = react[3 * b + 1];
+              const double Rn = sqrt(Rx * Rx + Ry * Ry);
+              gsum += (osign * Rx / Rn) * gxy[b * k + tid] + (osign * Ry / Rn) * gxy[nb * k + b * k + tid];
+            }
+          A.grad[cand * nvar + tid] = gsum;
+        }
+        if (tid == 0) {
+          for (int b = 0; b < nb; ++b) fval += sqrt(react[3 * b] * react[3 * b] + react[3 * b + 1] * react[3 * b + 1]);
+          fval *= osign;
+        }
       }
     } else if (want_ecomp) {
       // f = -sum(R o dXb) [+ sum stiff q^2] ;  grad = -sum_b dXb[b] . dR_b/dx [+ B^T (2 stiff q)]
       // (objectives.py:278-340, derivatives.py:503-620; dx/dq_ind and dy/dq_ind vanish on a fixed plan)
       if (A.grad)
         for (int col = tid; col < nvar; col += THREADS) {
+          if (col < k ? (col < cb || col >= cb + ncp) : pass != 0) continue;
           double gsum = 0.0;
           if (col < k) {
             for (int b = 0; b < nb; ++b) {
@@ -1064,72 +1112,97 @@ __global__ void __launch_bounds__(THREADS, MINB) k_onchip(const __grid_constant_
                 const int e = supedge_s[t];
                 dRz = fma(zb - zval(o), __ldg(P.B + (int64_t)e * k + col), dRz);  // C[e, b] (C z)_e = z_b - z_o
                 const int ro = vrow_s[o];
-                if (ro >= 0) dRz = fma(-qsup[t], R[ro * W + O.c_q + col], dRz);
+                if (ro >= 0) dRz = fma(-qsup[t], R[ro * W + col - cb], dRz);
               }
               gsum -= __ldg(P.dXb + 3 * b) * gxy[b * k + col] + __ldg(P.dXb + 3 * b + 1) * gxy[nb * k + b * k + col] +
                       __ldg(P.dXb + 3 * b + 2) * dRz;
             }
             if (want_ecomp_nl) gsum += lpa[col];
           } else {
-            const int cb = col - P.var.o_zb;
+            const int cbz = col - P.var.o_zb;
             for (int b = 0; b < nb; ++b) {
               double acc = 0.0;
-              for (int t = supptr_s[b]; t < supptr_s[b + 1]; ++t) acc = fma(qsup[t], (cb == b ? 1.0 : 0.0) - azsup[t * nb + cb], acc);
+              for (int t = supptr_s[b]; t < supptr_s[b + 1]; ++t) acc = fma(qsup[t], (cbz == b ? 1.0 : 0.0) - azsup[t * nb + cbz], acc);
               gsum -= __ldg(P.dXb + 3 * b + 2) * acc;
             }
           }
           A.grad[cand * nvar + col] = gsum;
         }
-      for (int off = 16; off > 0; off >>= 1) fpart += __shfl_xor_sync(0xffffffffu, fpart, off);
-      if (lane == 0) red[warp] = fpart;
-      __syncthreads();
-      if (tid == 0) {
-        for (int w = 0; w < THREADS / 32; ++w) fval += red[w];
-        for (int b = 0; b < nb; ++b)
-          fval -= react[3 * b] * P.dXb[3 * b] + react[3 * b + 1] * P.dXb[3 * b + 1] + react[3 * b + 2] * P.dXb[3 * b + 2];
+      if (last_pass) {
+        for (int off = 16; off > 0; off >>= 1) fpart += __shfl_xor_sync(0xffffffffu, fpart, off);
+        if (lane == 0) red[warp] = fpart;
+        oc_sync<THREADS>(bar);
+        if (tid == 0) {
+          for (int w = 0; w < THREADS / 32; ++w) fval += red[w];
+          for (int b = 0; b < nb; ++b)
+            fval -= react[3 * b] * P.dXb[3 * b] + react[3 * b + 1] * P.dXb[3 * b + 1] + react[3 * b + 2] * P.dXb[3 * b + 2];
+        }
+        oc_sync<THREADS>(bar);  // red is reused by the feasibility reduction below
       }
-      __syncthreads();  // red is reused by the feasibility reduction below
     } else if (want_wsum) {
-      if (A.grad) wcolsum(O.c_q, k, A.grad + cand * nvar, want_loadpath ? lpa : nullptr, false);
-      for (int off = 16; off > 0; off >>= 1) fpart += __shfl_xor_sync(0xffffffffu, fpart, off);
-      if (lane == 0) red[warp] = fpart;
-      __syncthreads();
-      if (tid == 0)
-        for (int w = 0; w < THREADS / 32; ++w) fval += red[w];
-      __syncthreads();  // red is reused by the feasibility reduction below
-    } else {
+      {
+        const int nq = min(cb + ncp, k) - cb;   // q_ind columns of this pass (the lambdh column is not part of these gradients)
+        if (A.grad && nq > 0) wcolsum(0, nq, A.grad + cand * nvar + cb, want_loadpath ? lpa + cb : nullptr, false);
+      }
+      if (last_pass) {
+        for (int off = 16; off > 0; off >>= 1) fpart += __shfl_xor_sync(0xffffffffu, fpart, off);
+        if (lane == 0) red[warp] = fpart;
+        oc_sync<THREADS>(bar);
+        if (tid == 0)
+          for (int w = 0; w < THREADS / 32; ++w) fval += red[w];
+        oc_sync<THREADS>(bar);  // red is reused by the feasibility reduction below
+      }
+    } else if (pass == 0) {
       if (tid < nvar && A.grad)
         A.grad[cand * nvar + tid] = (tid == nvar - 1) ? (P.objective == TNO_OBJ_T ? 1.0 : (P.objective == TNO_OBJ_NEG_LAST ? -1.0 : 0.0)) : 0.0;
       if (tid == 0)
         fval = P.objective == TNO_OBJ_T ? xs[nvar - 1]
                : (P.objective == TNO_OBJ_NEG_LAST ? -xs[nvar - 1] : (P.objective == TNO_OBJ_FEASIBILITY ? 1.0 : 0.0));
     }
-    if (tid == 0) {
+    if (last_pass && tid == 0) {
       bad |= !isfinite(fval);
       if (A.f) A.f[cand] = fval;
     }
 
-    if (A.phase_clocks && blockIdx.x == 0 && tid == 0 && cand == (int64_t)(A.N > 4 * gridDim.x ? 4 * gridDim.x : 0)) A.phase_clocks[11] = clock64();
-    // ---- 11. dense Jacobian: funicular block from B, envelope block from the panel -------------------
-    if (Jout) {
-      if (P.con.r_env >= 0) {
-        double* o1 = Jout + (int64_t)P.con.r_env * nvar;
-        double* o2 = o1 + (int64_t)n * nvar;
-        for (int e = tid; e < n * nvar; e += THREADS) {
-          const int v = __umulhi((unsigned)e, O.nvar_magic);
-          const int col = e - v * nvar;
+    if (clk_here && pass == 0) A.phase_clocks[11] = clock64();
+    // ---- 11. dense Jacobian: envelope block from the panel (the funicular block is k_fill_funicular's) ------
+    if (Jout && P.con.r_env >= 0) {
+      double* o1 = Jout + (int64_t)P.con.r_env * nvar;
+      double* o2 = o1 + (int64_t)n * nvar;
+      if (ncp > 0) {
+        // the lanes of a row walk the pass's panel columns (contiguous in the panel and in J), rows over the rest
+        const int es = O.emit_shift;
+        const int c = tid & ((1 << es) - 1);
+        if (c < ncp) {
+          const int gcol = cb + c;
+          const int col = gcol < k ? gcol : P.var.o_lambdh;
+          for (int v = tid >> es; v < n; v += THREADS >> es) {
+            const int r = vrow_s[v];
+            const double a = r >= 0 ? R[r * W + c] : 0.0;
+            o1[(int64_t)v * nvar + col] = a;
+            o2[(int64_t)v * nvar + col] = -a;
+          }
+        }
+      }
+      if (pass == 0) {
+        // columns that do not come from the phase-2 panel: lambdv (persistent copy), and zeros when there is no phase 2
+        // (zb and thickness columns were written in step 7)
+        for (int col = 0; col < nvar; ++col) {
           const int src = colsrc_s[col];
-          if (src == -1) continue;  // zb and thickness columns were written in step 7
-          const int r = vrow_s[v];
-          double a = 0.0;
-          if (r >= 0) a = src >= 0 ? R[r * W + src] : (src == -3 ? pers[r] : 0.0);
-          o1[e] = a;
-          o2[e] = -a;
+          if (src >= 0 || src == -1) continue;
+          for (int v = tid; v < n; v += THREADS) {
+            const int r = vrow_s[v];
+            const double a = (r >= 0 && src == -3) ? pers[r] : 0.0;
+            o1[(int64_t)v * nvar + col] = a;
+            o2[(int64_t)v * nvar + col] = -a;
+          }
         }
       }
     }
+    if (!last_pass) oc_sync<THREADS>(bar);   // the panel is rewritten by the next pass
+    }  // pass
 
-    if (A.phase_clocks && blockIdx.x == 0 && tid == 0 && cand == (int64_t)(A.N > 4 * gridDim.x ? 4 * gridDim.x : 0)) A.phase_clocks[12] = clock64();
+    if (clk_here) A.phase_clocks[12] = clock64();
     // ---- 12. feasibility margin and status -----------------------------------------------------------
     for (int off = 16; off > 0; off >>= 1) gmin = fmin(gmin, __shfl_xor_sync(0xffffffffu, gmin, off));
     const unsigned anybad = __ballot_sync(0xffffffffu, bad);
@@ -1137,15 +1210,15 @@ __global__ void __launch_bounds__(THREADS, MINB) k_onchip(const __grid_constant_
       red[warp] = gmin;
       if (anybad) atomicOr(&s_flags, TNO_STATUS_NONFINITE);
     }
-    __syncthreads();
+    oc_sync<THREADS>(bar);
     if (tid == 0) {
       double g = red[0];
       for (int w = 1; w < THREADS / 32; ++w) g = fmin(g, red[w]);
       if (A.gmin) A.gmin[cand] = g;
       if (A.status) A.status[cand] = s_flags;
     }
-    __syncthreads();  // panel, flags and small arrays are reused by the next candidate
-    if (A.phase_clocks && blockIdx.x == 0 && tid == 0 && cand == (int64_t)(A.N > 4 * gridDim.x ? 4 * gridDim.x : 0)) A.phase_clocks[13] = clock64();
+    oc_sync<THREADS>(bar);  // panel, flags and small arrays are reused by the next candidate
+    if (clk_here) A.phase_clocks[13] = clock64();
   }
 }
 
@@ -1166,30 +1239,56 @@ __global__ void __launch_bounds__(256) k_fill_funicular(const double2* __restric
 
 // ------------------------------------------------------------------------------------------------------
 // host: schedule construction
-static int build_onchip_impl(Plan* PL, const tno_problem_desc* D, const int THREADS);
+struct OcLayout {
+  int threads;     // threads per candidate group
+  int groups;      // candidate groups per CTA (they share the index region)
+  int multipass;   // 1: panel as wide as phase 1 needs, the phase-2 columns solved in several passes
+};
+static int build_onchip_impl(Plan* PL, const tno_problem_desc* D, const OcLayout LY, bool dry, int* cands_per_sm, int* npass_out);
 
-// Builds the on-chip schedule for 256-thread CTAs first; when only one CTA fits per SM anyway (large panels: dome,
-// fan), rebuilds it for 512-thread CTAs so that the wide phases get twice the threads.
+// Chooses the shared-memory layout that keeps the most candidates resident per SM (the kernel is bound by the latency of
+// a candidate's dependent steps, so throughput follows the number of candidates in flight), then builds that schedule.
+// Layouts tried: the full-width panel or a panel as wide as phase 1 needs with the phase-2 columns solved in passes;
+// one or two candidate groups per CTA sharing one index region (a third group would have to live with 80 registers per
+// thread and gained nothing when measured); 512-thread groups when only one candidate fits anyway.
 int build_onchip(Plan* PL, const tno_problem_desc* D) {
-  const size_t mark = PL->dev_allocs.size();
-  int rc = build_onchip_impl(PL, D, 256);
-  if (rc != TNO_OK || !PL->onchip_ok) return rc;
-  if (getenv("TNO_ONCHIP_512X2") && PL->onchip_ctas_per_sm >= 2) {   // experiment: 512-thread CTAs, two per SM (64 registers)
-    for (size_t i = mark; i < PL->dev_allocs.size(); ++i) cudaFree(PL->dev_allocs[i]);
-    PL->dev_allocs.resize(mark);
-    rc = build_onchip_impl(PL, D, 512);
-    return rc;
-  }
-  if (PL->onchip_ctas_per_sm == 1 && !getenv("TNO_ONCHIP_256")) {
-    for (size_t i = mark; i < PL->dev_allocs.size(); ++i) cudaFree(PL->dev_allocs[i]);
-    PL->dev_allocs.resize(mark);
-    rc = build_onchip_impl(PL, D, 512);
-    if (rc != TNO_OK) return rc;
-    if (!PL->onchip_ok) {  // should not happen (same memory footprint); fall back to the 256-thread schedule
-      for (size_t i = mark; i < PL->dev_allocs.size(); ++i) cudaFree(PL->dev_allocs[i]);
-      PL->dev_allocs.resize(mark);
-      rc = build_onchip_impl(PL, D, 256);
+  std::vector<OcLayout> tries;
+  if (const char* env = getenv("TNO_ONCHIP_LAYOUT")) {   // developer knob: "threads,groups,multipass"
+    OcLayout LY{256, 1, 0};
+    if (sscanf(env, "%d,%d,%d", &LY.threads, &LY.groups, &LY.multipass) != 3 || (LY.threads != 256 && LY.threads != 512) ||
+        LY.groups < 1 || LY.groups > 2 || (LY.threads == 512 && LY.groups != 1)) {
+      set_error("TNO_ONCHIP_LAYOUT must be threads(256|512),groups(1-2),multipass(0|1)");
+      return TNO_EINVAL;
     }
+    tries.push_back(LY);
+  } else {
+    for (int mp = 0; mp < 2; ++mp)
+      tries.push_back(OcLayout{256, 1, mp});   // two groups per CTA (TNO_ONCHIP_LAYOUT=256,2,x) measured 4 % slower than two CTAs
+  }
+  int best = -1, best_cands = 0, best_pass = 0;
+  for (size_t i = 0; i < tries.size(); ++i) {
+    int cands = 0, npass = 1;
+    const int rc = build_onchip_impl(PL, D, tries[i], true, &cands, &npass);
+    if (rc != TNO_OK) return rc;
+    if (!PL->onchip_ok) continue;
+    if (tries[i].multipass && npass == 1) continue;   // same as the single-pass layout
+    // more candidates in flight first; then fewer passes; then fewer groups (more registers per thread)
+    const bool better = best < 0 || cands > best_cands || (cands == best_cands && npass < best_pass);
+    if (better) {
+      best = (int)i;
+      best_cands = cands;
+      best_pass = npass;
+    }
+  }
+  PL->onchip_ok = false;
+  if (best < 0) return TNO_OK;
+  OcLayout LY = tries[best];
+  if (best_cands == 1 && LY.threads == 256 && !getenv("TNO_ONCHIP_256") && !getenv("TNO_ONCHIP_LAYOUT")) LY.threads = 512;
+  int cands = 0, npass = 1;
+  int rc = build_onchip_impl(PL, D, LY, false, &cands, &npass);
+  if (rc == TNO_OK && !PL->onchip_ok && LY.threads == 512) {   // should not happen (same memory footprint)
+    LY.threads = 256;
+    rc = build_onchip_impl(PL, D, LY, false, &cands, &npass);
   }
   return rc;
 }
@@ -1209,7 +1308,8 @@ void launch_fill_funicular(Plan* PL, const double* block, int64_t count, double*
   PL->prof_end(stream);
 }
 
-static int build_onchip_impl(Plan* PL, const tno_problem_desc* D, const int THREADS) {
+static int build_onchip_impl(Plan* PL, const tno_problem_desc* D, const OcLayout LY, bool dry, int* cands_per_sm, int* npass_out) {
+  const int THREADS = LY.threads;
   const Symbolic& S = PL->sym;
   DevPlan& P = PL->dp;
   DevOnchip& O = PL->oc;
@@ -1238,10 +1338,24 @@ static int build_onchip_impl(Plan* PL, const tno_problem_desc* D, const int THRE
     if (P.var.o_lambdh >= 0) O.c_lambdh = k;
   }
   O.W = (std::max(O.ncols1, O.ncols2) + 1) / 2 * 2;
+  O.npass2 = 1;
+  if (LY.multipass && O.ncols2 > 0) {
+    // panel as wide as phase 1 needs (at least 8 columns); the phase-2 columns are solved W at a time
+    O.W = std::max(8, (O.ncols1 + 1) / 2 * 2);
+    O.npass2 = (O.ncols2 + O.W - 1) / O.W;
+  }
+  O.pw2 = O.W;
+  {
+    int es = 0;
+    while ((1 << es) < std::max(1, std::min(O.pw2, O.ncols2))) ++es;
+    if (es > 8) { set_error("on-chip family not applicable: more than 256 panel columns"); return TNO_OK; }
+    O.emit_shift = es;
+  }
+  *npass_out = O.npass2;
   O.nvar_magic = (uint32_t)((((uint64_t)1 << 32) + nvar - 1) / nvar);
   O.rhs2_shift = 0;
   for (int ph = 0; ph < 2; ++ph) {
-    const int ncols = ph == 0 ? O.ncols1 : O.ncols2;
+    const int ncols = ph == 0 ? O.ncols1 : std::min(O.ncols2, O.pw2);
     const int lanes = std::max(1, (ncols + 1) / 2);
     int g = 0;
     while ((1 << g) < lanes) ++g;
@@ -1334,7 +1448,13 @@ static int build_onchip_impl(Plan* PL, const tno_problem_desc* D, const int THRE
   std::vector<uint32_t> stream;
   uint32_t max_units = 0;
   int max_tmp_items = 0;
-  const size_t CHUNK_BYTES = 12 * 1024;
+  // three staging buffers, the temp buffer of the rectangular chain rows and the inverse's nz doubles share the panel
+  // region while the matrix is factorised: the chunk size follows the panel so that they do not enlarge it
+  size_t CHUNK_BYTES = 12 * 1024;
+  {
+    const long long room = ((long long)std::max(ni * O.W, m) - nz - 2) * 8 - 4096;
+    CHUNK_BYTES = (size_t)std::min<long long>(12 * 1024, std::max<long long>(2048, room / 3 / 16 * 16));
+  }
   auto emit_step = [&](const std::vector<Item>& items, int kind) {
     size_t i0 = 0;
     while (i0 < items.size()) {
@@ -1604,7 +1724,7 @@ static int build_onchip_impl(Plan* PL, const tno_problem_desc* D, const int THRE
   std::vector<double> Br;
   {
     const int cols = k + (P.var.o_lambdh >= 0 ? 1 : 0) + (D->d_b ? 1 : 0);
-    O.br_stride = std::max(O.W, (cols + 1) / 2 * 2);
+    O.br_stride = std::max(O.W * O.npass2, (cols + 1) / 2 * 2);
     Br.assign(std::max<size_t>(radj.size(), 1) * O.br_stride, 0.0);
     for (size_t t = 0; t < radj.size(); ++t) {
       const int e = (int)(radj[t] >> 16);
@@ -1722,25 +1842,36 @@ static int build_onchip_impl(Plan* PL, const tno_problem_desc* D, const int THRE
   O.o_lpe = take((lp || enl) ? m : 0);
   O.o_lpa = take(lp ? std::max(m, k) : (enl ? k : 0));
   O.o_lpw = take(lp ? ni + P.nb : 0);
-  O.o_idx_bytes = off * 8;
+  O.o_idx_bytes = off * 8;   // bytes of one candidate group; the shared index region follows the last group
   int max_optin = 0, smem_sm = 0;
   TNO_CUDA_OK(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, PL->device));
   TNO_CUDA_OK(cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, PL->device));
+  const int G = LY.groups;
+  // resident CTAs per SM by shared memory and by registers (256-thread single-group CTAs are compiled for two per SM)
+  auto ctas = [&](int bytes) {
+    if (bytes > max_optin) return 0;
+    const int by_smem = smem_sm / (bytes + 1024);
+    return G > 1 || THREADS == 512 ? std::min(by_smem, 1) : std::min(by_smem, 2);
+  };
   {
     // keep the column-wise chain index in shared memory only if that does not cost a resident CTA
-    const int with_ct = O.o_idx_bytes + O.idx_bytes, without_ct = O.o_idx_bytes + idx_bytes_core;
-    auto ctas = [&](int bytes) { return bytes > max_optin ? 0 : smem_sm / (bytes + 1024); };
+    const int with_ct = G * O.o_idx_bytes + O.idx_bytes, without_ct = G * O.o_idx_bytes + idx_bytes_core;
     if (ctas(with_ct) < ctas(without_ct) || with_ct > max_optin) {
       O.ct_in_smem = 0;
       O.idx_bytes = idx_bytes_core;
     }
   }
-  O.smem_bytes = O.o_idx_bytes + O.idx_bytes;
+  O.smem_bytes = G * O.o_idx_bytes + O.idx_bytes;
   if (O.smem_bytes > max_optin) { set_error("on-chip family not applicable: O.smem_bytes > max_optin"); return TNO_OK; }
   PL->onchip_threads = THREADS;
-  PL->onchip_ctas_per_sm = std::max(1, std::min(8, smem_sm / (O.smem_bytes + 1024)));
-  if (THREADS == 512 && !getenv("TNO_ONCHIP_512X2")) PL->onchip_ctas_per_sm = 1;
-  if (THREADS == 512 && getenv("TNO_ONCHIP_512X2")) PL->onchip_ctas_per_sm = std::min(PL->onchip_ctas_per_sm, 2);
+  PL->onchip_groups = G;
+  PL->onchip_ctas = std::max(1, ctas(O.smem_bytes));
+  PL->onchip_ctas_per_sm = PL->onchip_ctas * G;   // candidates in flight per SM
+  *cands_per_sm = PL->onchip_ctas_per_sm;
+  if (dry) {
+    PL->onchip_ok = true;
+    return TNO_OK;
+  }
 
   std::vector<double> Bt((size_t)k * m);
   for (int e = 0; e < m; ++e)
@@ -1831,12 +1962,17 @@ int run_onchip(Plan* PL, const double* x_dev, int64_t N, int64_t ldx, const tno_
   }
   const size_t smem = (size_t)PL->oc.smem_bytes;
   static const char* force_ctas = getenv("TNO_CTAS_PER_SM");  // developer knob
-  const int ctas = force_ctas ? std::max(1, atoi(force_ctas)) : PL->onchip_ctas_per_sm;
-  const int grid = (int)std::min<int64_t>(N, (int64_t)PL->sm_count * ctas);
-  const int threads = PL->onchip_threads;
-  // <256, 2>: two CTAs per SM (the common case; also serves the rare 256-thread single-CTA fallback), <512, 1> otherwise
-  auto kern = (A.dir || A.bounds) ? (threads == 512 ? k_onchip<512, 1, true> : k_onchip<256, 2, true>)
-                                  : (threads == 512 ? (ctas >= 2 ? k_onchip<512, 2, false> : k_onchip<512, 1, false>) : k_onchip<256, 2, false>);
+  const int G = PL->onchip_groups;
+  const int ctas = force_ctas ? std::max(1, atoi(force_ctas)) : PL->onchip_ctas;
+  const int grid = (int)std::min<int64_t>((N + G - 1) / G, (int64_t)PL->sm_count * ctas);
+  const int threads = PL->onchip_threads * G;
+  const bool dir = A.dir || A.bounds;
+  // <256, 2, 1>: up to two single-candidate CTAs per SM; <256, 1, G>: one CTA of G candidate groups sharing the index
+  // region; <512, 1, 1>: one 512-thread candidate per SM (large panels)
+  void (*kern)(const DevPlan, const DevOnchip, const OcArgs) = nullptr;
+  if (PL->onchip_threads == 512) kern = dir ? k_onchip<512, 1, 1, true> : k_onchip<512, 1, 1, false>;
+  else if (G == 1) kern = dir ? k_onchip<256, 2, 1, true> : k_onchip<256, 2, 1, false>;
+  else kern = dir ? k_onchip<256, 1, 2, true> : k_onchip<256, 1, 2, false>;
   TNO_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   if (out->J && PL->dp.con.r_fun >= 0)
     launch_fill_funicular(PL, PL->oc.Jfun, (int64_t)2 * PL->dp.m * PL->dp.var.nvar, out->J, N, stream);

@@ -164,6 +164,9 @@ struct DevOnchip {
   int c_az, c_x, c_y;
   int npers;             // persistent phase-1 results kept outside the panel: z (, z_lambdv)
   int ncols1, ncols2;
+  int npass2;            // passes over the phase-2 columns (1 unless the panel is narrower than ncols2)
+  int pw2;               // phase-2 columns per pass
+  int emit_shift;        // log2 lanes walking the panel columns of one vertex when the envelope rows of J are written
   int rhs2_shift;        // log2 lanes walking the phase-2 right-hand-side columns of one row
   int gshift[2];         // log2 lanes covering the columns of one row (two columns per lane), per phase
   int nlo, nz, nv, pos_m1;
@@ -272,8 +275,10 @@ struct Plan {
   DevPlan dp{};
   DevOnchip oc{};
   bool onchip_ok = false;
-  int onchip_threads = 256;
-  int onchip_ctas_per_sm = 1;
+  int onchip_threads = 256;     // threads per candidate group
+  int onchip_groups = 1;        // candidate groups per CTA
+  int onchip_ctas = 1;          // resident CTAs per SM
+  int onchip_ctas_per_sm = 1;   // candidates in flight per SM = onchip_ctas * onchip_groups
   Symbolic sym;
   std::vector<int> h_vrow, h_vadj_ptr, h_vadj_edge, h_vadj_other, h_fixed;
   std::vector<float> h_vadj_sign;

@@ -311,9 +311,12 @@ void analyse(int ni, const std::vector<std::pair<int, int>>& edges, int ordering
           nchild[parent[j]]++;
           only_child[parent[j]] = j;
         }
+      // a chain block holds at most chain_max rows (the on-chip kernel addresses chain rows with 6 bits)
+      static const char* env_max = getenv("TNO_CHAIN_MAX");
+      const int chain_max = env_max ? std::max(1, atoi(env_max)) : 64;
       std::vector<int> chain_of(ni, -1), chain_first, chain_len, clev;
       for (int j = wide_rows; j < ni; ++j) {  // ascending = children first
-        if (nchild[j] == 1) {
+        if (nchild[j] == 1 && chain_len[chain_of[only_child[j]]] < chain_max) {
           const int c = chain_of[only_child[j]];
           chain_of[j] = c;
           chain_len[c]++;
@@ -347,7 +350,7 @@ void analyse(int ni, const std::vector<std::pair<int, int>>& edges, int ordering
         for (int c : byl) {
           if (cpar[c] < 0 || merge_len <= 0) continue;
           const int g = rep[cpar[c]];
-          if (chain_len[c] <= merge_len && glen[g] + chain_len[c] <= 48) {
+          if (chain_len[c] <= merge_len && glen[g] + chain_len[c] <= std::min(48, chain_max)) {
             rep[c] = g;
             glen[g] += chain_len[c];
           }
