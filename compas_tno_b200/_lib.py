@@ -22,6 +22,7 @@ EXPORTS = [
     "tno_abi_version", "tno_last_error", "tno_plan_create", "tno_plan_destroy", "tno_plan_query",
     "tno_plan_symbolic", "tno_eval_batch", "tno_eval_batch_host", "tno_plan_launch_count",
     "tno_plan_profile", "tno_plan_profile_read", "tno_symbolic_analyse", "tno_fetch_jacobian_host", "tno_device_peak",
+    "tno_sqp_qp_solve", "tno_sqp_bfgs_update",
 ]
 
 _dp = C.POINTER(C.c_double)
@@ -111,6 +112,12 @@ def load():
     lib.tno_symbolic_analyse.restype = C.c_int
     lib.tno_device_peak.argtypes = [C.c_int32, C.c_int32, _dp]
     lib.tno_device_peak.restype = C.c_int
+    vp = C.c_void_p
+    lib.tno_sqp_qp_solve.argtypes = [C.c_int64, C.c_int32, C.c_int32, C.c_int32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp,
+                                     vp, C.c_int32, C.c_double, C.c_int32, vp]
+    lib.tno_sqp_qp_solve.restype = C.c_int
+    lib.tno_sqp_bfgs_update.argtypes = [C.c_int64, C.c_int32, C.c_int32, C.c_int32, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+    lib.tno_sqp_bfgs_update.restype = C.c_int
     if lib.tno_abi_version() != ABI_VERSION:
         raise RuntimeError("libtno_b200.so ABI %d != binding ABI %d" % (lib.tno_abi_version(), ABI_VERSION))
     _lib = lib

@@ -245,6 +245,35 @@ int tno_fetch_jacobian_host(tno_plan* plan, const double* J_dev, double* J_host,
 #define TNO_PEAK_FP64_MMA 1
 int tno_device_peak(int32_t device, int32_t what, double* value);
 
+/* ---- batched multi-start driver -------------------------------------------------------------------
+ * Building blocks of S SQP iterations that advance together with iterates, f, grad f, g and the dense J resident in device
+ * memory.  They replace scipy.optimize.fmin_slsqp as the reference calls it (src/compas_tno/solvers/scipy.py:127-174:
+ * objective / gradient / f_ieqcons / fprime_ieqcons callables + per-variable bounds); the host loop with the line search is
+ * compas_tno_b200/multistart.py.  All pointers are DEVICE pointers, row-major, one CTA per start, asynchronous on
+ * `cuda_stream`.  1 <= nvar <= 64.
+ *
+ * tno_sqp_qp_solve: for every start s solve
+ *       min_d 1/2 d'H_s d + grad_s'd    s.t.   J_s d + g_s >= 0 ,   lb <= x_s + d <= ub
+ *   with a primal-dual interior point method (Mehrotra predictor-corrector) on the dense J.  Rows [0, nshared) of every J_s
+ *   are read from J_shared instead (the candidate-independent funicular rows [B 0; -B 0]: one L2-resident copy).
+ *     H (S x nvar x nvar), grad (S x nvar), g (S x ng), J (S x ng x nvar), x (S x nvar), lb / ub (nvar; +-1e20 = none),
+ *     active (S bytes or NULL; 0 = skip the start, d = 0)
+ *   out: d (S x nvar); lam (S x (ng + 2 nvar)) multipliers of [constraints | lower bounds | upper bounds];
+ *     info (S x 8) = { grad'd, sum lam |b|, sum max(0, -g), max lam, iterations, converged (0/1), mu, max |primal residual| };
+ *     lagr_grad (S x nvar) = grad - J' lam_g, the Lagrangian gradient at x with the NEW multipliers (for the BFGS update);
+ *     work (S x 4 x (ng + 2 nvar)) scratch.
+ *   use_mma != 0 forms the normal matrix H + J' diag(lam / s) J on the FP64 tensor pipe (mma.sync m8n8k4.f64).
+ *
+ * tno_sqp_bfgs_update: H_s <- damped BFGS update with step_s = x_new - x_old and
+ *       y = (grad_new - J_new' lam_g) - lagr_grad_old      (Powell damping keeps H positive definite). */
+int tno_sqp_qp_solve(int64_t n_starts, int32_t nvar, int32_t ng, int32_t nshared, const double* H, const double* grad,
+                     const double* g, const double* J, const double* J_shared, const double* x, const double* lb,
+                     const double* ub, const unsigned char* active, double* d, double* lam, double* info, double* lagr_grad,
+                     double* work, int32_t max_iter, double tol, int32_t use_mma, void* cuda_stream);
+int tno_sqp_bfgs_update(int64_t n_starts, int32_t nvar, int32_t ng, int32_t nshared, double* H, const double* grad_new,
+                        const double* J_new, const double* J_shared, const double* lam, const double* lagr_grad_old,
+                        const double* step, const unsigned char* active, void* cuda_stream);
+
 #ifdef __cplusplus
 }
 #endif
