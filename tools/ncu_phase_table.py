@@ -16,7 +16,7 @@ import sys
 import tempfile
 
 ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
-FUN = "_ZN3tno8k_onchipILi256ELi2ELb0E"
+FUN = "_ZN3tno8k_onchipILi256ELi2ELi1ELb0E"
 
 
 def main():
@@ -62,7 +62,7 @@ def main():
              ("8 phase-2 right-hand sides (edge colours)", find("// ---- 8. phase-2 right-hand")),
              ("9 solve 2 (call site)", find("// ---- 9. solve phase 2")), ("10 reac rows, objective, gradient", find("// ---- 10.")),
              ("11 J envelope rows", find("// ---- 11.")), ("12 gmin / status", find("// ---- 12."))]
-    kstart = find("__global__ void __launch_bounds__(THREADS, MINB) k_onchip")
+    kstart = find("__global__ void __launch_bounds__(THREADS * G, MINB) k_onchip")
     dense0 = find("// Dense work of one chain level")
     solve0 = find("// ---- kernels of the triangular solves")
 
