@@ -309,6 +309,161 @@ def run_sweeps(dev, local, world, rank, barrier):
     return sweeps
 
 
+def run_multistart(dev, local, world, rank, barrier):
+    """Configuration 2 as real optimisations: S starting points sharded over the ranks, every rank drives its
+    slice with the batched SQP driver (compas_tno_b200.multistart: evaluations, QP subproblems and BFGS updates on the
+    device, iterates resident in HBM); the best converged feasible optimum is found with one all_gather of (f, gmin, status).
+    Wall time between barriers, max over ranks."""
+    import time
+    import torch
+    import torch.distributed as dist
+    from compas_tno_b200 import workloads as W
+    from compas_tno_b200.distributed import shard_bounds
+    from compas_tno_b200.multistart import MultiStartSolver, variable_bounds
+    from compas_tno_b200.plan import TnoPlan
+    out = {}
+    for name, wl, S_total, spread, max_iter, cfg in (("multistart_crossvault_disc10", "crossvault_disc10", 4096, 0.02, 100, 1),
+                                                     ("multistart_dome_16x20", "dome_16x20", 1024, 0.02, 100, 2)):
+        P, xs, obj = build_workload(wl, n_states=6)
+        plan = TnoPlan(P, objective=obj, device=local)
+        xc, margin = W.max_margin_state(plan, xs, rows=W.margin_rows(P, plan))
+        xc = _bcast(xc, local)
+        lb, ub = variable_bounds(P)
+        lo, hi = shard_bounds(S_total, world, rank)
+        X0 = _ladder(xc, lo, hi, 20261019 + 60 + cfg, 0.2 * spread, spread)
+        solver = MultiStartSolver(plan, lb, ub, acc=1e-6, max_iter=max_iter)
+        solver.solve(X0[:min(64, len(X0))])        # warm-up: buffers, kernels, clocks
+        barrier()
+        t0 = time.perf_counter()
+        res = solver.solve(X0)
+        torch.cuda.synchronize()
+        barrier()
+        dt = time.perf_counter() - t0
+        ok = res.success & (res.gmin >= -1e-6) & (res.status == 0)
+        stats = torch.tensor([dt, float(ok.sum()), float(res.n_evals), float(res.f[ok].min()) if ok.any() else float("inf"),
+                              float(res.n_iterations)], device=dev, dtype=torch.float64)
+        if world > 1:
+            mx = stats.clone()
+            dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+            sm = stats.clone()
+            dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+            mn = stats.clone()
+            dist.all_reduce(mn, op=dist.ReduceOp.MIN)
+            dt, nok, nev, fbest, nit = float(mx[0]), float(sm[1]), float(sm[2]), float(mn[3]), float(mx[4])
+        else:
+            dt, nok, nev, fbest, nit = (float(v) for v in stats)
+        fo = res.f[ok]
+        out[name] = {
+            "what": "config %d as %d simultaneous optimisations (%s, objective %s): starts scattered %.1f %% around the widest-margin "
+                    "state, batched SQP on the device (interior-point QP on the dense J, damped BFGS, L1-merit line search), "
+                    "SLSQP's stopping rule at acc 1e-6" % (cfg, S_total, wl, obj, 100 * spread),
+            "baseline_config": cfg, "starts": S_total, "starts_per_gpu": hi - lo, "n_gpus": world, "scaling": "strong",
+            "wall_s": dt, "optimisations_per_s": S_total / dt, "converged_feasible": int(nok), "sqp_iterations": int(nit),
+            "evaluations": int(nev), "evals_per_s": nev / dt, "qp_iterations_mean": res.qp_iterations,
+            "f_best": fbest if np.isfinite(fbest) else None,
+            "f_spread_rank0": [float(fo.min()), float(np.median(fo)), float(fo.max())] if len(fo) else None,
+            "nvar": plan.nvar, "ng": plan.ng, "centre_margin": margin}
+        plan.close()
+        torch.cuda.empty_cache()
+    return out
+
+
+def run_geometry_montecarlo(dev, local, world, rank, barrier, n_div=20, G_total=64, per_geometry=1024):
+    """The geometry half of configuration 4: G_total plan geometries of the cross form diagram (grid-line
+    spacings perturbed, compas_tno_b200.preprocess.symmetric_grid_perturbations) sharded over the ranks.  For its slice a
+    rank computes B and d of every geometry in ONE batched pre-processing call on the device (blocked Householder QR of
+    E[:, dep], trailing updates on the FP64 tensor pipe), builds one plan per geometry and evaluates `per_geometry`
+    self-weight-scaled candidates on each.  The host recipe of the reference (numpy pinv, problems.py:516-528) is timed on
+    one geometry beside it."""
+    import time
+    import torch
+    import torch.distributed as dist
+    from compas_tno_b200 import preprocess as pre
+    from compas_tno_b200 import workloads as W
+    from compas_tno_b200.distributed import shard_bounds
+    from compas_tno_b200.plan import TnoPlan
+    P0, x_star = W.crossvault_problem(n_div, n_states=6)
+    xy0 = np.asarray(P0.X, dtype=np.float64)[:, :2]
+    XY = pre.symmetric_grid_perturbations(xy0, n_div, G_total, sigma=0.02, seed=20261019 + 43)
+    lo, hi = shard_bounds(G_total, world, rank)
+    ph = np.zeros(2 * P0.ni)
+    timings = {}
+    for tag, use_mma in (("warm", True), ("dfma", False), ("dmma", True)):
+        barrier()
+        t0 = time.perf_counter()
+        res = pre.batched_B_d(P0, XY[lo:hi], ph=ph, use_mma=use_mma, device=local)
+        torch.cuda.synchronize()
+        timings[tag] = time.perf_counter() - t0
+    fits = res.fits()
+    Bh, dh = res.B.cpu().numpy(), res.d.cpu().numpy()
+    # host recipe on one geometry (rank 0), same inputs
+    cpu_s = err = None
+    if rank == 0:
+        from scipy.sparse import diags, vstack
+        from scipy.sparse import csr_matrix
+        Ct = csr_matrix(P0.C).transpose().tocsr()[list(P0.free), :]
+        u, v = P0.C @ XY[lo, :, 0], P0.C @ XY[lo, :, 1]
+        t0 = time.perf_counter()
+        E = vstack((Ct @ diags(np.asarray(u).ravel()), Ct @ diags(np.asarray(v).ravel()))).toarray()
+        ind = list(P0.ind)
+        dep = [e for e in range(P0.m) if e not in set(ind)]
+        Edinv = -np.linalg.pinv(E[:, dep], rcond=1e-17)
+        Bref = np.zeros((P0.m, len(ind)))
+        Bref[dep] = Edinv @ E[:, ind]
+        Bref[ind] = np.identity(len(ind))
+        cpu_s = time.perf_counter() - t0
+        err = float(np.abs(Bh[0] - Bref).max() / np.abs(Bref).max())
+    # one plan per geometry, per_geometry candidates each: self-weight scale N(1, 0.05^2) clipped to [0.8, 1.2]
+    X = torch.from_numpy(W.sample_candidates(P0, x_star, per_geometry, sigma=0.01)).to(dev)
+    rng = np.random.default_rng([20261019 + 44, rank])
+    pzs = torch.from_numpy(np.clip(rng.normal(1.0, 0.05, size=per_geometry), 0.8, 1.2)).to(dev)
+    names = ("f", "gmin", "status")
+    outw = None
+    t_plan = t_eval = 0.0
+    feasible = bad = 0
+    barrier()
+    t_all0 = time.perf_counter()
+    for g in range(hi - lo):
+        t0 = time.perf_counter()
+        Pg = pre.problem_with_geometry(P0, XY[lo + g], Bh[g], dh[g])
+        plan = TnoPlan(Pg, objective="min", device=local)
+        t_plan += time.perf_counter() - t0
+        if outw is None:
+            outw = {key: torch.empty(plan._shape(key, per_geometry), device=dev, dtype=torch.int32 if key == "status" else torch.float64)
+                    for key in names}
+        t0 = time.perf_counter()
+        plan.evaluate_device(X, names, out=outw, pz_scale=pzs)
+        torch.cuda.synchronize()
+        t_eval += time.perf_counter() - t0
+        feasible += int(((outw["gmin"] >= -1e-9) & (outw["status"] == 0)).sum())
+        bad += int((outw["status"] != 0).sum())
+        plan.close()
+    barrier()
+    t_all = time.perf_counter() - t_all0
+    vals = torch.tensor([timings["dmma"], timings["dfma"], t_plan, t_eval, t_all], device=dev, dtype=torch.float64)
+    cnt = torch.tensor([float(fits.sum()), float(feasible), float(bad)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(vals, op=dist.ReduceOp.MAX)
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+    pre_s, pre_fma_s, plan_s, eval_s, all_s = (float(v) for v in vals)
+    M, N = 2 * P0.ni, P0.m - P0.k
+    flops = 2.0 * M * N * N - 2.0 / 3.0 * N ** 3 + 4.0 * M * N * (P0.k + 1)
+    return {
+        "what": "config 4, geometry half: %d plan geometries of the disc-%d cross form (grid-line spacings perturbed 2 %% of the "
+                "cell, symmetric), B and d of every geometry by ONE batched device call (blocked Householder QR of the %d x %d "
+                "matrix E[:, dep]), one plan per geometry, %d self-weight-scaled candidates each (f, gmin, status)"
+                % (G_total, n_div, M, N, per_geometry),
+        "baseline_config": 4, "geometries": G_total, "geometries_per_gpu": hi - lo, "n_gpus": world, "scaling": "strong",
+        "candidates": G_total * per_geometry,
+        "preprocess_s": pre_s, "geometries_per_s": G_total / pre_s, "preprocess_tflops": flops * (hi - lo) / pre_s / 1e12,
+        "preprocess_dfma_s": pre_fma_s, "tensor_pipe_speedup": pre_fma_s / pre_s,
+        "independents_still_fit": int(cnt[0]), "plan_creation_s": plan_s, "evaluation_s": eval_s, "wall_s_after_preprocess": all_s,
+        "evals_per_s_incl_plans": G_total * per_geometry / all_s, "feasible": int(cnt[1]), "status_nonzero": int(cnt[2]),
+        "host_recipe_s_per_geometry": cpu_s, "host_recipe": "numpy pinv of E[:, dep] as problems.py:516-528, one geometry, rank 0",
+        "max_rel_diff_B_vs_host": err,
+        "speedup_vs_host_per_geometry": (cpu_s * G_total / pre_s) if cpu_s else None}
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe).
     The sampler is started before the warm-up (nvidia-smi needs ~0.1 s to start); only samples whose time stamp falls
@@ -697,6 +852,13 @@ def run_ours(args):
     sweeps = None
     if not args.no_sweeps:
         sweeps = run_sweeps(dev, local, world, rank, barrier)
+        for extra in (run_multistart, lambda *a: {"crossvault_disc20_geometry_mc": run_geometry_montecarlo(*a)}):
+            try:
+                sweeps.update(extra(dev, local, world, rank, barrier))
+            except Exception as exc:    # a failed extra sweep must not lose the headline line; it is reported instead
+                if world > 1:
+                    raise
+                sweeps["error_%d" % len(sweeps)] = "%s: %s" % (type(exc).__name__, exc)
 
     # ---- batch-size dependence (N in {1, 256, 4096, 65536}), device-resident, all outputs ----
     batch_sizes = None

@@ -9,7 +9,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libtno_b200.so")
-SOURCES = ["tno_capi.cu", "tno_interleaved.cu", "tno_onchip.cu", "tno_util.cu", "tno_sqp.cu", "tno_symbolic.cpp"]
+SOURCES = ["tno_capi.cu", "tno_interleaved.cu", "tno_onchip.cu", "tno_util.cu", "tno_sqp.cu", "tno_preprocess.cu", "tno_symbolic.cpp"]
 HEADERS = ["tno_plan.hpp", "tno_symbolic.hpp", os.path.join("..", "..", "include", "tno_b200.h")]
 
 

@@ -22,7 +22,7 @@ EXPORTS = [
     "tno_abi_version", "tno_last_error", "tno_plan_create", "tno_plan_destroy", "tno_plan_query",
     "tno_plan_symbolic", "tno_eval_batch", "tno_eval_batch_host", "tno_plan_launch_count",
     "tno_plan_profile", "tno_plan_profile_read", "tno_symbolic_analyse", "tno_fetch_jacobian_host", "tno_device_peak",
-    "tno_sqp_qp_solve", "tno_sqp_bfgs_update",
+    "tno_sqp_qp_solve", "tno_sqp_bfgs_update", "tno_preprocess_batch", "tno_preprocess_work_bytes",
 ]
 
 _dp = C.POINTER(C.c_double)
@@ -118,6 +118,11 @@ def load():
     lib.tno_sqp_qp_solve.restype = C.c_int
     lib.tno_sqp_bfgs_update.argtypes = [C.c_int64, C.c_int32, C.c_int32, C.c_int32, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     lib.tno_sqp_bfgs_update.restype = C.c_int
+    lib.tno_preprocess_work_bytes.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int64]
+    lib.tno_preprocess_work_bytes.restype = C.c_int64
+    lib.tno_preprocess_batch.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int32, _ip, _ip, _ip, vp, vp, C.c_int64, C.c_int64,
+                                         vp, vp, vp, vp, C.c_int64, C.c_int32, vp]
+    lib.tno_preprocess_batch.restype = C.c_int
     if lib.tno_abi_version() != ABI_VERSION:
         raise RuntimeError("libtno_b200.so ABI %d != binding ABI %d" % (lib.tno_abi_version(), ABI_VERSION))
     _lib = lib

@@ -338,7 +338,14 @@ __device__ __forceinline__ void oc_solve(const DevOnchip& O, int phase, const Oc
 template <int THREADS>
 __device__ __forceinline__ void oc_chain_dense(const DevOnchip& O, const OcDense& DN, double* __restrict__ V,
                                                double* __restrict__ tmpz, int* s_flags, int tid, int bar, long long* t_b) {
-  const long long tb0 = t_b ? clock64() : 0;
+  long long tb0 = t_b ? clock64() : 0;
+  auto lapd = [&](int slot) {
+    if (t_b) {
+      const long long now = clock64();
+      t_b[slot] += now - tb0;
+      tb0 = now;
+    }
+  };
   const int zbase = O.nlo + (O.nv - O.nlo - O.nz);  // first dense position (= nlo + ni)
   // ---- (B) ----
   // every thread keeps its (up to OC_DE) element descriptors in registers for the whole factorisation of the level
@@ -376,6 +383,7 @@ __device__ __forceinline__ void oc_chain_dense(const DevOnchip& O, const OcDense
     }
   }
   oc_sync<THREADS>(bar);
+  lapd(0);
   for (int j = 0; j + 1 < (int)DN.tmax; ++j) {
     if (in_regs) {
       // elements are sorted by descending k: once a thread's first element is inactive, all of them are
@@ -393,25 +401,79 @@ __device__ __forceinline__ void oc_chain_dense(const DevOnchip& O, const OcDense
     const int kk = (int)(d.z & 0xffu), ii = (int)((d.z >> 8) & 0xffu);
     if (kk < ii) V[(int)(d.y & 0xffffu)] *= V[(int)(d.y >> 16) + kk];  // l_ik = u_ik / d_k
   }
+  lapd(1);
   oc_sync<THREADS>(bar);
-  if (t_b) *t_b += clock64() - tb0;
+  lapd(2);
   // ---- (C) ----
+  // Z = L^-1 by 8 x 8 blocks.  Stage 0: the diagonal blocks, one thread per column (at most 7 dependent rows).  Stage s =
+  // 1 .. nb - 1: the blocks (ib, ib - s) of the s-th block sub-diagonal, one warp per block, two elements per lane
+  // (lane = column c + 8 (row mod 4)):
+  //     M = sum_{kb = jb .. ib - 1} L(ib, kb) Z(kb, jb)      (everything it reads comes from earlier stages)
+  //     Z(ib, jb) = - Z(ib, ib) M                             (M passes between the lanes with shuffles)
+  // i.e. nb - 1 barrier-separated steps for a chain of 8 nb rows instead of a dependent sweep over all of its rows.
   for (uint32_t cidx = DN.dc0 + tid; cidx < DN.dc1; cidx += THREADS) {
     const uint32_t w = __ldg(O.dc + cidx);
     const int zoff = (int)(w & 0xffffu), T = (int)((w >> 16) & 0xffu), c = (int)(w >> 24);
     const double* Lz = V + zoff;
     double* Zt = tmpz + (zoff - zbase);
-    for (int i = c + 1; i < T; ++i) {
+    const int iend = min(T, (c | 7) + 1);
+    for (int i = c + 1; i < iend; ++i) {
       const int rb = (i * (i - 1)) / 2;
       double a = Lz[rb + c];
-#pragma unroll 4
       for (int kk = c + 1; kk < i; ++kk) a = fma(Lz[rb + kk], Zt[(kk * (kk - 1)) / 2 + c], a);
       Zt[rb + c] = -a;
     }
   }
   oc_sync<THREADS>(bar);
+  lapd(3);
+  {
+    const int lane = tid & 31, warp = tid >> 5;
+    const int c = lane & 7, r0 = lane >> 3;
+    for (int s = 1; s < (int)DN.nbmax; ++s) {
+      for (uint32_t bi = DN.db0 + DN.sb[s] + warp; bi < DN.db0 + DN.sb[s + 1]; bi += THREADS / 32) {
+        const uint32_t w = __ldg(O.db + bi);
+        const int zoff = (int)(w & 0xffffu), T = (int)((w >> 16) & 0xffu), ib = (int)((w >> 24) & 0xfu);
+        const double* Lz = V + zoff;
+        double* Zt = tmpz + (zoff - zbase);
+        const int j = 8 * (ib - s) + c, kend = 8 * ib;
+        double mm[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int i = 8 * ib + r0 + 4 * h;
+          double a = 0.0;
+          if (i < T) {
+            const int rb = (i * (i - 1)) / 2;
+            a = Lz[rb + j];
+#pragma unroll 4
+            for (int k = j + 1; k < kend; ++k) a = fma(Lz[rb + k], Zt[(k * (k - 1)) / 2 + j], a);
+          }
+          mm[h] = a;
+        }
+        double acc[2] = {0.0, 0.0};
+#pragma unroll
+        for (int kr = 0; kr < 8; ++kr) {
+          const double mk = __shfl_sync(0xffffffffu, kr < 4 ? mm[0] : mm[1], ((kr & 3) << 3) | c);
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int r = r0 + 4 * h, i = 8 * ib + r;
+            if (kr == r) acc[h] += mk;
+            else if (kr < r && i < T) acc[h] = fma(Zt[(i * (i - 1)) / 2 + 8 * ib + kr], mk, acc[h]);
+          }
+        }
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int i = 8 * ib + r0 + 4 * h;
+          if (i < T) Zt[(i * (i - 1)) / 2 + j] = -acc[h];
+        }
+      }
+      oc_sync<THREADS>(bar);
+    }
+  }
+  lapd(4);
+  oc_sync<THREADS>(bar);
   for (uint32_t p = DN.zlo + tid; p < DN.zhi; p += THREADS) V[p] = tmpz[p - zbase];
   oc_sync<THREADS>(bar);
+  lapd(5);
 }
 
 // DIR: per-candidate horizontal load directions (tno_batch_inputs.load_dir); a separate instantiation so that the
@@ -604,13 +666,13 @@ __global__ void __launch_bounds__(THREADS * G, MINB) k_onchip(const __grid_const
       issue(0);
       issue(1);
       const bool clk = clk_here;
-      long long t_dense = 0, t_wait = 0, t_ldl = 0, t_last = clk ? clock64() : 0;
+      long long t_dense = 0, t_wait = 0, t_ldl[6] = {0, 0, 0, 0, 0, 0};
       for (int op = 0; op < O.nops; ++op) {
         const OcOp OP = ops[op];
         if (OP.type == OC_OP_DENSE) {
           oc_sync<THREADS>(bar);
           const long long t0 = clk ? clock64() : 0;
-          oc_chain_dense<THREADS>(O, dense[OP.a], V, R + O.o_tmpz_doubles, &s_flags, tid, bar, clk ? &t_ldl : nullptr);
+          oc_chain_dense<THREADS>(O, dense[OP.a], V, R + O.o_tmpz_doubles, &s_flags, tid, bar, clk ? t_ldl : nullptr);
           oc_sync<THREADS>(bar);
           if (clk) t_dense += clock64() - t0;
           continue;
@@ -666,7 +728,9 @@ __global__ void __launch_bounds__(THREADS * G, MINB) k_onchip(const __grid_const
       oc_sync<THREADS>(bar);
       if (clk) {
         A.phase_clocks[14] = t_dense;
-        A.phase_clocks[15] = t_ldl;
+        A.phase_clocks[15] = t_ldl[0] + t_ldl[1] + t_ldl[2];
+        for (int q = 0; q < 6; ++q) A.phase_clocks[24 + q] = t_ldl[q];
+        A.phase_clocks[30] = t_wait;
       }
     }
     if (clk_here) A.phase_clocks[4] = clock64();
@@ -1444,7 +1508,7 @@ static int build_onchip_impl(Plan* PL, const tno_problem_desc* D, const OcLayout
   std::vector<OcOp> ops;
   std::vector<OcDense> dense_r;
   std::vector<uint4> de;
-  std::vector<uint32_t> dc;
+  std::vector<uint32_t> dc, db;
   std::vector<uint32_t> stream;
   uint32_t max_units = 0;
   int max_tmp_items = 0;
@@ -1580,6 +1644,18 @@ static int build_onchip_impl(Plan* PL, const tno_problem_desc* D, const OcLayout
                        [](const uint4& a, const uint4& b) { return (a.z & 0xffu) > (b.z & 0xffu); });
       DN.de1 = (uint32_t)de.size();
       DN.dc1 = (uint32_t)dc.size();
+      // blocked inversion: the 8 x 8 blocks below the block diagonal, grouped by their distance from it
+      DN.db0 = (uint32_t)db.size();
+      for (int c = c0; c < c1; ++c) DN.nbmax = std::max<unsigned short>(DN.nbmax, (unsigned short)((S.chain_ptr[c + 1] - S.chain_ptr[c] + 7) / 8));
+      for (int st = 1; st <= 8; ++st) {
+        DN.sb[st] = (unsigned short)(db.size() - DN.db0);
+        if (st == 8) break;
+        for (int c = c0; c < c1; ++c) {
+          const int T = S.chain_ptr[c + 1] - S.chain_ptr[c], nbk = (T + 7) / 8;
+          for (int ib = st; ib < nbk; ++ib)
+            db.push_back((uint32_t)(nlo + ni + zoff_rel[c]) | ((uint32_t)T << 16) | ((uint32_t)ib << 24) | ((uint32_t)st << 28));
+        }
+      }
       dense_r.push_back(DN);
     }
     if (!ritems.empty()) emit_step(ritems, 1);
@@ -1923,6 +1999,8 @@ static int build_onchip_impl(Plan* PL, const tno_problem_desc* D, const OcLayout
   if (dc.empty()) dc.push_back(0);
   UPO(de, de);
   UPO(dc, dc);
+  if (db.empty()) db.push_back(0);
+  UPO(db, db);
   UPO(Jfun, Jfun);
 #undef UPO
   PL->onchip_ok = true;
@@ -1957,8 +2035,8 @@ int run_onchip(Plan* PL, const double* x_dev, int64_t N, int64_t ldx, const tno_
   A.phase_clocks = nullptr;
   static const bool want_clocks = getenv("TNO_PHASE_CLOCKS") != nullptr;
   if (want_clocks) {
-    TNO_CUDA_OK(cudaMalloc((void**)&A.phase_clocks, 24 * sizeof(long long)));
-    TNO_CUDA_OK(cudaMemsetAsync(A.phase_clocks, 0, 24 * sizeof(long long), stream));
+    TNO_CUDA_OK(cudaMalloc((void**)&A.phase_clocks, 32 * sizeof(long long)));
+    TNO_CUDA_OK(cudaMemsetAsync(A.phase_clocks, 0, 32 * sizeof(long long), stream));
   }
   const size_t smem = (size_t)PL->oc.smem_bytes;
   static const char* force_ctas = getenv("TNO_CTAS_PER_SM");  // developer knob
@@ -1982,7 +2060,7 @@ int run_onchip(Plan* PL, const double* x_dev, int64_t N, int64_t ldx, const tno_
   PL->launches += 1;
   TNO_CUDA_OK(cudaGetLastError());
   if (want_clocks) {
-    long long h[24];
+    long long h[32];
     TNO_CUDA_OK(cudaStreamSynchronize(stream));
     TNO_CUDA_OK(cudaMemcpy(h, A.phase_clocks, sizeof(h), cudaMemcpyDeviceToHost));
     cudaFree(A.phase_clocks);
@@ -1992,7 +2070,8 @@ int run_onchip(Plan* PL, const double* x_dev, int64_t N, int64_t ldx, const tno_
             PL->oc.ct_in_smem, PL->oc.nv, PL->oc.o_zs - PL->oc.o_r);
     fprintf(stderr, "[tno phase clocks] N=%lld grid=%d total=%lld :", (long long)N, grid, h[13] - h[0]);
     for (int i = 0; i < 13; ++i) fprintf(stderr, " %s=%lld", names[i], h[i + 1] - h[i]);
-    fprintf(stderr, " | factor: dense=%lld (LDL^T part %lld)", h[14], h[15]);
+    fprintf(stderr, " | factor: dense=%lld (LDL^T part %lld: setup=%lld columns=%lld barrier=%lld; inverse: diagonal blocks=%lld stages=%lld copy=%lld) chunk waits=%lld",
+            h[14], h[15], h[24], h[25], h[26], h[27], h[28], h[29], h[30]);
     fprintf(stderr, " | solve2: pull-wide=%lld pull-chain=%lld Z=%lld diag=%lld Zt=%lld gather=%lld push-wide=%lld", h[16], h[17], h[18],
             h[19], h[20], h[21], h[22]);
     fprintf(stderr, "\n");

@@ -143,6 +143,9 @@ struct OcDense {
   uint32_t dc0, dc1;     // chain columns in dc[]
   uint32_t zlo, zhi;     // value positions of the dense blocks of this chain level
   uint32_t tmax;         // longest chain
+  uint32_t db0;          // first block descriptor of the blocked inversion in db[]
+  unsigned short sb[9];  // blocks of stage s (block sub-diagonal s = 1..7) are db[db0 + sb[s]] .. db[db0 + sb[s + 1])
+  unsigned short nbmax;  // 8 x 8 block rows of the longest chain
 };
 // Factorisation program: a short list of ops executed in order by the whole CTA.
 enum { OC_OP_CHUNK = 0, OC_OP_DENSE = 1 };
@@ -183,6 +186,7 @@ struct DevOnchip {
   int idx_dense;         // byte offset of the OcDense table inside the index region
   const uint4* de;       // element descriptors: x = rowbase_i | rowbase_k << 16, y = selfpos | dgbase << 16, z = k | i << 8
   const uint32_t* dc;    // column descriptors: zoff | T << 16 | c << 24
+  const uint32_t* db;    // block descriptors of the blocked inversion: zoff | T << 16 | block row << 24 | stage << 28
   int o_zs;              // smem offset (doubles) of zs[ni + nb]: z of the free rows, then zb of the supports
   int simple_asm;
   const double* Bt;      // k x m (transposed B)

@@ -274,6 +274,33 @@ int tno_sqp_bfgs_update(int64_t n_starts, int32_t nvar, int32_t ng, int32_t nsha
                         const double* J_new, const double* J_shared, const double* lam, const double* lagr_grad_old,
                         const double* step, const unsigned char* active, void* cuda_stream);
 
+/* ---- one-time pre-processing, batched over plan geometries ------------------------------------------
+ * Replaces, for G geometries of ONE form-diagram topology at once, what FixedProblem.from_formdiagram does on the host
+ * (src/compas_tno/problems/problems.py:516-528):
+ *       Edinv = -pinv(E[:, dep]) ;  B[dep] = Edinv E[:, ind] ;  B[ind] = I ;  d[dep] = -Edinv ph
+ * with E = [Cit diag(C x) ; Cit diag(C y)] (problems.py:314-326) assembled on the device from the vertex coordinates.  The set
+ * of independent edges `ind` is an INPUT (the reference picks it once per diagram with a pivoted QR,
+ * algorithms/independents.py:126-154, and the choice is LAPACK tie-break dependent): E[:, dep] must have full column rank,
+ * then pinv(Ed) Y is the least-squares solution of Ed X = Y, computed here by a blocked Householder QR (compact WY,
+ * 16-column panels; the trailing updates are dense contractions and run on the FP64 tensor pipe unless use_mma = 0).
+ *
+ *   edges       m x 2 (u, v): C[e, u] = -1, C[e, v] = +1                                   HOST
+ *   free_index  n: position of vertex v among the free vertices (ascending), or -1 for a support    HOST
+ *   ind         k independent edges                                                          HOST
+ *   xy          G x n x 2 plan coordinates                                                   DEVICE
+ *   ph          horizontal loads [px_free ; py_free] (2 ni), geometry g at ph + g * ph_stride
+ *               (ph_stride = 0: shared by all geometries); null = zero loads                 DEVICE
+ *   B           G x m x k row-major;  d  G x m                                               DEVICE, out
+ *   info        G x 4: { largest least-squares residual entry (0 when `ind` fits the geometry), min |r_jj|, max |r_jj|,
+ *               largest |entry| of the solution }                                            DEVICE, out
+ *   work        tno_preprocess_work_bytes(n, m, ni, k, G) bytes of device memory
+ * Asynchronous on `cuda_stream` after the index tables have been uploaded.  G <= 65535 per call. */
+int64_t tno_preprocess_work_bytes(int32_t n, int32_t m, int32_t ni, int32_t k, int64_t n_geometries);
+int tno_preprocess_batch(int32_t n, int32_t m, int32_t ni, int32_t k, const int32_t* edges, const int32_t* free_index,
+                         const int32_t* ind, const double* xy, const double* ph, int64_t ph_stride, int64_t n_geometries,
+                         double* B, double* d, double* info, void* work, int64_t work_bytes, int32_t use_mma,
+                         void* cuda_stream);
+
 #ifdef __cplusplus
 }
 #endif
