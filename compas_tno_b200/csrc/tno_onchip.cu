@@ -476,6 +476,145 @@ __device__ __forceinline__ void oc_chain_dense(const DevOnchip& O, const OcDense
   lapd(5);
 }
 
+// Register-tile variant of the dense work of one chain level.  Every thread owns one TS x TS tile (ti, tj), ti >= tj, of a
+// chain triangle (TS = 2, or 4 when the level has more 2 x 2 tiles than threads) and keeps two things in registers for the
+// whole level: the tile of S (becoming U = L D column by column) and the same tile of Z = L^-1.  Step j = 0 .. T - 2 is
+// ONE barrier-separated step for both:
+//     l_ij = u_ij / d_j                       (column j of U and 1 / d_j come from a small exchange buffer)
+//     S_ik -= l_ij u_kj      for k > j        (right-looking L D L^T, the same arithmetic as the element-wise variant)
+//     Z_i: -= l_ij Z_j:      for i > j        (the row operations that reduce L to the identity, applied to the identity)
+// after which the owners of column j + 1 / row j + 1 publish them (double buffered) and the owner of the diagonal
+// inverts d_{j+1}.  L itself is never stored: the solves only use Z and 1 / d.  Small tiles keep the FP64 work of a step
+// short per warp (a warp issues one DFMA every ~4 cycles: tools/latbench.cu), which is what the step latency is made of.
+// Only the warps that hold tiles take part (named barrier).
+template <int THREADS, int TS>
+__device__ __forceinline__ void oc_chain_tiles(const DevOnchip& O, const OcDense& DN, double* __restrict__ V,
+                                               double* __restrict__ buf, int* s_flags, int tid, int grp) {
+  static_assert(TS == 2 || TS == 4, "tile size");
+  constexpr int LTS = TS == 2 ? 1 : 2;
+  const int nthr = (int)DN.tile_threads;
+  if (tid >= nthr) return;
+  const int ntl = (int)(DN.dt1 - DN.dt0);
+  const bool has = tid < ntl;
+  const uint4 d = has ? __ldg(O.dt + DN.dt0 + tid) : make_uint4(0u, 0u, 0u, 0u);
+  const int zoff = (int)(d.x & 0xffffu), diag0 = (int)(d.x >> 16);
+  const int T = (int)(d.y & 0xffu), ti = (int)((d.y >> 8) & 0xffu), tj = (int)((d.y >> 16) & 0xffu);
+  const int cb = (int)d.z;
+  const int cbtot = (int)DN.cbtot;
+  double* colb[2] = {buf + cb, buf + cbtot + cb};                 // column j of U (rows > j), buffer j & 1
+  double* zrb[2] = {buf + 2 * cbtot + cb, buf + 3 * cbtot + cb};  // row j of Z, buffer j & 1
+  double* dinv = buf + 4 * cbtot + cb;
+  const int barid = 8 + grp;
+  const int i0 = TS * ti, k0 = TS * tj;
+  auto ld = [](const double* p, double* v) {   // TS doubles from a 16-byte aligned address
+#pragma unroll
+    for (int q = 0; q < TS / 2; ++q) {
+      const double2 t = *reinterpret_cast<const double2*>(p + 2 * q);
+      v[2 * q] = t.x;
+      v[2 * q + 1] = t.y;
+    }
+  };
+  auto st = [](double* p, const double* v) {
+#pragma unroll
+    for (int q = 0; q < TS / 2; ++q) *reinterpret_cast<double2*>(p + 2 * q) = make_double2(v[2 * q], v[2 * q + 1]);
+  };
+  double s[TS][TS], z[TS][TS];
+#pragma unroll
+  for (int r = 0; r < TS; ++r)
+#pragma unroll
+    for (int c = 0; c < TS; ++c) {
+      const int i = i0 + r, kk = k0 + c;
+      double v = 0.0;
+      if (has && i < T && kk <= i) v = V[i == kk ? diag0 + i : zoff + (i * (i - 1)) / 2 + kk];
+      s[r][c] = v;
+      z[r][c] = (i == kk) ? 1.0 : 0.0;
+    }
+  if (has && tj == 0) {
+    double v[TS];
+#pragma unroll
+    for (int r = 0; r < TS; ++r) v[r] = s[r][0];
+    st(colb[0] + i0, v);
+    if (ti == 0) {
+#pragma unroll
+      for (int c = 0; c < TS; ++c) v[c] = c == 0 ? 1.0 : 0.0;
+      st(zrb[0], v);
+      const double dd = s[0][0];
+      if (!(dd > 0.0)) atomicOr(s_flags, TNO_STATUS_NOT_PD);
+      const double rc = oc_rcp(dd);
+      dinv[0] = rc;
+      V[diag0] = rc;
+    }
+  }
+  asm volatile("bar.sync %0, %1;" ::"r"(barid), "r"(nthr) : "memory");
+  const int nsteps = (int)DN.tmax - 1;
+  for (int jb = 0; 4 * jb < nsteps; ++jb) {
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj) {
+      const int j = 4 * jb + jj;
+      if (j >= nsteps) break;
+      if (has && j < T - 1) {
+        if (i0 + TS - 1 > j) {
+          const double inv = dinv[j];
+          double lr[TS];
+          ld(colb[jj & 1] + i0, lr);
+#pragma unroll
+          for (int r = 0; r < TS; ++r) lr[r] = (i0 + r > j) ? lr[r] * inv : 0.0;
+          if (k0 + TS - 1 > j) {
+            double uc[TS];
+            ld(colb[jj & 1] + k0, uc);
+#pragma unroll
+            for (int c = 0; c < TS; ++c) uc[c] = (k0 + c > j) ? uc[c] : 0.0;
+#pragma unroll
+            for (int r = 0; r < TS; ++r)
+#pragma unroll
+              for (int c = 0; c < TS; ++c) s[r][c] = fma(-lr[r], uc[c], s[r][c]);
+          }
+          if (k0 <= j) {
+            double zc[TS];
+            ld(zrb[jj & 1] + k0, zc);
+#pragma unroll
+            for (int r = 0; r < TS; ++r)
+#pragma unroll
+              for (int c = 0; c < TS; ++c) z[r][c] = fma(-lr[r], zc[c], z[r][c]);
+          }
+        }
+        // column j + 1 of U and row j + 1 of Z are final now
+        const int c1i = (jj + 1) & (TS - 1);       // compile-time after unrolling
+        const int tb = (4 * jb + jj + 1) >> LTS;   // tile row / column holding index j + 1
+        if (tj == tb) {
+          double v[TS];
+#pragma unroll
+          for (int r = 0; r < TS; ++r) v[r] = s[r][c1i];
+          if (ti == tb) {   // the pivot first: its reciprocal is what the other threads wait for
+            const double dd = s[c1i][c1i];
+            if (!(dd > 0.0)) atomicOr(s_flags, TNO_STATUS_NOT_PD);
+            const double rc = oc_rcp(dd);
+            dinv[j + 1] = rc;
+            V[diag0 + j + 1] = rc;
+          }
+          st(colb[(jj + 1) & 1] + i0, v);
+        }
+        if (ti == tb) {
+          double v[TS];
+#pragma unroll
+          for (int c = 0; c < TS; ++c) v[c] = z[c1i][c];
+          st(zrb[(jj + 1) & 1] + k0, v);
+        }
+      }
+      asm volatile("bar.sync %0, %1;" ::"r"(barid), "r"(nthr) : "memory");
+    }
+  }
+  if (has) {
+#pragma unroll
+    for (int r = 0; r < TS; ++r)
+#pragma unroll
+      for (int c = 0; c < TS; ++c) {
+        const int i = i0 + r, kk = k0 + c;
+        if (i < T && kk < i) V[zoff + (i * (i - 1)) / 2 + kk] = z[r][c];
+      }
+  }
+}
+
 // DIR: per-candidate horizontal load directions (tno_batch_inputs.load_dir); a separate instantiation so that the
 // common single-basis path carries none of its registers or branches.
 // G: candidate groups per CTA.  Every group of THREADS threads works on its own candidate with its own value array and
@@ -672,7 +811,9 @@ __global__ void __launch_bounds__(THREADS * G, MINB) k_onchip(const __grid_const
         if (OP.type == OC_OP_DENSE) {
           oc_sync<THREADS>(bar);
           const long long t0 = clk ? clock64() : 0;
-          oc_chain_dense<THREADS>(O, dense[OP.a], V, R + O.o_tmpz_doubles, &s_flags, tid, bar, clk ? t_ldl : nullptr);
+          if (dense[OP.a].tile_threads > 0 && dense[OP.a].tile_size == 2) oc_chain_tiles<THREADS, 2>(O, dense[OP.a], V, R + O.o_tmpz_doubles, &s_flags, tid, grp);
+          else if (dense[OP.a].tile_threads > 0) oc_chain_tiles<THREADS, 4>(O, dense[OP.a], V, R + O.o_tmpz_doubles, &s_flags, tid, grp);
+          else oc_chain_dense<THREADS>(O, dense[OP.a], V, R + O.o_tmpz_doubles, &s_flags, tid, bar, clk ? t_ldl : nullptr);
           oc_sync<THREADS>(bar);
           if (clk) t_dense += clock64() - t0;
           continue;
@@ -1498,6 +1639,7 @@ static int build_onchip_impl(Plan* PL, const tno_problem_desc* D, const OcLayout
     sup_ptr[b + 1] = (int)sup_edge.size();
   }
   O.nsup = (int)sup_edge.size();
+  O.dbg = getenv("TNO_DBG") ? atoi(getenv("TNO_DBG")) : 0;
 
   // ---- factorisation program ----------------------------------------------------------------------------
   struct Item {
@@ -1509,6 +1651,8 @@ static int build_onchip_impl(Plan* PL, const tno_problem_desc* D, const OcLayout
   std::vector<OcDense> dense_r;
   std::vector<uint4> de;
   std::vector<uint32_t> dc, db;
+  std::vector<uint4> dt;
+  int max_tile_buf = 0;
   std::vector<uint32_t> stream;
   uint32_t max_units = 0;
   int max_tmp_items = 0;
@@ -1654,6 +1798,36 @@ static int build_onchip_impl(Plan* PL, const tno_problem_desc* D, const OcLayout
           const int T = S.chain_ptr[c + 1] - S.chain_ptr[c], nbk = (T + 7) / 8;
           for (int ib = st; ib < nbk; ++ib)
             db.push_back((uint32_t)(nlo + ni + zoff_rel[c]) | ((uint32_t)T << 16) | ((uint32_t)ib << 24) | ((uint32_t)st << 28));
+        }
+      }
+      // register tiles: one 4 x 4 tile of a triangle per thread, when the level has no more tiles than threads
+      {
+        static const bool elementwise = getenv("TNO_ONCHIP_DENSE_ELEMENTS") != nullptr;   // developer knob (A/B measurements)
+        DN.dt0 = DN.dt1 = (uint32_t)dt.size();
+        DN.tile_threads = 0;
+        for (int TS = 2; TS <= 4 && !elementwise && DN.tile_threads == 0; TS += 2) {
+          std::vector<uint4> tiles;
+          uint32_t cbo = 0;
+          for (int c = c0; c < c1; ++c) {
+            const int r0 = S.chain_ptr[c], T = S.chain_ptr[c + 1] - r0, nt = (T + TS - 1) / TS;
+            for (int ti = 0; ti < nt; ++ti)
+              for (int tj = 0; tj <= ti; ++tj) {
+                uint4 d;
+                d.x = (uint32_t)(nlo + ni + zoff_rel[c]) | ((uint32_t)(nlo + r0) << 16);
+                d.y = (uint32_t)T | ((uint32_t)ti << 8) | ((uint32_t)tj << 16);
+                d.z = cbo;
+                d.w = 0;
+                tiles.push_back(d);
+              }
+            cbo += (uint32_t)(TS * nt);
+          }
+          if ((int)tiles.size() > THREADS) continue;
+          dt.insert(dt.end(), tiles.begin(), tiles.end());
+          DN.dt1 = (uint32_t)dt.size();
+          DN.cbtot = cbo;
+          DN.tile_size = (uint32_t)TS;
+          DN.tile_threads = (uint32_t)((tiles.size() + 31) / 32 * 32);
+          max_tile_buf = std::max(max_tile_buf, (int)(5 * cbo));
         }
       }
       dense_r.push_back(DN);
@@ -1904,7 +2078,7 @@ static int build_onchip_impl(Plan* PL, const tno_problem_desc* D, const OcLayout
   const int stage_doubles = 3 * O.fseg_units * 2;
   O.o_tmp_doubles = stage_doubles;
   O.o_tmpz_doubles = (stage_doubles + max_tmp_items + 2) / 2 * 2;
-  O.o_r = take(std::max(panel, O.o_tmpz_doubles + nz + 2));
+  O.o_r = take(std::max(panel, O.o_tmpz_doubles + std::max(nz, max_tile_buf) + 2));
   O.o_zs = take(ni + nb);
   O.o_pers = take(O.npers > 1 ? ni : 0);
   O.o_qsup = take(O.nsup);
@@ -2001,6 +2175,8 @@ static int build_onchip_impl(Plan* PL, const tno_problem_desc* D, const OcLayout
   UPO(dc, dc);
   if (db.empty()) db.push_back(0);
   UPO(db, db);
+  if (dt.empty()) dt.push_back(uint4{0, 0, 0, 0});
+  UPO(dt, dt);
   UPO(Jfun, Jfun);
 #undef UPO
   PL->onchip_ok = true;
@@ -2070,7 +2246,7 @@ int run_onchip(Plan* PL, const double* x_dev, int64_t N, int64_t ldx, const tno_
             PL->oc.ct_in_smem, PL->oc.nv, PL->oc.o_zs - PL->oc.o_r);
     fprintf(stderr, "[tno phase clocks] N=%lld grid=%d total=%lld :", (long long)N, grid, h[13] - h[0]);
     for (int i = 0; i < 13; ++i) fprintf(stderr, " %s=%lld", names[i], h[i + 1] - h[i]);
-    fprintf(stderr, " | factor: dense=%lld (LDL^T part %lld: setup=%lld columns=%lld barrier=%lld; inverse: diagonal blocks=%lld stages=%lld copy=%lld) chunk waits=%lld",
+    fprintf(stderr, " | factor: dense=%lld (LDL^T part %lld: setup=%lld columns / tile steps=%lld barrier=%lld; inverse: diagonal blocks / tile publish=%lld stages=%lld copy=%lld) chunk waits=%lld",
             h[14], h[15], h[24], h[25], h[26], h[27], h[28], h[29], h[30]);
     fprintf(stderr, " | solve2: pull-wide=%lld pull-chain=%lld Z=%lld diag=%lld Zt=%lld gather=%lld push-wide=%lld", h[16], h[17], h[18],
             h[19], h[20], h[21], h[22]);

@@ -146,6 +146,11 @@ struct OcDense {
   uint32_t db0;          // first block descriptor of the blocked inversion in db[]
   unsigned short sb[9];  // blocks of stage s (block sub-diagonal s = 1..7) are db[db0 + sb[s]] .. db[db0 + sb[s + 1])
   unsigned short nbmax;  // 8 x 8 block rows of the longest chain
+  // register-tile variant (oc_chain_tiles): one 4 x 4 tile of a chain triangle per thread
+  uint32_t dt0, dt1;     // tile descriptors in dt[]
+  uint32_t cbtot;        // sum of the chains' padded sizes: length of one column / row exchange buffer
+  uint32_t tile_threads; // threads taking part (multiple of 32); 0 = more tiles than threads, element-wise variant
+  uint32_t tile_size;    // 2 or 4
 };
 // Factorisation program: a short list of ops executed in order by the whole CTA.
 enum { OC_OP_CHUNK = 0, OC_OP_DENSE = 1 };
@@ -174,6 +179,7 @@ struct DevOnchip {
   int gshift[2];         // log2 lanes covering the columns of one row (two columns per lane), per phase
   int nlo, nz, nv, pos_m1;
   int wide_rows, nwide, nclev, nchains, nchunks, nops, nsup;
+  int dbg;               // developer experiments (TNO_DBG)
   int adj_deg;           // padded adjacency width (0: use the pointer lists)
   uint32_t nvar_magic;   // ceil(2^32 / nvar)
   // shared memory layout: offsets in doubles, index region in bytes
@@ -187,6 +193,7 @@ struct DevOnchip {
   const uint4* de;       // element descriptors: x = rowbase_i | rowbase_k << 16, y = selfpos | dgbase << 16, z = k | i << 8
   const uint32_t* dc;    // column descriptors: zoff | T << 16 | c << 24
   const uint32_t* db;    // block descriptors of the blocked inversion: zoff | T << 16 | block row << 24 | stage << 28
+  const uint4* dt;       // tile descriptors: x = zoff | first diagonal slot << 16, y = T | tile row << 8 | tile column << 16, z = offset in the exchange buffers
   int o_zs;              // smem offset (doubles) of zs[ni + nb]: z of the free rows, then zb of the supports
   int simple_asm;
   const double* Bt;      // k x m (transposed B)
