@@ -83,7 +83,13 @@ def load():
     if not os.path.exists(LIB_PATH):
         raise RuntimeError("compas_tno_b200: CUDA library %s is missing and could not be built; "
                            "there is no CPU fallback" % LIB_PATH)
-    lib = C.CDLL(LIB_PATH)
+    path = LIB_PATH
+    variant = os.environ.get("TNO_LIB_VARIANT")   # developer knob: a library built by tools/build_variant.py (A/B timing)
+    if variant:
+        path = os.path.join(os.path.dirname(LIB_PATH), "variants", "libtno_b200_%s.so" % variant)
+        if not os.path.exists(path):
+            raise RuntimeError("compas_tno_b200: variant library %s is missing" % path)
+    lib = C.CDLL(path)
     lib.tno_abi_version.restype = C.c_int
     lib.tno_last_error.restype = C.c_char_p
     lib.tno_plan_create.argtypes = [C.POINTER(ProblemDesc), C.POINTER(C.c_void_p)]

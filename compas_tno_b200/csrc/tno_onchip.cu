@@ -24,6 +24,12 @@
 #include <map>
 
 #include "tno_plan.hpp"
+#ifndef TNO_AB
+#define TNO_AB 8
+#endif
+#ifndef TNO_QU
+#define TNO_QU 4
+#endif
 
 namespace tno {
 
@@ -620,7 +626,8 @@ __device__ __forceinline__ void oc_chain_tiles(const DevOnchip& O, const OcDense
 // G: candidate groups per CTA.  Every group of THREADS threads works on its own candidate with its own value array and
 // panel (o_idx_bytes bytes each) and its own named barrier; the index region behind them is shared by all groups, which is
 // what lets a third candidate fit on an SM.
-template <int THREADS, int MINB, int G, bool DIR>
+// CLK: in-kernel phase clocks (TNO_PHASE_CLOCKS=1); the production instantiations carry none of that code.
+template <int THREADS, int MINB, int G, bool DIR, bool CLK>
 __global__ void __launch_bounds__(THREADS * G, MINB) k_onchip(const __grid_constant__ DevPlan P, const __grid_constant__ DevOnchip O,
                                                                 const __grid_constant__ OcArgs A) {
   extern __shared__ __align__(16) unsigned char smraw[];
@@ -659,6 +666,8 @@ __global__ void __launch_bounds__(THREADS * G, MINB) k_onchip(const __grid_const
   const int* supedge_s = reinterpret_cast<const int*>(idxb + O.idx_supedge);
   const float* supsign_s = reinterpret_cast<const float*>(idxb + O.idx_supsign);
   const int* fixed_s = reinterpret_cast<const int*>(idxb + O.idx_fixed);
+  const unsigned short* radjp_s = reinterpret_cast<const unsigned short*>(idxb + O.idx_radjp);
+  const double* supxyz_s = reinterpret_cast<const double*>(idxb + O.idx_supxyz);   // x, y, z of the supports
   double* zs = sm + O.o_zs;        // z of the free rows (after phase 1) followed by zb of the supports
   const unsigned short* ct_ptr = O.ct_in_smem ? reinterpret_cast<const unsigned short*>(idxb + O.idx_ct_ptr) : O.ct_ptr;
   const unsigned short* ct_col = O.ct_in_smem ? reinterpret_cast<const unsigned short*>(idxb + O.idx_ct_col) : O.ct_col;
@@ -689,7 +698,7 @@ __global__ void __launch_bounds__(THREADS * G, MINB) k_onchip(const __grid_const
 
   const int64_t clk_cand = A.N > 4 * (int64_t)gridDim.x * G ? 4 * (int64_t)gridDim.x * G : 0;   // CTA 0, group 0, its 5th candidate
   for (int64_t cand = (int64_t)blockIdx.x * G + grp; cand < A.N; cand += (int64_t)gridDim.x * G) {
-    const bool clk_here = A.phase_clocks && tid == 0 && cand == clk_cand;
+    const bool clk_here = CLK && A.phase_clocks && tid == 0 && cand == clk_cand;
     if (clk_here) A.phase_clocks[0] = clock64();
     // ---- 0. variables ------------------------------------------------------------------------------
     if (tid < nvar) xs[tid] = A.x[cand * A.ldx + tid];
@@ -702,8 +711,8 @@ __global__ void __launch_bounds__(THREADS * G, MINB) k_onchip(const __grid_const
     const bool has_dir = DIR && A.dir != nullptr;
     const double dirc = has_dir ? A.dir[2 * cand] : 1.0, dirs = has_dir ? A.dir[2 * cand + 1] : 0.0;
     auto mix2 = [&](const double* a, const double* b, int i) -> double {
-      if constexpr (DIR) return has_dir ? fma(dirs, b[i], dirc * a[i]) : a[i];
-      else return a[i];
+      if constexpr (DIR) return has_dir ? fma(dirs, __ldg(b + i), dirc * __ldg(a + i)) : __ldg(a + i);
+      else return __ldg(a + i);
     };
     double gmin = 1e300;
     double fpart = 0.0;
@@ -715,10 +724,11 @@ __global__ void __launch_bounds__(THREADS * G, MINB) k_onchip(const __grid_const
     // ---- 1. q = B q_ind + lambdh d ; funicular rows of g -------------------------------------------
     for (int e0 = tid; e0 < m; e0 += 4 * THREADS) {
       // four edges per thread at once: 4 x unroll independent loads of B in flight
+      constexpr int QU = TNO_QU;
       double acc4[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) acc4[i] = (e0 + i * THREADS < m) ? lamh * mix2(P.d, P.d_b, e0 + i * THREADS) : 0.0;
-#pragma unroll 4
+#pragma unroll QU
       for (int j = 0; j < k; ++j) {
         const double xj = xs[j];
         const double* bj = O.Bt + (int64_t)j * m + e0;
@@ -744,7 +754,7 @@ __global__ void __launch_bounds__(THREADS * G, MINB) k_onchip(const __grid_const
       }
       if (A.q) A.q[cand * m + e] = acc;
       if (P.con.r_fun >= 0) {
-        const double g0 = acc - P.qmin[e], g1 = P.qmax[e] - acc;
+        const double g0 = acc - __ldg(P.qmin + e), g1 = __ldg(P.qmax + e) - acc;
         if (gout) {
           gout[P.con.r_fun + e] = g0;
           gout[P.con.r_fun + m + e] = g1;
@@ -760,19 +770,37 @@ __global__ void __launch_bounds__(THREADS * G, MINB) k_onchip(const __grid_const
     // ---- 2. assemble -(Ci^T Q Ci) into the pattern of L; keep q of the support edges ----------------
     if (O.simple_asm) {
       // off-diagonal positions: one edge or fill; diagonals: minus the sum over the incident edges
-      for (int p = tid; p < nlo; p += THREADS) {
-        const unsigned e = __ldg(O.asm_e16 + p);
-        V[p] = e == 0xffffu ? 0.0 : qs[e];
-      }
-      for (int p = tid; p < O.nz; p += THREADS) {
-        const unsigned e = __ldg(O.asm_z16 + p);
-        V[nlo + ni + p] = e == 0xffffu ? 0.0 : qs[e];
+      // all index loads of a thread (L2) are requested before the first of them is used
+      {
+        constexpr int AB = TNO_AB;
+        for (int p0 = tid; p0 < nlo; p0 += AB * THREADS) {
+          unsigned e[AB];
+#pragma unroll
+          for (int u = 0; u < AB; ++u) e[u] = p0 + u * THREADS < nlo ? __ldg(O.asm_e16 + p0 + u * THREADS) : 0xffffu;
+#pragma unroll
+          for (int u = 0; u < AB; ++u)
+            if (p0 + u * THREADS < nlo) V[p0 + u * THREADS] = e[u] == 0xffffu ? 0.0 : qs[e[u]];
+        }
+        for (int p0 = tid; p0 < O.nz; p0 += AB * THREADS) {
+          unsigned e[AB];
+#pragma unroll
+          for (int u = 0; u < AB; ++u) e[u] = p0 + u * THREADS < O.nz ? __ldg(O.asm_z16 + p0 + u * THREADS) : 0xffffu;
+#pragma unroll
+          for (int u = 0; u < AB; ++u)
+            if (p0 + u * THREADS < O.nz) V[nlo + ni + p0 + u * THREADS] = e[u] == 0xffffu ? 0.0 : qs[e[u]];
+        }
       }
       for (int r = tid; r < ni; r += THREADS) {
         double acc = 0.0;
-        const int t1 = O.radj_ptr[r + 1];
-#pragma unroll 4
-        for (int t = O.radj_ptr[r]; t < t1; ++t) acc -= qs[__ldg(O.radj + t) >> 16];
+        const int t0 = O.radjp_in_smem ? (int)radjp_s[r] : __ldg(O.radj_ptr + r);
+        const int t1 = O.radjp_in_smem ? (int)radjp_s[r + 1] : __ldg(O.radj_ptr + r + 1);
+        unsigned w[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) w[u] = t0 + u < t1 ? __ldg(O.radj + t0 + u) : 0u;
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+          if (t0 + u < t1) acc -= qs[w[u] >> 16];
+        for (int t = t0 + 8; t < t1; ++t) acc -= qs[__ldg(O.radj + t) >> 16];
         V[nlo + r] = acc;
       }
     } else {
@@ -885,34 +913,47 @@ __global__ void __launch_bounds__(THREADS * G, MINB) k_onchip(const __grid_const
     oc_sync<THREADS>(bar);
     for (int r = tid; r < ni; r += THREADS) {
       const int v = rowv_s[r];
+      // loads (L2) first: the vertex loads and the row's adjacency words travel together
+      const int t0 = O.radjp_in_smem ? (int)radjp_s[r] : __ldg(O.radj_ptr + r);
+      const int t1 = O.radjp_in_smem ? (int)radjp_s[r + 1] : __ldg(O.radj_ptr + r + 1);
+      unsigned w[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) w[u] = t0 + u < t1 ? __ldg(O.radj + t0 + u) : 0u;
       double px, py, pz;
       if (P.var.o_lambdh >= 0) {
         px = lamh * mix2(P.px0, P.px0_b, v);
         py = lamh * mix2(P.py0, P.py0_b, v);
       } else {
-        px = P.P[3 * v + 0];
-        py = P.P[3 * v + 1];
+        px = __ldg(P.P + 3 * v + 0);
+        py = __ldg(P.P + 3 * v + 1);
       }
-      pz = (P.var.o_lambdv >= 0) ? (lamv * P.pzv[v] + P.pz0[v]) : P.P[3 * v + 2];
+      const double pzv_v = (P.var.o_lambdv >= 0) ? __ldg(P.pzv + v) : 0.0;
+      pz = (P.var.o_lambdv >= 0) ? (lamv * pzv_v + __ldg(P.pz0 + v)) : __ldg(P.P + 3 * v + 2);
       pz *= pzs;
       double bx = -px, by = -py, bz = -pz;
       double* row = R + r * W;
-      for (int t = P.vadj_ptr[v]; t < P.vadj_ptr[v + 1]; ++t) {
-        const int o = P.vadj_other[t];
-        const int ro = vrow_s[o];
-        if (ro >= 0) continue;
-        const int b = -1 - ro;
-        const double qe = qsup[O.edge_sup[P.vadj_edge[t]]];
-        const double zb = P.var.o_zb >= 0 ? xs[P.var.o_zb + b] : P.X[3 * o + 2];
-        bx = fma(-qe, P.X[3 * o + 0], bx);
-        by = fma(-qe, P.X[3 * o + 1], by);
+      auto sup_edge_term = [&](unsigned ww) {   // an edge to support b: its q from the saved support-edge values
+        const int b = (int)(ww & 0x7fffu), e = (int)(ww >> 16);
+        double qe = 0.0;
+        for (int tt = supptr_s[b]; tt < supptr_s[b + 1]; ++tt)
+          if (supedge_s[tt] == e) qe = qsup[tt];
+        const double zb = P.var.o_zb >= 0 ? xs[P.var.o_zb + b] : supxyz_s[3 * b + 2];
+        bx = fma(-qe, supxyz_s[3 * b + 0], bx);
+        by = fma(-qe, supxyz_s[3 * b + 1], by);
         bz = fma(-qe, zb, bz);
         if (O.c_az >= 0) row[O.c_az + b] -= qe;
+      };
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        if (t0 + u < t1 && (w[u] & 0x8000u)) sup_edge_term(w[u]);
+      for (int t = t0 + 8; t < t1; ++t) {
+        const unsigned ww = __ldg(O.radj + t);
+        if (ww & 0x8000u) sup_edge_term(ww);
       }
       row[O.c_x] = bx;
       row[O.c_y] = by;
       row[O.c_z] = bz;
-      if (O.c_lambdv >= 0) row[O.c_lambdv] = -P.pzv[v] * pzs;   // d(pz)/d(lambdv) = pz_scale * pzv
+      if (O.c_lambdv >= 0) row[O.c_lambdv] = -pzv_v * pzs;   // d(pz)/d(lambdv) = pz_scale * pzv
     }
     oc_sync<THREADS>(bar);
 
@@ -922,7 +963,7 @@ __global__ void __launch_bounds__(THREADS * G, MINB) k_onchip(const __grid_const
 
     if (clk_here) A.phase_clocks[7] = clock64();
     // ---- 7. everything that needs the transient columns (x, y, Az) or only z ------------------------
-    auto zfix = [&](int b) -> double { return P.var.o_zb >= 0 ? xs[P.var.o_zb + b] : P.X[3 * fixed_s[b] + 2]; };
+    auto zfix = [&](int b) -> double { return P.var.o_zb >= 0 ? xs[P.var.o_zb + b] : supxyz_s[3 * b + 2]; };
     // persistent phase-1 results leave the panel: phase 2 reuses all of its columns
     for (int r = tid; r < ni; r += THREADS) {
       zs[r] = R[r * W + O.c_z];
@@ -936,7 +977,7 @@ __global__ void __launch_bounds__(THREADS * G, MINB) k_onchip(const __grid_const
     };
     auto xyval = [&](int v, int axis) -> double {
       const int r = vrow_s[v];
-      return r >= 0 ? R[r * W + O.c_x + axis] : P.X[3 * v + axis];
+      return r >= 0 ? R[r * W + O.c_x + axis] : supxyz_s[3 * (-1 - r) + axis];
     };
     for (int v = tid; v < n; v += THREADS) {
       const double z = zval(v);
@@ -956,8 +997,8 @@ __global__ void __launch_bounds__(THREADS * G, MINB) k_onchip(const __grid_const
             Jout[(int64_t)(P.con.r_env + n + v) * nvar + P.var.o_t] = dub;
           }
         } else {
-          ub = P.ub[v];
-          lb = P.lb[v];
+          ub = __ldg(P.ub + v);
+          lb = __ldg(P.lb + v);
           if (DIR && A.bounds) {   // per-candidate envelope (same instantiation as the load directions: off the common path)
             ub = A.bounds[cand * 2 * n + v];
             lb = A.bounds[cand * 2 * n + n + v];
@@ -1063,7 +1104,7 @@ __global__ void __launch_bounds__(THREADS * G, MINB) k_onchip(const __grid_const
       // R_b = Cb^T Q C X - P_b
       for (int b = tid; b < nb; b += THREADS) {
         const int vb = fixed_s[b];
-        const double xb = P.X[3 * vb + 0], yb = P.X[3 * vb + 1], zb = zfix(b);
+        const double xb = supxyz_s[3 * b + 0], yb = supxyz_s[3 * b + 1], zb = zfix(b);
         double Rx = 0.0, Ry = 0.0, Rz = 0.0, ud0 = 0.0, vd0 = 0.0;
         for (int t = supptr_s[b]; t < supptr_s[b + 1]; ++t) {
           const int o = supother_s[t];
@@ -1091,31 +1132,45 @@ __global__ void __launch_bounds__(THREADS * G, MINB) k_onchip(const __grid_const
           px = lamh * mix2(P.px0, P.px0_b, vb);
           py = lamh * mix2(P.py0, P.py0_b, vb);
         } else {
-          px = P.P[3 * vb + 0];
-          py = P.P[3 * vb + 1];
+          px = __ldg(P.P + 3 * vb + 0);
+          py = __ldg(P.P + 3 * vb + 1);
         }
-        pz = (P.var.o_lambdv >= 0) ? (lamv * P.pzv[vb] + P.pz0[vb]) : P.P[3 * vb + 2];
+        pz = (P.var.o_lambdv >= 0) ? (lamv * __ldg(P.pzv + vb) + __ldg(P.pz0 + vb)) : __ldg(P.P + 3 * vb + 2);
         pz *= pzs;
         react[3 * b + 0] = Rx - px;
         react[3 * b + 1] = Ry - py;
         react[3 * b + 2] = Rz - pz;
+        if (want_thrust) {   // |R_h| and the direction cosines of the thrust objective, once per support
+          const double Rhx = Rx - px, Rhy = Ry - py;
+          const double Rn = sqrt(Rhx * Rhx + Rhy * Rhy);
+          const double osign = (P.objective == TNO_OBJ_MAX) ? -1.0 : 1.0;
+          react[3 * nb + 3 * b + 0] = Rn;
+          react[3 * nb + 3 * b + 1] = osign * Rhx / Rn;
+          react[3 * nb + 3 * b + 2] = osign * Rhy / Rn;
+        }
       }
       // (Cb^T U B)[b, j], (Cb^T V B)[b, j]
       for (int it = tid; it < nb * k; it += THREADS) {
         const int b = it / k, j = it - b * k;
-        const int vb = fixed_s[b];
-        const double xb = P.X[3 * vb + 0], yb = P.X[3 * vb + 1];
+        const double xb = supxyz_s[3 * b + 0], yb = supxyz_s[3 * b + 1];
         double gx = 0.0, gy = 0.0;
-        for (int t = supptr_s[b]; t < supptr_s[b + 1]; ++t) {
+        const int t0 = supptr_s[b], t1 = supptr_s[b + 1];
+        double Bv[4];   // the coefficient loads (L2) of up to four support edges travel together
+#pragma unroll
+        for (int u = 0; u < 4; ++u) Bv[u] = t0 + u < t1 ? __ldg(P.B + (int64_t)supedge_s[t0 + u] * k + j) : 0.0;
+        auto term = [&](int t, double Bej) {
           const int o = supother_s[t];
           const double sg = (double)supsign_s[t];
           const double xo = xyval(o, 0), yo = xyval(o, 1);
           const double u = sg > 0 ? (xb - xo) : (xo - xb);
           const double vv = sg > 0 ? (yb - yo) : (yo - yb);
-          const double Bej = P.B[(int64_t)supedge_s[t] * k + j];
           gx = fma(sg * u, Bej, gx);
           gy = fma(sg * vv, Bej, gy);
-        }
+        };
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (t0 + u < t1) term(t0 + u, Bv[u]);
+        for (int t = t0 + 4; t < t1; ++t) term(t, __ldg(P.B + (int64_t)supedge_s[t] * k + j));
         gxy[it] = gx;
         gxy[nb * k + it] = gy;
       }
@@ -1148,12 +1203,15 @@ __global__ void __launch_bounds__(THREADS * G, MINB) k_onchip(const __grid_const
       // coefficient rows are stored in row-adjacency order (Br: one 16-byte-aligned record per (row, edge) pair), so a
       // row's loads are contiguous, independent of one another and issued back to back.
       {
+        // (Requesting a row's records one row ahead does not pay here: the loads of both rows end up on one scoreboard,
+        // so the wait for the current row also waits for the row just requested, and the extra registers spill.)
         const int gs = O.gshift[1];
         const int c = 2 * (tid & ((1 << gs) - 1));
         const int gc = cb + c;                // phase-2 column of the lane's first panel column
         const bool cok = c < W;
         for (int r = tid >> gs; r < ni; r += THREADS >> gs) {
-          const int t0 = __ldg(O.radj_ptr + r), t1 = __ldg(O.radj_ptr + r + 1);
+          const int t0 = O.radjp_in_smem ? (int)radjp_s[r] : __ldg(O.radj_ptr + r);
+          const int t1 = O.radjp_in_smem ? (int)radjp_s[r + 1] : __ldg(O.radj_ptr + r + 1);
           const double zr = zs[r];
           double ax = 0.0, ay = 0.0;
           if (cok) {
@@ -1289,15 +1347,12 @@ __global__ void __launch_bounds__(THREADS * G, MINB) k_onchip(const __grid_const
         if (tid < nvar && A.grad) {
           double gsum = 0.0;
           if (tid < k)
-            for (int b = 0; b < nb; ++b) {
-              const double Rx = react[3 * b], Ry = react[3 * b + 1];
-              const double Rn = sqrt(Rx * Rx + Ry * Ry);
-              gsum += (osign * Rx / Rn) * gxy[b * k + tid] + (osign * Ry / Rn) * gxy[nb * k + b * k + tid];
-            }
+            for (int b = 0; b < nb; ++b)
+              gsum += react[3 * nb + 3 * b + 1] * gxy[b * k + tid] + react[3 * nb + 3 * b + 2] * gxy[nb * k + b * k + tid];
           A.grad[cand * nvar + tid] = gsum;
         }
         if (tid == 0) {
-          for (int b = 0; b < nb; ++b) fval += sqrt(react[3 * b] * react[3 * b] + react[3 * b + 1] * react[3 * b + 1]);
+          for (int b = 0; b < nb; ++b) fval += react[3 * nb + 3 * b];
           fval *= osign;
         }
       }
@@ -2048,6 +2103,16 @@ static int build_onchip_impl(Plan* PL, const tno_problem_desc* D, const OcLayout
     put_table(&O.idx_supedge, sup_edge.data(), std::max<size_t>(sup_edge.size(), 1) * 4);
     put_table(&O.idx_supsign, sup_sign.data(), std::max<size_t>(sup_sign.size(), 1) * 4);
     put_table(&O.idx_fixed, PL->h_fixed.data(), PL->h_fixed.size() * 4);
+    // row pointers of the row adjacency (16 bit) when they fit
+    O.radjp_in_smem = radj.size() < 65535 ? 1 : 0;
+    std::vector<unsigned short> radjp16(O.radjp_in_smem ? ni + 1 : 1, 0);
+    if (O.radjp_in_smem)
+      for (int r = 0; r <= ni; ++r) radjp16[r] = (unsigned short)radj_ptr[r];
+    put_table(&O.idx_radjp, radjp16.data(), radjp16.size() * 2);
+    std::vector<double> supxyz((size_t)3 * std::max(nb, 1), 0.0);
+    for (int b = 0; b < nb; ++b)
+      for (int a = 0; a < 3; ++a) supxyz[3 * b + a] = D->X[(size_t)3 * PL->h_fixed[b] + a];
+    put_table(&O.idx_supxyz, supxyz.data(), supxyz.size() * 8);
   }
   const int idx_bytes_core = (int)idx.size();
   O.idx_ct_ptr = (int)idx.size();
@@ -2082,7 +2147,7 @@ static int build_onchip_impl(Plan* PL, const tno_problem_desc* D, const OcLayout
   O.o_zs = take(ni + nb);
   O.o_pers = take(O.npers > 1 ? ni : 0);
   O.o_qsup = take(O.nsup);
-  O.o_react = take(3 * nb);
+  O.o_react = take(6 * nb);   // reactions, then |R_h| and the direction cosines of the thrust objectives
   O.o_gxy = take(2 * nb * k + 2 * nb);
   O.o_azsup = take((((P.constraints & TNO_CON_REAC_BOUNDS) || P.objective == TNO_OBJ_ECOMP_LINEAR || P.objective == TNO_OBJ_ECOMP_NONLINEAR) &&
                      P.var.o_zb >= 0) ? O.nsup * nb : 0);
@@ -2224,9 +2289,9 @@ int run_onchip(Plan* PL, const double* x_dev, int64_t N, int64_t ldx, const tno_
   // <256, 2, 1>: up to two single-candidate CTAs per SM; <256, 1, G>: one CTA of G candidate groups sharing the index
   // region; <512, 1, 1>: one 512-thread candidate per SM (large panels)
   void (*kern)(const DevPlan, const DevOnchip, const OcArgs) = nullptr;
-  if (PL->onchip_threads == 512) kern = dir ? k_onchip<512, 1, 1, true> : k_onchip<512, 1, 1, false>;
-  else if (G == 1) kern = dir ? k_onchip<256, 2, 1, true> : k_onchip<256, 2, 1, false>;
-  else kern = dir ? k_onchip<256, 1, 2, true> : k_onchip<256, 1, 2, false>;
+  if (PL->onchip_threads == 512) kern = dir ? k_onchip<512, 1, 1, true, false> : (want_clocks ? k_onchip<512, 1, 1, false, true> : k_onchip<512, 1, 1, false, false>);
+  else if (G == 1) kern = dir ? k_onchip<256, 2, 1, true, false> : (want_clocks ? k_onchip<256, 2, 1, false, true> : k_onchip<256, 2, 1, false, false>);
+  else kern = dir ? k_onchip<256, 1, 2, true, false> : k_onchip<256, 1, 2, false, false>;
   TNO_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   if (out->J && PL->dp.con.r_fun >= 0)
     launch_fill_funicular(PL, PL->oc.Jfun, (int64_t)2 * PL->dp.m * PL->dp.var.nvar, out->J, N, stream);

@@ -226,6 +226,8 @@ struct DevOnchip {
   // small lookup tables copied into the shared-memory index region (byte offsets): no L2 round trip in front of
   // the accesses that depend on them
   int idx_vrow, idx_rowv, idx_colsrc, idx_supptr, idx_supother, idx_supedge, idx_supsign, idx_fixed;
+  int idx_supxyz;        // 3 nb doubles: coordinates of the supports
+  int idx_radjp, radjp_in_smem;   // 16-bit copy of radj_ptr in the index region (when the adjacency has < 65535 records)
   int ct_in_smem;        // 1: the three arrays live in the shared-memory index region at idx_ct_*
   int idx_ct_ptr, idx_ct_col, idx_ct_ent;
   const double* Jfun;    // 2m x nvar
