@@ -117,7 +117,7 @@ template <int NT>
 __device__ __forceinline__ void oc_pull_rows(int row0, int row1, int sshift, int gshift, int tl, int c0, int ncols, int W,
                                              const unsigned short* __restrict__ rowptr16,
                                              const unsigned short* __restrict__ rowcol16, const double* __restrict__ V,
-                                             double* __restrict__ R) {
+                                             double* __restrict__ R, const unsigned short* __restrict__ rowlist = nullptr) {
   const int lshift = sshift + gshift;
   const int rows = row1 - row0;
   const int r = tl & ((1 << gshift) - 1);
@@ -128,7 +128,7 @@ __device__ __forceinline__ void oc_pull_rows(int row0, int row1, int sshift, int
   for (int base = 0; base < rows; base += NT >> lshift) {
     const int it = base + (tl >> lshift);
     const bool valid = it < rows && colok;
-    const int row = row0 + it;
+    const int row = rowlist ? (it < rows ? (int)rowlist[it] : row0) : row0 + it;   // rowlist: processing order of the level's rows
     double ax = 0.0, ay = 0.0;
     if (valid) {
       const int t1 = rowptr16[row + 1];
@@ -243,6 +243,87 @@ __device__ __forceinline__ void oc_chain_apply(const OcRange& L, const OcChain* 
   }
 }
 
+// The same dense products on the FP64 tensor pipe: Y_C = Z_C R_C as 8 x 8 output tiles, one warp per tile,
+// mma.sync.m8n8k4: D (8 rows x 8 panel columns) = sum over 4-row blocks of  Z[tile rows, block] x R_C[block, columns],
+// the unit diagonal enters through the accumulator (C = R_C tile).  A lane loads ONE element of Z and ONE of R per 256
+// multiply-adds (the FMA variant above: a 16-byte panel load and a broadcast Z load per 2), which is what the kernel is
+// short of: shared-memory bandwidth and issue slots.  Tiles are ordered so that a batch never reads rows an earlier
+// batch has overwritten (forward: high rows first; transposed: low rows first).
+constexpr int OC_ZMMA_ITEMS = 3;   // work items (8 rows x 16 columns) per warp and batch
+template <int NT, bool TRANSPOSED>
+__device__ __forceinline__ void oc_chain_apply_mma(const OcRange& L, const uint2* __restrict__ zt, int tl, int c0, int ncols, int W,
+                                                   const double* __restrict__ V, double* __restrict__ R, int bar) {
+  constexpr int NW = NT / 32;
+  const int lane = tl & 31, warp = tl >> 5;
+  const int g = lane >> 2, kq = lane & 3;
+  const int ncols_e = (ncols + 1) & ~1;
+  const int npair = (ncols + 15) >> 4;          // pairs of 8-column tiles: one work item = an 8-row tile x one pair
+  const int nmt = (int)L.zt1 - (int)L.zt0;
+  const int nitems = nmt * npair;
+  for (int base = 0; base < nitems; base += NW * OC_ZMMA_ITEMS) {
+    double2 res[OC_ZMMA_ITEMS][2];
+#pragma unroll
+    for (int ps = 0; ps < OC_ZMMA_ITEMS; ++ps) {
+      const int t = base + ps * NW + warp;
+      res[ps][0] = res[ps][1] = make_double2(0.0, 0.0);
+      if (t < nitems) {   // warp-uniform
+        const int di = t / npair, np = t - di * npair;
+        const uint2 d = zt[(int)L.zt0 + (TRANSPOSED ? nmt - 1 - di : di)];
+        const int zoff = (int)(d.x & 0xffffu), row0 = (int)(d.x >> 16), T = (int)(d.y & 0xffu), mt = (int)((d.y >> 8) & 0xffu);
+        const int i = 8 * mt + g;
+        const bool rok = i < T;
+        const int colc = 16 * np + 2 * kq;      // first output column of this lane in the first tile (second: + 8)
+        double2 ca = make_double2(0.0, 0.0), cb2 = make_double2(0.0, 0.0);
+        if (rok && colc < ncols_e) ca = *reinterpret_cast<const double2*>(R + (row0 + i) * W + c0 + colc);
+        if (rok && colc + 8 < ncols_e) cb2 = *reinterpret_cast<const double2*>(R + (row0 + i) * W + c0 + colc + 8);
+        const bool bok0 = 16 * np + g < ncols_e, bok1 = 16 * np + 8 + g < ncols_e;
+        const double* rb = R + row0 * W + c0 + 16 * np + g;
+        const int nkb = (T + 3) >> 2;
+        const int kb0 = TRANSPOSED ? 2 * mt : 0;
+        const int kb1 = TRANSPOSED ? nkb : min(nkb, 2 * mt + 2);
+        const int ri = zoff + (i * (i - 1)) / 2;
+        int kk = 4 * kb0 + kq;
+        int zo = zoff + (kk * (kk - 1)) / 2 + i;   // transposed: position of Z[kk][i]
+#pragma unroll 2
+        for (int kb = kb0; kb < kb1; ++kb) {
+          double a = 0.0;
+          if (!TRANSPOSED) {
+            if (rok && kk < i) a = V[ri + kk];
+          } else {
+            if (rok && kk > i && kk < T) a = V[zo];
+          }
+          const double b0 = (bok0 && kk < T) ? rb[kk * W] : 0.0;
+          const double b1 = (bok1 && kk < T) ? rb[kk * W + 8] : 0.0;
+          asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+                       : "+d"(ca.x), "+d"(ca.y)
+                       : "d"(a), "d"(b0));
+          asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+                       : "+d"(cb2.x), "+d"(cb2.y)
+                       : "d"(a), "d"(b1));
+          zo += 4 * kk + 6;
+          kk += 4;
+        }
+        res[ps][0] = ca;
+        res[ps][1] = cb2;
+      }
+    }
+    oc_sync<NT>(bar);
+#pragma unroll
+    for (int ps = 0; ps < OC_ZMMA_ITEMS; ++ps) {
+      const int t = base + ps * NW + warp;
+      if (t < nitems) {
+        const int di = t / npair, np = t - di * npair;
+        const uint2 d = zt[(int)L.zt0 + (TRANSPOSED ? nmt - 1 - di : di)];
+        const int row0 = (int)(d.x >> 16), T = (int)(d.y & 0xffu), mt = (int)((d.y >> 8) & 0xffu);
+        const int i = 8 * mt + g, colc = 16 * np + 2 * kq;
+        if (i < T && colc < ncols_e) *reinterpret_cast<double2*>(R + (row0 + i) * W + c0 + colc) = res[ps][0];
+        if (i < T && colc + 8 < ncols_e) *reinterpret_cast<double2*>(R + (row0 + i) * W + c0 + colc + 8) = res[ps][1];
+      }
+    }
+    if (base + NW * OC_ZMMA_ITEMS < nitems) oc_sync<NT>(bar);
+  }
+}
+
 // L D L^T solve of the panel columns [c0, c0 + ncols) (c0 even) for all rows.
 template <int THREADS>
 __device__ __forceinline__ void oc_solve(const DevOnchip& O, int phase, const OcRange* __restrict__ wide,
@@ -251,7 +332,8 @@ __device__ __forceinline__ void oc_solve(const DevOnchip& O, int phase, const Oc
                                          const unsigned short* __restrict__ rowcol16, const double* __restrict__ V,
                                          double* __restrict__ R, int ni, int c0, int ncols, int tid,
                                          const unsigned short* ct_ptr, const unsigned short* ct_col, const unsigned short* ct_ent,
-                                         const unsigned char* ct_row, int bar, long long* tc = nullptr) {
+                                         const unsigned char* ct_row, int bar, const uint2* __restrict__ zt,
+                                         const unsigned short* __restrict__ rowlist, long long* tc = nullptr) {
   const int W = O.W;
   const int gshift = O.gshift[phase];
   long long tq = tc ? clock64() : 0;
@@ -271,10 +353,12 @@ __device__ __forceinline__ void oc_solve(const DevOnchip& O, int phase, const Oc
   lap(0);
   for (int cl = 0; cl < O.nclev; ++cl) {
     const OcRange L = clev[cl];
-    oc_pull_rows<THREADS>(L.row0, L.row1, L.pull_s[phase], gshift, tid, c0, ncols, W, rowptr16, rowcol16, V, R);
+    oc_pull_rows<THREADS>(L.row0, L.row1, L.pull_s[phase], gshift, tid, c0, ncols, W, rowptr16, rowcol16, V, R,
+                          L.rl_on ? rowlist + L.rl0 : nullptr);
     oc_sync<THREADS>(bar);
     lap(1);
-    oc_chain_apply<THREADS, false>(L, chains, rowchain, O.wide_rows, gshift, tid, c0, ncols, W, V, R, bar);
+    if (O.zmma) oc_chain_apply_mma<THREADS, false>(L, zt, tid, c0, ncols, W, V, R, bar);
+    else oc_chain_apply<THREADS, false>(L, chains, rowchain, O.wide_rows, gshift, tid, c0, ncols, W, V, R, bar);
     oc_sync<THREADS>(bar);
     lap(2);
   }
@@ -297,7 +381,8 @@ __device__ __forceinline__ void oc_solve(const DevOnchip& O, int phase, const Oc
   // ---- backward ----
   for (int cl = O.nclev - 1; cl >= 0; --cl) {
     const OcRange L = clev[cl];
-    oc_chain_apply<THREADS, true>(L, chains, rowchain, O.wide_rows, gshift, tid, c0, ncols, W, V, R, bar);
+    if (O.zmma) oc_chain_apply_mma<THREADS, true>(L, zt, tid, c0, ncols, W, V, R, bar);
+    else oc_chain_apply<THREADS, true>(L, chains, rowchain, O.wide_rows, gshift, tid, c0, ncols, W, V, R, bar);
     oc_sync<THREADS>(bar);
     lap(4);
     // the rows of one chain share their descendants, so their updates are gathered per outside column ("target")
@@ -668,6 +753,8 @@ __global__ void __launch_bounds__(THREADS * G, MINB) k_onchip(const __grid_const
   const int* fixed_s = reinterpret_cast<const int*>(idxb + O.idx_fixed);
   const unsigned short* radjp_s = reinterpret_cast<const unsigned short*>(idxb + O.idx_radjp);
   const double* supxyz_s = reinterpret_cast<const double*>(idxb + O.idx_supxyz);   // x, y, z of the supports
+  const uint2* zt_s = reinterpret_cast<const uint2*>(idxb + O.idx_zt);
+  const unsigned short* rowlist_s = reinterpret_cast<const unsigned short*>(idxb + O.idx_rowlist);
   double* zs = sm + O.o_zs;        // z of the free rows (after phase 1) followed by zb of the supports
   const unsigned short* ct_ptr = O.ct_in_smem ? reinterpret_cast<const unsigned short*>(idxb + O.idx_ct_ptr) : O.ct_ptr;
   const unsigned short* ct_col = O.ct_in_smem ? reinterpret_cast<const unsigned short*>(idxb + O.idx_ct_col) : O.ct_col;
@@ -959,7 +1046,7 @@ __global__ void __launch_bounds__(THREADS * G, MINB) k_onchip(const __grid_const
 
     if (clk_here) A.phase_clocks[6] = clock64();
     // ---- 6. solve phase 1 ---------------------------------------------------------------------------
-    oc_solve<THREADS>(O, 0, wide, clev, chains, rowchain, rowptr16, rowcol16, V, R, ni, 0, O.ncols1, tid, ct_ptr, ct_col, ct_ent, ct_row, bar);
+    oc_solve<THREADS>(O, 0, wide, clev, chains, rowchain, rowptr16, rowcol16, V, R, ni, 0, O.ncols1, tid, ct_ptr, ct_col, ct_ent, ct_row, bar, zt_s, rowlist_s);
 
     if (clk_here) A.phase_clocks[7] = clock64();
     // ---- 7. everything that needs the transient columns (x, y, Az) or only z ------------------------
@@ -1246,7 +1333,7 @@ __global__ void __launch_bounds__(THREADS * G, MINB) k_onchip(const __grid_const
         if (clk2)
           for (int q = 0; q < 7; ++q) tcs[q] = 0;
         oc_solve<THREADS>(O, 1, wide, clev, chains, rowchain, rowptr16, rowcol16, V, R, ni, 0, ncp, tid, ct_ptr, ct_col, ct_ent, ct_row,
-                          bar, clk2 ? tcs : nullptr);
+                          bar, zt_s, rowlist_s, clk2 ? tcs : nullptr);
         if (clk2)
           for (int q = 0; q < 7; ++q) A.phase_clocks[16 + q] = tcs[q];
       }
@@ -1714,17 +1801,46 @@ static int build_onchip_impl(Plan* PL, const tno_problem_desc* D, const OcLayout
   // three staging buffers, the temp buffer of the rectangular chain rows and the inverse's nz doubles share the panel
   // region while the matrix is factorised: the chunk size follows the panel so that they do not enlarge it
   size_t CHUNK_BYTES = 12 * 1024;
+  // dense scratch behind the staging buffers: the element-wise variant inverts into nz doubles, the register-tile variant
+  // only exchanges columns / rows (5 x the padded chain rows of a level)
+  int dense_scratch = 0;
   {
-    const long long room = ((long long)std::max(ni * O.W, m) - nz - 2) * 8 - 4096;
-    CHUNK_BYTES = (size_t)std::min<long long>(12 * 1024, std::max<long long>(2048, room / 3 / 16 * 16));
+    static const bool elementwise = getenv("TNO_ONCHIP_DENSE_ELEMENTS") != nullptr;
+    for (int cl = 0; cl < O.nclev; ++cl) {
+      const int c0 = S.clevel_ptr[cl], c1 = S.clevel_ptr[cl + 1];
+      int need = nz;
+      for (int TS = 2; TS <= 4 && !elementwise; TS += 2) {
+        int tiles = 0, cbo = 0;
+        for (int c = c0; c < c1; ++c) {
+          const int nt = (S.chain_ptr[c + 1] - S.chain_ptr[c] + TS - 1) / TS;
+          tiles += nt * (nt + 1) / 2;
+          cbo += TS * nt;
+        }
+        if (tiles <= THREADS) {
+          need = 5 * cbo;
+          break;
+        }
+      }
+      dense_scratch = std::max(dense_scratch, need);
+    }
+    static const char* cap_env = getenv("TNO_ONCHIP_CHUNK_KB");   // developer knob
+    const long long cap = (cap_env ? atoi(cap_env) : 20) * 1024LL;
+    const long long room = ((long long)std::max(ni * O.W, m) - dense_scratch - 2) * 8 - 4096;
+    CHUNK_BYTES = (size_t)std::min<long long>(cap, std::max<long long>(2048, room / 3 / 16 * 16));
   }
-  auto emit_step = [&](const std::vector<Item>& items, int kind) {
+  static const bool sort_items = getenv("TNO_ONCHIP_NO_ITEM_SORT") == nullptr;   // developer knob (A/B measurements)
+  auto emit_step = [&](std::vector<Item> items, int kind) {
+    // The items of a kind-0 step are independent of one another: longest dot products first, so that the items of one chunk
+    // have similar lengths (a chunk takes as long as its longest item; the lanes-per-item split is chosen per chunk).
+    // Kind-1 items keep their order (a later chunk must not overwrite what an earlier one still reads).
+    if (kind == 0 && sort_items)
+      std::stable_sort(items.begin(), items.end(), [](const Item& a, const Item& b) { return a.prs.size() > b.prs.size(); });
     size_t i0 = 0;
     while (i0 < items.size()) {
       size_t i1 = i0, bytes = 8;
       while (i1 < items.size()) {
         const size_t add = 8 + 8 * items[i1].prs.size();
-        if (i1 > i0 && bytes + add > CHUNK_BYTES) break;
+        if (i1 > i0 && (bytes + add > CHUNK_BYTES || (kind == 1 && i1 - i0 >= 448))) break;   // kind 1: the temp buffer holds 4 KB
         bytes += add;
         ++i1;
       }
@@ -1930,6 +2046,63 @@ static int build_onchip_impl(Plan* PL, const tno_problem_desc* D, const OcLayout
       for (int r = S.chain_ptr[c]; r < S.chain_ptr[c + 1]; ++r) rowchain[r - wide_rows] = (unsigned char)(c - c0);
     }
   }
+  // 8-row tiles of the chains' dense blocks (tensor-pipe variant of the dense chain products), high tile rows first
+  std::vector<uint2> zt_tab;
+  for (int cl = 0; cl < O.nclev; ++cl) {
+    const int c0 = S.clevel_ptr[cl], c1 = S.clevel_ptr[cl + 1];
+    clev_r[cl].zt0 = (unsigned short)zt_tab.size();
+    int mtmax = 0;
+    for (int c = c0; c < c1; ++c) mtmax = std::max(mtmax, (S.chain_ptr[c + 1] - S.chain_ptr[c] + 7) / 8);
+    for (int mt = mtmax - 1; mt >= 0; --mt)
+      for (int c = c0; c < c1; ++c) {
+        const int T = S.chain_ptr[c + 1] - S.chain_ptr[c];
+        if (8 * mt >= T) continue;
+        uint2 d;
+        d.x = (uint32_t)(nlo + ni + zoff_rel[c]) | ((uint32_t)S.chain_ptr[c] << 16);
+        d.y = (uint32_t)T | ((uint32_t)mt << 8);
+        zt_tab.push_back(d);
+      }
+    clev_r[cl].zt1 = (unsigned short)zt_tab.size();
+  }
+  if (zt_tab.empty()) zt_tab.push_back(uint2{0, 0});
+  // processing order of the rows of a chain level in the forward (pull) step: longest rows first, and as many sub-slots per
+  // row as minimise  sum over passes of (longest row of the pass / sub-slots + a per-pass overhead)
+  std::vector<unsigned short> rowlist;
+  {
+    static const bool off = getenv("TNO_ONCHIP_ROWLIST") == nullptr;   // developer knob: measured 1 % slower than row order at disc 20, off
+    for (int cl = 0; cl < O.nclev && !off; ++cl) {
+      OcRange& L = clev_r[cl];
+      std::vector<int> rows;
+      for (int r = L.row0; r < L.row1; ++r) rows.push_back(r);
+      std::stable_sort(rows.begin(), rows.end(), [&](int a, int b) {
+        return rowptr_o[a + 1] - rowptr_o[a] > rowptr_o[b + 1] - rowptr_o[b];
+      });
+      L.rl0 = (unsigned short)rowlist.size();
+      L.rl_on = 1;
+      for (int r : rows) rowlist.push_back((unsigned short)r);
+      for (int ph = 0; ph < 2; ++ph) {
+        const int g = O.gshift[ph];
+        int best_s = 0;
+        double best = 1e300;
+        for (int sft = 0; sft + g <= 5; ++sft) {
+          const int per_pass = THREADS >> (sft + g);
+          if (per_pass < 1) break;
+          double cost = 0.0;
+          for (size_t i0 = 0; i0 < rows.size(); i0 += per_pass) {
+            const int len = rowptr_o[rows[i0] + 1] - rowptr_o[rows[i0]];   // longest row of the pass
+            cost += (double)((len + (1 << sft) - 1) >> sft) + 4.0 + 1.5 * sft;
+          }
+          if (cost < best) {
+            best = cost;
+            best_s = sft;
+          }
+        }
+        L.pull_s[ph] = (unsigned char)best_s;
+      }
+    }
+    if (rowlist.empty()) rowlist.push_back(0);
+  }
+  O.zmma = getenv("TNO_ONCHIP_NO_DMMA") ? 0 : 1;   // developer knob (A/B measurements): dense chain products with DFMA
   std::vector<unsigned short> ct_ptr(1, 0);
   std::vector<unsigned short> ct_col;
   std::vector<unsigned short> ct_ent;
@@ -1938,20 +2111,26 @@ static int build_onchip_impl(Plan* PL, const tno_problem_desc* D, const OcLayout
   for (int cl = 0; cl < O.nclev; ++cl) {
     const int c0 = S.clevel_ptr[cl], c1 = S.clevel_ptr[cl + 1];
     clev_r[cl].tgt0 = (unsigned short)ct_col.size();
-    for (int c = c0; c < c1; ++c) {
-      std::map<int, std::vector<uint32_t>> by_col;  // outside column -> entries of this chain's rows
+    // outside column -> entries of the level's chain rows in it (the chains of one level reach disjoint columns)
+    std::map<int, std::vector<uint32_t>> by_col;
+    for (int c = c0; c < c1; ++c)
       for (int i = S.chain_ptr[c]; i < S.chain_ptr[c + 1]; ++i)
         for (int t = rowptr_o[i]; t < rowptr_o[i + 1]; ++t) by_col[rowcol_o[t]].push_back((uint32_t)t | ((uint32_t)i << 16));
-      for (auto& kv : by_col) {
-        ct_col.push_back((unsigned short)kv.first);
-        for (uint32_t w : kv.second) {
-          const int rel = (int)(w >> 16) - S.chain_ptr[c0];
-          if (rel > 255) ct_rows_fit = false;
-          ct_ent.push_back((unsigned short)(w & 0xffffu));
-          ct_row.push_back((unsigned char)(rel & 0xff));
-        }
-        ct_ptr.push_back((unsigned short)ct_ent.size());
+    // longest targets first: the targets of one pass (THREADS >> gshift of them) then have similar lengths, and a pass
+    // takes as long as its longest target
+    std::vector<std::pair<int, std::vector<uint32_t>>> tl(by_col.begin(), by_col.end());
+    std::stable_sort(tl.begin(), tl.end(), [](const std::pair<int, std::vector<uint32_t>>& a, const std::pair<int, std::vector<uint32_t>>& b) {
+      return a.second.size() > b.second.size();
+    });
+    for (auto& kv : tl) {
+      ct_col.push_back((unsigned short)kv.first);
+      for (uint32_t w : kv.second) {
+        const int rel = (int)(w >> 16) - S.chain_ptr[c0];
+        if (rel > 255) ct_rows_fit = false;
+        ct_ent.push_back((unsigned short)(w & 0xffffu));
+        ct_row.push_back((unsigned char)(rel & 0xff));
       }
+      ct_ptr.push_back((unsigned short)ct_ent.size());
     }
     clev_r[cl].tgt1 = (unsigned short)ct_col.size();
   }
@@ -2113,6 +2292,8 @@ static int build_onchip_impl(Plan* PL, const tno_problem_desc* D, const OcLayout
     for (int b = 0; b < nb; ++b)
       for (int a = 0; a < 3; ++a) supxyz[3 * b + a] = D->X[(size_t)3 * PL->h_fixed[b] + a];
     put_table(&O.idx_supxyz, supxyz.data(), supxyz.size() * 8);
+    put_table(&O.idx_zt, zt_tab.data(), zt_tab.size() * sizeof(uint2));
+    put_table(&O.idx_rowlist, rowlist.data(), rowlist.size() * 2);
   }
   const int idx_bytes_core = (int)idx.size();
   O.idx_ct_ptr = (int)idx.size();
@@ -2143,7 +2324,7 @@ static int build_onchip_impl(Plan* PL, const tno_problem_desc* D, const OcLayout
   const int stage_doubles = 3 * O.fseg_units * 2;
   O.o_tmp_doubles = stage_doubles;
   O.o_tmpz_doubles = (stage_doubles + max_tmp_items + 2) / 2 * 2;
-  O.o_r = take(std::max(panel, O.o_tmpz_doubles + std::max(nz, max_tile_buf) + 2));
+  O.o_r = take(std::max(panel, O.o_tmpz_doubles + std::max(dense_scratch, max_tile_buf) + 2));
   O.o_zs = take(ni + nb);
   O.o_pers = take(O.npers > 1 ? ni : 0);
   O.o_qsup = take(O.nsup);
@@ -2307,8 +2488,9 @@ int run_onchip(Plan* PL, const double* x_dev, int64_t N, int64_t ldx, const tno_
     cudaFree(A.phase_clocks);
     static const char* names[13] = {"x", "q", "assemble", "factor", "scale", "rhs1", "solve1", "post1", "rhs2", "solve2",
                                     "reac/obj", "emitJ", "final"};
-    fprintf(stderr, "[tno smem] total=%d idx=%d ct_in_smem=%d V=%d panel=%d doubles\n", PL->oc.smem_bytes, PL->oc.idx_bytes,
-            PL->oc.ct_in_smem, PL->oc.nv, PL->oc.o_zs - PL->oc.o_r);
+    fprintf(stderr, "[tno smem] total=%d idx=%d ct_in_smem=%d V=%d panel=%d doubles; factor program: %d ops, %d staged chunks of <= %d bytes\n",
+            PL->oc.smem_bytes, PL->oc.idx_bytes, PL->oc.ct_in_smem, PL->oc.nv, PL->oc.o_zs - PL->oc.o_r, PL->oc.nops, PL->oc.nchunks,
+            PL->oc.fseg_units * 16);
     fprintf(stderr, "[tno phase clocks] N=%lld grid=%d total=%lld :", (long long)N, grid, h[13] - h[0]);
     for (int i = 0; i < 13; ++i) fprintf(stderr, " %s=%lld", names[i], h[i + 1] - h[i]);
     fprintf(stderr, " | factor: dense=%lld (LDL^T part %lld: setup=%lld columns / tile steps=%lld barrier=%lld; inverse: diagonal blocks / tile publish=%lld stages=%lld copy=%lld) chunk waits=%lld",

@@ -125,6 +125,8 @@ struct OcRange {
   unsigned char push_s[2];   // backward (push) sub-slots per row: any power of two
   unsigned short chain0, chain1;   // chain levels only: chains [chain0, chain1)
   unsigned short tgt0, tgt1;       // chain levels only: outside columns reached by those chains, [tgt0, tgt1) in ct_*
+  unsigned short zt0, zt1;         // chain levels only: 8-row tiles of the chains' dense blocks, [zt0, zt1) in the zt table
+  unsigned short rl0, rl_on;       // chain levels only: the rows in processing order (longest first) start at rowlist[rl0]
 };
 struct OcChain {
   unsigned short row0, T;    // rows [row0, row0 + T)
@@ -227,6 +229,9 @@ struct DevOnchip {
   // the accesses that depend on them
   int idx_vrow, idx_rowv, idx_colsrc, idx_supptr, idx_supother, idx_supedge, idx_supsign, idx_fixed;
   int idx_supxyz;        // 3 nb doubles: coordinates of the supports
+  int idx_rowlist;       // u16: rows of every chain level sorted by their number of outside entries, descending
+  int idx_zt;            // uint2 per 8-row tile of a chain block: x = zoff | first row << 16, y = T | tile row << 8 (sorted by tile row, descending, per chain level)
+  int zmma;              // 1: the dense chain products Z R, Z^T R run on the FP64 tensor pipe (mma.sync m8n8k4)
   int idx_radjp, radjp_in_smem;   // 16-bit copy of radj_ptr in the index region (when the adjacency has < 65535 records)
   int ct_in_smem;        // 1: the three arrays live in the shared-memory index region at idx_ct_*
   int idx_ct_ptr, idx_ct_col, idx_ct_ent;
