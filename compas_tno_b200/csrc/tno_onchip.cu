@@ -22,6 +22,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <numeric>
 
 #include "tno_plan.hpp"
 #ifndef TNO_AB
@@ -160,7 +161,7 @@ template <int NT>
 __device__ __forceinline__ void oc_push_rows(int row0, int row1, int sshift, int gshift, int tl, int c0, int ncols, int W,
                                              const unsigned short* __restrict__ rowptr16,
                                              const unsigned short* __restrict__ rowcol16, const double* __restrict__ V,
-                                             double* __restrict__ R) {
+                                             double* __restrict__ R, const unsigned short* __restrict__ rowlist = nullptr) {
   const int lshift = sshift + gshift;
   const int rows = row1 - row0;
   const int r = tl & ((1 << gshift) - 1);
@@ -171,7 +172,7 @@ __device__ __forceinline__ void oc_push_rows(int row0, int row1, int sshift, int
   for (int base = 0; base < rows; base += NT >> lshift) {
     const int it = base + (tl >> lshift);
     if (it < rows && colok) {
-      const int row = row0 + it;
+      const int row = rowlist ? (int)rowlist[it] : row0 + it;
       const double2 xi = *reinterpret_cast<const double2*>(R + row * W + col);
       const int t1 = rowptr16[row + 1];
 #pragma unroll 4
@@ -324,6 +325,12 @@ __device__ __forceinline__ void oc_chain_apply_mma(const OcRange& L, const uint2
   }
 }
 
+struct OcWarpLocal {
+  const unsigned short* ptr;
+  const unsigned short* rows;
+  const unsigned char* s;
+};
+
 // L D L^T solve of the panel columns [c0, c0 + ncols) (c0 even) for all rows.
 template <int THREADS>
 __device__ __forceinline__ void oc_solve(const DevOnchip& O, int phase, const OcRange* __restrict__ wide,
@@ -333,7 +340,7 @@ __device__ __forceinline__ void oc_solve(const DevOnchip& O, int phase, const Oc
                                          double* __restrict__ R, int ni, int c0, int ncols, int tid,
                                          const unsigned short* ct_ptr, const unsigned short* ct_col, const unsigned short* ct_ent,
                                          const unsigned char* ct_row, int bar, const uint2* __restrict__ zt,
-                                         const unsigned short* __restrict__ rowlist, long long* tc = nullptr) {
+                                         const unsigned short* __restrict__ rowlist, const OcWarpLocal wl, long long* tc = nullptr) {
   const int W = O.W;
   const int gshift = O.gshift[phase];
   long long tq = tc ? clock64() : 0;
@@ -345,10 +352,23 @@ __device__ __forceinline__ void oc_solve(const DevOnchip& O, int phase, const Oc
     }
   };
   // ---- forward ----
-  for (int lev = 1; lev < O.nwide; ++lev) {
-    const OcRange L = wide[lev];
-    oc_pull_rows<THREADS>(L.row0, L.row1, L.pull_s[phase], gshift, tid, c0, ncols, W, rowptr16, rowcol16, V, R);
+  const int wlw = tid >> 5, wll = tid & 31;
+  if (O.wl_on) {
+    // every warp runs the rows of its own subtrees level by level: no block-wide barrier inside the wide part
+    for (int lev = 1; lev < O.nwide; ++lev) {
+      const int a = wl.ptr[wlw * (O.nwide + 1) + lev], b = wl.ptr[wlw * (O.nwide + 1) + lev + 1];
+      if (b > a)
+        oc_pull_rows<32>(0, b - a, wl.s[((wlw * O.nwide + lev) * 2 + phase) * 2], gshift, wll, c0, ncols, W, rowptr16, rowcol16, V, R,
+                         wl.rows + a);
+      __syncwarp();
+    }
     oc_sync<THREADS>(bar);
+  } else {
+    for (int lev = 1; lev < O.nwide; ++lev) {
+      const OcRange L = wide[lev];
+      oc_pull_rows<THREADS>(L.row0, L.row1, L.pull_s[phase], gshift, tid, c0, ncols, W, rowptr16, rowcol16, V, R);
+      oc_sync<THREADS>(bar);
+    }
   }
   lap(0);
   for (int cl = 0; cl < O.nclev; ++cl) {
@@ -412,10 +432,21 @@ __device__ __forceinline__ void oc_solve(const DevOnchip& O, int phase, const Oc
     oc_sync<THREADS>(bar);
     lap(5);
   }
-  for (int lev = O.nwide - 1; lev >= 1; --lev) {
-    const OcRange L = wide[lev];
-    oc_push_rows<THREADS>(L.row0, L.row1, L.push_s[phase], gshift, tid, c0, ncols, W, rowptr16, rowcol16, V, R);
+  if (O.wl_on) {
+    for (int lev = O.nwide - 1; lev >= 1; --lev) {
+      const int a = wl.ptr[wlw * (O.nwide + 1) + lev], b = wl.ptr[wlw * (O.nwide + 1) + lev + 1];
+      if (b > a)
+        oc_push_rows<32>(0, b - a, wl.s[((wlw * O.nwide + lev) * 2 + phase) * 2 + 1], gshift, wll, c0, ncols, W, rowptr16, rowcol16, V, R,
+                         wl.rows + a);
+      __syncwarp();
+    }
     oc_sync<THREADS>(bar);
+  } else {
+    for (int lev = O.nwide - 1; lev >= 1; --lev) {
+      const OcRange L = wide[lev];
+      oc_push_rows<THREADS>(L.row0, L.row1, L.push_s[phase], gshift, tid, c0, ncols, W, rowptr16, rowcol16, V, R);
+      oc_sync<THREADS>(bar);
+    }
   }
   lap(6);
 }
@@ -755,6 +786,8 @@ __global__ void __launch_bounds__(THREADS * G, MINB) k_onchip(const __grid_const
   const double* supxyz_s = reinterpret_cast<const double*>(idxb + O.idx_supxyz);   // x, y, z of the supports
   const uint2* zt_s = reinterpret_cast<const uint2*>(idxb + O.idx_zt);
   const unsigned short* rowlist_s = reinterpret_cast<const unsigned short*>(idxb + O.idx_rowlist);
+  const OcWarpLocal wl_s = {reinterpret_cast<const unsigned short*>(idxb + O.idx_wl_ptr),
+                            reinterpret_cast<const unsigned short*>(idxb + O.idx_wl_rows), idxb + O.idx_wl_s};
   double* zs = sm + O.o_zs;        // z of the free rows (after phase 1) followed by zb of the supports
   const unsigned short* ct_ptr = O.ct_in_smem ? reinterpret_cast<const unsigned short*>(idxb + O.idx_ct_ptr) : O.ct_ptr;
   const unsigned short* ct_col = O.ct_in_smem ? reinterpret_cast<const unsigned short*>(idxb + O.idx_ct_col) : O.ct_col;
@@ -807,6 +840,16 @@ __global__ void __launch_bounds__(THREADS * G, MINB) k_onchip(const __grid_const
     double* gout = A.g ? A.g + cand * ng : nullptr;
     double* Jout = A.J ? A.J + cand * (int64_t)ng * nvar : nullptr;
 
+    if (O.dbg & 256) {
+      // touch the candidate's output pages long before they are written (address translation in the background)
+      const double* pf = nullptr;
+      if (tid == 0 && Jout) pf = Jout + (int64_t)(P.con.r_env >= 0 ? P.con.r_env : 0) * nvar;
+      if (tid == 32 && Jout) pf = Jout + (int64_t)ng * nvar - 1;
+      if (tid == 64 && gout) pf = gout;
+      if (tid == 96 && A.z) pf = A.z + cand * n;
+      if (tid == 128 && A.grad) pf = A.grad + cand * nvar;
+      if (pf) asm volatile("prefetch.global.L2 [%0];" ::"l"(pf));
+    }
     if (clk_here) A.phase_clocks[1] = clock64();
     // ---- 1. q = B q_ind + lambdh d ; funicular rows of g -------------------------------------------
     for (int e0 = tid; e0 < m; e0 += 4 * THREADS) {
@@ -923,6 +966,7 @@ __global__ void __launch_bounds__(THREADS * G, MINB) k_onchip(const __grid_const
       long long t_dense = 0, t_wait = 0, t_ldl[6] = {0, 0, 0, 0, 0, 0};
       for (int op = 0; op < O.nops; ++op) {
         const OcOp OP = ops[op];
+        if (clk && op < 96) A.phase_clocks[32 + op] = clock64();
         if (OP.type == OC_OP_DENSE) {
           oc_sync<THREADS>(bar);
           const long long t0 = clk ? clock64() : 0;
@@ -938,14 +982,14 @@ __global__ void __launch_bounds__(THREADS * G, MINB) k_onchip(const __grid_const
         cp_async_wait<1>();
         oc_sync<THREADS>(bar);
         if (clk) t_wait += clock64() - tw0;
-        issue(c + 2);
+        if (!(O.dbg & 32)) issue(c + 2);
         const OcChunk K = chunks[c];
         const uint2* rec = reinterpret_cast<const uint2*>(stage_base + (c % 3) * seg_bytes);
         const unsigned long long* pairs = reinterpret_cast<const unsigned long long*>(rec + K.nitems + 1);
         const int lpi = 1 << K.lpi_shift;
         const int sub = tid & (lpi - 1);
         const int per_pass = THREADS >> K.lpi_shift;
-        for (int base = 0; base < K.nitems; base += per_pass) {
+        for (int base = 0; base < ((O.dbg & 16) ? 0 : (int)K.nitems); base += per_pass) {
           const int it = base + (tid >> K.lpi_shift);
           const bool valid = it < K.nitems;
           double acc = 0.0;
@@ -1046,7 +1090,7 @@ __global__ void __launch_bounds__(THREADS * G, MINB) k_onchip(const __grid_const
 
     if (clk_here) A.phase_clocks[6] = clock64();
     // ---- 6. solve phase 1 ---------------------------------------------------------------------------
-    oc_solve<THREADS>(O, 0, wide, clev, chains, rowchain, rowptr16, rowcol16, V, R, ni, 0, O.ncols1, tid, ct_ptr, ct_col, ct_ent, ct_row, bar, zt_s, rowlist_s);
+    oc_solve<THREADS>(O, 0, wide, clev, chains, rowchain, rowptr16, rowcol16, V, R, ni, 0, O.ncols1, tid, ct_ptr, ct_col, ct_ent, ct_row, bar, zt_s, rowlist_s, wl_s);
 
     if (clk_here) A.phase_clocks[7] = clock64();
     // ---- 7. everything that needs the transient columns (x, y, Az) or only z ------------------------
@@ -1183,6 +1227,7 @@ __global__ void __launch_bounds__(THREADS * G, MINB) k_onchip(const __grid_const
         const int v = idx / nb, b = idx - v * nb;
         const int r = vrow_s[v];
         const double a = r >= 0 ? R[r * W + O.c_az + b] : ((-1 - r) == b ? 1.0 : 0.0);
+        if (O.dbg & 128) continue;
         Jout[(int64_t)(P.con.r_env + v) * nvar + P.var.o_zb + b] = a;
         Jout[(int64_t)(P.con.r_env + n + v) * nvar + P.var.o_zb + b] = -a;
       }
@@ -1333,7 +1378,7 @@ __global__ void __launch_bounds__(THREADS * G, MINB) k_onchip(const __grid_const
         if (clk2)
           for (int q = 0; q < 7; ++q) tcs[q] = 0;
         oc_solve<THREADS>(O, 1, wide, clev, chains, rowchain, rowptr16, rowcol16, V, R, ni, 0, ncp, tid, ct_ptr, ct_col, ct_ent, ct_row,
-                          bar, zt_s, rowlist_s, clk2 ? tcs : nullptr);
+                          bar, zt_s, rowlist_s, wl_s, clk2 ? tcs : nullptr);
         if (clk2)
           for (int q = 0; q < 7; ++q) A.phase_clocks[16 + q] = tcs[q];
       }
@@ -1526,6 +1571,7 @@ __global__ void __launch_bounds__(THREADS * G, MINB) k_onchip(const __grid_const
           for (int v = tid >> es; v < n; v += THREADS >> es) {
             const int r = vrow_s[v];
             const double a = r >= 0 ? R[r * W + c] : 0.0;
+            if (O.dbg & 64) continue;
             o1[(int64_t)v * nvar + col] = a;
             o2[(int64_t)v * nvar + col] = -a;
           }
@@ -1865,9 +1911,28 @@ static int build_onchip_impl(Plan* PL, const tno_problem_desc* D, const OcLayout
       while (stream.size() % 4) stream.push_back(0);
       K.seg_units = (uint32_t)(stream.size() / 4) - K.seg_off;
       const int nitems = (int)(i1 - i0);
+      // lanes per item: minimise  passes x (pairs of the longest item per lane + shuffle steps + a per-pass overhead),
+      // all in units of one dependent pair iteration
       int lpi_shift = 0;
-      if (nitems > 0 && npairs / nitems >= 4)
-        while (lpi_shift < 5 && (nitems << (lpi_shift + 1)) <= THREADS) ++lpi_shift;
+      {
+        size_t maxp = 0;
+        for (size_t i = i0; i < i1; ++i) maxp = std::max(maxp, items[i].prs.size());
+        double best = 1e300;
+        for (int sft = 0; sft <= 5; ++sft) {
+          const int passes = ((nitems << sft) + THREADS - 1) / THREADS;
+          const double cost = passes * ((double)((maxp + (1u << sft) - 1) >> sft) + 0.8 * sft + 2.0);
+          if (cost < best - 1e-9) {
+            best = cost;
+            lpi_shift = sft;
+          }
+        }
+        static const bool old_rule = getenv("TNO_ONCHIP_OLD_LPI") != nullptr;   // developer knob (A/B measurements)
+        if (old_rule) {
+          lpi_shift = 0;
+          if (nitems > 0 && npairs / nitems >= 4)
+            while (lpi_shift < 5 && (nitems << (lpi_shift + 1)) <= THREADS) ++lpi_shift;
+        }
+      }
       K.lpi_shift = (unsigned char)lpi_shift;
       max_units = std::max(max_units, K.seg_units);
       if (kind == 1) max_tmp_items = std::max(max_tmp_items, nitems);
@@ -2007,6 +2072,15 @@ static int build_onchip_impl(Plan* PL, const tno_problem_desc* D, const OcLayout
   }
   O.nchunks = (int)chunks.size();
   O.nops = (int)ops.size();
+  if (getenv("TNO_PHASE_CLOCKS") && !dry) {
+    fprintf(stderr, "[tno factor program]");
+    for (const OcOp& op : ops) {
+      if (op.type == OC_OP_DENSE) fprintf(stderr, " DENSE(level %d)", (int)op.a);
+      else fprintf(stderr, " chunk(kind %d, %d items, %u bytes, %d lanes/item)", (int)chunks[op.a].kind, (int)chunks[op.a].nitems,
+                   chunks[op.a].seg_units * 16, 1 << chunks[op.a].lpi_shift);
+    }
+    fprintf(stderr, "\n");
+  }
   O.fseg_units = (int)max_units;
   if (chunks.size() >= 65535) { set_error("on-chip family not applicable: chunks.size() >= 65535"); return TNO_OK; }
 
@@ -2065,6 +2139,68 @@ static int build_onchip_impl(Plan* PL, const tno_problem_desc* D, const OcLayout
     clev_r[cl].zt1 = (unsigned short)zt_tab.size();
   }
   if (zt_tab.empty()) zt_tab.push_back(uint2{0, 0});
+  // ---- warp-local wide part: subtrees of the wide forest dealt to the warps, heaviest first to the lightest warp ----
+  std::vector<unsigned short> wl_ptr, wl_rows;
+  std::vector<unsigned char> wl_sub;
+  O.wl_on = 0;
+  {
+    const int NW = THREADS / 32;
+    static const bool off = getenv("TNO_ONCHIP_NO_WARP_LOCAL") != nullptr;   // developer knob (A/B measurements)
+    std::vector<int> lvl(ni, 0), root(ni), cnt(ni, 0);
+    for (int j = 0; j < wide_rows; ++j) {
+      int l = 0;
+      while (l + 1 < nwide && j >= S.level_ptr[l + 1]) ++l;
+      lvl[j] = l;
+    }
+    std::iota(root.begin(), root.end(), 0);
+    for (int j = wide_rows - 1; j >= 0; --j)
+      if (S.parent[j] >= 0 && S.parent[j] < wide_rows) root[j] = root[S.parent[j]];
+    std::vector<long long> weight(ni, 0);
+    for (int j = 0; j < wide_rows; ++j) weight[root[j]] += 1 + (rowptr_o[j + 1] - rowptr_o[j]);
+    std::vector<int> roots;
+    for (int j = 0; j < wide_rows; ++j)
+      if (root[j] == j) roots.push_back(j);
+    std::stable_sort(roots.begin(), roots.end(), [&](int a, int b) { return weight[a] > weight[b]; });
+    std::vector<long long> load(NW, 0);
+    std::vector<int> warp_of(ni, 0);
+    long long total = 0;
+    for (int r : roots) {
+      const int w = (int)(std::min_element(load.begin(), load.end()) - load.begin());
+      load[w] += weight[r];
+      warp_of[r] = w;
+      total += weight[r];
+    }
+    const long long maxload = *std::max_element(load.begin(), load.end());
+    // worth it when the heaviest warp carries at most twice its share (one subtree = the whole tree would not be)
+    if (!off && nch > 0 && nwide > 1 && total > 0 && maxload * NW <= 2 * total) {
+      O.wl_on = 1;
+      wl_ptr.assign((size_t)NW * (nwide + 1), 0);
+      wl_sub.assign((size_t)NW * nwide * 4, 0);
+      for (int w = 0; w < NW; ++w) {
+        for (int l = 0; l < nwide; ++l) {
+          wl_ptr[(size_t)w * (nwide + 1) + l] = (unsigned short)wl_rows.size();   // start of level l = end of level l - 1
+          if (l == 0) continue;   // the leaves have no entries: nothing to pull or push
+          int count = 0;
+          for (int j = S.level_ptr[l]; j < S.level_ptr[l + 1]; ++j)
+            if (warp_of[root[j]] == w) {
+              wl_rows.push_back((unsigned short)j);
+              ++count;
+            }
+          for (int ph = 0; ph < 2; ++ph) {
+            const int g = O.gshift[ph];
+            int sp = 0;
+            while (count > 0 && sp + 1 + g <= 5 && (count << (sp + 1 + g)) <= 32) ++sp;   // S * G <= 32 (shuffle reduction)
+            wl_sub[(((size_t)w * nwide + l) * 2 + ph) * 2 + 0] = (unsigned char)sp;   // pull
+            wl_sub[(((size_t)w * nwide + l) * 2 + ph) * 2 + 1] = (unsigned char)sp;   // push
+          }
+        }
+        wl_ptr[(size_t)w * (nwide + 1) + nwide] = (unsigned short)wl_rows.size();
+      }
+    }
+    if (wl_ptr.empty()) wl_ptr.push_back(0);
+    if (wl_rows.empty()) wl_rows.push_back(0);
+    if (wl_sub.empty()) wl_sub.push_back(0);
+  }
   // processing order of the rows of a chain level in the forward (pull) step: longest rows first, and as many sub-slots per
   // row as minimise  sum over passes of (longest row of the pass / sub-slots + a per-pass overhead)
   std::vector<unsigned short> rowlist;
@@ -2294,6 +2430,9 @@ static int build_onchip_impl(Plan* PL, const tno_problem_desc* D, const OcLayout
     put_table(&O.idx_supxyz, supxyz.data(), supxyz.size() * 8);
     put_table(&O.idx_zt, zt_tab.data(), zt_tab.size() * sizeof(uint2));
     put_table(&O.idx_rowlist, rowlist.data(), rowlist.size() * 2);
+    put_table(&O.idx_wl_ptr, wl_ptr.data(), wl_ptr.size() * 2);
+    put_table(&O.idx_wl_rows, wl_rows.data(), wl_rows.size() * 2);
+    put_table(&O.idx_wl_s, wl_sub.data(), wl_sub.size());
   }
   const int idx_bytes_core = (int)idx.size();
   O.idx_ct_ptr = (int)idx.size();
@@ -2457,8 +2596,8 @@ int run_onchip(Plan* PL, const double* x_dev, int64_t N, int64_t ldx, const tno_
   A.phase_clocks = nullptr;
   static const bool want_clocks = getenv("TNO_PHASE_CLOCKS") != nullptr;
   if (want_clocks) {
-    TNO_CUDA_OK(cudaMalloc((void**)&A.phase_clocks, 32 * sizeof(long long)));
-    TNO_CUDA_OK(cudaMemsetAsync(A.phase_clocks, 0, 32 * sizeof(long long), stream));
+    TNO_CUDA_OK(cudaMalloc((void**)&A.phase_clocks, 128 * sizeof(long long)));
+    TNO_CUDA_OK(cudaMemsetAsync(A.phase_clocks, 0, 128 * sizeof(long long), stream));
   }
   const size_t smem = (size_t)PL->oc.smem_bytes;
   static const char* force_ctas = getenv("TNO_CTAS_PER_SM");  // developer knob
@@ -2482,7 +2621,7 @@ int run_onchip(Plan* PL, const double* x_dev, int64_t N, int64_t ldx, const tno_
   PL->launches += 1;
   TNO_CUDA_OK(cudaGetLastError());
   if (want_clocks) {
-    long long h[32];
+    long long h[128];
     TNO_CUDA_OK(cudaStreamSynchronize(stream));
     TNO_CUDA_OK(cudaMemcpy(h, A.phase_clocks, sizeof(h), cudaMemcpyDeviceToHost));
     cudaFree(A.phase_clocks);
@@ -2497,7 +2636,9 @@ int run_onchip(Plan* PL, const double* x_dev, int64_t N, int64_t ldx, const tno_
             h[14], h[15], h[24], h[25], h[26], h[27], h[28], h[29], h[30]);
     fprintf(stderr, " | solve2: pull-wide=%lld pull-chain=%lld Z=%lld diag=%lld Zt=%lld gather=%lld push-wide=%lld", h[16], h[17], h[18],
             h[19], h[20], h[21], h[22]);
-    fprintf(stderr, "\n");
+    fprintf(stderr, "\n[tno factor ops] start clocks relative to the factor phase:");
+    for (int op = 0; op < PL->oc.nops && op < 96; ++op) fprintf(stderr, " %lld", h[32 + op] - h[3]);
+    fprintf(stderr, " end=%lld\n", h[4] - h[3]);
   }
   return TNO_OK;
 }

@@ -229,6 +229,12 @@ struct DevOnchip {
   // the accesses that depend on them
   int idx_vrow, idx_rowv, idx_colsrc, idx_supptr, idx_supother, idx_supedge, idx_supsign, idx_fixed;
   int idx_supxyz;        // 3 nb doubles: coordinates of the supports
+  // warp-local wide part of the solves: the wide rows above level 0 form a forest of subtrees below the chains; whole
+  // subtrees are dealt to the warps (balanced), and a warp runs its rows level by level with __syncwarp() only
+  int wl_on;             // 1: in use (the partition is balanced enough)
+  int idx_wl_ptr;        // u16 [warp][level 0 .. nwide]: start of the warp's rows of each level in wl_rows
+  int idx_wl_rows;       // u16 rows, by warp, then level
+  int idx_wl_s;          // u8 [warp][level][phase][pull, push]: log2 sub-slots
   int idx_rowlist;       // u16: rows of every chain level sorted by their number of outside entries, descending
   int idx_zt;            // uint2 per 8-row tile of a chain block: x = zoff | first row << 16, y = T | tile row << 8 (sorted by tile row, descending, per chain level)
   int zmma;              // 1: the dense chain products Z R, Z^T R run on the FP64 tensor pipe (mma.sync m8n8k4)

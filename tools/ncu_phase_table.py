@@ -4,7 +4,8 @@ The CSV of ncu's source page is SASS-level without line numbers; `nvdisasm -g` o
 the line of every instruction.  Both are joined on the instruction offset and aggregated over the line ranges of the
 numbered phases of the kernel.
 
-usage: python tools/ncu_phase_table.py report.ncu-rep candidates_per_launch
+usage: python tools/ncu_phase_table.py report.ncu-rep candidates_per_launch [top_lines]
+(top_lines > 0 also lists the source lines with the most stall samples)
 """
 import collections
 import csv
@@ -16,7 +17,7 @@ import sys
 import tempfile
 
 ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
-FUN = "_ZN3tno8k_onchipILi256ELi2ELi1ELb0E"
+FUN = "_ZN3tno8k_onchipILi256ELi2ELi1ELb0ELb0E"
 
 
 def main():
@@ -94,6 +95,26 @@ def main():
         a["excess"] += int(r[col["L1 Wavefronts Shared Excessive"]] or 0)
         for sc in stalls:
             a[sc] += int(r[col[sc]] or 0)
+    if len(sys.argv) > 3 and int(sys.argv[3]) > 0:
+        byline = collections.defaultdict(collections.Counter)
+        for r in data:
+            li = lines.get(int(r[0], 16) - base)
+            a = byline[li[0]]
+            a["instr"] += int(r[col["Instructions Executed"]] or 0)
+            a["samples"] += int(r[col["# Samples"]] or 0)
+            a["smem"] += int(r[col["L1 Wavefronts Shared"]] or 0)
+            for sc in stalls:
+                a[sc] += int(r[col[sc]] or 0)
+        tot = sum(a["samples"] for a in byline.values())
+        print("| line | source | stall samples | warp instr / candidate | smem wavefronts / candidate | top stall reasons |")
+        print("|---|---|---|---|---|---|")
+        for ln, a in sorted(byline.items(), key=lambda kv: -kv[1]["samples"])[:int(sys.argv[3])]:
+            top = sorted(((sc, a[sc]) for sc in stalls), key=lambda kv: -kv[1])[:3]
+            text = src[ln - 1].strip()[:90] if ln else "(no line)"
+            print("| %s | `%s` | %.2f %% | %.2f k | %.2f k | %s |" % (
+                ln, text.replace("|", "\\|"), 100 * a["samples"] / tot, a["instr"] / per / 1e3, a["smem"] / per / 1e3,
+                ", ".join("%s %.0f %%" % (k.replace("stall_", ""), 100 * v / max(1, a["samples"])) for k, v in top)))
+        print()
     ti = sum(a["instr"] for a in agg.values())
     ts = sum(a["samples"] for a in agg.values())
     print("| phase | warp instr / candidate | share | stall samples | smem wavefronts / candidate (excess) | top stall reasons |")
