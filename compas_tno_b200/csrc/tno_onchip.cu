@@ -931,12 +931,20 @@ __global__ void __launch_bounds__(THREADS * G, MINB) k_onchip(const __grid_const
         for (int u = 0; u < 8; ++u)
           if (t0 + u < t1) acc -= qs[w[u] >> 16];
         for (int t = t0 + 8; t < t1; ++t) acc -= qs[__ldg(O.radj + t) >> 16];
+        if (r < O.lev0_rows) {   // a leaf of the elimination tree: its pivot is final as assembled
+          if (!(acc > 0.0)) atomicOr(&s_flags, TNO_STATUS_NOT_PD);
+          acc = oc_rcp(acc);
+        }
         V[nlo + r] = acc;
       }
     } else {
       for (int p = tid; p < O.nv; p += THREADS) {
         double acc = 0.0;
         for (int t = O.asm_ptr[p]; t < O.asm_ptr[p + 1]; ++t) acc += (double)O.asm_coef[t] * qs[O.asm_edge[t]];
+        if (p >= nlo && p < nlo + O.lev0_rows) {
+          if (!(acc > 0.0)) atomicOr(&s_flags, TNO_STATUS_NOT_PD);
+          acc = oc_rcp(acc);
+        }
         V[p] = acc;
       }
     }
@@ -1956,7 +1964,10 @@ static int build_onchip_impl(Plan* PL, const tno_problem_desc* D, const OcLayout
     }
     return it;
   };
-  for (int lev = 0; lev < nwide; ++lev) {
+  // The leaves (level 0) have no updates at all: their off-diagonal entries are final as assembled and the assembly
+  // step inverts their pivots, so the factor program starts at level 1.
+  O.lev0_rows = S.level_ptr[1];
+  for (int lev = 1; lev < nwide; ++lev) {
     std::vector<Item> items;
     for (int j = S.level_ptr[lev]; j < S.level_ptr[lev + 1]; ++j) {
       if (S.level_cols[j] != j) {

@@ -198,6 +198,7 @@ struct DevOnchip {
   const uint4* dt;       // tile descriptors: x = zoff | first diagonal slot << 16, y = T | tile row << 8 | tile column << 16, z = offset in the exchange buffers
   int o_zs;              // smem offset (doubles) of zs[ni + nb]: z of the free rows, then zb of the supports
   int simple_asm;
+  int lev0_rows;         // rows of level 0 (leaves): pivots inverted by the assembly step
   const double* Bt;      // k x m (transposed B)
   const int* asm_ptr;    // generic assembly gather lists in V position order (nlo + ni entries)
   const int* asm_edge;
