@@ -18,6 +18,10 @@ WANT = {
     "sm__warps_active.avg.pct_of_peak_sustained_active": "warps_active_pct",
     "smsp__inst_executed.sum": "warp_instructions",
     "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active": "fp64_pipe_pct",
+    "SM_C.TriageCompute.smsp__pipe_tensor_subpipe_dmma_cycles_active.avg": "dmma_cycles_active_per_smsp",
+    "TPC.TriageCompute.sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed": "tensor_pipe_pct",
+    "TPC.TriageCompute.sm__pipe_fp64_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed": "fp64_pipe_cycles_pct",
+    "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed": "lsu_data_pipe_pct",
     "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum": "smem_wavefronts",
     "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed": "smem_wavefronts_pct_of_peak",
     "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum": "smem_bank_conflicts",
