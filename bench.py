@@ -806,6 +806,9 @@ def run_ours(args):
            "note": "every output incl. the dense J delivered to pinned host memory; d2h_bytes_per_step = delivered bytes, of which the "
                    "candidate-independent funicular rows of J (host_filled_bytes_per_step) are written by host threads from the plan's "
                    "copy and only d2h_bytes_over_pcie_per_step cross PCIe"}
+    e2e["delivered_gb_per_s"] = e2e["value"] * d2h / Ne / 1e9
+    if rank == 0:
+        e2e["host_dram_copy_gb_per_s"] = host_copy_bandwidth()
     # the sweep use-case: only objectives + feasibility cross PCIe, g / J / z stay in HBM for an on-device consumer
     bufs2 = {}
     xh2 = torch.from_numpy(X).pin_memory()
@@ -909,6 +912,23 @@ def run_ours(args):
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def host_copy_bandwidth(threads=16, mib=128, reps=3):
+    """Host DRAM copy bandwidth (read + written GB/s) of this box with `threads` threads: the yardstick of the full-J host
+    path, whose delivered bytes all land in host DRAM (numpy copies release the GIL)."""
+    from concurrent.futures import ThreadPoolExecutor
+    threads = max(1, min(threads, os.cpu_count() or 1))
+    n = mib * (1 << 20) // 8
+    src = [np.ones(n) for _ in range(threads)]
+    dst = [np.empty(n) for _ in range(threads)]
+    best = 0.0
+    with ThreadPoolExecutor(max_workers=threads) as pool:
+        for _ in range(reps + 1):
+            t0 = time.perf_counter()
+            list(pool.map(lambda i: np.copyto(dst[i], src[i]), range(threads)))
+            best = max(best, 2.0 * threads * n * 8 / (time.perf_counter() - t0) / 1e9)
+    return best
 
 
 def main():
