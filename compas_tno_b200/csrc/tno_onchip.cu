@@ -737,6 +737,121 @@ __device__ __forceinline__ void oc_chain_tiles(const DevOnchip& O, const OcDense
   }
 }
 
+// Two columns per exchange step (2 x 2 tiles only).  Block step b eliminates columns j = 2b and j + 1 at once: the owners
+// publish BOTH columns of U and BOTH rows of Z as they are before the block is touched, plus the pivot record
+//     inv0 = 1 / u_jj ,  m = u_{j+1,j} inv0 (= l_{j+1,j}) ,  inv1 = 1 / (u_{j+1,j+1} - u_{j+1,j} m)
+// and every consumer applies the elimination of column j to column j + 1 / row j + 1 itself (two extra DFMA per row and
+// column of its tile) before the rank-2 update.  Half as many exchange steps (31 instead of 61 at disc 20) for ~60 %
+// more arithmetic per step; the exchange step is what the dense part costs (see the note above oc_chain_tiles).
+template <int THREADS>
+__device__ __forceinline__ void oc_chain_tiles2(const DevOnchip& O, const OcDense& DN, double* __restrict__ V,
+                                                double* __restrict__ buf, int* s_flags, int tid, int grp) {
+  const int nthr = (int)DN.tile_threads;
+  if (tid >= nthr) return;
+  const int ntl = (int)(DN.dt1 - DN.dt0);
+  const bool has = tid < ntl;
+  const uint4 d = has ? __ldg(O.dt + DN.dt0 + tid) : make_uint4(0u, 0u, 0u, 0u);
+  const int zoff = (int)(d.x & 0xffffu), diag0 = (int)(d.x >> 16);
+  const int T = (int)(d.y & 0xffu), ti = (int)((d.y >> 8) & 0xffu), tj = (int)((d.y >> 16) & 0xffu);
+  const int cb = (int)d.z;
+  const int cbtot = (int)DN.cbtot;
+  // exchange buffers (double2 per row / column), two generations each, and the pivot records (4 doubles per block)
+  double2* const xb = reinterpret_cast<double2*>(buf) + cb;
+  auto colb = [&](int gen) { return xb + gen * cbtot; };         // column pair of block b, generation b & 1
+  auto zrb = [&](int gen) { return xb + (2 + gen) * cbtot; };    // row pair
+  double* piv = buf + 8 * cbtot + 2 * cb;   // block b of this chain at piv + 4 b
+  const int barid = 8 + grp;
+  const int i0 = 2 * ti, k0 = 2 * tj;
+  const int nbT = (T + 1) >> 1;             // blocks of this chain
+  double s[2][2], z[2][2];
+#pragma unroll
+  for (int r = 0; r < 2; ++r)
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      const int i = i0 + r, kk = k0 + c;
+      double v = (i == kk && i >= T) ? 1.0 : 0.0;   // padding row of an odd chain: identity
+      if (has && i < T && kk <= i) v = V[i == kk ? diag0 + i : zoff + (i * (i - 1)) / 2 + kk];
+      s[r][c] = v;
+      z[r][c] = (i == kk) ? 1.0 : 0.0;
+    }
+  auto publish = [&](int gen, int b) {   // this thread's share of block b: column pair, row pair, pivot record
+    if (tj == b) {
+      colb(gen)[i0] = make_double2(s[0][0], s[0][1]);
+      colb(gen)[i0 + 1] = make_double2(s[1][0], s[1][1]);
+      if (ti == b) {
+        // two INDEPENDENT reciprocals: 1 / d0 and 1 / det of the 2 x 2 pivot block; the second pivot of the scalar
+        // factorisation is d1 = det / d0, so 1 / d1 = d0 / det without waiting for 1 / d0
+        const double d0 = s[0][0];
+        const double det = fma(d0, s[1][1], -s[1][0] * s[1][0]);
+        if (!(d0 > 0.0) || !(det > 0.0)) atomicOr(s_flags, TNO_STATUS_NOT_PD);
+        const double inv0 = oc_rcp(d0);
+        const double inv1 = d0 * oc_rcp(det);
+        const double m = s[1][0] * inv0;
+        *reinterpret_cast<double2*>(piv + 4 * b) = make_double2(inv0, m);
+        piv[4 * b + 2] = inv1;
+        V[diag0 + 2 * b] = inv0;
+        if (2 * b + 1 < T) V[diag0 + 2 * b + 1] = inv1;
+      }
+    }
+    if (ti == b) {
+      zrb(gen)[k0] = make_double2(z[0][0], z[1][0]);
+      zrb(gen)[k0 + 1] = make_double2(z[0][1], z[1][1]);
+    }
+  };
+  if (has) publish(0, 0);
+  asm volatile("bar.sync %0, %1;" ::"r"(barid), "r"(nthr) : "memory");
+  const int nblocks = ((int)DN.tmax + 1) >> 1;
+  for (int b = 0; b < nblocks; ++b) {
+    const int gen = b & 1;
+    if (has && b < nbT) {
+      const double2 p01 = *reinterpret_cast<const double2*>(piv + 4 * b);
+      const double inv0 = p01.x, m = p01.y;
+      if (ti > b) {
+        const double inv1 = piv[4 * b + 2];
+        double l0[2], l1[2];
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+          const double2 a = colb(gen)[i0 + r];
+          l0[r] = a.x * inv0;
+          l1[r] = fma(-a.x, m, a.y) * inv1;
+        }
+        if (tj > b) {
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            const double2 u = colb(gen)[k0 + c];
+            const double u1 = fma(-u.x, m, u.y);
+#pragma unroll
+            for (int r = 0; r < 2; ++r) s[r][c] = fma(-l1[r], u1, fma(-l0[r], u.x, s[r][c]));
+          }
+        } else {
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            const double2 zz = zrb(gen)[k0 + c];
+            const double z1 = fma(-m, zz.x, zz.y);
+#pragma unroll
+            for (int r = 0; r < 2; ++r) z[r][c] = fma(-l1[r], z1, fma(-l0[r], zz.x, z[r][c]));
+          }
+        }
+      } else if (ti == b) {
+        // the block's own rows: row 2b of Z is final, row 2b + 1 takes the elimination of column 2b
+#pragma unroll
+        for (int c = 0; c < 2; ++c) z[1][c] = fma(-m, z[0][c], z[1][c]);
+      }
+      if (b + 1 < nbT) publish(gen ^ 1, b + 1);
+    }
+    asm volatile("bar.sync %0, %1;" ::"r"(barid), "r"(nthr) : "memory");
+  }
+  if (has) {
+#pragma unroll
+    for (int r = 0; r < 2; ++r)
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        const int i = i0 + r, kk = k0 + c;
+        if (i < T && kk < i) V[zoff + (i * (i - 1)) / 2 + kk] = z[r][c];
+      }
+  }
+}
+
 // DIR: per-candidate horizontal load directions (tno_batch_inputs.load_dir); a separate instantiation so that the
 // common single-basis path carries none of its registers or branches.
 // G: candidate groups per CTA.  Every group of THREADS threads works on its own candidate with its own value array and
@@ -978,7 +1093,8 @@ __global__ void __launch_bounds__(THREADS * G, MINB) k_onchip(const __grid_const
         if (OP.type == OC_OP_DENSE) {
           oc_sync<THREADS>(bar);
           const long long t0 = clk ? clock64() : 0;
-          if (dense[OP.a].tile_threads > 0 && dense[OP.a].tile_size == 2) oc_chain_tiles<THREADS, 2>(O, dense[OP.a], V, R + O.o_tmpz_doubles, &s_flags, tid, grp);
+          if (dense[OP.a].tile_threads > 0 && dense[OP.a].tile_size == 2 && !(O.dbg & 512)) oc_chain_tiles2<THREADS>(O, dense[OP.a], V, R + O.o_tmpz_doubles, &s_flags, tid, grp);
+          else if (dense[OP.a].tile_threads > 0 && dense[OP.a].tile_size == 2) oc_chain_tiles<THREADS, 2>(O, dense[OP.a], V, R + O.o_tmpz_doubles, &s_flags, tid, grp);
           else if (dense[OP.a].tile_threads > 0) oc_chain_tiles<THREADS, 4>(O, dense[OP.a], V, R + O.o_tmpz_doubles, &s_flags, tid, grp);
           else oc_chain_dense<THREADS>(O, dense[OP.a], V, R + O.o_tmpz_doubles, &s_flags, tid, bar, clk ? t_ldl : nullptr);
           oc_sync<THREADS>(bar);
@@ -1871,7 +1987,7 @@ static int build_onchip_impl(Plan* PL, const tno_problem_desc* D, const OcLayout
           cbo += TS * nt;
         }
         if (tiles <= THREADS) {
-          need = 5 * cbo;
+          need = 10 * cbo;   // two-column steps of the 2 x 2 tiles: (column pair, row pair) x 2 buffers + pivot records
           break;
         }
       }
@@ -2074,7 +2190,7 @@ static int build_onchip_impl(Plan* PL, const tno_problem_desc* D, const OcLayout
           DN.cbtot = cbo;
           DN.tile_size = (uint32_t)TS;
           DN.tile_threads = (uint32_t)((tiles.size() + 31) / 32 * 32);
-          max_tile_buf = std::max(max_tile_buf, (int)(5 * cbo));
+          max_tile_buf = std::max(max_tile_buf, (int)(10 * cbo));
         }
       }
       dense_r.push_back(DN);
