@@ -325,6 +325,10 @@ __device__ __forceinline__ void oc_chain_apply_mma(const OcRange& L, const uint2
   }
 }
 
+struct OcWarpFactor {
+  const uint32_t* off;    // [warp]: start of the warp's record stream in wf_stream, 16-byte units (NW + 1 entries)
+  const uint32_t* desc;   // [warp][level]: offset inside the warp's buffer (16-byte units) | items << 16 | log2 lanes per item << 28
+};
 struct OcWarpLocal {
   const unsigned short* ptr;
   const unsigned short* rows;
@@ -596,6 +600,48 @@ __device__ __forceinline__ void oc_chain_dense(const DevOnchip& O, const OcDense
   for (uint32_t p = DN.zlo + tid; p < DN.zhi; p += THREADS) V[p] = tmpz[p - zbase];
   oc_sync<THREADS>(bar);
   lapd(5);
+}
+
+// Pull-form items of one staged piece of the factorisation: item = one entry of L (position, diagonal flag) with its
+// list of (a, b, d) triples; 2^lpi_shift lanes share an item's dot product.  NT threads (the CTA, or one warp for the
+// warp-local wide levels) walk the items.
+template <int NT>
+__device__ __forceinline__ void oc_factor_items(const uint2* __restrict__ rec, const unsigned long long* __restrict__ pairs, int nitems,
+                                                int lpi_shift, int kind, int tl, double* __restrict__ V, double* __restrict__ tmpbuf,
+                                                int* s_flags) {
+  const int lpi = 1 << lpi_shift;
+  const int sub = tl & (lpi - 1);
+  const int per_pass = NT >> lpi_shift;
+  for (int base = 0; base < nitems; base += per_pass) {
+    const int it = base + (tl >> lpi_shift);
+    const bool valid = it < nitems;
+    double acc = 0.0;
+    unsigned pf = 0;
+    if (valid) {
+      const uint2 r0 = rec[it];
+      pf = r0.x;
+      const int t1 = rec[it + 1].y;
+#pragma unroll 2
+      for (int t = r0.y + sub; t < t1; t += lpi) {
+        const unsigned long long pr = pairs[t];
+        const int a = (int)(pr & 0xffffu), b = (int)((pr >> 16) & 0xffffu), dp = (int)((pr >> 32) & 0xffffu);
+        acc = fma(V[a] * V[dp], V[b], acc);  // U_ic * (1 / d_c) * U_jc   (rectangular rows: S_ic * (-1) * Z_jc)
+      }
+    }
+    for (int off = lpi >> 1; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+    if (valid && sub == 0) {
+      const int pos = (int)(pf & 0xffffu);
+      const double v = V[pos] - acc;
+      if (kind == 1) {
+        tmpbuf[it] = v;
+      } else if (pf >> 31) {
+        if (!(v > 0.0)) atomicOr(s_flags, TNO_STATUS_NOT_PD);
+        V[pos] = oc_rcp(v);
+      } else {
+        V[pos] = v;
+      }
+    }
+  }
 }
 
 // Register-tile variant of the dense work of one chain level.  Every thread owns one TS x TS tile (ti, tj), ti >= tj, of a
@@ -900,6 +946,7 @@ __global__ void __launch_bounds__(THREADS * G, MINB) k_onchip(const __grid_const
   const unsigned short* radjp_s = reinterpret_cast<const unsigned short*>(idxb + O.idx_radjp);
   const double* supxyz_s = reinterpret_cast<const double*>(idxb + O.idx_supxyz);   // x, y, z of the supports
   const uint2* zt_s = reinterpret_cast<const uint2*>(idxb + O.idx_zt);
+  const OcWarpFactor wf_s = {reinterpret_cast<const uint32_t*>(idxb + O.idx_wf_off), reinterpret_cast<const uint32_t*>(idxb + O.idx_wf_desc)};
   const unsigned short* rowlist_s = reinterpret_cast<const unsigned short*>(idxb + O.idx_rowlist);
   const OcWarpLocal wl_s = {reinterpret_cast<const unsigned short*>(idxb + O.idx_wl_ptr),
                             reinterpret_cast<const unsigned short*>(idxb + O.idx_wl_rows), idxb + O.idx_wl_s};
@@ -1077,13 +1124,36 @@ __global__ void __launch_bounds__(THREADS * G, MINB) k_onchip(const __grid_const
       auto issue = [&](int c) {
         if (c < O.nchunks) {
           const OcChunk K = chunks[c];
-          unsigned char* dst = stage_base + (c % 3) * seg_bytes;
+          unsigned char* dst = stage_base + ((c + 2) % 3) * seg_bytes;   // chunk 0 lands in the third buffer (see the warp-local part)
           const uint4* src = O.f_stream + K.seg_off;
           for (unsigned u = tid; u < K.seg_units; u += THREADS) cp_async16(dst + 16 * u, src + u);
         }
         cp_async_commit();
       };
       issue(0);
+      if (O.wf_on) {
+        // Wide levels, warp-local: every warp stages the records of its own subtrees (a few KB, all levels at once) into its
+        // slice of the first two ring buffers and factorises them level by level with __syncwarp() only -- the operands of an
+        // item are entries of columns of the same subtree, produced by the same warp one level earlier.
+        const int w = tid >> 5, ln = tid & 31;
+        unsigned char* wbuf = stage_base + (size_t)w * O.wf_buf_bytes;
+        const uint4* src = O.wf_stream + wf_s.off[w];
+        for (int u = ln; u < (int)wf_s.off[w + 1] - (int)wf_s.off[w]; u += 32) cp_async16(wbuf + 16 * u, src + u);
+        cp_async_commit();
+        cp_async_wait<0>();
+        __syncwarp();
+        for (int lev = 1; lev < O.nwide; ++lev) {
+          const uint32_t dsc = wf_s.desc[w * O.nwide + lev];
+          const int ni_l = (int)((dsc >> 16) & 0xfffu);
+          if (ni_l > 0) {
+            const uint2* rec = reinterpret_cast<const uint2*>(wbuf + 16 * (dsc & 0xffffu));
+            oc_factor_items<32>(rec, reinterpret_cast<const unsigned long long*>(rec + ni_l + 1), ni_l, (int)(dsc >> 28), 0, ln, V, nullptr,
+                                &s_flags);
+          }
+          __syncwarp();
+        }
+        oc_sync<THREADS>(bar);
+      }
       issue(1);
       const bool clk = clk_here;
       long long t_dense = 0, t_wait = 0, t_ldl[6] = {0, 0, 0, 0, 0, 0};
@@ -1108,41 +1178,9 @@ __global__ void __launch_bounds__(THREADS * G, MINB) k_onchip(const __grid_const
         if (clk) t_wait += clock64() - tw0;
         if (!(O.dbg & 32)) issue(c + 2);
         const OcChunk K = chunks[c];
-        const uint2* rec = reinterpret_cast<const uint2*>(stage_base + (c % 3) * seg_bytes);
+        const uint2* rec = reinterpret_cast<const uint2*>(stage_base + ((c + 2) % 3) * seg_bytes);
         const unsigned long long* pairs = reinterpret_cast<const unsigned long long*>(rec + K.nitems + 1);
-        const int lpi = 1 << K.lpi_shift;
-        const int sub = tid & (lpi - 1);
-        const int per_pass = THREADS >> K.lpi_shift;
-        for (int base = 0; base < ((O.dbg & 16) ? 0 : (int)K.nitems); base += per_pass) {
-          const int it = base + (tid >> K.lpi_shift);
-          const bool valid = it < K.nitems;
-          double acc = 0.0;
-          unsigned pf = 0;
-          if (valid) {
-            const uint2 r0 = rec[it];
-            pf = r0.x;
-            const int t1 = rec[it + 1].y;
-#pragma unroll 2
-            for (int t = r0.y + sub; t < t1; t += lpi) {
-              const unsigned long long pr = pairs[t];
-              const int a = (int)(pr & 0xffffu), b = (int)((pr >> 16) & 0xffffu), dp = (int)((pr >> 32) & 0xffffu);
-              acc = fma(V[a] * V[dp], V[b], acc);  // U_ic * (1 / d_c) * U_jc   (rectangular rows: S_ic * (-1) * Z_jc)
-            }
-          }
-          for (int off = lpi >> 1; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
-          if (valid && sub == 0) {
-            const int pos = (int)(pf & 0xffffu);
-            const double v = V[pos] - acc;
-            if (K.kind == 1) {
-              tmpbuf[it] = v;
-            } else if (pf >> 31) {
-              if (!(v > 0.0)) atomicOr(&s_flags, TNO_STATUS_NOT_PD);
-              V[pos] = oc_rcp(v);
-            } else {
-              V[pos] = v;
-            }
-          }
-        }
+        if (!(O.dbg & 16)) oc_factor_items<THREADS>(rec, pairs, (int)K.nitems, (int)K.lpi_shift, (int)K.kind, tid, V, tmpbuf, &s_flags);
         if (K.kind == 1) {  // rectangular chain rows read each other's S values: write back after everyone has read
           oc_sync<THREADS>(bar);
           for (int it = tid; it < K.nitems; it += THREADS) V[(int)(rec[it].x & 0xffffu)] = tmpbuf[it];
@@ -1937,6 +1975,34 @@ static int build_onchip_impl(Plan* PL, const tno_problem_desc* D, const OcLayout
     for (int t = S.rowptr[i]; t < S.rowptr[i + 1]; ++t)
       newpos[S.rowpos[t]] = csr_of_t[t] >= 0 ? csr_of_t[t] : zpos(i, S.rowcol[t]);
 
+  // ---- partition of the wide forest: whole subtrees dealt to the warps, heaviest first to the lightest warp.  Used by the
+  //      warp-local wide part of the solves and of the factorisation.
+  const int NW = THREADS / 32;
+  std::vector<int> wl_root(ni), wl_warp_of(ni, 0);
+  bool wl_balanced = false;
+  {
+    std::iota(wl_root.begin(), wl_root.end(), 0);
+    for (int j = wide_rows - 1; j >= 0; --j)
+      if (S.parent[j] >= 0 && S.parent[j] < wide_rows) wl_root[j] = wl_root[S.parent[j]];
+    std::vector<long long> weight(ni, 0);
+    for (int j = 0; j < wide_rows; ++j) weight[wl_root[j]] += 1 + (rowptr_o[j + 1] - rowptr_o[j]);
+    std::vector<int> roots;
+    for (int j = 0; j < wide_rows; ++j)
+      if (wl_root[j] == j) roots.push_back(j);
+    std::stable_sort(roots.begin(), roots.end(), [&](int a, int b) { return weight[a] > weight[b]; });
+    std::vector<long long> load(NW, 0);
+    long long total = 0;
+    for (int r : roots) {
+      const int w = (int)(std::min_element(load.begin(), load.end()) - load.begin());
+      load[w] += weight[r];
+      wl_warp_of[r] = w;
+      total += weight[r];
+    }
+    const long long maxload = *std::max_element(load.begin(), load.end());
+    // worth it when the heaviest warp carries at most twice its share (one subtree = the whole tree would not be)
+    wl_balanced = nch > 0 && nwide > 1 && total > 0 && maxload * NW <= 2 * total;
+  }
+
   // ---- support incidence ----
   std::vector<int> sup_ptr(nb + 1, 0), sup_edge, sup_other, edge_sup(m, -1);
   std::vector<float> sup_sign;
@@ -2083,16 +2149,82 @@ static int build_onchip_impl(Plan* PL, const tno_problem_desc* D, const OcLayout
   // The leaves (level 0) have no updates at all: their off-diagonal entries are final as assembled and the assembly
   // step inverts their pivots, so the factor program starts at level 1.
   O.lev0_rows = S.level_ptr[1];
-  for (int lev = 1; lev < nwide; ++lev) {
-    std::vector<Item> items;
-    for (int j = S.level_ptr[lev]; j < S.level_ptr[lev + 1]; ++j) {
+  for (int lev = 1; lev < nwide; ++lev)
+    for (int j = S.level_ptr[lev]; j < S.level_ptr[lev + 1]; ++j)
       if (S.level_cols[j] != j) {
         set_error("internal: level ordering is not contiguous");
         return TNO_EINVAL;
       }
-      for (int p = S.colptr[j]; p < S.colptr[j + 1]; ++p) items.push_back(make_item(p, p == S.colptr[j], -1));
+  // Wide levels 1 ..: warp-local when the forest partition is balanced (every warp gets the items of the columns of its own
+  // subtrees as one small record stream: [records | pairs] per level, the layout of a staged chunk), else one staged step per
+  // level for the whole CTA.
+  std::vector<uint32_t> wf_words, wf_off(NW + 1, 0), wf_desc((size_t)NW * std::max(nwide, 1), 0);
+  O.wf_on = 0;
+  O.wf_buf_bytes = 0;
+  {
+    static const bool off = getenv("TNO_ONCHIP_NO_WARP_FACTOR") != nullptr;   // developer knob (A/B measurements)
+    bool wf = wl_balanced && !off;
+    size_t maxbytes = 0;
+    for (int w = 0; w < NW && wf; ++w) {
+      wf_off[w] = (uint32_t)(wf_words.size() / 4);
+      const size_t w0 = wf_words.size();
+      for (int lev = 1; lev < nwide && wf; ++lev) {
+        std::vector<Item> items;
+        for (int j = S.level_ptr[lev]; j < S.level_ptr[lev + 1]; ++j)
+          if (wl_warp_of[wl_root[j]] == w)
+            for (int p = S.colptr[j]; p < S.colptr[j + 1]; ++p) items.push_back(make_item(p, p == S.colptr[j], -1));
+        if (items.empty()) continue;
+        std::stable_sort(items.begin(), items.end(), [](const Item& a, const Item& b) { return a.prs.size() > b.prs.size(); });
+        const size_t off_units = (wf_words.size() - w0) / 4;
+        const int nitems = (int)items.size();
+        size_t npairs = 0;
+        for (const Item& it : items) {
+          wf_words.push_back(it.pf);
+          wf_words.push_back((uint32_t)npairs);
+          npairs += it.prs.size();
+        }
+        wf_words.push_back(0);
+        wf_words.push_back((uint32_t)npairs);
+        for (const Item& it : items)
+          for (unsigned long long pr : it.prs) {
+            wf_words.push_back((uint32_t)(pr & 0xffffffffu));
+            wf_words.push_back((uint32_t)(pr >> 32));
+          }
+        while (wf_words.size() % 4) wf_words.push_back(0);
+        int lpi_shift = 0;
+        double best = 1e300;
+        const size_t maxp = items[0].prs.size();
+        for (int sft = 0; sft <= 5; ++sft) {
+          const int passes = ((nitems << sft) + 31) / 32;
+          const double cost = passes * ((double)((maxp + (1u << sft) - 1) >> sft) + 0.8 * sft + 2.0);
+          if (cost < best - 1e-9) {
+            best = cost;
+            lpi_shift = sft;
+          }
+        }
+        if (off_units >= 65536 || nitems >= 4096) wf = false;
+        wf_desc[(size_t)w * nwide + lev] = (uint32_t)off_units | ((uint32_t)nitems << 16) | ((uint32_t)lpi_shift << 28);
+      }
+      maxbytes = std::max(maxbytes, (wf_words.size() - w0) * 4);
     }
-    emit_step(items, 0);
+    wf_off[NW] = (uint32_t)(wf_words.size() / 4);
+    // the warps' buffers share the first two ring buffers while the first chain chunk is already on its way into the third
+    if (wf && (size_t)NW * maxbytes > 2 * (CHUNK_BYTES / 16 * 16)) wf = false;
+    if (wf) {
+      O.wf_on = 1;
+      O.wf_buf_bytes = (int)maxbytes;
+      max_units = std::max<uint32_t>(max_units, (uint32_t)(((size_t)NW * maxbytes + 31) / 32));   // 2 buffers >= NW x maxbytes
+    } else {
+      wf_words.clear();
+      std::fill(wf_desc.begin(), wf_desc.end(), 0u);
+      for (int lev = 1; lev < nwide; ++lev) {
+        std::vector<Item> items;
+        for (int j = S.level_ptr[lev]; j < S.level_ptr[lev + 1]; ++j)
+          for (int p = S.colptr[j]; p < S.colptr[j + 1]; ++p) items.push_back(make_item(p, p == S.colptr[j], -1));
+        emit_step(items, 0);
+      }
+    }
+    if (wf_words.empty()) wf_words.assign(4, 0);
   }
   for (int cl = 0; cl < O.nclev; ++cl) {
     const int c0 = S.clevel_ptr[cl], c1 = S.clevel_ptr[cl + 1];
@@ -2266,40 +2398,15 @@ static int build_onchip_impl(Plan* PL, const tno_problem_desc* D, const OcLayout
     clev_r[cl].zt1 = (unsigned short)zt_tab.size();
   }
   if (zt_tab.empty()) zt_tab.push_back(uint2{0, 0});
-  // ---- warp-local wide part: subtrees of the wide forest dealt to the warps, heaviest first to the lightest warp ----
+  // ---- warp-local wide part of the solves: row lists per warp and level ----
   std::vector<unsigned short> wl_ptr, wl_rows;
   std::vector<unsigned char> wl_sub;
   O.wl_on = 0;
   {
-    const int NW = THREADS / 32;
     static const bool off = getenv("TNO_ONCHIP_NO_WARP_LOCAL") != nullptr;   // developer knob (A/B measurements)
-    std::vector<int> lvl(ni, 0), root(ni), cnt(ni, 0);
-    for (int j = 0; j < wide_rows; ++j) {
-      int l = 0;
-      while (l + 1 < nwide && j >= S.level_ptr[l + 1]) ++l;
-      lvl[j] = l;
-    }
-    std::iota(root.begin(), root.end(), 0);
-    for (int j = wide_rows - 1; j >= 0; --j)
-      if (S.parent[j] >= 0 && S.parent[j] < wide_rows) root[j] = root[S.parent[j]];
-    std::vector<long long> weight(ni, 0);
-    for (int j = 0; j < wide_rows; ++j) weight[root[j]] += 1 + (rowptr_o[j + 1] - rowptr_o[j]);
-    std::vector<int> roots;
-    for (int j = 0; j < wide_rows; ++j)
-      if (root[j] == j) roots.push_back(j);
-    std::stable_sort(roots.begin(), roots.end(), [&](int a, int b) { return weight[a] > weight[b]; });
-    std::vector<long long> load(NW, 0);
-    std::vector<int> warp_of(ni, 0);
-    long long total = 0;
-    for (int r : roots) {
-      const int w = (int)(std::min_element(load.begin(), load.end()) - load.begin());
-      load[w] += weight[r];
-      warp_of[r] = w;
-      total += weight[r];
-    }
-    const long long maxload = *std::max_element(load.begin(), load.end());
-    // worth it when the heaviest warp carries at most twice its share (one subtree = the whole tree would not be)
-    if (!off && nch > 0 && nwide > 1 && total > 0 && maxload * NW <= 2 * total) {
+    const std::vector<int>& root = wl_root;
+    const std::vector<int>& warp_of = wl_warp_of;
+    if (!off && wl_balanced) {
       O.wl_on = 1;
       wl_ptr.assign((size_t)NW * (nwide + 1), 0);
       wl_sub.assign((size_t)NW * nwide * 4, 0);
@@ -2557,6 +2664,8 @@ static int build_onchip_impl(Plan* PL, const tno_problem_desc* D, const OcLayout
     put_table(&O.idx_supxyz, supxyz.data(), supxyz.size() * 8);
     put_table(&O.idx_zt, zt_tab.data(), zt_tab.size() * sizeof(uint2));
     put_table(&O.idx_rowlist, rowlist.data(), rowlist.size() * 2);
+    put_table(&O.idx_wf_off, wf_off.data(), wf_off.size() * 4);
+    put_table(&O.idx_wf_desc, wf_desc.data(), wf_desc.size() * 4);
     put_table(&O.idx_wl_ptr, wl_ptr.data(), wl_ptr.size() * 2);
     put_table(&O.idx_wl_rows, wl_rows.data(), wl_rows.size() * 2);
     put_table(&O.idx_wl_s, wl_sub.data(), wl_sub.size());
@@ -2667,6 +2776,8 @@ static int build_onchip_impl(Plan* PL, const tno_problem_desc* D, const OcLayout
   O.f_stream = reinterpret_cast<const uint4*>(dptr);
   if ((rc = upload_bytes(PL, idx.data(), idx.size(), &dptr))) return rc;
   O.idx_init = reinterpret_cast<const unsigned char*>(dptr);
+  if ((rc = upload_bytes(PL, wf_words.data(), wf_words.size() * 4, &dptr))) return rc;
+  O.wf_stream = reinterpret_cast<const uint4*>(dptr);
   UPO(edge_sup, edge_sup);
   UPO(sup_ptr, sup_ptr);
   UPO(sup_edge, sup_edge);

@@ -233,6 +233,10 @@ struct DevOnchip {
   // warp-local wide part of the solves: the wide rows above level 0 form a forest of subtrees below the chains; whole
   // subtrees are dealt to the warps (balanced), and a warp runs its rows level by level with __syncwarp() only
   int wl_on;             // 1: in use (the partition is balanced enough)
+  // warp-local factorisation of the wide levels (same partition): per-warp record streams staged into the ring buffers
+  int wf_on, wf_buf_bytes;
+  int idx_wf_off, idx_wf_desc;
+  const uint4* wf_stream;
   int idx_wl_ptr;        // u16 [warp][level 0 .. nwide]: start of the warp's rows of each level in wl_rows
   int idx_wl_rows;       // u16 rows, by warp, then level
   int idx_wl_s;          // u8 [warp][level][phase][pull, push]: log2 sub-slots
