@@ -234,9 +234,9 @@ def sweep_specs():
          "what": "config 4: cross vault disc 40, Monte-Carlo: self-weight scale N(1, 0.05^2) clipped to [0.8, 1.2] (pz_scale) AND "
                  "intrados / extrados heights perturbed N(0, 2 cm) per vertex (bounds), distinct x per candidate; 8192 candidates "
                  "per GPU = 65,536 on 8 GPUs; objectives + feasibility only"},
-        {"name": "crossvault_disc40_full", "config": 4, "scaling": "weak", "total": lambda world: 4096 * world, "build": disc40_full,
+        {"name": "crossvault_disc40_full", "config": 4, "scaling": "weak", "total": lambda world: 8192 * world, "build": disc40_full,
          "reps": 3,
-         "what": "cross vault disc 40, every output incl. the dense 10082 x 29 Jacobian, 4096 candidates per GPU"},
+         "what": "cross vault disc 40, every output incl. the dense 10082 x 29 Jacobian, 8192 candidates per GPU"},
         {"name": "dome_lambdh", "config": 5, "scaling": "strong", "total": lambda world: 8192, "build": dome_lambdh, "reps": 3,
          "what": "config 5: dome, horizontal-load multiplier lambdh as a variable + reac_bounds, 8192 load directions "
                  "theta_j = 2 pi j / 8192 (d0(theta) = cos d0x + sin d0y per candidate), multiplier ladder 1e-4 .. 0.05, batched Jacobians"},

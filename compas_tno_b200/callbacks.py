@@ -34,6 +34,7 @@ class _State:
         self.objective = objective
         self.key = None
         self.res = None
+        self.warned = False
 
     def eval1(self, x, problem):
         x = np.ascontiguousarray(np.asarray(x, dtype=np.float64).reshape(-1))
@@ -51,8 +52,12 @@ class _State:
                     r0 = 2 * m if "funicular" in self.plan.constraints else 0
                     problem.X[:, 0] = g[r0: r0 + n] + np.asarray(problem.xlimits)[:, 0]
                     problem.X[:, 1] = g[r0 + 2 * n: r0 + 3 * n] + np.asarray(problem.ylimits)[:, 0]
-            except Exception:
-                pass
+            except (AttributeError, TypeError, ValueError) as exc:
+                # a frozen / read-only problem object cannot take the state write-back; the returned values are unaffected
+                if not self.warned:
+                    import warnings
+                    warnings.warn("tno_b200: problem.q / problem.X not updated after an evaluation (%s: %s)" % (type(exc).__name__, exc))
+                    self.warned = True
         return self.res
 
 

@@ -2045,7 +2045,7 @@ static int build_onchip_impl(Plan* PL, const tno_problem_desc* D, const OcLayout
     for (int cl = 0; cl < O.nclev; ++cl) {
       const int c0 = S.clevel_ptr[cl], c1 = S.clevel_ptr[cl + 1];
       int need = nz;
-      for (int TS = 2; TS <= 4 && !elementwise; TS += 2) {
+      for (int TS = getenv("TNO_ONCHIP_TILE4") ? 4 : 2; TS <= 4 && !elementwise; TS += 2) {
         int tiles = 0, cbo = 0;
         for (int c = c0; c < c1; ++c) {
           const int nt = (S.chain_ptr[c + 1] - S.chain_ptr[c] + TS - 1) / TS;
@@ -2162,7 +2162,9 @@ static int build_onchip_impl(Plan* PL, const tno_problem_desc* D, const OcLayout
   O.wf_on = 0;
   O.wf_buf_bytes = 0;
   {
-    static const bool off = getenv("TNO_ONCHIP_NO_WARP_FACTOR") != nullptr;   // developer knob (A/B measurements)
+    // Built and measured (round 2): neutral at disc 20 (1.992 vs 1.996 M evals/s) -- a warp's own dependent chain through
+    // the levels takes as long as the block-wide steps it replaces -- so it stays behind a knob.
+    static const bool off = getenv("TNO_ONCHIP_WARP_FACTOR") == nullptr;
     bool wf = wl_balanced && !off;
     size_t maxbytes = 0;
     for (int w = 0; w < NW && wf; ++w) {
@@ -2300,7 +2302,7 @@ static int build_onchip_impl(Plan* PL, const tno_problem_desc* D, const OcLayout
         static const bool elementwise = getenv("TNO_ONCHIP_DENSE_ELEMENTS") != nullptr;   // developer knob (A/B measurements)
         DN.dt0 = DN.dt1 = (uint32_t)dt.size();
         DN.tile_threads = 0;
-        for (int TS = 2; TS <= 4 && !elementwise && DN.tile_threads == 0; TS += 2) {
+        for (int TS = getenv("TNO_ONCHIP_TILE4") ? 4 : 2; TS <= 4 && !elementwise && DN.tile_threads == 0; TS += 2) {   // TNO_ONCHIP_TILE4: developer knob (tests)
           std::vector<uint4> tiles;
           uint32_t cbo = 0;
           for (int c = c0; c < c1; ++c) {
@@ -2403,7 +2405,9 @@ static int build_onchip_impl(Plan* PL, const tno_problem_desc* D, const OcLayout
   std::vector<unsigned char> wl_sub;
   O.wl_on = 0;
   {
-    static const bool off = getenv("TNO_ONCHIP_NO_WARP_LOCAL") != nullptr;   // developer knob (A/B measurements)
+    // Built and measured (round 2): +1.2 % before the other changes of the round, -0.7 % after them (1.993 vs 2.008 M evals/s
+    // at disc 20): the barriers of the wide levels are not what their steps cost.  Behind a knob.
+    static const bool off = getenv("TNO_ONCHIP_WARP_LOCAL") == nullptr;
     const std::vector<int>& root = wl_root;
     const std::vector<int>& warp_of = wl_warp_of;
     if (!off && wl_balanced) {

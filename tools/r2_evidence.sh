@@ -23,7 +23,7 @@ timeout 300 python tools/r2_probe.py 2>&1 | grep PROBE >> $O/r2_ab_dmma.log
 TNO_ONCHIP_NO_DMMA=1 timeout 300 python tools/r2_probe.py dome_16x20 4096 2>&1 | grep PROBE >> $O/r2_ab_dmma.log
 timeout 300 python tools/r2_probe.py dome_16x20 4096 2>&1 | grep PROBE >> $O/r2_ab_dmma.log
 TNO_ONCHIP_DENSE_ELEMENTS=1 timeout 300 python tools/r2_probe.py 2>&1 | grep PROBE >> $O/r2_ab_dmma.log
-TNO_ONCHIP_NO_WARP_LOCAL=1 timeout 300 python tools/r2_probe.py 2>&1 | grep PROBE >> $O/r2_ab_dmma.log
+TNO_ONCHIP_WARP_LOCAL=1 TNO_ONCHIP_WARP_FACTOR=1 timeout 300 python tools/r2_probe.py 2>&1 | grep PROBE >> $O/r2_ab_dmma.log
 TNO_ONCHIP_NO_ITEM_SORT=1 timeout 300 python tools/r2_probe.py 2>&1 | grep PROBE >> $O/r2_ab_dmma.log
 ./tools/latbench > $O/r2_latbench.log 2>&1
 cat $O/r2_ab_dmma.log
