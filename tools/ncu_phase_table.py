@@ -66,10 +66,14 @@ def main():
     kstart = find("__global__ void __launch_bounds__(THREADS * G, MINB) k_onchip")
     dense0 = find("// Dense work of one chain level")
     solve0 = find("// ---- kernels of the triangular solves")
+    items0 = find("// Pull-form items of one staged piece of the factorisation")
+    items1 = find("// Register-tile variant of the dense work of one chain level")
 
     def phase(line):
         if line is None:
             return "inlined library code (no line)"
+        if items0 <= line < items1:
+            return "3 numeric LDL^T: staged pull chunks"
         if solve0 <= line < dense0:
             return "6 + 9 triangular solves (pull / push / chain apply / gather)"
         if dense0 <= line < kstart:
