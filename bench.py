@@ -797,6 +797,9 @@ def run_ours(args):
     _thr = max(1, min(int(os.environ.get("TNO_HOST_THREADS", "16")), os.cpu_count() or 1, Ne // 64 + 1))
     _cst, _per = 2 * plan.m * plan.nvar if "funicular" in plan.constraints else 0, plan.ng * plan.nvar
     _phi = float(os.environ.get("TNO_HOST_FILL_FRACTION", min(1.0, _per / (_cst * (1.0 + 52.0 / (4.5 * _thr)))) if _cst else 0.0))
+    _fs = plan.fetch_stats   # the split the library actually used in the last fetch (it follows the measured host / DMA rates)
+    if _cst and "TNO_HOST_FILL_FRACTION" not in os.environ and _fs["host_threads"] > 0:
+        _phi, _thr = _fs["host_fill_fraction"], _fs["host_threads"]
     _rows = min(2 * plan.m, int(_phi * 2 * plan.m + 0.5)) if _cst else 0
     _rows -= (_rows * plan.nvar) & 1
     host_filled = Ne * 8 * _rows * plan.nvar
@@ -807,6 +810,7 @@ def run_ours(args):
                    "candidate-independent funicular rows of J (host_filled_bytes_per_step) are written by host threads from the plan's "
                    "copy and only d2h_bytes_over_pcie_per_step cross PCIe"}
     e2e["delivered_gb_per_s"] = e2e["value"] * d2h / Ne / 1e9
+    e2e["measured_host_fill_gb_per_s"], e2e["measured_dma_gb_per_s"] = _fs["host_fill_gb_per_s"], _fs["dma_gb_per_s"]
     if rank == 0:
         e2e["host_dram_copy_gb_per_s"] = host_copy_bandwidth()
     # the sweep use-case: only objectives + feasibility cross PCIe, g / J / z stay in HBM for an on-device consumer

@@ -21,7 +21,7 @@ STATUS_OK, STATUS_NOT_PD, STATUS_NONFINITE = 0, 1, 2
 EXPORTS = [
     "tno_abi_version", "tno_last_error", "tno_plan_create", "tno_plan_destroy", "tno_plan_query",
     "tno_plan_symbolic", "tno_eval_batch", "tno_eval_batch_host", "tno_plan_launch_count",
-    "tno_plan_profile", "tno_plan_profile_read", "tno_symbolic_analyse", "tno_fetch_jacobian_host", "tno_device_peak",
+    "tno_plan_profile", "tno_plan_profile_read", "tno_symbolic_analyse", "tno_fetch_jacobian_host", "tno_device_peak", "tno_plan_fetch_stats",
     "tno_sqp_qp_solve", "tno_sqp_bfgs_update", "tno_preprocess_batch", "tno_preprocess_work_bytes",
 ]
 
@@ -118,6 +118,8 @@ def load():
     lib.tno_symbolic_analyse.restype = C.c_int
     lib.tno_device_peak.argtypes = [C.c_int32, C.c_int32, _dp]
     lib.tno_device_peak.restype = C.c_int
+    lib.tno_plan_fetch_stats.argtypes = [C.c_void_p, _dp]
+    lib.tno_plan_fetch_stats.restype = C.c_int
     vp = C.c_void_p
     lib.tno_sqp_qp_solve.argtypes = [C.c_int64, C.c_int32, C.c_int32, C.c_int32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp,
                                      vp, C.c_int32, C.c_double, C.c_int32, vp]

@@ -7,6 +7,7 @@
 #include <map>
 #include <new>
 #include <string>
+#include <chrono>
 #include <thread>
 #include <vector>
 #if defined(__SSE2__)
@@ -130,6 +131,8 @@ void tno_plan_destroy(tno_plan* plan) {
     cudaEventDestroy(r.b);
   }
   for (auto& e : P->prof_pool) cudaEventDestroy(e);
+  if (P->fetch_ev0) cudaEventDestroy(P->fetch_ev0);
+  if (P->fetch_ev1) cudaEventDestroy(P->fetch_ev1);
   if (P->stream) cudaStreamDestroy(P->stream);
   delete P;
 }
@@ -814,16 +817,46 @@ int tno_fetch_jacobian_host(tno_plan* plan, const double* J_dev, double* J_host,
   // D = PCIe rate and H = host fill rate (~4.5 GB/s per streaming thread), both finish together when the host takes
   //   phi = (v + c) / (c (1 + D / H))     of the c constant bytes (v = candidate-dependent bytes per candidate).
   // Few threads per rank (8 ranks sharing one host) => small phi, the DMA engines of the 8 GPUs carry the load.
+  // The model only starts the split: every fetch measures the DMA rate (events around the copy, read at the next call) and
+  // the host fill rate (wall clock of the threads), both while the other side is running, and the next call uses them.
   static const char* env_phi = getenv("TNO_HOST_FILL_FRACTION");
-  double phi = env_phi ? atof(env_phi) : ((double)per / ((double)cst * (1.0 + 52.0 / (4.5 * (double)nthreads))));
+  static const bool adaptive = getenv("TNO_HOST_FILL_STATIC") == nullptr;
+  if (P->fetch_pending && cudaEventQuery(P->fetch_ev1) == cudaSuccess) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, P->fetch_ev0, P->fetch_ev1) == cudaSuccess && ms > 0.f) {
+      const double rate = P->fetch_pending_bytes / (1e-3 * (double)ms);
+      P->fetch_rate_d = P->fetch_rate_d > 0.0 ? 0.5 * (P->fetch_rate_d + rate) : rate;
+    }
+    P->fetch_pending = false;
+  }
+  double phi = (double)per / ((double)cst * (1.0 + 52.0 / (4.5 * (double)nthreads)));
+  if (adaptive && P->fetch_rate_h > 0.0 && P->fetch_rate_d > 0.0 && N >= 256)
+    phi = (double)per / ((double)cst * (1.0 + P->fetch_rate_d / P->fetch_rate_h));
+  if (env_phi) phi = atof(env_phi);
   phi = std::min(1.0, std::max(0.0, phi));
+  P->fetch_phi = phi;
+  P->fetch_threads = (int)nthreads;
   const size_t row = (size_t)P->dp.var.nvar;
   size_t rows_h = std::min(cst / row, (size_t)(phi * (double)(cst / row) + 0.5));   // whole rows of J
   if ((rows_h * row) & 1) rows_h -= 1;                                              // the DMA part starts 16-byte aligned
   const size_t cst_h = rows_h * row;
+  const bool measure = adaptive && !P->fetch_pending && N >= 256;
+  if (measure) {
+    if (!P->fetch_ev0) {
+      TNO_CUDA_OK(cudaEventCreate(&P->fetch_ev0));
+      TNO_CUDA_OK(cudaEventCreate(&P->fetch_ev1));
+    }
+    TNO_CUDA_OK(cudaEventRecord(P->fetch_ev0, s));
+  }
   TNO_CUDA_OK(cudaMemcpy2DAsync(J_host + cst_h, per * 8, J_dev + cst_h, per * 8, (per - cst_h) * 8, (size_t)N, cudaMemcpyDeviceToHost, s));
+  if (measure) {
+    TNO_CUDA_OK(cudaEventRecord(P->fetch_ev1, s));
+    P->fetch_pending = true;
+    P->fetch_pending_bytes = (double)(per - cst_h) * 8.0 * (double)N;
+  }
   const size_t cst_fill = cst_h;
   if (cst_fill == 0) return TNO_OK;
+  const auto fill_t0 = std::chrono::steady_clock::now();
   const double* src = P->h_jfun.data();
   auto work = [=](int64_t a, int64_t b) {
     for (int64_t c = a; c < b; ++c) copy_streaming(J_host + (size_t)c * per, src, cst_fill);
@@ -840,6 +873,23 @@ int tno_fetch_jacobian_host(tno_plan* plan, const double* J_dev, double* J_host,
     work(0, std::min(N, step));
     for (auto& t : pool) t.join();
   }
+  if (N >= 256) {
+    const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - fill_t0).count();
+    if (dt > 0.0) {
+      const double rate = (double)cst_fill * 8.0 * (double)N / dt;
+      P->fetch_rate_h = P->fetch_rate_h > 0.0 ? 0.5 * (P->fetch_rate_h + rate) : rate;
+    }
+  }
+  return TNO_OK;
+}
+
+int tno_plan_fetch_stats(const tno_plan* plan, double* stats) {
+  const Plan* P = reinterpret_cast<const Plan*>(plan);
+  if (!P || !stats) return fail(TNO_EINVAL, "null argument");
+  stats[0] = P->fetch_phi;
+  stats[1] = P->fetch_rate_h * 1e-9;
+  stats[2] = P->fetch_rate_d * 1e-9;
+  stats[3] = (double)P->fetch_threads;
   return TNO_OK;
 }
 

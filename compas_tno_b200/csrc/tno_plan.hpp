@@ -321,6 +321,13 @@ struct Plan {
   const double* jfun = nullptr;           // 2m x nvar candidate-independent rows [B 0; -B 0] (+ d0 column) of J
   int64_t jfun_count = 0;
   std::vector<double> h_jfun;             // host copy of the same block (tno_fetch_jacobian_host)
+  // adaptive split of the constant rows between host threads and the DMA engine (tno_fetch_jacobian_host)
+  double fetch_rate_h = 0.0, fetch_rate_d = 0.0;   // measured bytes / s (smoothed), 0 = not measured yet
+  double fetch_phi = 0.0;                          // fraction used by the last fetch
+  int fetch_threads = 0;
+  cudaEvent_t fetch_ev0 = nullptr, fetch_ev1 = nullptr;
+  bool fetch_pending = false;
+  double fetch_pending_bytes = 0.0;
   // scratch (interleaved family): nslots x chunk doubles
   double* scratch = nullptr;
   int32_t* status_scratch = nullptr;

@@ -162,6 +162,14 @@ class TnoPlan:
         return info.as_dict()
 
     @property
+    def fetch_stats(self) -> Dict[str, float]:
+        """Split and measured rates of the most recent Jacobian fetch to host memory (tno_plan_fetch_stats)."""
+        st = (C.c_double * 4)()
+        _lib.check(self._lib.tno_plan_fetch_stats(self._handle, st))
+        return {"host_fill_fraction": float(st[0]), "host_fill_gb_per_s": float(st[1]), "dma_gb_per_s": float(st[2]),
+                "host_threads": int(st[3])}
+
+    @property
     def launch_count(self) -> int:
         return int(self._lib.tno_plan_launch_count(self._handle))
 

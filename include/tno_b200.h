@@ -245,6 +245,12 @@ int tno_fetch_jacobian_host(tno_plan* plan, const double* J_dev, double* J_host,
 #define TNO_PEAK_FP64_MMA 1
 int tno_device_peak(int32_t device, int32_t what, double* value);
 
+/* Statistics of the most recent tno_fetch_jacobian_host of a plan: stats[4] = { fraction of the constant (funicular) rows
+ * written by the host threads, measured host fill rate [GB/s], measured DMA rate [GB/s], host threads used }.  The split
+ * between the host threads and the DMA engine follows the two measured rates (both finish together), starting from a
+ * model (52 GB/s PCIe, 4.5 GB/s per thread); TNO_HOST_FILL_FRACTION fixes it. */
+int tno_plan_fetch_stats(const tno_plan* plan, double* stats);
+
 /* ---- batched multi-start driver -------------------------------------------------------------------
  * Building blocks of S SQP iterations that advance together with iterates, f, grad f, g and the dense J resident in device
  * memory.  They replace scipy.optimize.fmin_slsqp as the reference calls it (src/compas_tno/solvers/scipy.py:127-174:
