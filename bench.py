@@ -808,7 +808,8 @@ def run_ours(args):
            "candidates_per_step": Ne, "numa": numa, "host_fill_threads": _thr, "host_fill_fraction_of_constant_rows": _phi,
            "note": "every output incl. the dense J delivered to pinned host memory; d2h_bytes_per_step = delivered bytes, of which the "
                    "candidate-independent funicular rows of J (host_filled_bytes_per_step) are written by host threads from the plan's "
-                   "copy and only d2h_bytes_over_pcie_per_step cross PCIe"}
+                   "copy and only d2h_bytes_over_pcie_per_step cross PCIe; the split follows the measured host-fill and DMA rates "
+                   "(tno_plan_fetch_stats)"}
     e2e["delivered_gb_per_s"] = e2e["value"] * d2h / Ne / 1e9
     e2e["measured_host_fill_gb_per_s"], e2e["measured_dma_gb_per_s"] = _fs["host_fill_gb_per_s"], _fs["dma_gb_per_s"]
     if rank == 0:
