@@ -88,7 +88,7 @@ class MultiStartSolver:
     """S simultaneous SQP runs on one plan.  ``solve(X0)`` returns a :class:`MultiStartResult`."""
 
     def __init__(self, plan: TnoPlan, lb, ub, acc: float = 1e-6, max_iter: int = 100, qp_iter: int = 40, qp_tol: float = 1e-10,
-                 max_backtracks: int = 10, use_mma: bool = False, feas_tol: float = 1e-8):
+                 max_backtracks: int = 10, use_mma: bool = False, feas_tol: float = 1e-8, patience: int = 20):
         import torch
         self.plan = plan
         self.torch = torch
@@ -96,6 +96,7 @@ class MultiStartSolver:
         self.lib = _lib.load()
         self.acc, self.max_iter, self.qp_iter, self.qp_tol = float(acc), int(max_iter), int(qp_iter), float(qp_tol)
         self.max_backtracks, self.use_mma, self.feas_tol = int(max_backtracks), bool(use_mma), float(feas_tol)
+        self.patience = int(patience)   # iterations without progress after which the last <= 0.5 % of the starts are given up
         nv = plan.nvar
         if nv > 64:
             raise NotImplementedError("multi-start driver: more than 64 variables per start")
@@ -160,6 +161,7 @@ class MultiStartSolver:
         niter = t.zeros(S, dtype=t.int32, device=self.dev)
         rho = t.zeros(S, dtype=t.float64, device=self.dev)
         qp_its, qp_cnt, it = 0.0, 0, 0
+        stall_count, stall_iters = -1, 0
         for it in range(1, self.max_iter + 1):
             _lib.check(self.lib.tno_sqp_qp_solve(
                 S, nv, ng, self.nshared, self._ptr(B["H"]), self._ptr(B["grad"]), self._ptr(B["g"]), self._ptr(B["J"]),
@@ -181,9 +183,20 @@ class MultiStartSolver:
                     int((act & (info[:, 5] == 0)).sum()), float(B["d"][act & ~nf].abs().max()) if bool((act & ~nf).any()) else 0.0,
                     float(viol[act].max())), flush=True)
             act = act & ~done & ~bad
-            if not bool(act.any()):
+            n_act = int(act.sum())
+            if n_act == 0:
                 active = act.to(t.uint8)
                 break
+            # stragglers: the starts advance in lock step, so a handful that do not converge would keep the whole batch
+            # iterating to max_iter.  Once at most 0.5 % of the starts (at least one) are left and none of them has
+            # finished for `patience` iterations, they are given up (reported as not converged).
+            if n_act <= max(1, S // 200) and n_act == stall_count:
+                stall_iters += 1
+                if stall_iters >= self.patience:
+                    active = act.to(t.uint8)
+                    break
+            else:
+                stall_count, stall_iters = n_act, 0
             niter += act.to(t.int32)
             # penalty of the L1 merit function: above the largest multiplier, never decreased by more than half a step
             rho = t.where(act, t.maximum(0.5 * (rho + lmax), 1.01 * lmax), rho)
